@@ -1,0 +1,341 @@
+"""ctypes binding of include/klu.h (libklu_b200.so).
+
+This is plumbing for tests and bench.py; the reference-facing host code is the
+C++ tools under host/.  There is no CPU fallback: Engine() raises when the CUDA
+library is missing or no GPU is usable.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD = range(8)
+TOOL_NAMES = {SEGMENT: "lattice-word-index-segment", POSITION: "lattice-word-index-position",
+              UTTERANCE: "lattice-word-index-utterance", FRAME_POST: "lattice-to-word-frame-post",
+              PRUNE_DYN_BEAM: "lattice-prune-dyn-beam", BEST_PATH2: "lattice-best-path2",
+              CHAR_POSITION: "lattice-char-index-position", FWD_BWD: "fwd-bwd"}
+INT_MAX = 2**31 - 1
+
+# every symbol include/klu.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = ["klu_last_error", "klu_version", "klu_opts_default", "klu_device_count", "klu_create", "klu_destroy",
+           "klu_host_alloc", "klu_host_free", "klu_topsort", "klu_load", "klu_run", "klu_sync", "klu_result_offsets",
+           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post",
+           "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position",
+           "klu_fetch_fwd_bwd", "klu_timer_start", "klu_timer_stop", "klu_launch_count", "klu_profile_enable",
+           "klu_profile_json", "klu_batch_stats", "klu_flush_l2"]
+
+
+class KluLattices(C.Structure):
+    _fields_ = [("num_lattices", C.c_int32), ("state_off", C.c_void_p), ("arc_off", C.c_void_p),
+                ("arc_src", C.c_void_p), ("arc_dst", C.c_void_p), ("arc_label", C.c_void_p), ("arc_dur", C.c_void_p),
+                ("arc_graph", C.c_void_p), ("arc_acoustic", C.c_void_p), ("fin_graph", C.c_void_p),
+                ("fin_acoustic", C.c_void_p), ("fin_dur", C.c_void_p)]
+
+
+class KluOpts(C.Structure):
+    _fields_ = [("acoustic_scale", C.c_float), ("graph_scale", C.c_float), ("insertion_penalty", C.c_float),
+                ("beam", C.c_float), ("include_words", C.c_void_p), ("num_include", C.c_int32),
+                ("exclude_words", C.c_void_p), ("num_exclude", C.c_int32), ("beam_ratio", C.c_float),
+                ("min_beam", C.c_float), ("max_arcs", C.c_int32), ("max_states", C.c_int32), ("nbest", C.c_int32),
+                ("group_labels", C.c_void_p), ("group_ids", C.c_void_p), ("num_group_labels", C.c_int32),
+                ("inc_groups", C.c_void_p), ("num_inc_groups", C.c_int32), ("del_groups", C.c_void_p),
+                ("num_del_groups", C.c_int32)]
+
+
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "libklu_b200.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise RuntimeError("%s is not built (run __graft_entry__.build()); there is no CPU fallback" % p)
+        L = C.CDLL(p)
+        L.klu_last_error.restype = C.c_char_p
+        for name in SYMBOLS:
+            getattr(L, name)  # fail loudly on a missing export
+        _LIB = L
+    return _LIB
+
+
+class KluError(RuntimeError):
+    pass
+
+
+def _chk(rc):
+    if rc != 0:
+        raise KluError(lib().klu_last_error().decode())
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else None
+
+
+def _i32(v):
+    return np.ascontiguousarray(np.asarray(list(v), dtype=np.int32))
+
+
+def char_groups(wspace, other_groups=()):
+    """kwsbin2/utils.h:41-84 ParseSeparatorGroups."""
+    label_group = {0: 0}
+    for w in wspace:
+        if w in label_group:
+            raise ValueError("label %d assigned to two groups" % w)
+        label_group[w] = 1
+    inc = [INT_MAX]
+    for gi, grp in enumerate(other_groups):
+        for lab in grp:
+            if lab in label_group:
+                raise ValueError("label %d assigned to two groups" % lab)
+            label_group[lab] = gi + 2
+        inc.append(gi + 2)
+    return label_group, inc, [1]
+
+
+def make_opts(acoustic_scale=1.0, graph_scale=1.0, insertion_penalty=0.0, beam=float("inf"), include_words=(),
+              exclude_words=(), beam_ratio=0.9, min_beam=1e-3, max_arcs=INT_MAX, max_states=INT_MAX, nbest=100,
+              label_group=None, inc_groups=(), del_groups=()):
+    o = KluOpts()
+    lib().klu_opts_default(C.byref(o))
+    keep = [_i32(include_words), _i32(exclude_words)]
+    lg = label_group or {}
+    keep += [_i32(lg.keys()), _i32(lg.values()), _i32(inc_groups), _i32(del_groups)]
+    o.acoustic_scale, o.graph_scale, o.insertion_penalty, o.beam = acoustic_scale, graph_scale, insertion_penalty, beam
+    o.include_words, o.num_include = _p(keep[0]), keep[0].size
+    o.exclude_words, o.num_exclude = _p(keep[1]), keep[1].size
+    o.beam_ratio, o.min_beam, o.max_arcs, o.max_states, o.nbest = beam_ratio, min_beam, max_arcs, max_states, nbest
+    o.group_labels, o.group_ids, o.num_group_labels = _p(keep[2]), _p(keep[3]), keep[2].size
+    o.inc_groups, o.num_inc_groups = _p(keep[4]), keep[4].size
+    o.del_groups, o.num_del_groups = _p(keep[5]), keep[5].size
+    return o, keep
+
+
+class Engine:
+    """One context on one GPU (klu_create .. klu_destroy)."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        _chk(self.L.klu_create(device, C.byref(self.h)))
+        self.batch = None
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.L.klu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- memory ---------------------------------------------------------------
+    def pinned(self, nbytes):
+        """Pinned host buffer (klu_host_alloc) as a writable memoryview-able object."""
+        p = C.c_void_p()
+        _chk(self.L.klu_host_alloc(C.c_size_t(nbytes), C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        return buf
+
+    # -- data -----------------------------------------------------------------
+    def load(self, batch):
+        kl = KluLattices(len(batch), _p(batch.state_off), _p(batch.arc_off), _p(batch.src), _p(batch.dst),
+                         _p(batch.label), _p(batch.dur), _p(batch.graph), _p(batch.acoustic), _p(batch.fin_graph),
+                         _p(batch.fin_acoustic), _p(batch.fin_dur))
+        _chk(self.L.klu_load(self.h, C.byref(kl)))
+        self.batch = batch
+
+    def run(self, tool, **opts):
+        o, keep = make_opts(**opts)
+        _chk(self.L.klu_run(self.h, tool, C.byref(o)))
+
+    def run_opts(self, tool, o):
+        _chk(self.L.klu_run(self.h, tool, C.byref(o)))
+
+    def sync(self):
+        _chk(self.L.klu_sync(self.h))
+
+    # -- results --------------------------------------------------------------
+    def offsets(self):
+        off = np.zeros(len(self.batch) + 1, np.int64)
+        _chk(self.L.klu_result_offsets(self.h, _p(off)))
+        return off
+
+    def fetch_segment(self):
+        off = self.offsets()
+        n = int(off[-1])
+        w, t0, t1 = (np.zeros(n, np.int32) for _ in range(3))
+        lp = np.zeros(n, np.float64)
+        _chk(self.L.klu_fetch_segment(self.h, _p(w), _p(t0), _p(t1), _p(lp)))
+        return off, w, t0, t1, lp
+
+    def fetch_position(self):
+        off = self.offsets()
+        n = int(off[-1])
+        w, pos, t0, t1 = (np.zeros(n, np.int32) for _ in range(4))
+        lp = np.zeros(n, np.float64)
+        _chk(self.L.klu_fetch_position(self.h, _p(w), _p(pos), _p(t0), _p(t1), _p(lp)))
+        return off, w, pos, t0, t1, lp
+
+    def fetch_utterance(self):
+        off = self.offsets()
+        n = int(off[-1])
+        w = np.zeros(n, np.int32)
+        lp = np.zeros(n, np.float64)
+        _chk(self.L.klu_fetch_utterance(self.h, _p(w), _p(lp)))
+        return off, w, lp
+
+    def fetch_frame_post(self):
+        off = self.offsets()
+        n = int(off[-1])
+        nf = np.zeros(len(self.batch), np.int32)
+        fr, w = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lp = np.zeros(n, np.float32)
+        _chk(self.L.klu_fetch_frame_post(self.h, _p(nf), _p(fr), _p(w), _p(lp)))
+        return off, nf, fr, w, lp
+
+    def fetch_best_path2(self):
+        off = self.offsets()
+        n = int(off[-1])
+        lab = np.zeros(n, np.int32)
+        cost = np.zeros(len(self.batch), np.float32)
+        nf = np.zeros(len(self.batch), np.int32)
+        _chk(self.L.klu_fetch_best_path2(self.h, _p(lab), _p(cost), _p(nf)))
+        return off, lab, cost, nf
+
+    def fetch_prune(self):
+        off = self.offsets()
+        n = int(off[-1])
+        b = self.batch
+        ai, ns, nd = (np.zeros(n, np.int32) for _ in range(3))
+        g, a = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        smap = np.zeros(b.num_states, np.int32)
+        fg, fa = np.zeros(b.num_states, np.float32), np.zeros(b.num_states, np.float32)
+        beams = np.zeros(2 * len(b), np.float64)
+        _chk(self.L.klu_fetch_prune(self.h, _p(ai), _p(ns), _p(nd), _p(g), _p(a), _p(smap), _p(fg), _p(fa),
+                                    _p(beams)))
+        return off, ai, ns, nd, g, a, smap, fg, fa, beams
+
+    def fetch_char_position(self):
+        off = self.offsets()
+        n = int(off[-1])
+        tot = C.c_int64()
+        _chk(self.L.klu_result_char_sizes(self.h, C.byref(tot)))
+        coff = np.zeros(n + 1, np.int64)
+        chars = np.zeros(tot.value, np.int32)
+        pos, t0, t1 = (np.zeros(n, np.int32) for _ in range(3))
+        lp = np.zeros(n, np.float64)
+        _chk(self.L.klu_fetch_char_position(self.h, _p(coff), _p(chars), _p(pos), _p(t0), _p(t1), _p(lp)))
+        return off, coff, chars, pos, t0, t1, lp
+
+    def fetch_fwd_bwd(self):
+        b = self.batch
+        al, be = np.zeros(b.num_states, np.float64), np.zeros(b.num_states, np.float64)
+        tot = np.zeros(len(b), np.float64)
+        _chk(self.L.klu_fetch_fwd_bwd(self.h, _p(al), _p(be), _p(tot)))
+        return al, be, tot
+
+    # -- python views used by the parity tests ---------------------------------
+    def segment(self, **o):
+        self.run(SEGMENT, **o)
+        off, w, t0, t1, lp = self.fetch_segment()
+        return [list(zip(w[a:b].tolist(), t0[a:b].tolist(), t1[a:b].tolist(), lp[a:b].tolist()))
+                for a, b in zip(off[:-1], off[1:])]
+
+    def position(self, **o):
+        self.run(POSITION, **o)
+        off, w, p, t0, t1, lp = self.fetch_position()
+        return [list(zip(w[a:b].tolist(), p[a:b].tolist(), t0[a:b].tolist(), t1[a:b].tolist(), lp[a:b].tolist()))
+                for a, b in zip(off[:-1], off[1:])]
+
+    def utterance(self, **o):
+        self.run(UTTERANCE, **o)
+        off, w, lp = self.fetch_utterance()
+        return [list(zip(w[a:b].tolist(), lp[a:b].tolist())) for a, b in zip(off[:-1], off[1:])]
+
+    def frame_post(self, **o):
+        self.run(FRAME_POST, **o)
+        off, nf, fr, w, lp = self.fetch_frame_post()
+        res = []
+        for l, (a, b) in enumerate(zip(off[:-1], off[1:])):
+            frames = [[] for _ in range(int(nf[l]))]
+            for k, ww, p in zip(fr[a:b].tolist(), w[a:b].tolist(), lp[a:b].tolist()):
+                frames[k].append((ww, p))
+            res.append(frames)
+        return res
+
+    def best_path2(self, **o):
+        self.run(BEST_PATH2, **o)
+        off, lab, cost, nf = self.fetch_best_path2()
+        return [(lab[a:b].tolist(), float(cost[l])) for l, (a, b) in enumerate(zip(off[:-1], off[1:]))]
+
+    def prune_dyn_beam(self, **o):
+        self.run(PRUNE_DYN_BEAM, **o)
+        off, ai, ns, nd, g, a, smap, fg, fa, beams = self.fetch_prune()
+        b = self.batch
+        res = []
+        for l, (x, y) in enumerate(zip(off[:-1], off[1:])):
+            s0, s1 = int(b.state_off[l]), int(b.state_off[l + 1])
+            e0 = int(b.arc_off[l])
+            arcs = [(int(ai[k]), int(ns[k]), int(nd[k]), int(b.label[e0 + ai[k]]), float(g[k]), float(a[k]))
+                    for k in range(x, y)]
+            m = smap[s0:s1]
+            finals = [(int(m[s]), float(fg[s0 + s]), float(fa[s0 + s])) for s in range(s1 - s0)
+                      if m[s] >= 0 and not (np.isinf(fg[s0 + s]) and np.isinf(fa[s0 + s]))]
+            res.append(dict(arcs=arcs, finals=finals, nstates=int((m >= 0).sum()), beam0=float(beams[2 * l]),
+                            beam=float(beams[2 * l + 1])))
+        return res
+
+    def char_position(self, wspace, other_groups=(), **o):
+        lg, inc, dele = char_groups(wspace, other_groups)
+        self.run(CHAR_POSITION, label_group=lg, inc_groups=inc, del_groups=dele, **o)
+        off, coff, chars, pos, t0, t1, lp = self.fetch_char_position()
+        res = []
+        for a, b in zip(off[:-1], off[1:]):
+            rows = []
+            for i in range(a, b):
+                s = "_".join(str(c) for c in chars[coff[i]:coff[i + 1]].tolist())
+                rows.append((s, int(pos[i]), int(t0[i]), int(t1[i]), float(lp[i])))
+            res.append(rows)
+        return res
+
+    # -- measurement ------------------------------------------------------------
+    def timer_start(self):
+        _chk(self.L.klu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _chk(self.L.klu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        _chk(self.L.klu_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def profile(self, on):
+        _chk(self.L.klu_profile_enable(self.h, 1 if on else 0))
+
+    def profile_json(self):
+        buf = C.create_string_buffer(1 << 16)
+        _chk(self.L.klu_profile_json(self.h, buf, C.c_size_t(len(buf))))
+        return json.loads(buf.value.decode())
+
+    def stats(self):
+        s = (C.c_int64 * 8)()
+        _chk(self.L.klu_batch_stats(self.h, s))
+        return dict(lattices=s[0], states=s[1], arcs=s[2], levels=s[3], entries=s[4], band=s[5], max_len=s[6],
+                    max_time=s[7])
+
+    def flush_l2(self):
+        _chk(self.L.klu_flush_l2(self.h))

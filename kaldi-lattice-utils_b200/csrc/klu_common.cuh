@@ -1,0 +1,236 @@
+// klu_common.cuh -- shared declarations of the B200 lattice engine (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "klu.h"
+
+namespace klu {
+
+void set_error(const std::string& msg);
+
+#define KLU_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t err__ = (call);                                                             \
+    if (err__ != cudaSuccess) {                                                             \
+      klu::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " at " + __FILE__ + ":" + \
+                     std::to_string(__LINE__));                                             \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+#define KLU_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+// Growable device buffer, reused across runs (no cudaMalloc in steady state).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// How arc/final weights become costs.
+struct CostParams {
+  double gs, as;   // graph / acoustic scale (double products, float storage)
+  float pen;       // insertion penalty (float add on arcs with label != 0)
+  int scale;       // apply gs/as (either != 1)
+  int float_sum;   // cost = (double)(float)(g + a) instead of (double)g + (double)a
+};
+
+// Packed batch, device side.  States are renumbered per lattice by (level, input
+// id); "level" = longest arc distance from any source state, so all arcs into a
+// level come from earlier levels and a level is a contiguous state range.
+struct BatchView {
+  int32_t L;          // lattices
+  int32_t S;          // states
+  int32_t E;          // arcs
+  const int32_t* s_off;      // [L+1] first state of each lattice
+  const int32_t* e_off;      // [L+1] first arc of each lattice
+  const int32_t* lvl_off;    // [L+1] index into lvl_start (each lattice has nl+1 entries)
+  const int32_t* lvl_start;  // first (global) state of each level, + sentinel per lattice
+  const int4* in_rec;        // [E] arcs sorted by dst: {src(global), g bits, a bits, label}
+  const int4* out_rec;       // [E] arcs sorted by src: {dst(global), g bits, a bits, label}
+  const int32_t* in_off;     // [S+1]
+  const int32_t* out_off;    // [S+1]
+  const int32_t* out_src;    // [E] (global) src of out-order arcs
+  const int32_t* out_orig;   // [E] lattice-local index of the arc in the caller's arrays
+  const float* fin_g;        // [S]
+  const float* fin_a;        // [S]
+  const int32_t* time;       // [S] frame of each state (CompactLatticeStateTimes)
+  const int32_t* orig;       // [S] lattice-local input id of each state
+  const int32_t* band_lo;    // [S] min #non-eps labels on paths from the start (-1: unreachable)
+  const int32_t* band_off;   // [S+1] offsets into the (state,len) band arrays
+  const int32_t* order;      // [L] lattices by descending arc count (work queue order)
+};
+
+struct KernelStat {
+  int64_t launches = 0;
+  double ms = 0;
+};
+
+}  // namespace klu
+
+struct klu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 148;
+  int64_t launches = 0;
+  bool profile = false;
+  std::map<std::string, klu::KernelStat> prof;
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t> > > prof_pending;
+  std::vector<cudaEvent_t> event_pool;
+
+  // ---- loaded batch (host metadata) ----
+  bool loaded = false;
+  int32_t L = 0;
+  int64_t S = 0, E = 0, NL = 0;
+  std::vector<int64_t> h_s_off, h_e_off;     // input offsets
+  std::vector<int32_t> h_new2old;            // per packed state: input local id
+  std::vector<int32_t> h_old2new;            // per input state (global): packed global id
+  std::vector<int32_t> h_num_frames;         // utterance length per lattice
+  std::vector<uint8_t> h_times_ok;           // consistent state times per lattice
+  std::vector<int64_t> h_cap_frame, h_cap_pos;  // per lattice entry upper bounds
+  std::vector<int32_t> h_maxlen;             // max #non-eps labels on a path, per lattice
+  int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0;
+  double avg_deg = 0;
+  int64_t band_total = 0;
+
+  // ---- device: packed batch ----
+  klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
+      d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_band_lo, d_band_off, d_order;
+  // ---- device: per-run state ----
+  klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
+  klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps
+  klu::DevBuf d_alpha2;                // banded alpha[s][len]
+  klu::DevBuf d_scratch[12];           // tool scratch (keys, indices, values ...)
+  klu::DevBuf d_res[8];                // dense results of the last run
+  klu::DevBuf d_flush;
+
+  // ---- last run ----
+  int last_tool = -1;
+  std::vector<int64_t> h_res_off;  // [L+1] entries per lattice of the last run
+  int64_t last_entries = 0;
+  int64_t last_chars = 0;
+
+  klu::BatchView view() const;
+};
+
+namespace klu {
+
+// Launch bookkeeping: counts launches and (when profiling) brackets the launch
+// with CUDA events on the context's stream.
+struct LaunchScope {
+  klu_ctx* c;
+  const char* name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(klu_ctx* ctx, const char* n);
+  ~LaunchScope();
+};
+#define KLU_LAUNCH(ctx, name) klu::LaunchScope scope__(ctx, name)
+
+int check_launch(const char* what);
+
+// klu_pack.cu
+int pack_and_upload(klu_ctx* c, const klu_lattices* lats);
+// klu_sweep.cu
+int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam);
+int run_tropical_sweeps(klu_ctx* c, const CostParams& cp);
+int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam);
+// klu_index.cu
+int run_index_tool(klu_ctx* c, int tool, const klu_opts* o);
+// klu_prune.cu
+int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o);
+// klu_bestpath.cu
+int run_best_path2(klu_ctx* c, const klu_opts* o);
+// klu_utt.cu
+int run_utterance(klu_ctx* c, const klu_opts* o);
+// klu_char.cu
+int run_char_position(klu_ctx* c, const klu_opts* o);
+
+CostParams make_cost_params(const klu_opts* o, bool float_sum);
+int upload_filter(klu_ctx* c, const klu_opts* o, int* mode_out, int* n_out);
+
+}  // namespace klu
+
+// ---------------------------------------------------------------------------
+// Device helpers
+#ifdef __CUDACC__
+namespace klu {
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+__device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// Arc cost exactly as the reference builds it: ScaleLattice (double product ->
+// float), AddWordInsPenToCompactLattice (float add), then ConvertToCost (double
+// sum) or the float sum of ComputeCompactLatticeBetas / word-frame-post.
+__device__ __forceinline__ void scaled_weights(float g, float a, int label, const CostParams& cp, float* go,
+                                               float* ao) {
+  if (cp.scale && !(isinf(g) && isinf(a) && g > 0 && a > 0)) {
+    g = (float)__dmul_rn(cp.gs, (double)g);
+    a = (float)__dmul_rn(cp.as, (double)a);
+  }
+  if (label != 0) g = __fadd_rn(g, cp.pen);
+  *go = g;
+  *ao = a;
+}
+
+__device__ __forceinline__ double arc_cost(float g, float a, int label, const CostParams& cp) {
+  float g2, a2;
+  scaled_weights(g, a, label, cp, &g2, &a2);
+  if (cp.float_sum) return (double)__fadd_rn(g2, a2);
+  return __dadd_rn((double)g2, (double)a2);
+}
+
+__device__ __forceinline__ double rec_cost(const int4& r, const CostParams& cp) {
+  return arc_cost(__int_as_float(r.y), __int_as_float(r.z), r.w, cp);
+}
+
+// final weights: no insertion penalty (label 0)
+__device__ __forceinline__ double final_cost(float g, float a, const CostParams& cp) {
+  return arc_cost(g, a, 0, cp);
+}
+
+// [ext] kaldi LogAdd(double,double): max + log1p(exp(-|d|)), cut at log(DBL_EPSILON)
+__device__ __forceinline__ double log_add(double x, double y) {
+  double diff;
+  if (x < y) {
+    diff = x - y;
+    x = y;
+  } else {
+    diff = y - x;
+  }
+  if (diff >= -36.04365338911715) return x + log1p(exp(diff));
+  return x;
+}
+
+// order-preserving map double -> uint64 (ascending)
+__device__ __forceinline__ unsigned long long ord_f64(double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ unsigned int ord_f32(float x) {
+  unsigned int b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace klu
+#endif

@@ -1,0 +1,372 @@
+// klu_core.cu -- context, buffers, launch bookkeeping and the C ABI entry points
+// that are not tool specific.  See include/klu.h for the contract.
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "klu_common.cuh"
+
+namespace klu {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (p) {
+    cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    p = nullptr;
+    return 1;
+  }
+  cap = want;
+  return 0;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+LaunchScope::LaunchScope(klu_ctx* ctx, const char* n) : c(ctx), name(n) {
+  c->launches++;
+  if (c->profile) {
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->event_pool.empty()) {
+        e = c->event_pool.back();
+        c->event_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, c->stream);
+  }
+}
+
+LaunchScope::~LaunchScope() {
+  if (c->profile && a) {
+    cudaEventRecord(b, c->stream);
+    c->prof_pending.push_back(std::make_pair(std::string(name), std::make_pair(a, b)));
+  }
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+CostParams make_cost_params(const klu_opts* o, bool float_sum) {
+  CostParams cp;
+  cp.gs = (double)o->graph_scale;
+  cp.as = (double)o->acoustic_scale;
+  cp.pen = o->insertion_penalty;
+  cp.scale = (o->acoustic_scale != 1.0f || o->graph_scale != 1.0f) ? 1 : 0;
+  cp.float_sum = float_sum ? 1 : 0;
+  return cp;
+}
+
+// Label filter (kwsbin2/lattice-word-index-position.cc:150-155): mode 0 = none,
+// 1 = include list, 2 = exclude list; sorted unique labels on the device.
+int upload_filter(klu_ctx* c, const klu_opts* o, int* mode_out, int* n_out) {
+  std::vector<int32_t> v;
+  int mode = 0;
+  if (o->num_include > 0) {
+    mode = 1;
+    v.assign(o->include_words, o->include_words + o->num_include);
+  } else if (o->num_exclude > 0) {
+    mode = 2;
+    v.assign(o->exclude_words, o->exclude_words + o->num_exclude);
+  }
+  std::sort(v.begin(), v.end());
+  v.erase(std::unique(v.begin(), v.end()), v.end());
+  if (!v.empty()) {
+    KLU_TRY(c->d_filter.reserve(v.size() * sizeof(int32_t)));
+    KLU_CUDA(cudaMemcpyAsync(c->d_filter.p, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    KLU_CUDA(cudaStreamSynchronize(c->stream));  // v goes out of scope
+  }
+  *mode_out = mode;
+  *n_out = (int)v.size();
+  return 0;
+}
+
+}  // namespace klu
+
+klu::BatchView klu_ctx::view() const {
+  klu::BatchView v;
+  v.L = L;
+  v.S = (int32_t)S;
+  v.E = (int32_t)E;
+  v.s_off = d_s_off.as<int32_t>();
+  v.e_off = d_e_off.as<int32_t>();
+  v.lvl_off = d_lvl_off.as<int32_t>();
+  v.lvl_start = d_lvl_start.as<int32_t>();
+  v.in_rec = d_in_rec.as<int4>();
+  v.out_rec = d_out_rec.as<int4>();
+  v.in_off = d_in_off.as<int32_t>();
+  v.out_off = d_out_off.as<int32_t>();
+  v.out_src = d_out_src.as<int32_t>();
+  v.out_orig = d_out_orig.as<int32_t>();
+  v.fin_g = d_fin_g.as<float>();
+  v.fin_a = d_fin_a.as<float>();
+  v.time = d_time.as<int32_t>();
+  v.orig = d_orig.as<int32_t>();
+  v.band_lo = d_band_lo.as<int32_t>();
+  v.band_off = d_band_off.as<int32_t>();
+  v.order = d_order.as<int32_t>();
+  return v;
+}
+
+using namespace klu;
+
+extern "C" {
+
+const char* klu_last_error(void) { return g_error.c_str(); }
+int klu_version(void) { return KLU_VERSION; }
+
+void klu_opts_default(klu_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->acoustic_scale = 1.0f;
+  o->graph_scale = 1.0f;
+  o->insertion_penalty = 0.0f;
+  o->beam = INFINITY;
+  o->beam_ratio = 0.9f;
+  o->min_beam = 1e-3f;
+  o->max_arcs = INT_MAX;
+  o->max_states = INT_MAX;
+  o->nbest = 100;
+}
+
+int klu_device_count(int* n) {
+  *n = 0;
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    *n = 0;
+    return 1;
+  }
+  return 0;
+}
+
+int klu_create(int device, klu_ctx** out) {
+  *out = nullptr;
+  int n = 0;
+  if (klu_device_count(&n) != 0 || n <= 0) {
+    if (g_error.empty()) set_error("no CUDA device: this library has no CPU fallback");
+    return 1;
+  }
+  if (device < 0 || device >= n) {
+    set_error("invalid device index");
+    return 1;
+  }
+  KLU_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KLU_CUDA(cudaGetDeviceProperties(&prop, device));
+  klu_ctx* c = new klu_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  KLU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  KLU_CUDA(cudaEventCreate(&c->ev0));
+  KLU_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return 0;
+}
+
+int klu_destroy(klu_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
+                    &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_fin_g, &c->d_fin_a,
+                    &c->d_time, &c->d_orig, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_alpha, &c->d_beta,
+                    &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
+                    &c->d_alpha2, &c->d_flush};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& b : c->d_scratch) b.release();
+  for (auto& b : c->d_res) b.release();
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  for (auto& p : c->prof_pending) {
+    cudaEventDestroy(p.second.first);
+    cudaEventDestroy(p.second.second);
+  }
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int klu_host_alloc(size_t bytes, void** out) {
+  *out = nullptr;
+  KLU_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int klu_host_free(void* p) {
+  if (p) KLU_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int klu_load(klu_ctx* c, const klu_lattices* lats) {
+  KLU_CUDA(cudaSetDevice(c->device));
+  c->loaded = false;
+  c->last_tool = -1;
+  KLU_TRY(pack_and_upload(c, lats));
+  c->loaded = true;
+  return 0;
+}
+
+int klu_run(klu_ctx* c, int tool, const klu_opts* opts) {
+  if (!c->loaded) {
+    set_error("klu_run: no batch loaded");
+    return 1;
+  }
+  KLU_CUDA(cudaSetDevice(c->device));
+  klu_opts def;
+  if (!opts) {
+    klu_opts_default(&def);
+    opts = &def;
+  }
+  c->last_tool = -1;
+  int rc = 0;
+  switch (tool) {
+    case KLU_SEGMENT:
+    case KLU_POSITION:
+    case KLU_FRAME_POST:
+    case KLU_FWD_BWD:
+      rc = run_index_tool(c, tool, opts);
+      break;
+    case KLU_UTTERANCE:
+      rc = run_utterance(c, opts);
+      break;
+    case KLU_PRUNE_DYN_BEAM:
+      rc = run_prune_dyn_beam(c, opts);
+      break;
+    case KLU_BEST_PATH2:
+      rc = run_best_path2(c, opts);
+      break;
+    case KLU_CHAR_POSITION:
+      rc = run_char_position(c, opts);
+      break;
+    default:
+      set_error("klu_run: unknown tool");
+      return 1;
+  }
+  if (rc == 0) c->last_tool = tool;
+  return rc;
+}
+
+int klu_sync(klu_ctx* c) {
+  KLU_CUDA(cudaSetDevice(c->device));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int klu_timer_start(klu_ctx* c) {
+  KLU_CUDA(cudaSetDevice(c->device));
+  KLU_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+
+int klu_timer_stop(klu_ctx* c, float* ms) {
+  KLU_CUDA(cudaSetDevice(c->device));
+  KLU_CUDA(cudaEventRecord(c->ev1, c->stream));
+  KLU_CUDA(cudaEventSynchronize(c->ev1));
+  KLU_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int klu_launch_count(klu_ctx* c, int64_t* n) {
+  *n = c->launches;
+  return 0;
+}
+
+int klu_profile_enable(klu_ctx* c, int on) {
+  c->profile = on != 0;
+  if (on) c->prof.clear();
+  return 0;
+}
+
+int klu_profile_json(klu_ctx* c, char* buf, size_t cap) {
+  KLU_CUDA(cudaSetDevice(c->device));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& p : c->prof_pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+    auto& st = c->prof[p.first];
+    st.launches++;
+    st.ms += ms;
+    c->event_pool.push_back(p.second.first);
+    c->event_pool.push_back(p.second.second);
+  }
+  c->prof_pending.clear();
+  std::string s = "{";
+  bool first = true;
+  for (auto& kv : c->prof) {
+    if (!first) s += ", ";
+    first = false;
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "\"%s\": {\"launches\": %lld, \"ms\": %.6f}", kv.first.c_str(),
+             (long long)kv.second.launches, kv.second.ms);
+    s += tmp;
+  }
+  s += "}";
+  if (s.size() + 1 > cap) {
+    set_error("klu_profile_json: buffer too small");
+    return 1;
+  }
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+
+int klu_batch_stats(klu_ctx* c, int64_t stats[8]) {
+  stats[0] = c->L;
+  stats[1] = c->S;
+  stats[2] = c->E;
+  stats[3] = c->NL;
+  stats[4] = c->last_entries;
+  stats[5] = c->band_total;
+  stats[6] = c->max_len;
+  stats[7] = c->max_time;
+  return 0;
+}
+
+__global__ void k_flush(int4* p, size_t n, int v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = make_int4(v, v, v, v);
+}
+
+int klu_flush_l2(klu_ctx* c) {
+  KLU_CUDA(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+  KLU_TRY(c->d_flush.reserve(bytes));
+  static int v = 0;
+  k_flush<<<c->num_sms * 4, 256, 0, c->stream>>>(c->d_flush.as<int4>(), bytes / sizeof(int4), ++v);
+  return check_launch("k_flush");
+}
+
+}  // extern "C"

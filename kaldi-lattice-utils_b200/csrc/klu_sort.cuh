@@ -1,0 +1,148 @@
+// klu_sort.cuh -- batched segmented LSD radix sort (SURVEY.md K7/K8 building block).
+//
+// One CTA sorts one segment (one lattice's index entries) of (u64 key, u32 value)
+// pairs, stable, 8 bits per pass, ping-ponging between two global buffers.  All
+// digit histograms are taken in ONE read of the keys; passes whose digit is the
+// same for every key of the segment are skipped, so keys may be laid out
+// generously.  where[l] tells the consumer which buffer holds segment l.
+#pragma once
+#include "klu_common.cuh"
+
+namespace klu {
+
+constexpr int kSortThreads = 512;
+constexpr int kSortItems = 4;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+struct SegSortArgs {
+  const int64_t* seg_base;  // [nseg] first element of each segment
+  const int32_t* seg_cnt;   // [nseg] elements in each segment
+  unsigned long long* key_a;
+  unsigned int* val_a;
+  unsigned long long* key_b;
+  unsigned int* val_b;
+  unsigned char* where;  // [nseg] out: 0 = result in a, 1 = result in b
+  int lo_bit, hi_bit;
+};
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort(SegSortArgs a) {
+  __shared__ unsigned int hist[8][256];
+  __shared__ unsigned int bin_base[256];
+  __shared__ unsigned int warp_cnt[kSortWarps][256];
+  __shared__ int skip_flag;
+  const int seg = blockIdx.x;
+  const int n = a.seg_cnt[seg];
+  const int64_t base = a.seg_base[seg];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int npass = (a.hi_bit - a.lo_bit + 7) / 8;
+  if (n <= 1 || npass <= 0) {
+    if (tid == 0) a.where[seg] = 0;
+    return;
+  }
+  unsigned long long* kin = a.key_a + base;
+  unsigned int* vin = a.val_a + base;
+  unsigned long long* kout = a.key_b + base;
+  unsigned int* vout = a.val_b + base;
+  for (int i = tid; i < 8 * 256; i += kSortThreads) (&hist[0][0])[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kSortThreads) {
+    const unsigned long long k = kin[i] >> a.lo_bit;
+    for (int p = 0; p < npass; ++p) atomicAdd(&hist[p][(k >> (8 * p)) & 255], 1u);
+  }
+  __syncthreads();
+  int executed = 0;
+  for (int p = 0; p < npass; ++p) {
+    const int shift = a.lo_bit + 8 * p;
+    if (tid == 0) skip_flag = 0;
+    __syncthreads();
+    if (tid < 256 && hist[p][tid] == (unsigned)n) skip_flag = 1;
+    __syncthreads();
+    if (skip_flag) continue;
+    // exclusive scan of hist[p] -> bin_base (first 256 threads = 8 warps)
+    if (tid < 256) {
+      unsigned int v = hist[p][tid];
+      unsigned int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      warp_cnt[0][tid] = x;  // inclusive within warp (scratch)
+      __syncwarp();
+      bin_base[tid] = x - v;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      unsigned int add = 0;
+      for (int w = 0; w < warp; ++w) add += warp_cnt[0][w * 32 + 31];
+      __syncwarp();
+      bin_base[tid] += add;
+    }
+    __syncthreads();
+    for (int tile = 0; tile < n; tile += kSortTile) {
+      for (int i = lane; i < 256; i += 32) warp_cnt[warp][i] = 0;
+      __syncwarp();
+      unsigned long long k[kSortItems];
+      unsigned int v[kSortItems];
+      int d[kSortItems];
+#pragma unroll
+      for (int r = 0; r < kSortItems; ++r) {
+        const int i = tile + (warp * kSortItems + r) * 32 + lane;
+        const bool valid = i < n;
+        k[r] = valid ? kin[i] : 0ULL;
+        v[r] = valid ? vin[i] : 0u;
+        d[r] = valid ? (int)((k[r] >> shift) & 255) : 256 + lane;
+        const unsigned int mask = __match_any_sync(0xffffffffu, d[r]);
+        if (valid && lane == __ffs(mask) - 1) warp_cnt[warp][d[r]] += __popc(mask);
+        __syncwarp();
+      }
+      __syncthreads();
+      if (tid < 256) {
+        unsigned int run = bin_base[tid];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+          const unsigned int cnt = warp_cnt[w][tid];
+          warp_cnt[w][tid] = run;
+          run += cnt;
+        }
+        bin_base[tid] = run;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kSortItems; ++r) {
+        const int i = tile + (warp * kSortItems + r) * 32 + lane;
+        const bool valid = i < n;
+        const unsigned int mask = __match_any_sync(0xffffffffu, d[r]);
+        const int leader = __ffs(mask) - 1;
+        unsigned int pos = 0;
+        if (valid && lane == leader) {
+          pos = warp_cnt[warp][d[r]];
+          warp_cnt[warp][d[r]] = pos + __popc(mask);
+        }
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (valid) {
+          const unsigned int dst = pos + __popc(mask & ((1u << lane) - 1u));
+          kout[dst] = k[r];
+          vout[dst] = v[r];
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+    // swap buffers
+    unsigned long long* tk = kin;
+    kin = kout;
+    kout = tk;
+    unsigned int* tv = vin;
+    vin = vout;
+    vout = tv;
+    ++executed;
+    __syncthreads();
+  }
+  if (tid == 0) a.where[seg] = (unsigned char)(executed & 1);
+}
+#endif
+
+}  // namespace klu

@@ -1,0 +1,467 @@
+// klu_sweep.cu -- level-synchronous semiring sweeps.
+//
+//   log semiring   ComputeLatticeAlphasAndBetas [ext] (called at
+//                  kwsbin2/lattice-word-index-position.cc:66, -segment.cc:63,
+//                  latbin/lattice-to-word-frame-post.cc:89, lattice-best-path2.cc:118)
+//                  and ComputeCompactLatticeBetas [ext] (-utterance.cc:121-123)
+//   tropical       the Viterbi forward/backward of PruneLattice [ext] and
+//                  ComputeLatticeBeam (latbin/lattice-prune-dyn-beam.cc:27-90)
+//   banded log     alpha over (state, #labels so far): the forward half of the
+//                  lattice that DisambiguateStateInputSequenceLength
+//                  (fstext/fstext-utils2.h:109-215) would materialise.
+//
+// One warp owns one (lattice, direction) work item, pulled from a queue sorted by
+// descending arc count.  Inside a level the warp is split into 32/G groups of G
+// lanes; a group owns one state and pulls over its incoming (forward) or outgoing
+// (backward) arcs with coalesced 16-byte record loads, reduces max and sum-exp
+// with shuffles, and lane 0 of the group writes the f64 score.  State scores live
+// in global memory and are re-read through L1 (same-SM producer/consumer, ordered
+// by __syncwarp between levels).
+#include "klu_common.cuh"
+
+namespace klu {
+
+namespace {
+
+struct SweepArgs {
+  BatchView b;
+  CostParams cp;
+  double* alpha;
+  double* beta;
+  const double* vfwd;  // tropical scores for inline --beam pruning (or null)
+  const double* vbwd;
+  const double* best;  // per lattice best final cost
+  double beam;         // (double)(float)beam
+  int* counter;
+  int do_fwd, do_bwd;
+};
+
+template <int G>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double group_min(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// PruneLattice's arc test, evaluated on the fly: the arc is dropped when
+// fwd[s] + (cost + bwd[next]) > best_final + beam.
+__device__ __forceinline__ bool arc_pruned(const SweepArgs& a, int l, int src, int dst, const int4& r) {
+  CostParams cp = a.cp;
+  cp.float_sum = 0;  // PruneLattice always uses ConvertToCost (double sum)
+  const double cost = rec_cost(r, cp);
+  const double fb = __dadd_rn(a.vfwd[src], __dadd_rn(cost, a.vbwd[dst]));
+  return fb > __dadd_rn(a.best[l], a.beam);
+}
+__device__ __forceinline__ bool final_pruned(const SweepArgs& a, int l, int s, double) {
+  CostParams cp = a.cp;
+  cp.float_sum = 0;
+  const double fcost = final_cost(a.b.fin_g[s], a.b.fin_a[s], cp);
+  return __dadd_rn(fcost, a.vfwd[s]) > __dadd_rn(a.best[l], a.beam) && fcost != pos_inf();
+}
+
+template <int G, bool BEAM>
+__device__ void log_forward(const SweepArgs& a, int l, int lane) {
+  const BatchView& b = a.b;
+  const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
+  if (s_begin == s_end) return;
+  const int* lv = b.lvl_start + b.lvl_off[l];
+  const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
+  double* alpha = a.alpha;
+  for (int s = lv[0] + lane; s < lv[1]; s += 32) alpha[s] = (s == s_begin) ? 0.0 : neg_inf();
+  __syncwarp();
+  constexpr int SPW = 32 / G;
+  const int grp = lane / G, sl = lane % G;
+  for (int j = 1; j < nl; ++j) {
+    const int a0 = lv[j], a1 = lv[j + 1];
+    for (int base = a0; base < a1; base += SPW) {
+      const int s = base + grp;
+      const bool act = s < a1;
+      const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
+      double m = neg_inf();
+      for (int e = e0 + sl; e < e1; e += G) {
+        const int4 r = __ldg(b.in_rec + e);
+        const double cost = rec_cost(r, a.cp);
+        if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
+        m = fmax(m, alpha[r.x] - cost);
+      }
+      m = group_max<G>(m);
+      double sum = 0.0;
+      if (m > neg_inf()) {
+        for (int e = e0 + sl; e < e1; e += G) {
+          const int4 r = __ldg(b.in_rec + e);
+          const double cost = rec_cost(r, a.cp);
+          if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
+          sum += exp(alpha[r.x] - cost - m);
+        }
+      }
+      sum = group_sum<G>(sum);
+      if (act && sl == 0) alpha[s] = (m > neg_inf()) ? m + log(sum) : neg_inf();
+    }
+    __syncwarp();
+  }
+}
+
+template <int G, bool BEAM>
+__device__ void log_backward(const SweepArgs& a, int l, int lane) {
+  const BatchView& b = a.b;
+  const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
+  if (s_begin == s_end) return;
+  const int* lv = b.lvl_start + b.lvl_off[l];
+  const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
+  double* beta = a.beta;
+  constexpr int SPW = 32 / G;
+  const int grp = lane / G, sl = lane % G;
+  for (int j = nl - 1; j >= 0; --j) {
+    const int a0 = lv[j], a1 = lv[j + 1];
+    for (int base = a0; base < a1; base += SPW) {
+      const int s = base + grp;
+      const bool act = s < a1;
+      const int e0 = act ? b.out_off[s] : 0, e1 = act ? b.out_off[s + 1] : 0;
+      double fin = neg_inf();
+      if (act && sl == 0) {
+        const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
+        if (!(BEAM && final_pruned(a, l, s, fc))) fin = -fc;
+      }
+      double m = fin;
+      for (int e = e0 + sl; e < e1; e += G) {
+        const int4 r = __ldg(b.out_rec + e);
+        const double cost = rec_cost(r, a.cp);
+        if (BEAM && arc_pruned(a, l, s, r.x, r)) continue;
+        m = fmax(m, beta[r.x] - cost);
+      }
+      m = group_max<G>(m);
+      double sum = 0.0;
+      if (m > neg_inf()) {
+        if (fin > neg_inf()) sum = exp(fin - m);
+        for (int e = e0 + sl; e < e1; e += G) {
+          const int4 r = __ldg(b.out_rec + e);
+          const double cost = rec_cost(r, a.cp);
+          if (BEAM && arc_pruned(a, l, s, r.x, r)) continue;
+          sum += exp(beta[r.x] - cost - m);
+        }
+      }
+      sum = group_sum<G>(sum);
+      if (act && sl == 0) beta[s] = (m > neg_inf()) ? m + log(sum) : neg_inf();
+    }
+    __syncwarp();
+  }
+}
+
+template <int G, bool BEAM>
+__global__ void __launch_bounds__(128) k_log_sweeps(SweepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int ndir = a.do_fwd + a.do_bwd;
+  const int nitems = a.b.L * ndir;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) break;
+    const int l = a.b.order[item / ndir];
+    const bool fwd = a.do_fwd && (ndir == 1 || (item % ndir) == 0);
+    if (fwd) log_forward<G, BEAM>(a, l, lane);
+    else log_backward<G, BEAM>(a, l, lane);
+  }
+}
+
+// total = 0.5 * (tot_forward + beta[start]) as ComputeLatticeAlphasAndBetas
+// returns it; tot_forward folds the final states in ascending packed order.
+template <bool BEAM>
+__global__ void k_totals(SweepArgs a, double* total, double* totfwd) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.b.L) return;
+  const int l = warp;
+  const int s0 = a.b.s_off[l], s1 = a.b.s_off[l + 1];
+  if (s0 == s1) {
+    if (lane == 0) {
+      total[l] = 0.0;
+      totfwd[l] = 0.0;
+    }
+    return;
+  }
+  double acc = neg_inf();
+  for (int s = s0 + lane; s < s1; s += 32) {
+    const float fg = a.b.fin_g[s], fa = a.b.fin_a[s];
+    if (isinf(fg) && isinf(fa)) continue;
+    const double fc = final_cost(fg, fa, a.cp);
+    if (BEAM && final_pruned(a, l, s, fc)) continue;
+    acc = log_add(acc, a.alpha[s] - fc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = log_add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if (lane == 0) {
+    totfwd[l] = acc;
+    total[l] = 0.5 * (acc + a.beta[s0]);
+  }
+}
+
+// ---------------------------------------------------------------- tropical ---
+template <int G>
+__device__ void trop_forward(const SweepArgs& a, double* vfwd, double* best, int l, int lane) {
+  const BatchView& b = a.b;
+  const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
+  if (s_begin == s_end) {
+    if (lane == 0) best[l] = pos_inf();
+    return;
+  }
+  const int* lv = b.lvl_start + b.lvl_off[l];
+  const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
+  for (int s = lv[0] + lane; s < lv[1]; s += 32) vfwd[s] = (s == s_begin) ? 0.0 : pos_inf();
+  __syncwarp();
+  constexpr int SPW = 32 / G;
+  const int grp = lane / G, sl = lane % G;
+  for (int j = 1; j < nl; ++j) {
+    const int a0 = lv[j], a1 = lv[j + 1];
+    for (int base = a0; base < a1; base += SPW) {
+      const int s = base + grp;
+      const bool act = s < a1;
+      const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
+      double m = pos_inf();
+      for (int e = e0 + sl; e < e1; e += G) {
+        const int4 r = __ldg(b.in_rec + e);
+        m = fmin(m, __dadd_rn(vfwd[r.x], rec_cost(r, a.cp)));
+      }
+      m = group_min<G>(m);
+      if (act && sl == 0) vfwd[s] = m;
+    }
+    __syncwarp();
+  }
+  // best_final_cost = min_s fwd[s] + final(s)
+  double bf = pos_inf();
+  for (int s = s_begin + lane; s < s_end; s += 32)
+    bf = fmin(bf, __dadd_rn(vfwd[s], final_cost(b.fin_g[s], b.fin_a[s], a.cp)));
+  bf = group_min<32>(bf);
+  if (lane == 0) best[l] = bf;
+}
+
+template <int G>
+__device__ void trop_backward(const SweepArgs& a, double* vbwd, int l, int lane) {
+  const BatchView& b = a.b;
+  const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
+  if (s_begin == s_end) return;
+  const int* lv = b.lvl_start + b.lvl_off[l];
+  const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
+  constexpr int SPW = 32 / G;
+  const int grp = lane / G, sl = lane % G;
+  for (int j = nl - 1; j >= 0; --j) {
+    const int a0 = lv[j], a1 = lv[j + 1];
+    for (int base = a0; base < a1; base += SPW) {
+      const int s = base + grp;
+      const bool act = s < a1;
+      const int e0 = act ? b.out_off[s] : 0, e1 = act ? b.out_off[s + 1] : 0;
+      double m = pos_inf();
+      if (act && sl == 0) m = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
+      for (int e = e0 + sl; e < e1; e += G) {
+        const int4 r = __ldg(b.out_rec + e);
+        m = fmin(m, __dadd_rn(rec_cost(r, a.cp), vbwd[r.x]));
+      }
+      m = group_min<G>(m);
+      if (act && sl == 0) vbwd[s] = m;
+    }
+    __syncwarp();
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) k_trop_sweeps(SweepArgs a, double* vfwd, double* vbwd, double* best) {
+  const int lane = threadIdx.x & 31;
+  const int nitems = a.b.L * 2;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) break;
+    const int l = a.b.order[item >> 1];
+    if ((item & 1) == 0) trop_forward<G>(a, vfwd, best, l, lane);
+    else trop_backward<G>(a, vbwd, l, lane);
+  }
+}
+
+// ------------------------------------------------------------- banded log ---
+// alpha2[band_off[s] + (len - band_lo[s])] = log-sum of all paths start -> s that
+// carry exactly `len` non-epsilon labels.  A group owns one (state, len) cell.
+template <int G, bool BEAM>
+__global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha2) {
+  const int lane = threadIdx.x & 31;
+  const BatchView& b = a.b;
+  constexpr int SPW = 32 / G;
+  const int grp = lane / G, sl = lane % G;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= b.L) break;
+    const int l = b.order[item];
+    const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
+    if (s_begin == s_end) continue;
+    const int* lv = b.lvl_start + b.lvl_off[l];
+    const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
+    for (int s = lv[0] + lane; s < lv[1]; s += 32)
+      if (s == s_begin) alpha2[b.band_off[s]] = 0.0;  // other level-0 states are unreachable (width 0)
+    __syncwarp();
+    for (int j = 1; j < nl; ++j) {
+      const int a0 = lv[j], a1 = lv[j + 1];
+      const int c0 = b.band_off[a0], c1 = b.band_off[a1];  // cells of this level
+      for (int base = c0; base < c1; base += SPW) {
+        const int cell = base + grp;
+        const bool act = cell < c1;
+        int s = a0;
+        if (act) {  // binary search: last state with band_off[s] <= cell
+          int lo = a0, hi = a1 - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (b.band_off[mid] <= cell) lo = mid;
+            else hi = mid - 1;
+          }
+          s = lo;
+        }
+        const int len = act ? b.band_lo[s] + (cell - b.band_off[s]) : 0;
+        const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
+        double m = neg_inf();
+        for (int e = e0 + sl; e < e1; e += G) {
+          const int4 r = __ldg(b.in_rec + e);
+          const int plen = len - (r.w != 0 ? 1 : 0);
+          const int plo = b.band_lo[r.x];
+          const int pw = b.band_off[r.x + 1] - b.band_off[r.x];
+          if (plo < 0 || plen < plo || plen >= plo + pw) continue;
+          const double cost = rec_cost(r, a.cp);
+          if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
+          m = fmax(m, alpha2[b.band_off[r.x] + plen - plo] - cost);
+        }
+        m = group_max<G>(m);
+        double sum = 0.0;
+        if (m > neg_inf()) {
+          for (int e = e0 + sl; e < e1; e += G) {
+            const int4 r = __ldg(b.in_rec + e);
+            const int plen = len - (r.w != 0 ? 1 : 0);
+            const int plo = b.band_lo[r.x];
+            const int pw = b.band_off[r.x + 1] - b.band_off[r.x];
+            if (plo < 0 || plen < plo || plen >= plo + pw) continue;
+            const double cost = rec_cost(r, a.cp);
+            if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
+            sum += exp(alpha2[b.band_off[r.x] + plen - plo] - cost - m);
+          }
+        }
+        sum = group_sum<G>(sum);
+        if (act && sl == 0) alpha2[cell] = (m > neg_inf()) ? m + log(sum) : neg_inf();
+      }
+      __syncwarp();
+    }
+  }
+}
+
+int pick_group(double avg_deg) {
+  if (avg_deg <= 3.0) return 2;
+  if (avg_deg <= 6.0) return 4;
+  if (avg_deg <= 48.0) return 8;
+  if (avg_deg <= 160.0) return 16;
+  return 32;
+}
+
+int sweep_grid(klu_ctx* c, int items) {
+  const int warps_per_block = 4;
+  const int max_blocks = c->num_sms * 16;  // 64 resident warps per SM
+  int blocks = (items + warps_per_block - 1) / warps_per_block;
+  return std::max(1, std::min(blocks, max_blocks));
+}
+
+SweepArgs make_args(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) {
+  SweepArgs a;
+  a.b = c->view();
+  a.cp = cp;
+  a.alpha = c->d_alpha.as<double>();
+  a.beta = c->d_beta.as<double>();
+  a.vfwd = use_beam ? c->d_vfwd.as<double>() : nullptr;
+  a.vbwd = use_beam ? c->d_vbwd.as<double>() : nullptr;
+  a.best = use_beam ? c->d_best.as<double>() : nullptr;
+  a.beam = (double)beam;
+  a.counter = c->d_counter.as<int>();
+  a.do_fwd = 1;
+  a.do_bwd = 1;
+  return a;
+}
+
+}  // namespace
+
+#define KLU_DISPATCH_G(G, ...)                       \
+  switch (G) {                                       \
+    case 2: { constexpr int kG = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int kG = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int kG = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int kG = 16; __VA_ARGS__; } break; \
+    default: { constexpr int kG = 32; __VA_ARGS__; } break; \
+  }
+
+int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) {
+  KLU_TRY(c->d_alpha.reserve(sizeof(double) * std::max<int64_t>(c->S, 1)));
+  KLU_TRY(c->d_beta.reserve(sizeof(double) * std::max<int64_t>(c->S, 1)));
+  KLU_TRY(c->d_total.reserve(sizeof(double) * std::max<int32_t>(c->L, 1)));
+  KLU_TRY(c->d_totfwd.reserve(sizeof(double) * std::max<int32_t>(c->L, 1)));
+  KLU_TRY(c->d_counter.reserve(64));
+  if (c->L == 0) return 0;
+  KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
+  SweepArgs a = make_args(c, cp, use_beam, beam);
+  const int G = pick_group(c->avg_deg);
+  const int grid = sweep_grid(c, c->L * 2);
+  {
+    KLU_LAUNCH(c, "k_log_sweeps");
+    KLU_DISPATCH_G(G, if (use_beam) k_log_sweeps<kG, true><<<grid, 128, 0, c->stream>>>(a);
+                   else k_log_sweeps<kG, false><<<grid, 128, 0, c->stream>>>(a));
+  }
+  KLU_TRY(check_launch("k_log_sweeps"));
+  {
+    KLU_LAUNCH(c, "k_totals");
+    const int blocks = (c->L * 32 + 127) / 128;
+    if (use_beam) k_totals<true><<<blocks, 128, 0, c->stream>>>(a, c->d_total.as<double>(), c->d_totfwd.as<double>());
+    else k_totals<false><<<blocks, 128, 0, c->stream>>>(a, c->d_total.as<double>(), c->d_totfwd.as<double>());
+  }
+  return check_launch("k_totals");
+}
+
+int run_tropical_sweeps(klu_ctx* c, const CostParams& cp) {
+  KLU_TRY(c->d_vfwd.reserve(sizeof(double) * std::max<int64_t>(c->S, 1)));
+  KLU_TRY(c->d_vbwd.reserve(sizeof(double) * std::max<int64_t>(c->S, 1)));
+  KLU_TRY(c->d_best.reserve(sizeof(double) * std::max<int32_t>(c->L, 1)));
+  KLU_TRY(c->d_counter.reserve(64));
+  if (c->L == 0) return 0;
+  KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
+  SweepArgs a = make_args(c, cp, false, 0.f);
+  const int G = pick_group(c->avg_deg);
+  const int grid = sweep_grid(c, c->L * 2);
+  {
+    KLU_LAUNCH(c, "k_trop_sweeps");
+    KLU_DISPATCH_G(G, k_trop_sweeps<kG><<<grid, 128, 0, c->stream>>>(a, c->d_vfwd.as<double>(),
+                                                                      c->d_vbwd.as<double>(), c->d_best.as<double>()));
+  }
+  return check_launch("k_trop_sweeps");
+}
+
+int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) {
+  KLU_TRY(c->d_alpha2.reserve(sizeof(double) * std::max<int64_t>(c->band_total, 1)));
+  KLU_TRY(c->d_counter.reserve(64));
+  if (c->L == 0) return 0;
+  KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
+  SweepArgs a = make_args(c, cp, use_beam, beam);
+  const int G = pick_group(c->avg_deg);
+  const int grid = sweep_grid(c, c->L);
+  {
+    KLU_LAUNCH(c, "k_banded_alpha");
+    KLU_DISPATCH_G(G, if (use_beam) k_banded_alpha<kG, true><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>());
+                   else k_banded_alpha<kG, false><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>()));
+  }
+  return check_launch("k_banded_alpha");
+}
+
+}  // namespace klu

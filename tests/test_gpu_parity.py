@@ -1,0 +1,106 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLD, TOL, assert_rows_match, goldens
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def word_lat(klu):
+    return klu.read_text_ark(os.path.join(GOLD, "lattice.ark.txt"))[0]
+
+
+def _load(klu, engine, lats):
+    engine.load(klu.LatticeBatch.from_lattices(lats))
+
+
+def test_readme_segment_text(klu, engine, word_lat):
+    _load(klu, engine, [word_lat])
+    assert klu.format_tuples("lat1", engine.segment()[0]).strip() == goldens()["segment"]
+
+
+def test_readme_position_text(klu, engine, word_lat):
+    _load(klu, engine, [word_lat])
+    assert klu.format_tuples("lat1", engine.position()[0]).strip() == goldens()["position"]
+
+
+def test_fwd_bwd_matches_oracle(klu, ora, engine):
+    batch = klu.synth_batch("small", 8, seed=11)
+    engine.load(batch)
+    engine.run(klu.FWD_BWD)
+    al, be, tot = engine.fetch_fwd_bwd()
+    for l, lat in enumerate(batch.lattices()):
+        seg = ora.run(ora.SEGMENT, lat)
+        assert abs(tot[l] - seg.ds0) < 1e-9
+
+
+SHAPES = [("tiny", 24, 5), ("small", 12, 6)]
+FLAGS = [dict(), dict(acoustic_scale=0.1), dict(graph_scale=0.7, insertion_penalty=0.5),
+         dict(acoustic_scale=0.3, beam=6.0)]
+
+
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", FLAGS)
+def test_segment_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed)
+    engine.load(batch)
+    got = engine.segment(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        assert_rows_match(got[l], ora.segment(lat, **flags), 3, what="segment lat %d" % l)
+
+
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", FLAGS)
+def test_position_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 50)
+    engine.load(batch)
+    got = engine.position(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        assert_rows_match(got[l], ora.position(lat, **flags), 2, what="position lat %d" % l)
+
+
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", FLAGS[:3])
+def test_frame_post_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 90)
+    engine.load(batch)
+    got = engine.frame_post(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        want = ora.frame_post(lat, **flags)
+        assert len(got[l]) == len(want)
+        for k, (g, w) in enumerate(zip(got[l], want)):
+            assert_rows_match([(a, b) for a, b in g], [(a, b) for a, b in w], 1, what="frame %d lat %d" % (k, l))
+
+
+def test_include_exclude_words(klu, ora, engine):
+    batch = klu.synth_batch("tiny", 6, seed=77)
+    engine.load(batch)
+    for flags in (dict(include_words=[1, 2, 3]), dict(exclude_words=[1, 4]), dict(include_words=[2], exclude_words=[2])):
+        got = engine.segment(**flags)
+        gotp = engine.position(**flags)
+        for l, lat in enumerate(batch.lattices()):
+            assert_rows_match(got[l], ora.segment(lat, **flags), 3)
+            assert_rows_match(gotp[l], ora.position(lat, **flags), 2)
+
+
+def test_empty_and_ragged_batch(klu, ora, engine):
+    lats = klu.synth_batch("tiny", 3, seed=5).lattices()
+    empty = klu.make_lattice("empty", 0, [], {})
+    single = klu.make_lattice("single", 1, [], {0: (0.5, 0.25)})
+    engine.load(klu.LatticeBatch.from_lattices([lats[0], empty, lats[1], single, lats[2]]))
+    got = engine.segment()
+    assert got[1] == [] and got[3] == []
+    for i, j in ((0, 0), (2, 1), (4, 2)):
+        assert_rows_match(got[i], ora.segment(lats[j]), 3)
+    fp = engine.frame_post()
+    assert fp[1] == [] and fp[3] == []
+
+
+def test_rejects_unsorted_lattice(klu, engine):
+    bad = klu.make_lattice("bad", 3, [(0, 2, 1, 0.1, 0.2, 1), (2, 1, 2, 0.1, 0.2, 1)], {1: (0.0, 0.0)})
+    with pytest.raises(klu.KluError):
+        engine.load(klu.LatticeBatch.from_lattices([bad]))

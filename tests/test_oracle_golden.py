@@ -1,0 +1,124 @@
+"""Pins the CPU oracle (oracle/klu_oracle.cc) to every golden vector the
+reference holds for the hot path: the worked examples of kwsbin2/README.md, and
+to brute-force path enumeration for the tools the reference has no golden for."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLD, TOL, assert_rows_match, goldens
+
+
+@pytest.fixture(scope="module")
+def word_lat(klu):
+    return klu.read_text_ark(os.path.join(GOLD, "lattice.ark.txt"))[0]
+
+
+@pytest.fixture(scope="module")
+def char_lat(klu):
+    return klu.read_text_ark(os.path.join(GOLD, "lattice.char.ark.txt"))[0]
+
+
+def test_readme_utterance_exact_text(klu, ora, word_lat):
+    assert klu.format_tuples("lat1", ora.utterance(word_lat)).strip() == goldens()["utterance"]
+
+
+def test_readme_segment_exact_text(klu, ora, word_lat):
+    assert klu.format_tuples("lat1", ora.segment(word_lat)).strip() == goldens()["segment"]
+
+
+def test_readme_position_exact_text(klu, ora, word_lat):
+    assert klu.format_tuples("lat1", ora.position(word_lat)).strip() == goldens()["position"]
+
+
+def _parse_char_golden(s):
+    body = s.split(" ", 1)[1]
+    rows = []
+    for t in body.split(";"):
+        f = t.split()
+        rows.append((f[0], int(f[1]), int(f[2]), int(f[3]), float(f[4])))
+    return rows
+
+
+def test_readme_char_position(ora, char_lat):
+    # keys, positions, segments and order exact; values within 1e-4 (the
+    # reference computes this tool in float32 log semiring with determinize
+    # delta, its README deviates from exact math by up to 5.9e-5)
+    want = _parse_char_golden(goldens()["char_position"])
+    got = ora.char_position(char_lat, [28])
+    assert [r[:4] for r in got] == [r[:4] for r in want]
+    for g, w in zip(got, want):
+        assert abs(g[4] - w[4]) <= TOL
+
+
+def test_readme_state_times(klu, ora, word_lat):
+    # kwsbin2/README.md:61-64; times come out of the segment keys
+    times = goldens()["state_times"]
+    seg = ora.segment(word_lat)
+    t0s = {t0 for _, t0, _, _ in seg} | {t1 for _, _, t1, _ in seg}
+    assert t0s <= set(times)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_vs_bruteforce(klu, ora, seed):
+    batch = klu.synth_batch("tiny", 4, seed=100 + seed)
+    for lat in batch.lattices():
+        seg = {(w, a, b): v for w, a, b, v in ora.segment(lat)}
+        bs = ora.brute(ora.BRUTE_SEGMENT, lat)
+        assert set(seg) == set(bs)
+        assert max(abs(seg[k] - bs[k]) for k in seg) < 1e-9
+        pos = {(w, p, 0): v for w, p, _, _, v in ora.position(lat)}
+        bp = ora.brute(ora.BRUTE_POSITION, lat)
+        assert set(pos) == set(bp)
+        assert max(abs(pos[k] - bp[k]) for k in pos) < 1e-9
+        utt = {(w, 0, 0): v for w, v in ora.utterance(lat)}
+        bu = ora.brute(ora.BRUTE_UTTERANCE, lat)
+        assert set(utt) == set(bu)
+        # ComputeCompactLatticeBetas adds the two float weights in float
+        assert max(abs(utt[k] - bu[k]) for k in utt) < 1e-4
+        fr = ora.frame_post(lat)
+        bf = ora.brute(ora.BRUTE_FRAME, lat)
+        got = {(k, w, 0): p for k, row in enumerate(fr) for w, p in row}
+        assert set(got) == set(bf)
+        assert max(abs(got[k] - bf[k]) for k in got) < 1e-4
+
+
+def test_oracle_flags_consistency(klu, ora):
+    # --acoustic-scale / --graph-scale / --insertion-penalty: equal to running the
+    # default tool on a lattice whose float weights were transformed the way
+    # ScaleLattice / AddWordInsPenToCompactLattice [ext] do it
+    batch = klu.synth_batch("tiny", 3, seed=7)
+    for lat in batch.lattices():
+        g2 = (np.float64(0.7) * lat.graph.astype(np.float64)).astype(np.float32)
+        a2 = (np.float64(np.float32(0.1)) * lat.acoustic.astype(np.float64)).astype(np.float32)
+        g2 = np.where(lat.label != 0, g2 + np.float32(0.5), g2).astype(np.float32)
+        fg = np.where(np.isinf(lat.fin_graph), lat.fin_graph,
+                      (np.float64(np.float32(0.7)) * lat.fin_graph.astype(np.float64)).astype(np.float32))
+        fa = np.where(np.isinf(lat.fin_acoustic), lat.fin_acoustic,
+                      (np.float64(np.float32(0.1)) * lat.fin_acoustic.astype(np.float64)).astype(np.float32))
+        g2 = (np.float64(np.float32(0.7)) * lat.graph.astype(np.float64)).astype(np.float32)
+        g2 = np.where(lat.label != 0, g2 + np.float32(0.5), g2).astype(np.float32)
+        lat2 = klu.Lattice(lat.key, lat.nstates, lat.src, lat.dst, lat.label, lat.dur, g2, a2,
+                           fg.astype(np.float32), fa.astype(np.float32), lat.fin_dur)
+        a = ora.segment(lat, acoustic_scale=0.1, graph_scale=0.7, insertion_penalty=0.5)
+        b = ora.segment(lat2)
+        assert a == b
+
+
+def test_oracle_best_path2_readme_lattice(ora, word_lat):
+    labels, cost = ora.best_path2(word_lat)
+    # the 0.8-probability path "the dog is the man's best friend"
+    assert labels == [2, 3, 5, 2, 6, 7, 8]
+    assert abs(cost - 0.4) < 1e-6  # (1-0.8) + (1-0.8), float accumulation
+
+
+def test_oracle_prune_dyn_beam_noop_and_prune(klu, ora):
+    lat = klu.synth_batch("small", 1, seed=3)[0]
+    r = ora.prune_dyn_beam(lat)  # defaults: limits INT_MAX -> untouched
+    assert len(r["arcs"]) == lat.narcs and r["nstates"] == lat.nstates and r["iters"] == 0
+    r2 = ora.prune_dyn_beam(lat, max_arcs=lat.narcs // 4, max_states=lat.nstates)
+    assert 0 < len(r2["arcs"]) <= lat.narcs // 4 or r2["beam"] <= 1e-3
+    assert r2["beam"] < r2["beam0"]
+    # survivors keep their relative order
+    idx = [a[0] for a in r2["arcs"]]
+    assert idx == sorted(idx)
