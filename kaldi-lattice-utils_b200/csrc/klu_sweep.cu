@@ -55,6 +55,18 @@ __device__ __forceinline__ double group_sum(double v) {
   return v;
 }
 
+// The log-sum of a state is formed as  max + log1p(sum of the OTHER terms), which
+// for two terms is exactly Kaldi's LogAdd (max + log1p(exp(-|d|))) and for more
+// terms rounds once instead of once per pair.  One lane of the group (the lowest
+// whose local maximum is the group maximum) leaves its arg-max term out.
+template <int G>
+__device__ __forceinline__ bool elect_max_lane(double local_m, double m, int lane) {
+  const unsigned int bal = __ballot_sync(0xffffffffu, local_m == m && m > neg_inf());
+  const unsigned int gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((lane / G) * G);
+  const unsigned int cand = bal & gmask;
+  return cand != 0 && lane == __ffs(cand) - 1;
+}
+
 // PruneLattice's arc test, evaluated on the fly: the arc is dropped when
 // fwd[s] + (cost + bwd[next]) > best_final + beam.
 __device__ __forceinline__ bool arc_pruned(const SweepArgs& a, int l, int src, int dst, const int4& r) {
@@ -90,16 +102,24 @@ __device__ void log_forward(const SweepArgs& a, int l, int lane) {
       const bool act = s < a1;
       const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
       double m = neg_inf();
+      int arg = -1;
       for (int e = e0 + sl; e < e1; e += G) {
         const int4 r = __ldg(b.in_rec + e);
         const double cost = rec_cost(r, a.cp);
         if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
-        m = fmax(m, alpha[r.x] - cost);
+        const double x = alpha[r.x] - cost;
+        if (x > m) {
+          m = x;
+          arg = e;
+        }
       }
+      const double lm = m;
       m = group_max<G>(m);
+      if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
       double sum = 0.0;
       if (m > neg_inf()) {
         for (int e = e0 + sl; e < e1; e += G) {
+          if (e == arg) continue;
           const int4 r = __ldg(b.in_rec + e);
           const double cost = rec_cost(r, a.cp);
           if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
@@ -107,7 +127,7 @@ __device__ void log_forward(const SweepArgs& a, int l, int lane) {
         }
       }
       sum = group_sum<G>(sum);
-      if (act && sl == 0) alpha[s] = (m > neg_inf()) ? m + log(sum) : neg_inf();
+      if (act && sl == 0) alpha[s] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
     }
     __syncwarp();
   }
@@ -135,17 +155,25 @@ __device__ void log_backward(const SweepArgs& a, int l, int lane) {
         if (!(BEAM && final_pruned(a, l, s, fc))) fin = -fc;
       }
       double m = fin;
+      int arg = fin > neg_inf() ? -2 : -1;  // -2: the final weight is the local max
       for (int e = e0 + sl; e < e1; e += G) {
         const int4 r = __ldg(b.out_rec + e);
         const double cost = rec_cost(r, a.cp);
         if (BEAM && arc_pruned(a, l, s, r.x, r)) continue;
-        m = fmax(m, beta[r.x] - cost);
+        const double x = beta[r.x] - cost;
+        if (x > m) {
+          m = x;
+          arg = e;
+        }
       }
+      const double lm = m;
       m = group_max<G>(m);
+      if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
       double sum = 0.0;
       if (m > neg_inf()) {
-        if (fin > neg_inf()) sum = exp(fin - m);
+        if (fin > neg_inf() && arg != -2) sum = exp(fin - m);
         for (int e = e0 + sl; e < e1; e += G) {
+          if (e == arg) continue;
           const int4 r = __ldg(b.out_rec + e);
           const double cost = rec_cost(r, a.cp);
           if (BEAM && arc_pruned(a, l, s, r.x, r)) continue;
@@ -153,7 +181,7 @@ __device__ void log_backward(const SweepArgs& a, int l, int lane) {
         }
       }
       sum = group_sum<G>(sum);
-      if (act && sl == 0) beta[s] = (m > neg_inf()) ? m + log(sum) : neg_inf();
+      if (act && sl == 0) beta[s] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
     }
     __syncwarp();
   }
@@ -330,6 +358,7 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
         const int len = act ? b.band_lo[s] + (cell - b.band_off[s]) : 0;
         const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
         double m = neg_inf();
+        int arg = -1;
         for (int e = e0 + sl; e < e1; e += G) {
           const int4 r = __ldg(b.in_rec + e);
           const int plen = len - (r.w != 0 ? 1 : 0);
@@ -338,12 +367,19 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
           if (plo < 0 || plen < plo || plen >= plo + pw) continue;
           const double cost = rec_cost(r, a.cp);
           if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
-          m = fmax(m, alpha2[b.band_off[r.x] + plen - plo] - cost);
+          const double x = alpha2[b.band_off[r.x] + plen - plo] - cost;
+          if (x > m) {
+            m = x;
+            arg = e;
+          }
         }
+        const double lm = m;
         m = group_max<G>(m);
+        if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
         double sum = 0.0;
         if (m > neg_inf()) {
           for (int e = e0 + sl; e < e1; e += G) {
+            if (e == arg) continue;
             const int4 r = __ldg(b.in_rec + e);
             const int plen = len - (r.w != 0 ? 1 : 0);
             const int plo = b.band_lo[r.x];
@@ -355,7 +391,7 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
           }
         }
         sum = group_sum<G>(sum);
-        if (act && sl == 0) alpha2[cell] = (m > neg_inf()) ? m + log(sum) : neg_inf();
+        if (act && sl == 0) alpha2[cell] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
       }
       __syncwarp();
     }
