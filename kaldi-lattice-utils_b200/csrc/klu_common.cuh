@@ -68,8 +68,9 @@ struct BatchView {
   const float* fin_a;        // [S]
   const int32_t* time;       // [S] frame of each state (CompactLatticeStateTimes)
   const int32_t* orig;       // [S] lattice-local input id of each state
+  const int32_t* level;      // [S] level index of each state within its lattice
   const int32_t* band_lo;    // [S] min #non-eps labels on paths from the start (-1: unreachable)
-  const int32_t* band_off;   // [S+1] offsets into the (state,len) band arrays
+  const int64_t* band_off;   // [S+1] offsets into the (state,len) band arrays
   const int32_t* order;      // [L] lattices by descending arc count (work queue order)
 };
 
@@ -102,13 +103,14 @@ struct klu_ctx {
   std::vector<uint8_t> h_times_ok;           // consistent state times per lattice
   std::vector<int64_t> h_cap_frame, h_cap_pos;  // per lattice entry upper bounds
   std::vector<int32_t> h_maxlen;             // max #non-eps labels on a path, per lattice
-  int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0;
+  std::vector<int64_t> h_band_off;           // [L+1] first band cell of each lattice
+  int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0, max_states = 0;
   double avg_deg = 0;
   int64_t band_total = 0;
 
   // ---- device: packed batch ----
   klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
-      d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_band_lo, d_band_off, d_order;
+      d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order;
   // ---- device: per-run state ----
   klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
   klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps
@@ -146,19 +148,28 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* lats);
 // klu_sweep.cu
 int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam);
 int run_tropical_sweeps(klu_ctx* c, const CostParams& cp);
-int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam);
+int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam, int l0, int l1);
 // klu_index.cu
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o);
 // klu_prune.cu
 int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o);
 // klu_bestpath.cu
 int run_best_path2(klu_ctx* c, const klu_opts* o);
-// klu_utt.cu
-int run_utterance(klu_ctx* c, const klu_opts* o);
 // klu_char.cu
 int run_char_position(klu_ctx* c, const klu_opts* o);
 
 CostParams make_cost_params(const klu_opts* o, bool float_sum);
+int pick_group(double avg_deg);  // lanes cooperating on one state, from the mean degree
+
+#define KLU_DISPATCH_G(G, ...)                              \
+  switch (G) {                                              \
+    case 2: { constexpr int kG = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int kG = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int kG = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int kG = 16; __VA_ARGS__; } break; \
+    default: { constexpr int kG = 32; __VA_ARGS__; } break; \
+  }
+
 int upload_filter(klu_ctx* c, const klu_opts* o, int* mode_out, int* n_out);
 
 }  // namespace klu
@@ -222,6 +233,36 @@ __device__ __forceinline__ unsigned long long ord_f64(double x) {
 __device__ __forceinline__ unsigned int ord_f32(float x) {
   unsigned int b = __float_as_uint(x);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <int G>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double group_min(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// The log-sum of a state is formed as  max + log1p(sum of the OTHER terms), which
+// for two terms is exactly Kaldi's LogAdd (max + log1p(exp(-|d|))) and for more
+// terms rounds once instead of once per pair.  One lane of the group (the lowest
+// whose local maximum is the group maximum) leaves its arg-max term out.
+template <int G>
+__device__ __forceinline__ bool elect_max_lane(double local_m, double m, int lane) {
+  const unsigned int bal = __ballot_sync(0xffffffffu, local_m == m && m > neg_inf());
+  const unsigned int gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((lane / G) * G);
+  const unsigned int cand = bal & gmask;
+  return cand != 0 && lane == __ffs(cand) - 1;
 }
 
 __device__ __forceinline__ int4 ld_stream(const int4* p) {

@@ -133,8 +133,9 @@ klu::BatchView klu_ctx::view() const {
   v.fin_a = d_fin_a.as<float>();
   v.time = d_time.as<int32_t>();
   v.orig = d_orig.as<int32_t>();
+  v.level = d_level.as<int32_t>();
   v.band_lo = d_band_lo.as<int32_t>();
-  v.band_off = d_band_off.as<int32_t>();
+  v.band_off = d_band_off.as<int64_t>();
   v.order = d_order.as<int32_t>();
   return v;
 }
@@ -201,7 +202,7 @@ int klu_destroy(klu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
                     &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_fin_g, &c->d_fin_a,
-                    &c->d_time, &c->d_orig, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_alpha, &c->d_beta,
+                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
   for (DevBuf* b : bufs) b->release();
@@ -257,10 +258,8 @@ int klu_run(klu_ctx* c, int tool, const klu_opts* opts) {
     case KLU_POSITION:
     case KLU_FRAME_POST:
     case KLU_FWD_BWD:
-      rc = run_index_tool(c, tool, opts);
-      break;
     case KLU_UTTERANCE:
-      rc = run_utterance(c, opts);
+      rc = run_index_tool(c, tool, opts);
       break;
     case KLU_PRUNE_DYN_BEAM:
       rc = run_prune_dyn_beam(c, opts);

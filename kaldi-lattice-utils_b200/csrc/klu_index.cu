@@ -14,6 +14,7 @@
 // produces the reference's output order (ties fall back to key order because the
 // reduced entries are already key-sorted).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -53,6 +54,8 @@ struct IndexArgs {
   unsigned int* idx;
   double* val;
   unsigned int* aux;
+  int l0;                   // first lattice of the chunk being processed
+  long long band_base;      // first band cell of the chunk (alpha2 is chunk-local)
 };
 
 __device__ __forceinline__ bool label_valid(const IndexArgs& a, int label) {
@@ -82,16 +85,16 @@ __device__ __forceinline__ int arc_entry_count(const IndexArgs& a, int e) {
     return d > 0 ? d : 0;
   }
   if (!label_valid(a, r.w)) return 0;
-  if (a.tool == KLU_SEGMENT) return 1;
+  if (a.tool == KLU_SEGMENT || a.tool == KLU_UTTERANCE) return 1;
   const int s = a.b.out_src[e];
-  return a.b.band_off[s + 1] - a.b.band_off[s];
+  return (int)(a.b.band_off[s + 1] - a.b.band_off[s]);
 }
 
 // One CTA per lattice: exclusive scan of per-arc entry counts.
 __global__ void __launch_bounds__(256) k_count_scan(IndexArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
-  const int l = blockIdx.x;
+  const int l = a.l0 + blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0;
@@ -127,7 +130,7 @@ __device__ __forceinline__ bool emit_arc_pruned(const IndexArgs& a, int l, int s
 
 // grid (tiles, lattices): one thread per out-order arc.
 __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
-  const int l = blockIdx.y;
+  const int l = a.l0 + blockIdx.y;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int64_t base = a.ent_base[l];
   for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
@@ -146,6 +149,15 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
       a.val[base + off] = v;
       a.aux[base + off] = arc_local;
       a.idx[base + off] = (unsigned int)off;
+    } else if (a.tool == KLU_UTTERANCE) {
+      // one entry per valid arc, grouped by word; the per-word score is computed
+      // by k_utt_tasks from the sorted arc lists
+      if (!label_valid(a, r.w)) continue;
+      const bool dead = a.use_beam && emit_arc_pruned(a, l, s, r);
+      a.key[base + off] = dead ? a.drop_key : (unsigned long long)r.w;
+      a.val[base + off] = 0.0;
+      a.aux[base + off] = arc_local;
+      a.idx[base + off] = (unsigned int)off;
     } else if (a.tool == KLU_FRAME_POST) {
       if (r.w == 0) continue;
       const int t0 = a.b.time[s], t1 = a.b.time[r.x];
@@ -161,13 +173,13 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
       }
     } else {  // KLU_POSITION
       if (!label_valid(a, r.w)) continue;
-      const int w = a.b.band_off[s + 1] - a.b.band_off[s];
+      const int w = (int)(a.b.band_off[s + 1] - a.b.band_off[s]);
       if (w <= 0) continue;
       const bool dead = a.use_beam && emit_arc_pruned(a, l, s, r);
       const int lo = a.b.band_lo[s];
       const double tail = __dadd_rn(-rec_cost(r, a.cp), 0.0);
       for (int i = 0; i < w; ++i) {
-        const double al = a.alpha2[a.b.band_off[s] + i];
+        const double al = a.alpha2[a.b.band_off[s] - a.band_base + i];
         // fw[(len,s)] + arc_lkh + bw[next]; beta of the unfolded lattice = beta[next]
         const double v = __dadd_rn(__dadd_rn(al, tail), a.beta[r.x]);
         const unsigned long long k = ((unsigned long long)r.w << a.bits_len) | (unsigned long long)(lo + i);
@@ -201,6 +213,7 @@ struct ReduceArgs {
   unsigned int* idx2;
   int bits_label;
   unsigned long long drop_key;
+  int l0;
 };
 
 // One CTA per lattice: fold each run of equal keys with LogAdd (in sorted =
@@ -209,7 +222,7 @@ struct ReduceArgs {
 __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
-  const int l = blockIdx.x;
+  const int l = a.l0 + blockIdx.x;
   const int n = a.ent_cnt[l];
   const int64_t base = a.ent_base[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + base;
@@ -239,7 +252,22 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
     __syncthreads();
     int add = carry_s;
     for (int w = 0; w < warp; ++w) add += warp_sum[w];
-    if (head) {
+    if (head && a.tool == KLU_UTTERANCE) {
+      // run of arcs carrying word k: record where it starts, how long it is and
+      // the span of source levels it covers
+      const int slot = add + x - 1;
+      int q = i, lo = 0x7fffffff, hi = -1;
+      for (; q < n && key[q] == k; ++q) {
+        const int lev = a.b.level[a.b.out_src[e0 + aux[idx[q]]]];
+        lo = min(lo, lev);
+        hi = max(hi, lev);
+      }
+      a.rkey[base + slot] = k;
+      a.rval[base + slot] = 0.0;
+      a.raux[base + slot] = (unsigned int)i;
+      a.key2[base + slot] = ((unsigned long long)(unsigned int)lo << 32) | (unsigned long long)(unsigned int)hi;
+      a.idx2[base + slot] = (unsigned int)(q - i);
+    } else if (head) {
       const int slot = add + x - 1;
       unsigned int j = idx[i];
       double sum = val[j];
@@ -280,13 +308,14 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
 }
 
 // res_off[l] = sum_{l' < l} rcnt[l'] (single block, L is small next to the arcs)
-__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* cnt, int L, int64_t* off) {
+// off[l0] must already hold the running total of the previous chunks.
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* cnt, int l0, int L, int64_t* off) {
   __shared__ long long warp_sum[32];
   __shared__ long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  if (tid == 0) carry_s = off[l0];
   __syncthreads();
-  for (int tile = 0; tile < L; tile += 1024) {
+  for (int tile = l0; tile < L; tile += 1024) {
     const int i = tile + tid;
     const long long c = i < L ? cnt[i] : 0;
     long long x = c;
@@ -322,10 +351,11 @@ struct GatherArgs {
   int32_t *c0, *c1, *c2, *c3;
   double* v;
   float* vf;
+  int l0;
 };
 
 __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
-  const int l = blockIdx.y;
+  const int l = a.l0 + blockIdx.y;
   const int n = a.rcnt[l];
   const int64_t base = a.ent_base[l];
   const int64_t out = a.res_off[l];
@@ -335,7 +365,10 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
     const unsigned int j = idx[i];
     const unsigned long long k = a.rkey[base + j];
     const double logp = a.rval[base + j];
-    if (a.tool == KLU_SEGMENT) {
+    if (a.tool == KLU_UTTERANCE) {
+      a.c0[out + i] = (int32_t)k;
+      a.v[out + i] = logp;
+    } else if (a.tool == KLU_SEGMENT) {
       const unsigned long long tm = (1ULL << a.bits_time) - 1ULL;
       a.c0[out + i] = (int32_t)(k >> (2 * a.bits_time));
       a.c1[out + i] = (int32_t)((k >> a.bits_time) & tm);
@@ -358,6 +391,135 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
   }
 }
 
+// ---------------------------------------------------------------- utterance ---
+// kwsbin2/lattice-word-index-utterance.cc:161-180 composes the lattice with a
+// 2-state "seen w" automaton per word and runs a backward pass on the product.
+// Equivalent first-occurrence form:
+//   P(w occurs) = sum over arcs a labelled w of  A_w[src(a)] * exp(-cost(a)) * beta[dst(a)]
+// where A_w is the forward score over paths that use no w arc.  A_w equals alpha up
+// to the first level holding a w arc, so only the levels between the first and the
+// last w arc are recomputed (into a per-warp scratch strip).
+struct UttArgs {
+  BatchView b;
+  CostParams cp;
+  int l0, nl;
+  const int64_t* ent_base;
+  const int32_t* rcnt;
+  const unsigned char* where;
+  const unsigned int *idx_a, *idx_b;
+  const unsigned int* aux;
+  const unsigned long long* rkey;
+  const unsigned int* raux;
+  double* rval;
+  unsigned long long* key2;
+  unsigned int* idx2;
+  const double* alpha;
+  const double* beta;
+  double* scratch;
+  int max_states;
+  int use_beam;
+  const double* vfwd;
+  const double* vbwd;
+  const double* best;
+  double beam;
+  int* counter;
+};
+
+__device__ __forceinline__ bool utt_arc_pruned(const UttArgs& a, int l, int src, int dst, const int4& r) {
+  CostParams cp = a.cp;
+  cp.float_sum = 0;
+  const double fb = __dadd_rn(a.vfwd[src], __dadd_rn(rec_cost(r, cp), a.vbwd[dst]));
+  return fb > __dadd_rn(a.best[l], a.beam);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_utt_tasks(UttArgs a) {
+  __shared__ int lat_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int SPW = 32 / G;
+  const int grp = lane / G, sl = lane % G;
+  double* anw = a.scratch + ((size_t)blockIdx.x * 8 + warp) * (size_t)a.max_states;
+  const BatchView& b = a.b;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) lat_s = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int item = lat_s;
+    if (item >= a.nl) break;
+    const int l = a.l0 + item;
+    const int n = a.rcnt[l];
+    if (n == 0) continue;
+    const int64_t base = a.ent_base[l];
+    const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + base;
+    const unsigned int* aux = a.aux + base;
+    const int e0 = b.e_off[l], s0 = b.s_off[l];
+    const int* lv = b.lvl_start + b.lvl_off[l];
+    const double total = a.beta[s0];  // bw_lkh[clat->Start()], :123
+    for (int slot = warp; slot < n; slot += 8) {
+      const int w = (int)a.rkey[base + slot];
+      const int start = (int)a.raux[base + slot];
+      const int len = (int)a.idx2[base + slot];
+      const unsigned long long span = a.key2[base + slot];
+      const int first = (int)(span >> 32), last = (int)(span & 0xffffffffu);
+      const int sb = lv[first + 1];  // first state whose no-w forward score may differ from alpha
+      for (int j = first + 1; j <= last; ++j) {
+        const int a0 = lv[j], a1 = lv[j + 1];
+        for (int bs = a0; bs < a1; bs += SPW) {
+          const int s = bs + grp;
+          const bool act = s < a1;
+          const int i0 = act ? b.in_off[s] : 0, i1 = act ? b.in_off[s + 1] : 0;
+          double m = neg_inf();
+          int arg = -1;
+          for (int e = i0 + sl; e < i1; e += G) {
+            const int4 r = __ldg(b.in_rec + e);
+            if (r.w == w) continue;
+            if (a.use_beam && utt_arc_pruned(a, l, r.x, s, r)) continue;
+            const double x = (r.x < sb ? a.alpha[r.x] : anw[r.x - sb]) - rec_cost(r, a.cp);
+            if (x > m) {
+              m = x;
+              arg = e;
+            }
+          }
+          const double lm = m;
+          m = group_max<G>(m);
+          if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
+          double sum = 0.0;
+          if (m > neg_inf()) {
+            for (int e = i0 + sl; e < i1; e += G) {
+              if (e == arg) continue;
+              const int4 r = __ldg(b.in_rec + e);
+              if (r.w == w) continue;
+              if (a.use_beam && utt_arc_pruned(a, l, r.x, s, r)) continue;
+              sum += exp((r.x < sb ? a.alpha[r.x] : anw[r.x - sb]) - rec_cost(r, a.cp) - m);
+            }
+          }
+          sum = group_sum<G>(sum);
+          if (act && sl == 0) anw[s - sb] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
+        }
+        __syncwarp();
+      }
+      double acc = neg_inf();
+      for (int q = lane; q < len; q += 32) {
+        const int e = e0 + (int)aux[idx[start + q]];
+        const int4 r = b.out_rec[e];
+        const int src = b.out_src[e];
+        const double fw = src < sb ? a.alpha[src] : anw[src - sb];
+        acc = log_add(acc, __dadd_rn(__dadd_rn(fw, -rec_cost(r, a.cp)), a.beta[r.x]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc = log_add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+      __syncwarp();
+      if (lane == 0) {
+        const double logp = acc - total;
+        a.rval[base + slot] = logp;
+        a.key2[base + slot] = ~ord_f64(logp + 0.0);
+        a.idx2[base + slot] = (unsigned int)slot;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 int bits_for(int64_t maxv) {
   int b = 1;
   while (b < 63 && ((int64_t)1 << b) <= maxv) ++b;
@@ -368,7 +530,7 @@ int bits_for(int64_t maxv) {
 
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   const int32_t L = c->L;
-  const bool needs_times = tool != KLU_FWD_BWD;
+  const bool needs_times = tool != KLU_FWD_BWD && tool != KLU_UTTERANCE;
   if (needs_times)
     for (int32_t l = 0; l < L; ++l)
       if (!c->h_times_ok[l]) {
@@ -383,24 +545,49 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   }
   CostParams cp = make_cost_params(o, false);
   if (use_beam) KLU_TRY(run_tropical_sweeps(c, cp));
+  // the utterance tool scores with ComputeCompactLatticeBetas [ext]: float-summed costs
+  if (tool == KLU_UTTERANCE) cp.float_sum = 1;
   KLU_TRY(run_log_sweeps(c, cp, use_beam, o->beam));
   c->h_res_off.assign(L + 1, 0);
   c->last_entries = 0;
   if (tool == KLU_FWD_BWD || L == 0) return 0;
-  if (tool == KLU_POSITION) KLU_TRY(run_banded_alpha(c, cp, use_beam, o->beam));
 
-  // ---- entry slots ----
-  std::vector<int64_t> ent_base(L + 1, 0);
-  for (int32_t l = 0; l < L; ++l) {
-    const int64_t cap = tool == KLU_SEGMENT ? (c->h_e_off[l + 1] - c->h_e_off[l])
-                        : tool == KLU_FRAME_POST ? c->h_cap_frame[l] : c->h_cap_pos[l];
-    if (cap >= ((int64_t)1 << 31)) {
-      set_error("lattice " + std::to_string(l) + ": more than 2^31 index entries");
-      return 1;
+  // ---- chunk plan: contiguous lattice ranges with bounded scratch ----
+  int64_t kEntryBudget = (int64_t)1 << 28;  // entries per chunk (~92 B of scratch each)
+  if (const char* env = getenv("KLU_ENTRY_BUDGET")) kEntryBudget = std::max<long long>(1, atoll(env));  // tests
+  const int64_t kBandBudget = (int64_t)1 << 30;   // (state,len) cells per chunk (8 B each)
+  std::vector<int64_t> ent_base(L + 1, 0);        // chunk-local first entry slot of each lattice
+  std::vector<int32_t> chunk_first;
+  {
+    int64_t acc = 0, band_acc = 0;
+    chunk_first.push_back(0);
+    for (int32_t l = 0; l < L; ++l) {
+      const int64_t cap = (tool == KLU_SEGMENT || tool == KLU_UTTERANCE) ? (c->h_e_off[l + 1] - c->h_e_off[l])
+                          : tool == KLU_FRAME_POST ? c->h_cap_frame[l] : c->h_cap_pos[l];
+      const int64_t band = tool == KLU_POSITION ? c->h_band_off[l + 1] - c->h_band_off[l] : 0;
+      if (cap >= ((int64_t)1 << 31)) {
+        set_error("lattice " + std::to_string(l) + ": more than 2^31 index entries");
+        return 1;
+      }
+      if (l > chunk_first.back() && (acc + cap > kEntryBudget || band_acc + band > kBandBudget)) {
+        chunk_first.push_back(l);
+        acc = 0;
+        band_acc = 0;
+      }
+      ent_base[l] = acc;
+      acc += cap;
+      band_acc += band;
     }
-    ent_base[l + 1] = ent_base[l] + cap;
+    chunk_first.push_back(L);
   }
-  const int64_t N = std::max<int64_t>(ent_base[L], 1);
+  int64_t N = 1;  // largest chunk
+  for (size_t k = 0; k + 1 < chunk_first.size(); ++k) {
+    const int32_t last = chunk_first[k + 1] - 1;
+    const int64_t cap = (tool == KLU_SEGMENT || tool == KLU_UTTERANCE) ? (c->h_e_off[last + 1] - c->h_e_off[last])
+                        : tool == KLU_FRAME_POST ? c->h_cap_frame[last] : c->h_cap_pos[last];
+    N = std::max(N, ent_base[last] + cap);
+  }
+  const bool single_chunk = chunk_first.size() == 2;
   enum { S_BASE = 0, S_ARCOFF, S_CNT, S_KEYA, S_KEYB, S_IDXA, S_IDXB, S_VAL, S_AUX, S_WHERE, S_RCNT, S_R };
   KLU_TRY(c->d_scratch[S_BASE].reserve(sizeof(int64_t) * (L + 1)));
   KLU_TRY(c->d_scratch[S_ARCOFF].reserve(sizeof(int32_t) * std::max<int64_t>(c->E, 1)));
@@ -415,8 +602,12 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   KLU_TRY(c->d_scratch[S_RCNT].reserve(sizeof(int32_t) * L));
   // reduced entries: key (8) + val (8) + aux (4) per slot
   KLU_TRY(c->d_scratch[S_R].reserve(20 * (size_t)N + 64));
+  KLU_TRY(c->d_res[6].reserve(sizeof(int64_t) * N));  // ordering-sort keys
+  KLU_TRY(c->d_res[7].reserve(sizeof(int32_t) * N));  // ordering-sort values
+  KLU_TRY(c->d_res[5].reserve(sizeof(int64_t) * (L + 1)));
   KLU_CUDA(cudaMemcpyAsync(c->d_scratch[S_BASE].p, ent_base.data(), sizeof(int64_t) * (L + 1),
                            cudaMemcpyHostToDevice, c->stream));
+  KLU_CUDA(cudaMemsetAsync(c->d_res[5].p, 0, sizeof(int64_t), c->stream));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // ent_base is a stack object
 
   int fmode = 0, fn = 0;
@@ -431,7 +622,6 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   a.filter = c->d_filter.as<int32_t>();
   a.alpha = c->d_alpha.as<double>();
   a.beta = c->d_beta.as<double>();
-  a.alpha2 = c->d_alpha2.as<double>();
   a.total = c->d_total.as<double>();
   a.use_beam = use_beam ? 1 : 0;
   a.vfwd = c->d_vfwd.as<double>();
@@ -449,128 +639,209 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   a.val = c->d_scratch[S_VAL].as<double>();
   a.aux = c->d_scratch[S_AUX].as<unsigned int>();
   int key_bits = 0;
-  if (tool == KLU_SEGMENT) key_bits = a.bits_label + 2 * a.bits_time;
+  if (tool == KLU_UTTERANCE) key_bits = a.bits_label;
+  else if (tool == KLU_SEGMENT) key_bits = a.bits_label + 2 * a.bits_time;
   else if (tool == KLU_POSITION) key_bits = a.bits_label + a.bits_len;
   else key_bits = a.bits_time + a.bits_label;
-  if (key_bits > 63 || (tool == KLU_FRAME_POST && a.bits_time > 31)) {
-    set_error("index key does not fit 63 bits (labels/times too large)");
+  if (key_bits > 62 || (tool == KLU_FRAME_POST && a.bits_time > 31)) {
+    set_error("index key does not fit 62 bits (labels/times too large)");
     return 1;
   }
   a.drop_key = 1ULL << key_bits;
-  {
-    KLU_LAUNCH(c, "k_count_scan");
-    k_count_scan<<<L, 256, 0, c->stream>>>(a);
-  }
-  KLU_TRY(check_launch("k_count_scan"));
-  int64_t max_arcs = 0;
-  for (int32_t l = 0; l < L; ++l) max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
-  const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
-  {
-    KLU_LAUNCH(c, "k_emit");
-    k_emit<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
-  }
-  KLU_TRY(check_launch("k_emit"));
 
-  SegSortArgs s1;
-  s1.seg_base = a.ent_base;
-  s1.seg_cnt = a.ent_cnt;
-  s1.key_a = c->d_scratch[S_KEYA].as<unsigned long long>();
-  s1.val_a = c->d_scratch[S_IDXA].as<unsigned int>();
-  s1.key_b = c->d_scratch[S_KEYB].as<unsigned long long>();
-  s1.val_b = c->d_scratch[S_IDXB].as<unsigned int>();
-  s1.where = c->d_scratch[S_WHERE].as<unsigned char>();
-  s1.lo_bit = 0;
-  s1.hi_bit = key_bits + 1;  // + the drop bit; degenerate digits are skipped per lattice
-  {
-    KLU_LAUNCH(c, "k_seg_radix_sort");
-    k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(s1);
-  }
-  KLU_TRY(check_launch("k_seg_radix_sort(keys)"));
+  int64_t res_cap = 0, res_used = 0;  // result columns: capacity / entries known to be in use
+  auto grow_results = [&](int64_t need) -> int {
+    if (need <= res_cap) return 0;
+    const int64_t want = std::max<int64_t>(need, res_cap * 2);
+    for (int i = 0; i < 5; ++i) {
+      const size_t w = i == 4 ? 8 : 4;
+      if (c->d_res[i].cap >= (size_t)want * w) continue;
+      DevBuf nb;
+      KLU_TRY(nb.reserve((size_t)want * w));
+      if (res_used > 0)
+        KLU_CUDA(cudaMemcpyAsync(nb.p, c->d_res[i].p, (size_t)res_used * w, cudaMemcpyDeviceToDevice, c->stream));
+      KLU_CUDA(cudaStreamSynchronize(c->stream));
+      c->d_res[i].release();
+      c->d_res[i] = nb;
+    }
+    res_cap = want;
+    return 0;
+  };
 
-  ReduceArgs r;
-  r.b = a.b;
-  r.tool = tool;
-  r.ent_base = a.ent_base;
-  r.ent_cnt = a.ent_cnt;
-  r.where = s1.where;
-  r.key_a = s1.key_a;
-  r.key_b = s1.key_b;
-  r.idx_a = s1.val_a;
-  r.idx_b = s1.val_b;
-  r.val = a.val;
-  r.aux = a.aux;
-  r.total = a.total;
-  char* rp = c->d_scratch[S_R].as<char>();
-  r.rkey = reinterpret_cast<unsigned long long*>(rp);
-  r.rval = reinterpret_cast<double*>(rp + 8 * (size_t)N);
-  r.raux = reinterpret_cast<unsigned int*>(rp + 16 * (size_t)N);
-  r.rcnt = c->d_scratch[S_RCNT].as<int32_t>();
-  // the ordering sort's input pair is separate from the first sort's buffers
-  // (the reduce reads those); its ping-pong partner is the then-free A side.
-  KLU_TRY(c->d_res[6].reserve(sizeof(int64_t) * N));   // key2 a
-  KLU_TRY(c->d_res[7].reserve(sizeof(int32_t) * N));   // idx2 a
-  r.key2 = c->d_res[6].as<unsigned long long>();
-  r.idx2 = c->d_res[7].as<unsigned int>();
-  r.bits_label = a.bits_label;
-  r.drop_key = a.drop_key;
-  {
-    KLU_LAUNCH(c, "k_reduce");
-    k_reduce<<<L, 256, 0, c->stream>>>(r);
-  }
-  KLU_TRY(check_launch("k_reduce"));
+  for (size_t k = 0; k + 1 < chunk_first.size(); ++k) {
+    const int32_t l0 = chunk_first[k], l1 = chunk_first[k + 1];
+    const int nl = l1 - l0;
+    if (nl <= 0) continue;
+    a.l0 = l0;
+    a.band_base = 0;
+    if (tool == KLU_POSITION) {
+      KLU_TRY(run_banded_alpha(c, cp, use_beam, o->beam, l0, l1));
+      a.band_base = c->h_band_off[l0];
+    }
+    a.alpha2 = c->d_alpha2.as<double>();
+    {
+      KLU_LAUNCH(c, "k_count_scan");
+      k_count_scan<<<nl, 256, 0, c->stream>>>(a);
+    }
+    KLU_TRY(check_launch("k_count_scan"));
+    int64_t max_arcs = 0, chunk_cap = 0;
+    for (int32_t l = l0; l < l1; ++l) max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
+    {
+      const int32_t last = l1 - 1;
+      const int64_t cap = (tool == KLU_SEGMENT || tool == KLU_UTTERANCE)
+                              ? (c->h_e_off[last + 1] - c->h_e_off[last])
+                              : tool == KLU_FRAME_POST ? c->h_cap_frame[last] : c->h_cap_pos[last];
+      chunk_cap = ent_base[last] + cap;
+    }
+    const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
+    {
+      KLU_LAUNCH(c, "k_emit");
+      k_emit<<<dim3(tiles, nl), 256, 0, c->stream>>>(a);
+    }
+    KLU_TRY(check_launch("k_emit"));
 
-  // ---- output ordering: stable sort on key2, ping-pong into the (now free)
-  // first-sort buffers ----
-  SegSortArgs s2;
-  s2.seg_base = a.ent_base;
-  s2.seg_cnt = r.rcnt;
-  s2.key_a = r.key2;
-  s2.val_a = r.idx2;
-  s2.key_b = c->d_scratch[S_KEYA].as<unsigned long long>();
-  s2.val_b = c->d_scratch[S_IDXA].as<unsigned int>();
-  s2.where = c->d_scratch[S_WHERE].as<unsigned char>() + L;
-  s2.lo_bit = 0;
-  s2.hi_bit = 64;
-  {
-    KLU_LAUNCH(c, "k_seg_radix_sort");
-    k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(s2);
-  }
-  KLU_TRY(check_launch("k_seg_radix_sort(order)"));
+    SegSortArgs s1;
+    s1.seg_base = a.ent_base + l0;
+    s1.seg_cnt = a.ent_cnt + l0;
+    s1.key_a = c->d_scratch[S_KEYA].as<unsigned long long>();
+    s1.val_a = c->d_scratch[S_IDXA].as<unsigned int>();
+    s1.key_b = c->d_scratch[S_KEYB].as<unsigned long long>();
+    s1.val_b = c->d_scratch[S_IDXB].as<unsigned int>();
+    s1.where = c->d_scratch[S_WHERE].as<unsigned char>() + l0;
+    s1.lo_bit = 0;
+    s1.hi_bit = key_bits + 1;  // + the drop bit; degenerate digits are skipped per lattice
+    {
+      KLU_LAUNCH(c, "k_seg_radix_sort");
+      k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s1);
+    }
+    KLU_TRY(check_launch("k_seg_radix_sort(keys)"));
 
-  KLU_TRY(c->d_res[5].reserve(sizeof(int64_t) * (L + 1)));
-  {
-    KLU_LAUNCH(c, "k_scan_counts");
-    k_scan_counts<<<1, 1024, 0, c->stream>>>(r.rcnt, L, c->d_res[5].as<int64_t>());
+    ReduceArgs r;
+    r.b = a.b;
+    r.tool = tool;
+    r.l0 = l0;
+    r.ent_base = a.ent_base;
+    r.ent_cnt = a.ent_cnt;
+    r.where = c->d_scratch[S_WHERE].as<unsigned char>();
+    r.key_a = s1.key_a;
+    r.key_b = s1.key_b;
+    r.idx_a = s1.val_a;
+    r.idx_b = s1.val_b;
+    r.val = a.val;
+    r.aux = a.aux;
+    r.total = a.total;
+    char* rp = c->d_scratch[S_R].as<char>();
+    r.rkey = reinterpret_cast<unsigned long long*>(rp);
+    r.rval = reinterpret_cast<double*>(rp + 8 * (size_t)N);
+    r.raux = reinterpret_cast<unsigned int*>(rp + 16 * (size_t)N);
+    r.rcnt = c->d_scratch[S_RCNT].as<int32_t>();
+    // the ordering sort's input pair is separate from the first sort's buffers
+    // (the reduce reads those); its ping-pong partner is the then-free A side.
+    r.key2 = c->d_res[6].as<unsigned long long>();
+    r.idx2 = c->d_res[7].as<unsigned int>();
+    r.bits_label = a.bits_label;
+    r.drop_key = a.drop_key;
+    {
+      KLU_LAUNCH(c, "k_reduce");
+      k_reduce<<<nl, 256, 0, c->stream>>>(r);
+    }
+    KLU_TRY(check_launch("k_reduce"));
+
+    if (tool == KLU_UTTERANCE) {
+      UttArgs u;
+      u.b = a.b;
+      u.cp = cp;
+      u.l0 = l0;
+      u.nl = nl;
+      u.ent_base = a.ent_base;
+      u.rcnt = r.rcnt;
+      u.where = r.where;
+      u.idx_a = s1.val_a;
+      u.idx_b = s1.val_b;
+      u.aux = a.aux;
+      u.rkey = r.rkey;
+      u.raux = r.raux;
+      u.rval = r.rval;
+      u.key2 = r.key2;
+      u.idx2 = r.idx2;
+      u.alpha = a.alpha;
+      u.beta = a.beta;
+      u.max_states = std::max(1, c->max_states);
+      u.use_beam = a.use_beam;
+      u.vfwd = a.vfwd;
+      u.vbwd = a.vbwd;
+      u.best = a.best;
+      u.beam = a.beam;
+      const int grid = std::max(1, std::min(nl, c->num_sms * 4));
+      KLU_TRY(c->d_alpha2.reserve(sizeof(double) * (size_t)grid * 8 * (size_t)u.max_states));
+      u.scratch = c->d_alpha2.as<double>();
+      KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
+      u.counter = c->d_counter.as<int>();
+      const int G = pick_group(c->avg_deg);
+      {
+        KLU_LAUNCH(c, "k_utt_tasks");
+        KLU_DISPATCH_G(G, k_utt_tasks<kG><<<grid, 256, 0, c->stream>>>(u));
+      }
+      KLU_TRY(check_launch("k_utt_tasks"));
+    }
+    SegSortArgs s2;
+    s2.seg_base = a.ent_base + l0;
+    s2.seg_cnt = r.rcnt + l0;
+    s2.key_a = r.key2;
+    s2.val_a = r.idx2;
+    s2.key_b = c->d_scratch[S_KEYA].as<unsigned long long>();
+    s2.val_b = c->d_scratch[S_IDXA].as<unsigned int>();
+    s2.where = c->d_scratch[S_WHERE].as<unsigned char>() + L + l0;
+    s2.lo_bit = 0;
+    s2.hi_bit = 64;
+    {
+      KLU_LAUNCH(c, "k_seg_radix_sort");
+      k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s2);
+    }
+    KLU_TRY(check_launch("k_seg_radix_sort(order)"));
+    {
+      KLU_LAUNCH(c, "k_scan_counts");
+      k_scan_counts<<<1, 1024, 0, c->stream>>>(r.rcnt, l0, l1, c->d_res[5].as<int64_t>());
+    }
+    KLU_TRY(check_launch("k_scan_counts"));
+    if (single_chunk) {
+      KLU_TRY(grow_results(chunk_cap));
+    } else {
+      int64_t upto = 0;
+      KLU_CUDA(cudaMemcpyAsync(&upto, c->d_res[5].as<int64_t>() + l1, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                               c->stream));
+      KLU_CUDA(cudaStreamSynchronize(c->stream));
+      KLU_TRY(grow_results(upto));
+      res_used = upto;
+    }
+    GatherArgs g;
+    g.b = a.b;
+    g.tool = tool;
+    g.l0 = l0;
+    g.ent_base = a.ent_base;
+    g.rcnt = r.rcnt;
+    g.res_off = c->d_res[5].as<int64_t>();
+    g.where = c->d_scratch[S_WHERE].as<unsigned char>() + L;
+    g.idx_a = s2.val_a;
+    g.idx_b = s2.val_b;
+    g.rkey = r.rkey;
+    g.rval = r.rval;
+    g.raux = r.raux;
+    g.bits_label = a.bits_label;
+    g.bits_time = a.bits_time;
+    g.bits_len = a.bits_len;
+    g.c0 = c->d_res[0].as<int32_t>();
+    g.c1 = c->d_res[1].as<int32_t>();
+    g.c2 = c->d_res[2].as<int32_t>();
+    g.c3 = c->d_res[3].as<int32_t>();
+    g.v = c->d_res[4].as<double>();
+    g.vf = c->d_res[4].as<float>();
+    {
+      KLU_LAUNCH(c, "k_gather");
+      k_gather<<<dim3(tiles, nl), 256, 0, c->stream>>>(g);
+    }
+    KLU_TRY(check_launch("k_gather"));
   }
-  KLU_TRY(check_launch("k_scan_counts"));
-  for (int i = 0; i < 4; ++i) KLU_TRY(c->d_res[i].reserve(sizeof(int32_t) * N));
-  KLU_TRY(c->d_res[4].reserve(sizeof(double) * N));
-  GatherArgs g;
-  g.b = a.b;
-  g.tool = tool;
-  g.ent_base = a.ent_base;
-  g.rcnt = r.rcnt;
-  g.res_off = c->d_res[5].as<int64_t>();
-  g.where = s2.where;
-  g.idx_a = s2.val_a;
-  g.idx_b = s2.val_b;
-  g.rkey = r.rkey;
-  g.rval = r.rval;
-  g.raux = r.raux;
-  g.bits_label = a.bits_label;
-  g.bits_time = a.bits_time;
-  g.bits_len = a.bits_len;
-  g.c0 = c->d_res[0].as<int32_t>();
-  g.c1 = c->d_res[1].as<int32_t>();
-  g.c2 = c->d_res[2].as<int32_t>();
-  g.c3 = c->d_res[3].as<int32_t>();
-  g.v = c->d_res[4].as<double>();
-  g.vf = c->d_res[4].as<float>();
-  {
-    KLU_LAUNCH(c, "k_gather");
-    k_gather<<<dim3(tiles, L), 256, 0, c->stream>>>(g);
-  }
-  KLU_TRY(check_launch("k_gather"));
   c->last_entries = -1;  // known after klu_result_offsets()
   return 0;
 }
@@ -638,6 +909,19 @@ int klu_fetch_position(klu_ctx* c, int32_t* word, int32_t* pos, int32_t* t0, int
   KLU_TRY(d2h(c, pos, c->d_res[1].p, n * 4));
   KLU_TRY(d2h(c, t0, c->d_res[2].p, n * 4));
   KLU_TRY(d2h(c, t1, c->d_res[3].p, n * 4));
+  KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 8));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int klu_fetch_utterance(klu_ctx* c, int32_t* word, double* logp) {
+  if (c->last_tool != KLU_UTTERANCE) {
+    set_error("klu_fetch_utterance: last run was not KLU_UTTERANCE");
+    return 1;
+  }
+  KLU_TRY(ensure_offsets(c));
+  const size_t n = (size_t)c->last_entries;
+  KLU_TRY(d2h(c, word, c->d_res[0].p, n * 4));
   KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 8));
   KLU_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -29,8 +29,9 @@ namespace klu {
 namespace {
 
 struct Staging {
-  std::vector<int32_t> s_off, e_off, lvl_off, lvl_start, in_off, out_off, out_src, out_orig, time, orig, band_lo,
-      band_off, order;
+  std::vector<int32_t> s_off, e_off, lvl_off, lvl_start, in_off, out_off, out_src, out_orig, time, orig, level, band_lo,
+      order;
+  std::vector<int64_t> band_off;
   std::vector<int4> in_rec, out_rec;
   std::vector<float> fin_g, fin_a;
 };
@@ -113,6 +114,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   st.fin_a.resize(S);
   st.time.resize(S);
   st.orig.resize(S);
+  st.level.resize(S);
   st.band_lo.resize(S);
   st.band_off.assign(S + 1, 0);
   c->h_new2old.resize(S);
@@ -220,6 +222,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
             st.fin_a[n] = in->fin_acoustic[s0 + s];
             st.time[n] = times[s];
             st.orig[n] = s;
+            st.level[n] = level[s];
             st.band_lo[n] = hi[s] >= 0 ? lo[s] : -1;
             st.band_off[n + 1] = hi[s] >= 0 ? hi[s] - lo[s] + 1 : 0;  // widths; prefix-summed later
             c->h_new2old[n] = s;
@@ -278,13 +281,11 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
     int64_t acc = 0;
     for (int64_t s = 0; s < S; ++s) {
       acc += st.band_off[s + 1];
-      if (acc >= (int64_t)1 << 31) {
-        set_error("klu_load: (state, length) band exceeds 32-bit indices; split the batch");
-        return 1;
-      }
-      st.band_off[s + 1] = (int32_t)acc;
+      st.band_off[s + 1] = acc;
     }
     c->band_total = acc;
+    c->h_band_off.resize(L + 1);
+    for (int32_t l = 0; l <= L; ++l) c->h_band_off[l] = st.band_off[in->state_off[l]];
   }
   // work queue order: lattices by descending arc count
   st.order.resize(L);
@@ -305,7 +306,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   c->h_cap_frame.resize(L);
   c->h_cap_pos.resize(L);
   c->h_maxlen.resize(L);
-  c->max_label = c->max_time = c->max_len = c->max_indeg = c->max_outdeg = 0;
+  c->max_label = c->max_time = c->max_len = c->max_indeg = c->max_outdeg = c->max_states = 0;
   for (int32_t l = 0; l < L; ++l) {
     c->h_num_frames[l] = info[l].num_frames;
     c->h_times_ok[l] = info[l].times_ok;
@@ -317,6 +318,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
     c->max_len = std::max(c->max_len, info[l].max_len);
     c->max_indeg = std::max(c->max_indeg, info[l].max_indeg);
     c->max_outdeg = std::max(c->max_outdeg, info[l].max_outdeg);
+    c->max_states = std::max<int32_t>(c->max_states, (int32_t)(in->state_off[l + 1] - in->state_off[l]));
   }
   c->avg_deg = S ? (double)E / (double)S : 0.0;
 
@@ -340,8 +342,9 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(up(c->d_fin_a, st.fin_a.data(), st.fin_a.size() * 4));
   KLU_TRY(up(c->d_time, st.time.data(), st.time.size() * 4));
   KLU_TRY(up(c->d_orig, st.orig.data(), st.orig.size() * 4));
+  KLU_TRY(up(c->d_level, st.level.data(), st.level.size() * 4));
   KLU_TRY(up(c->d_band_lo, st.band_lo.data(), st.band_lo.size() * 4));
-  KLU_TRY(up(c->d_band_off, st.band_off.data(), st.band_off.size() * 4));
+  KLU_TRY(up(c->d_band_off, st.band_off.data(), st.band_off.size() * 8));
   KLU_TRY(up(c->d_order, st.order.data(), st.order.size() * 4));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // staging vectors die here
   return 0;

@@ -36,37 +36,6 @@ struct SweepArgs {
   int do_fwd, do_bwd;
 };
 
-template <int G>
-__device__ __forceinline__ double group_max(double v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-template <int G>
-__device__ __forceinline__ double group_min(double v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-template <int G>
-__device__ __forceinline__ double group_sum(double v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// The log-sum of a state is formed as  max + log1p(sum of the OTHER terms), which
-// for two terms is exactly Kaldi's LogAdd (max + log1p(exp(-|d|))) and for more
-// terms rounds once instead of once per pair.  One lane of the group (the lowest
-// whose local maximum is the group maximum) leaves its arg-max term out.
-template <int G>
-__device__ __forceinline__ bool elect_max_lane(double local_m, double m, int lane) {
-  const unsigned int bal = __ballot_sync(0xffffffffu, local_m == m && m > neg_inf());
-  const unsigned int gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((lane / G) * G);
-  const unsigned int cand = bal & gmask;
-  return cand != 0 && lane == __ffs(cand) - 1;
-}
-
 // PruneLattice's arc test, evaluated on the fly: the arc is dropped when
 // fwd[s] + (cost + bwd[next]) > best_final + beam.
 __device__ __forceinline__ bool arc_pruned(const SweepArgs& a, int l, int src, int dst, const int4& r) {
@@ -321,7 +290,9 @@ __global__ void __launch_bounds__(128) k_trop_sweeps(SweepArgs a, double* vfwd, 
 // alpha2[band_off[s] + (len - band_lo[s])] = log-sum of all paths start -> s that
 // carry exactly `len` non-epsilon labels.  A group owns one (state, len) cell.
 template <int G, bool BEAM>
-__global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha2) {
+__global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha2_chunk, int l0, int l1,
+                                                      long long band_base) {
+  double* alpha2 = alpha2_chunk - band_base;  // indexed with global band offsets
   const int lane = threadIdx.x & 31;
   const BatchView& b = a.b;
   constexpr int SPW = 32 / G;
@@ -330,8 +301,8 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
     int item = 0;
     if (lane == 0) item = atomicAdd(a.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= b.L) break;
-    const int l = b.order[item];
+    if (item >= l1 - l0) break;
+    const int l = l0 + item;
     const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
     if (s_begin == s_end) continue;
     const int* lv = b.lvl_start + b.lvl_off[l];
@@ -341,9 +312,9 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
     __syncwarp();
     for (int j = 1; j < nl; ++j) {
       const int a0 = lv[j], a1 = lv[j + 1];
-      const int c0 = b.band_off[a0], c1 = b.band_off[a1];  // cells of this level
-      for (int base = c0; base < c1; base += SPW) {
-        const int cell = base + grp;
+      const long long c0 = b.band_off[a0], c1 = b.band_off[a1];  // cells of this level
+      for (long long base = c0; base < c1; base += SPW) {
+        const long long cell = base + grp;
         const bool act = cell < c1;
         int s = a0;
         if (act) {  // binary search: last state with band_off[s] <= cell
@@ -355,7 +326,7 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
           }
           s = lo;
         }
-        const int len = act ? b.band_lo[s] + (cell - b.band_off[s]) : 0;
+        const int len = act ? b.band_lo[s] + (int)(cell - b.band_off[s]) : 0;
         const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
         double m = neg_inf();
         int arg = -1;
@@ -363,7 +334,7 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
           const int4 r = __ldg(b.in_rec + e);
           const int plen = len - (r.w != 0 ? 1 : 0);
           const int plo = b.band_lo[r.x];
-          const int pw = b.band_off[r.x + 1] - b.band_off[r.x];
+          const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
           if (plo < 0 || plen < plo || plen >= plo + pw) continue;
           const double cost = rec_cost(r, a.cp);
           if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
@@ -383,7 +354,7 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
             const int4 r = __ldg(b.in_rec + e);
             const int plen = len - (r.w != 0 ? 1 : 0);
             const int plo = b.band_lo[r.x];
-            const int pw = b.band_off[r.x + 1] - b.band_off[r.x];
+            const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
             if (plo < 0 || plen < plo || plen >= plo + pw) continue;
             const double cost = rec_cost(r, a.cp);
             if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
@@ -396,14 +367,6 @@ __global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha
       __syncwarp();
     }
   }
-}
-
-int pick_group(double avg_deg) {
-  if (avg_deg <= 3.0) return 2;
-  if (avg_deg <= 6.0) return 4;
-  if (avg_deg <= 48.0) return 8;
-  if (avg_deg <= 160.0) return 16;
-  return 32;
 }
 
 int sweep_grid(klu_ctx* c, int items) {
@@ -431,14 +394,13 @@ SweepArgs make_args(klu_ctx* c, const CostParams& cp, bool use_beam, float beam)
 
 }  // namespace
 
-#define KLU_DISPATCH_G(G, ...)                       \
-  switch (G) {                                       \
-    case 2: { constexpr int kG = 2; __VA_ARGS__; } break;   \
-    case 4: { constexpr int kG = 4; __VA_ARGS__; } break;   \
-    case 8: { constexpr int kG = 8; __VA_ARGS__; } break;   \
-    case 16: { constexpr int kG = 16; __VA_ARGS__; } break; \
-    default: { constexpr int kG = 32; __VA_ARGS__; } break; \
-  }
+int pick_group(double avg_deg) {
+  if (avg_deg <= 3.0) return 2;
+  if (avg_deg <= 6.0) return 4;
+  if (avg_deg <= 48.0) return 8;
+  if (avg_deg <= 160.0) return 16;
+  return 32;
+}
 
 int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) {
   KLU_TRY(c->d_alpha.reserve(sizeof(double) * std::max<int64_t>(c->S, 1)));
@@ -484,18 +446,20 @@ int run_tropical_sweeps(klu_ctx* c, const CostParams& cp) {
   return check_launch("k_trop_sweeps");
 }
 
-int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) {
-  KLU_TRY(c->d_alpha2.reserve(sizeof(double) * std::max<int64_t>(c->band_total, 1)));
+int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam, int l0, int l1) {
+  const long long band_base = c->h_band_off[l0];
+  const long long cells = c->h_band_off[l1] - band_base;
+  KLU_TRY(c->d_alpha2.reserve(sizeof(double) * std::max<long long>(cells, 1)));
   KLU_TRY(c->d_counter.reserve(64));
-  if (c->L == 0) return 0;
+  if (l1 <= l0) return 0;
   KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
   SweepArgs a = make_args(c, cp, use_beam, beam);
   const int G = pick_group(c->avg_deg);
-  const int grid = sweep_grid(c, c->L);
+  const int grid = sweep_grid(c, l1 - l0);
   {
     KLU_LAUNCH(c, "k_banded_alpha");
-    KLU_DISPATCH_G(G, if (use_beam) k_banded_alpha<kG, true><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>());
-                   else k_banded_alpha<kG, false><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>()));
+    KLU_DISPATCH_G(G, if (use_beam) k_banded_alpha<kG, true><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>(), l0, l1, band_base);
+                   else k_banded_alpha<kG, false><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>(), l0, l1, band_base));
   }
   return check_launch("k_banded_alpha");
 }

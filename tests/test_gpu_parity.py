@@ -28,6 +28,11 @@ def test_readme_position_text(klu, engine, word_lat):
     assert klu.format_tuples("lat1", engine.position()[0]).strip() == goldens()["position"]
 
 
+def test_readme_utterance_text(klu, engine, word_lat):
+    _load(klu, engine, [word_lat])
+    assert klu.format_tuples("lat1", engine.utterance()[0]).strip() == goldens()["utterance"]
+
+
 def test_fwd_bwd_matches_oracle(klu, ora, engine):
     batch = klu.synth_batch("small", 8, seed=11)
     engine.load(batch)
@@ -76,15 +81,39 @@ def test_frame_post_parity(klu, ora, engine, shape, n, seed, flags):
             assert_rows_match([(a, b) for a, b in g], [(a, b) for a, b in w], 1, what="frame %d lat %d" % (k, l))
 
 
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", FLAGS)
+def test_utterance_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 130)
+    engine.load(batch)
+    got = engine.utterance(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        assert_rows_match(got[l], ora.utterance(lat, **flags), 1, what="utterance lat %d" % l)
+
+
+def test_chunked_execution_matches_single_chunk(klu, ora, engine, monkeypatch):
+    # tiny scratch budget -> many chunks; results must not change
+    batch = klu.synth_batch("tiny", 16, seed=321)
+    engine.load(batch)
+    ref = dict(seg=engine.segment(), pos=engine.position(), fp=engine.frame_post(), utt=engine.utterance())
+    monkeypatch.setenv("KLU_ENTRY_BUDGET", "150")
+    assert engine.segment() == ref["seg"]
+    assert engine.position() == ref["pos"]
+    assert engine.frame_post() == ref["fp"]
+    assert engine.utterance() == ref["utt"]
+
+
 def test_include_exclude_words(klu, ora, engine):
     batch = klu.synth_batch("tiny", 6, seed=77)
     engine.load(batch)
     for flags in (dict(include_words=[1, 2, 3]), dict(exclude_words=[1, 4]), dict(include_words=[2], exclude_words=[2])):
         got = engine.segment(**flags)
         gotp = engine.position(**flags)
+        gotu = engine.utterance(**flags)
         for l, lat in enumerate(batch.lattices()):
             assert_rows_match(got[l], ora.segment(lat, **flags), 3)
             assert_rows_match(gotp[l], ora.position(lat, **flags), 2)
+            assert_rows_match(gotu[l], ora.utterance(lat, **flags), 1)
 
 
 def test_empty_and_ragged_batch(klu, ora, engine):
