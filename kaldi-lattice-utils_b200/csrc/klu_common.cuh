@@ -64,6 +64,7 @@ struct BatchView {
   const int32_t* out_off;    // [S+1]
   const int32_t* out_src;    // [E] (global) src of out-order arcs
   const int32_t* out_orig;   // [E] lattice-local index of the arc in the caller's arrays
+  const int32_t* in2out;     // [E] position (global) of each in-order arc in the out-order arrays
   const float* fin_g;        // [S]
   const float* fin_a;        // [S]
   const int32_t* time;       // [S] frame of each state (CompactLatticeStateTimes)
@@ -110,7 +111,7 @@ struct klu_ctx {
 
   // ---- device: packed batch ----
   klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
-      d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order;
+      d_in2out, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order;
   // ---- device: per-run state ----
   klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
   klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps
@@ -153,8 +154,18 @@ int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o);
 // klu_prune.cu
 int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o);
-// klu_bestpath.cu
-int run_best_path2(klu_ctx* c, const klu_opts* o);
+// klu_bestpath.cu: decode stage of lattice-best-path2 for lattices [l0, l1); the
+// (label, position) posteriors were already turned into per-entry float costs.
+struct BestPathChunk {
+  int l0, l1;
+  long long band_base;          // first band cell of the chunk
+  const double* alpha2;         // chunk-local banded alpha
+  const int64_t* ent_base;      // [L] chunk-local first entry slot per lattice
+  const int32_t* arc_ent_off;   // [E] lattice-local first entry of each out-order arc
+  const double* ecost;          // per entry: (double)(float) cost of its (label, position)
+  bool first_chunk;
+};
+int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch);
 // klu_char.cu
 int run_char_position(klu_ctx* c, const klu_opts* o);
 

@@ -129,6 +129,7 @@ klu::BatchView klu_ctx::view() const {
   v.out_off = d_out_off.as<int32_t>();
   v.out_src = d_out_src.as<int32_t>();
   v.out_orig = d_out_orig.as<int32_t>();
+  v.in2out = d_in2out.as<int32_t>();
   v.fin_g = d_fin_g.as<float>();
   v.fin_a = d_fin_a.as<float>();
   v.time = d_time.as<int32_t>();
@@ -201,7 +202,7 @@ int klu_destroy(klu_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
-                    &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_fin_g, &c->d_fin_a,
+                    &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_in2out, &c->d_fin_g, &c->d_fin_a,
                     &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
@@ -259,13 +260,11 @@ int klu_run(klu_ctx* c, int tool, const klu_opts* opts) {
     case KLU_FRAME_POST:
     case KLU_FWD_BWD:
     case KLU_UTTERANCE:
+    case KLU_BEST_PATH2:
       rc = run_index_tool(c, tool, opts);
       break;
     case KLU_PRUNE_DYN_BEAM:
       rc = run_prune_dyn_beam(c, opts);
-      break;
-    case KLU_BEST_PATH2:
-      rc = run_best_path2(c, opts);
       break;
     case KLU_CHAR_POSITION:
       rc = run_char_position(c, opts);

@@ -84,7 +84,11 @@ __device__ __forceinline__ int arc_entry_count(const IndexArgs& a, int e) {
     const int d = a.b.time[r.x] - a.b.time[a.b.out_src[e]];
     return d > 0 ? d : 0;
   }
-  if (!label_valid(a, r.w)) return 0;
+  if (a.tool == KLU_BEST_PATH2) {
+    if (r.w == 0) return 0;
+  } else if (!label_valid(a, r.w)) {
+    return 0;
+  }
   if (a.tool == KLU_SEGMENT || a.tool == KLU_UTTERANCE) return 1;
   const int s = a.b.out_src[e];
   return (int)(a.b.band_off[s + 1] - a.b.band_off[s]);
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
         a.aux[base + o] = arc_local;
         a.idx[base + o] = (unsigned int)o;
       }
-    } else {  // KLU_POSITION
-      if (!label_valid(a, r.w)) continue;
+    } else {  // KLU_POSITION, KLU_BEST_PATH2: one entry per (arc, #labels before it)
+      if (a.tool == KLU_BEST_PATH2 ? (r.w == 0) : !label_valid(a, r.w)) continue;
       const int w = (int)(a.b.band_off[s + 1] - a.b.band_off[s]);
       if (w <= 0) continue;
       const bool dead = a.use_beam && emit_arc_pruned(a, l, s, r);
@@ -180,8 +184,10 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
       const double tail = __dadd_rn(-rec_cost(r, a.cp), 0.0);
       for (int i = 0; i < w; ++i) {
         const double al = a.alpha2[a.b.band_off[s] - a.band_base + i];
-        // fw[(len,s)] + arc_lkh + bw[next]; beta of the unfolded lattice = beta[next]
-        const double v = __dadd_rn(__dadd_rn(al, tail), a.beta[r.x]);
+        // fw[(len,s)] + arc_lkh + bw[next] (position tool, :162-163) or
+        // fw[u] + bw[v] - cost (best-path2, :134); beta of the unfolded lattice = beta[next]
+        const double v = a.tool == KLU_BEST_PATH2 ? __dadd_rn(__dadd_rn(al, a.beta[r.x]), tail)
+                                                  : __dadd_rn(__dadd_rn(al, tail), a.beta[r.x]);
         const unsigned long long k = ((unsigned long long)r.w << a.bits_len) | (unsigned long long)(lo + i);
         const int o = off + i;
         a.key[base + o] = (dead || !(al > neg_inf())) ? a.drop_key : k;
@@ -214,6 +220,8 @@ struct ReduceArgs {
   int bits_label;
   unsigned long long drop_key;
   int l0;
+  const double* beta;  // best-path2 normalises by bw[start]
+  double* val_rw;      // best-path2: per-entry cost written back over the values
 };
 
 // One CTA per lattice: fold each run of equal keys with LogAdd (in sorted =
@@ -267,6 +275,26 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       a.raux[base + slot] = (unsigned int)i;
       a.key2[base + slot] = ((unsigned long long)(unsigned int)lo << 32) | (unsigned long long)(unsigned int)hi;
       a.idx2[base + slot] = (unsigned int)(q - i);
+    } else if (head && a.tool == KLU_BEST_PATH2) {
+      // latbin/lattice-best-path2.cc:122-147,175: posterior of (label, position),
+      // clamped to <= 0, turned into the float cost 1 - P of every arc carrying it
+      const int slot = add + x - 1;
+      double sum = val[idx[i]];
+      int q = i + 1;
+      for (; q < n && key[q] == k; ++q) sum = log_add(sum, val[idx[q]]);
+      const double post = fmin(0.0, sum - a.beta[a.b.s_off[l]]);
+      double ls;  // LogSub(0, post) [ext]
+      if (post >= 0.0) ls = neg_inf();
+      else {
+        ls = log(1.0 - exp(post));
+        if (ls != ls) ls = neg_inf();
+      }
+      const double cost = (double)(float)exp(ls);
+      double* vw = a.val_rw + base;
+      for (int t = i; t < q; ++t) vw[idx[t]] = cost;
+      a.rkey[base + slot] = k;
+      a.rval[base + slot] = post;
+      a.raux[base + slot] = 0;
     } else if (head) {
       const int slot = add + x - 1;
       unsigned int j = idx[i];
@@ -530,7 +558,7 @@ int bits_for(int64_t maxv) {
 
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   const int32_t L = c->L;
-  const bool needs_times = tool != KLU_FWD_BWD && tool != KLU_UTTERANCE;
+  const bool needs_times = tool != KLU_FWD_BWD && tool != KLU_UTTERANCE;  // best-path2 reports frames (:102)
   if (needs_times)
     for (int32_t l = 0; l < L; ++l)
       if (!c->h_times_ok[l]) {
@@ -538,7 +566,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
         set_error("lattice " + std::to_string(l) + ": inconsistent state times (lattice is not aligned)");
         return 1;
       }
-  const bool use_beam = tool != KLU_FRAME_POST && tool != KLU_FWD_BWD && o->beam != INFINITY;
+  const bool use_beam = tool != KLU_FRAME_POST && tool != KLU_FWD_BWD && tool != KLU_BEST_PATH2 && o->beam != INFINITY;
   if (use_beam && !(o->beam > 0.0f)) {
     set_error("--beam must be positive");  // KALDI_ASSERT(beam > 0.0) in PruneLattice [ext]
     return 1;
@@ -564,7 +592,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     for (int32_t l = 0; l < L; ++l) {
       const int64_t cap = (tool == KLU_SEGMENT || tool == KLU_UTTERANCE) ? (c->h_e_off[l + 1] - c->h_e_off[l])
                           : tool == KLU_FRAME_POST ? c->h_cap_frame[l] : c->h_cap_pos[l];
-      const int64_t band = tool == KLU_POSITION ? c->h_band_off[l + 1] - c->h_band_off[l] : 0;
+      const int64_t band = (tool == KLU_POSITION || tool == KLU_BEST_PATH2) ? c->h_band_off[l + 1] - c->h_band_off[l] : 0;
       if (cap >= ((int64_t)1 << 31)) {
         set_error("lattice " + std::to_string(l) + ": more than 2^31 index entries");
         return 1;
@@ -611,7 +639,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // ent_base is a stack object
 
   int fmode = 0, fn = 0;
-  if (tool != KLU_FRAME_POST) KLU_TRY(upload_filter(c, o, &fmode, &fn));
+  if (tool != KLU_FRAME_POST && tool != KLU_BEST_PATH2) KLU_TRY(upload_filter(c, o, &fmode, &fn));
 
   IndexArgs a;
   a.b = c->view();
@@ -641,7 +669,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   int key_bits = 0;
   if (tool == KLU_UTTERANCE) key_bits = a.bits_label;
   else if (tool == KLU_SEGMENT) key_bits = a.bits_label + 2 * a.bits_time;
-  else if (tool == KLU_POSITION) key_bits = a.bits_label + a.bits_len;
+  else if (tool == KLU_POSITION || tool == KLU_BEST_PATH2) key_bits = a.bits_label + a.bits_len;
   else key_bits = a.bits_time + a.bits_label;
   if (key_bits > 62 || (tool == KLU_FRAME_POST && a.bits_time > 31)) {
     set_error("index key does not fit 62 bits (labels/times too large)");
@@ -674,7 +702,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     if (nl <= 0) continue;
     a.l0 = l0;
     a.band_base = 0;
-    if (tool == KLU_POSITION) {
+    if (tool == KLU_POSITION || tool == KLU_BEST_PATH2) {
       KLU_TRY(run_banded_alpha(c, cp, use_beam, o->beam, l0, l1));
       a.band_base = c->h_band_off[l0];
     }
@@ -741,11 +769,26 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     r.idx2 = c->d_res[7].as<unsigned int>();
     r.bits_label = a.bits_label;
     r.drop_key = a.drop_key;
+    r.beta = a.beta;
+    r.val_rw = a.val;
     {
       KLU_LAUNCH(c, "k_reduce");
       k_reduce<<<nl, 256, 0, c->stream>>>(r);
     }
     KLU_TRY(check_launch("k_reduce"));
+    if (tool == KLU_BEST_PATH2) {
+      BestPathChunk ch;
+      ch.l0 = l0;
+      ch.l1 = l1;
+      ch.band_base = a.band_base;
+      ch.alpha2 = a.alpha2;
+      ch.ent_base = a.ent_base;
+      ch.arc_ent_off = a.arc_ent_off;
+      ch.ecost = a.val;
+      ch.first_chunk = k == 0;
+      KLU_TRY(best_path2_decode(c, cp, ch));
+      continue;
+    }
 
     if (tool == KLU_UTTERANCE) {
       UttArgs u;

@@ -29,7 +29,7 @@ namespace klu {
 namespace {
 
 struct Staging {
-  std::vector<int32_t> s_off, e_off, lvl_off, lvl_start, in_off, out_off, out_src, out_orig, time, orig, level, band_lo,
+  std::vector<int32_t> s_off, e_off, lvl_off, lvl_start, in_off, out_off, out_src, out_orig, in2out, time, orig, level, band_lo,
       order;
   std::vector<int64_t> band_off;
   std::vector<int4> in_rec, out_rec;
@@ -108,6 +108,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   st.out_off.assign(S + 1, 0);
   st.out_src.resize(E);
   st.out_orig.resize(E);
+  st.in2out.resize(E);
   st.in_rec.resize(E);
   st.out_rec.resize(E);
   st.fin_g.resize(S);
@@ -265,6 +266,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
           for (int32_t p = 0; p < na; ++p) {
             const int4 r = st.out_rec[e0 + p];
             const int32_t d = r.x - (int32_t)s0;
+            st.in2out[e0 + cursor[d]] = (int32_t)(e0 + p);
             st.in_rec[e0 + cursor[d]++] = make_int4(st.out_src[e0 + p], r.y, r.z, r.w);
           }
           lat_level[l] = std::vector<int32_t>();
@@ -338,6 +340,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(up(c->d_out_off, st.out_off.data(), st.out_off.size() * 4));
   KLU_TRY(up(c->d_out_src, st.out_src.data(), st.out_src.size() * 4));
   KLU_TRY(up(c->d_out_orig, st.out_orig.data(), st.out_orig.size() * 4));
+  KLU_TRY(up(c->d_in2out, st.in2out.data(), st.in2out.size() * 4));
   KLU_TRY(up(c->d_fin_g, st.fin_g.data(), st.fin_g.size() * 4));
   KLU_TRY(up(c->d_fin_a, st.fin_a.data(), st.fin_a.size() * 4));
   KLU_TRY(up(c->d_time, st.time.data(), st.time.size() * 4));

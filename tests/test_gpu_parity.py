@@ -133,3 +133,64 @@ def test_rejects_unsorted_lattice(klu, engine):
     bad = klu.make_lattice("bad", 3, [(0, 2, 1, 0.1, 0.2, 1), (2, 1, 2, 0.1, 0.2, 1)], {1: (0.0, 0.0)})
     with pytest.raises(klu.KluError):
         engine.load(klu.LatticeBatch.from_lattices([bad]))
+
+
+# ---- lattice-best-path2 ---------------------------------------------------------
+def test_best_path2_readme_lattice(klu, engine, word_lat):
+    _load(klu, engine, [word_lat])
+    (labels, cost), = engine.best_path2()
+    assert labels == [2, 3, 5, 2, 6, 7, 8]
+    assert abs(cost - 0.4) < 1e-6
+
+
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", FLAGS[:3])
+def test_best_path2_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 170)
+    engine.load(batch)
+    got = engine.best_path2(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        labels, cost = ora.best_path2(lat, **flags)
+        assert got[l][0] == labels, "best-path2 labels, lattice %d" % l      # bit-exact label sequence
+        assert abs(got[l][1] - cost) <= 1e-4 * max(1.0, abs(cost))
+
+
+# ---- lattice-prune-dyn-beam -----------------------------------------------------
+def _check_prune(got, want, lat):
+    assert got["nstates"] == want["nstates"]
+    assert [a[:4] for a in got["arcs"]] == [a[:4] for a in want["arcs"]]          # surviving arc set, bit-exact
+    assert [a[4:] for a in got["arcs"]] == [a[4:] for a in want["arcs"]]          # output weights, bit-exact floats
+    assert got["finals"] == want["finals"]
+    assert got["beam0"] == want["beam0"] and got["beam"] == want["beam"]           # doubles, bit-exact
+
+
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", [dict(), dict(max_arcs=40, max_states=30), dict(max_arcs=15),
+                                   dict(max_states=12, beam_ratio=0.5),
+                                   dict(acoustic_scale=0.1, graph_scale=0.7, insertion_penalty=0.5, max_arcs=60),
+                                   dict(max_arcs=1, min_beam=0.5)])
+def test_prune_dyn_beam_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 210)
+    engine.load(batch)
+    got = engine.prune_dyn_beam(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        _check_prune(got[l], ora.prune_dyn_beam(lat, **flags), lat)
+
+
+def test_prune_then_best_path_pipeline(klu, ora, engine):
+    # configs[2]: prune-dyn-beam piped into best-path2
+    batch = klu.synth_batch("small", 6, seed=999)
+    engine.load(batch)
+    flags = dict(max_arcs=200, max_states=120)
+    pruned = engine.prune_dyn_beam(**flags)
+    lats2 = []
+    for l, lat in enumerate(batch.lattices()):
+        p = pruned[l]
+        arcs = [(s, d, lab, g, a, int(lat.dur[i])) for i, s, d, lab, g, a in p["arcs"]]
+        finals = {s: (g, a) for s, g, a in p["finals"]}
+        lats2.append(klu.make_lattice(lat.key, p["nstates"], arcs, finals))
+    engine.load(klu.LatticeBatch.from_lattices(lats2))
+    got = engine.best_path2()
+    for l, lat in enumerate(lats2):
+        labels, cost = ora.best_path2(lat)
+        assert got[l][0] == labels
