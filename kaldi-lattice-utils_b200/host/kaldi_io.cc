@@ -1,0 +1,810 @@
+// kaldi_io.cc -- see kaldi_io.h.
+#include "kaldi_io.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace kio {
+
+std::string g_program = "klu";
+int g_verbose = 0;
+
+// ------------------------------------------------------------ ParseOptions ---
+std::string ParseOptions::Normalize(const std::string& name) {
+  std::string out;
+  for (char ch : name) out += (ch == '_') ? '-' : (char)tolower(ch);
+  return out;
+}
+
+void ParseOptions::Add(const std::string& name, Type t, void* p, const std::string& doc, const std::string& def) {
+  opts_[Normalize(name)] = Opt{t, p, doc, def};
+}
+
+static bool ToBool(const std::string& v, bool* out) {
+  std::string s;
+  for (char ch : v) s += (char)tolower(ch);
+  if (s == "true" || s == "t" || s == "1" || s.empty()) {
+    *out = true;
+    return true;
+  }
+  if (s == "false" || s == "f" || s == "0") {
+    *out = false;
+    return true;
+  }
+  return false;
+}
+
+bool ParseOptions::SetOption(const std::string& key_in, const std::string& value, bool has_value) {
+  const std::string key = Normalize(key_in);
+  if (key == "help") {
+    PrintUsage();
+    exit(0);
+  }
+  if (key == "verbose") {
+    g_verbose = atoi(value.c_str());
+    return true;
+  }
+  if (key == "print-args") return true;
+  if (key == "config") {
+    ReadConfigFile(value);
+    return true;
+  }
+  auto it = opts_.find(key);
+  if (it == opts_.end()) return false;
+  Opt& o = it->second;
+  char* end = nullptr;
+  switch (o.type) {
+    case kFloat: {
+      if (!has_value || value.empty()) KIO_ERR("Invalid floating-point option \"" << value << "\" for --" << key);
+      const std::string low = Normalize(value);
+      float f;
+      if (low == "inf" || low == "+inf" || low == "infinity") f = std::numeric_limits<float>::infinity();
+      else if (low == "-inf" || low == "-infinity") f = -std::numeric_limits<float>::infinity();
+      else {
+        f = strtof(value.c_str(), &end);
+        if (end == value.c_str() || *end != '\0') KIO_ERR("Invalid floating-point option \"" << value << "\"");
+      }
+      *static_cast<float*>(o.ptr) = f;
+      break;
+    }
+    case kInt: {
+      if (!has_value || value.empty()) KIO_ERR("Invalid integer option \"" << value << "\" for --" << key);
+      const long long v = strtoll(value.c_str(), &end, 10);
+      if (end == value.c_str() || *end != '\0') KIO_ERR("Invalid integer option \"" << value << "\"");
+      *static_cast<int32_t*>(o.ptr) = (int32_t)v;
+      break;
+    }
+    case kBool: {
+      bool b;
+      if (!ToBool(has_value ? value : "", &b)) KIO_ERR("Invalid format for boolean argument [expected true or false]: " << value);
+      *static_cast<bool*>(o.ptr) = b;
+      break;
+    }
+    case kString:
+      *static_cast<std::string*>(o.ptr) = value;
+      break;
+  }
+  return true;
+}
+
+void ParseOptions::ReadConfigFile(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) KIO_ERR("Cannot open config file: " << path);
+  std::string line;
+  while (std::getline(f, line)) {
+    const size_t hash = line.find('#');
+    if (hash != std::string::npos) line = line.substr(0, hash);
+    size_t a = line.find_first_not_of(" \t\r"), b = line.find_last_not_of(" \t\r");
+    if (a == std::string::npos) continue;
+    line = line.substr(a, b - a + 1);
+    if (line.compare(0, 2, "--") != 0) KIO_ERR("Reading config file " << path << ": line does not start with --: " << line);
+    const size_t eq = line.find('=');
+    const std::string key = line.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+    const std::string val = eq == std::string::npos ? "" : line.substr(eq + 1);
+    if (!SetOption(key, val, eq != std::string::npos)) KIO_ERR("Invalid option " << line << " in config file " << path);
+  }
+}
+
+void ParseOptions::Read(int argc, const char* const* argv) {
+  if (argc > 0) {
+    const char* slash = strrchr(argv[0], '/');
+    g_program = slash ? slash + 1 : argv[0];
+  }
+  for (int i = 0; i < argc; ++i) argv_.push_back(argv[i]);
+  bool print_args = true;
+  int i = 1;
+  for (; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a.compare(0, 2, "--") != 0) break;
+    if (a == "--") {
+      ++i;
+      break;
+    }
+    const size_t eq = a.find('=');
+    const std::string key = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+    const std::string val = eq == std::string::npos ? "" : a.substr(eq + 1);
+    if (Normalize(key) == "print-args") {
+      bool b = true;
+      ToBool(val, &b);
+      print_args = b;
+      continue;
+    }
+    if (!SetOption(key, val, eq != std::string::npos)) {
+      PrintUsage(true);
+      KIO_ERR("Invalid option " << a);
+    }
+  }
+  for (; i < argc; ++i) args_.push_back(argv[i]);
+  if (print_args) {
+    std::ostringstream os;
+    for (int k = 0; k < argc; ++k) os << argv[k] << (k + 1 < argc ? " " : "");
+    std::cerr << os.str() << std::endl;
+  }
+}
+
+std::string ParseOptions::GetArg(int i) const {
+  if (i < 1 || i > (int)args_.size()) KIO_ERR("ParseOptions::GetArg, invalid index " << i);
+  return args_[i - 1];
+}
+
+void ParseOptions::PrintUsage(bool print_command_line) const {
+  std::cerr << "\n" << usage_ << "\n";
+  std::cerr << "Options:\n";
+  for (const auto& kv : opts_)
+    std::cerr << "  --" << kv.first << " : " << kv.second.doc << " (default = " << kv.second.def << ")\n";
+  std::cerr << "\nStandard options:\n  --config, --help, --print-args, --verbose\n\n";
+  if (print_command_line) {
+    std::ostringstream os;
+    for (const auto& a : argv_) os << a << " ";
+    std::cerr << "Command line was: " << os.str() << "\n";
+  }
+}
+
+bool SplitStringToIntegers(const std::string& full, const char* delim, bool omit_empty, std::vector<int32_t>* out) {
+  out->clear();
+  size_t start = 0;
+  while (start <= full.size()) {
+    size_t end = full.find_first_of(delim, start);
+    if (end == std::string::npos) end = full.size();
+    const std::string tok = full.substr(start, end - start);
+    if (!tok.empty() || !omit_empty) {
+      char* e = nullptr;
+      const long long v = strtoll(tok.c_str(), &e, 10);
+      if (tok.empty() || e == tok.c_str() || *e != '\0') return false;
+      out->push_back((int32_t)v);
+    }
+    start = end + 1;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------- basic types ---
+void WriteKaldiFloat(std::ostream& os, double v) {
+  if (std::isinf(v)) {
+    os << (v > 0 ? "inf" : "-inf");
+    return;
+  }
+  if (std::isnan(v)) {
+    os << "nan";
+    return;
+  }
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.7g", v);  // ostream general format, precision 7
+  os << buf;
+}
+
+void WriteBasicInt32(std::ostream& os, bool binary, int32_t v) {
+  if (binary) {
+    os.put((char)4);
+    os.write(reinterpret_cast<const char*>(&v), 4);
+  } else {
+    os << v << " ";
+  }
+}
+
+void WriteBasicFloat(std::ostream& os, bool binary, float v) {
+  if (binary) {
+    os.put((char)4);
+    os.write(reinterpret_cast<const char*>(&v), 4);
+  } else {
+    WriteKaldiFloat(os, v);
+    os << " ";
+  }
+}
+
+void WriteBasicDouble(std::ostream& os, bool binary, double v) {
+  if (binary) {
+    os.put((char)8);
+    os.write(reinterpret_cast<const char*>(&v), 8);
+  } else {
+    WriteKaldiFloat(os, v);
+    os << " ";
+  }
+}
+
+void WriteToken(std::ostream& os, bool, const std::string& tok) { os << tok << " "; }
+
+// --------------------------------------------------------------- specifiers ---
+Specifier ParseSpecifier(const std::string& spec, bool writing) {
+  Specifier s;
+  const size_t colon = spec.find(':');
+  if (colon == std::string::npos) KIO_ERR("Invalid " << (writing ? "wspecifier " : "rspecifier ") << spec);
+  const std::string head = spec.substr(0, colon), rest = spec.substr(colon + 1);
+  size_t start = 0;
+  bool both = false;
+  std::vector<std::string> kinds;
+  while (start <= head.size()) {
+    size_t end = head.find(',', start);
+    if (end == std::string::npos) end = head.size();
+    const std::string t = head.substr(start, end - start);
+    if (t == "ark") { s.is_ark = true; kinds.push_back(t); }
+    else if (t == "scp") { s.is_scp = true; kinds.push_back(t); }
+    else if (t == "t") s.text = true;
+    else if (t == "b") s.text = false;
+    else if (t == "s" || t == "cs" || t == "o" || t == "p" || t == "f" || t == "ns" || t == "ncs" || t == "no" ||
+             t == "np" || t == "nf" || t == "bg") { /* sorted/once/permissive/flush hints: no effect here */ }
+    else KIO_ERR("Invalid " << (writing ? "wspecifier " : "rspecifier ") << spec);
+    start = end + 1;
+  }
+  both = s.is_ark && s.is_scp;
+  if (!s.is_ark && !s.is_scp) KIO_ERR("Invalid specifier " << spec);
+  if (both) {
+    if (!writing) KIO_ERR("Invalid rspecifier " << spec);
+    const size_t comma = rest.find(',');
+    if (comma == std::string::npos) KIO_ERR("Invalid wspecifier " << spec);
+    if (kinds[0] == "ark") { s.ark = rest.substr(0, comma); s.scp = rest.substr(comma + 1); }
+    else { s.scp = rest.substr(0, comma); s.ark = rest.substr(comma + 1); }
+  } else if (s.is_ark) {
+    s.ark = rest;
+  } else {
+    s.scp = rest;
+  }
+  return s;
+}
+
+Input::Input(const std::string& name_in) {
+  std::string name = name_in;
+  while (!name.empty() && isspace((unsigned char)name.back())) name.pop_back();
+  if (name == "-" || name.empty()) {
+    is_ = &std::cin;
+  } else if (name.back() == '|') {
+    pipe_ = popen(name.substr(0, name.size() - 1).c_str(), "r");
+    if (!pipe_) KIO_ERR("Failed opening pipe for reading, command is: " << name);
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), pipe_)) > 0) buffer_.append(buf, n);
+    pclose(pipe_);
+    pipe_ = nullptr;
+    owned_.reset(new std::istringstream(buffer_, std::ios::in | std::ios::binary));
+    is_ = owned_.get();
+  } else {
+    // "path:offset" (scp entries)
+    size_t off = 0;
+    const size_t colon = name.rfind(':');
+    if (colon != std::string::npos && colon + 1 < name.size() &&
+        name.find_first_not_of("0123456789", colon + 1) == std::string::npos) {
+      off = (size_t)strtoull(name.c_str() + colon + 1, nullptr, 10);
+      name = name.substr(0, colon);
+    }
+    auto* f = new std::ifstream(name, std::ios::in | std::ios::binary);
+    owned_.reset(f);
+    if (!*f) KIO_ERR("Error opening input stream " << name);
+    if (off) f->seekg((std::streamoff)off);
+    is_ = f;
+  }
+}
+
+Input::~Input() {}
+
+Output::Output(const std::string& name) {
+  if (name == "-" || name.empty()) {
+    os_ = &std::cout;
+  } else if (name[0] == '|') {
+    pipe_ = popen(name.substr(1).c_str(), "w");
+    if (!pipe_) KIO_ERR("Failed opening pipe for writing, command is: " << name);
+    os_ = &pipe_buf_;
+  } else {
+    auto* f = new std::ofstream(name, std::ios::out | std::ios::binary);
+    owned_.reset(f);
+    if (!*f) KIO_ERR("Error opening output stream " << name);
+    os_ = f;
+  }
+}
+
+void Output::Close() {
+  if (pipe_) {
+    const std::string s = pipe_buf_.str();
+    fwrite(s.data(), 1, s.size(), pipe_);
+    pclose(pipe_);
+    pipe_ = nullptr;
+  } else if (os_) {
+    os_->flush();
+  }
+}
+
+Output::~Output() { Close(); }
+
+// ---------------------------------------------------------------- lattices ---
+namespace {
+
+struct RawArc {
+  int32_t src, dst, ilabel, olabel;
+  float g, a;
+  std::vector<int32_t> tids;
+};
+
+void ParseWeight(const std::string& tok, bool compact, float* g, float* a, std::vector<int32_t>* tids) {
+  // "g,a" or "g,a,t1_t2_..."; empty fields mean 0
+  *g = 0.0f;
+  *a = 0.0f;
+  tids->clear();
+  std::vector<std::string> parts;
+  size_t start = 0;
+  while (start <= tok.size()) {
+    size_t end = tok.find(',', start);
+    if (end == std::string::npos) end = tok.size();
+    parts.push_back(tok.substr(start, end - start));
+    start = end + 1;
+  }
+  auto tof = [&](const std::string& s) -> float {
+    if (s.empty()) return 0.0f;
+    std::string low;
+    for (char ch : s) low += (char)tolower(ch);
+    if (low == "infinity" || low == "inf") return std::numeric_limits<float>::infinity();
+    if (low == "-infinity" || low == "-inf") return -std::numeric_limits<float>::infinity();
+    char* e = nullptr;
+    const float f = strtof(s.c_str(), &e);
+    if (e == s.c_str() || *e != '\0') KIO_ERR("Bad lattice weight: " << tok);
+    return f;
+  };
+  if (parts.size() < 1 || parts.size() > 3) KIO_ERR("Bad lattice weight: " << tok);
+  *g = tof(parts[0]);
+  if (parts.size() > 1) *a = tof(parts[1]);
+  if (compact && parts.size() > 2 && !parts[2].empty()) {
+    size_t s2 = 0;
+    const std::string& str = parts[2];
+    while (s2 <= str.size()) {
+      size_t e2 = str.find('_', s2);
+      if (e2 == std::string::npos) e2 = str.size();
+      tids->push_back(atoi(str.substr(s2, e2 - s2).c_str()));
+      s2 = e2 + 1;
+    }
+  }
+}
+
+struct RawLat {
+  std::vector<RawArc> arcs;  // any order
+  std::map<int32_t, std::tuple<float, float, std::vector<int32_t> > > finals;
+  int32_t nstates = 0;
+  int32_t start = -1;
+  bool compact = true;
+};
+
+// [ext] ConvertLattice(Lattice -> CompactLattice): kaldi's Factor() collapses
+// linear chains (one arc in, one arc out, not initial/final, no olabel on the
+// outgoing arc) into one arc whose string is the chain's ilabels.
+void FactorLattice(RawLat* lat) {
+  const int32_t n = lat->nstates;
+  std::vector<int32_t> nin(n, 0), nout(n, 0), only_out(n, -1);
+  for (size_t i = 0; i < lat->arcs.size(); ++i) {
+    const RawArc& a = lat->arcs[i];
+    nin[a.dst]++;
+    nout[a.src]++;
+    only_out[a.src] = (int32_t)i;
+  }
+  std::vector<char> remove(n, 0);
+  for (int32_t s = 0; s < n; ++s)
+    remove[s] = nin[s] == 1 && nout[s] == 1 && s != lat->start && !lat->finals.count(s) &&
+                lat->arcs[only_out[s]].olabel == 0;
+  std::vector<RawArc> out;
+  for (const RawArc& a0 : lat->arcs) {
+    if (remove[a0.src]) continue;
+    RawArc a = a0;
+    a.tids.clear();
+    if (a0.ilabel != 0) a.tids.push_back(a0.ilabel);
+    while (remove[a.dst]) {
+      const RawArc& nx = lat->arcs[only_out[a.dst]];
+      if (nx.ilabel != 0) a.tids.push_back(nx.ilabel);
+      a.g = a.g + nx.g;  // Times() of LatticeWeight = component-wise float add
+      a.a = a.a + nx.a;
+      a.dst = nx.dst;
+    }
+    out.push_back(a);
+  }
+  // renumber the surviving states, keeping their relative order
+  std::vector<int32_t> newid(n, -1);
+  int32_t m = 0;
+  for (int32_t s = 0; s < n; ++s)
+    if (!remove[s]) newid[s] = m++;
+  for (RawArc& a : out) {
+    a.src = newid[a.src];
+    a.dst = newid[a.dst];
+  }
+  std::map<int32_t, std::tuple<float, float, std::vector<int32_t> > > fin;
+  for (auto& kv : lat->finals) fin[newid[kv.first]] = kv.second;
+  lat->finals.swap(fin);
+  lat->arcs.swap(out);
+  lat->start = lat->start >= 0 ? newid[lat->start] : -1;
+  lat->nstates = m;
+}
+
+void Finish(RawLat* raw, CompactLat* lat) {
+  if (!raw->compact) FactorLattice(raw);
+  // OpenFst requires the start state to be 0 for Kaldi's lattice functions; text
+  // lattices start at the source of the first line.
+  int32_t n = raw->nstates;
+  if (raw->start > 0) {  // swap ids so the start is 0
+    const int32_t st = raw->start;
+    auto sw = [&](int32_t s) { return s == st ? 0 : (s == 0 ? st : s); };
+    for (RawArc& a : raw->arcs) {
+      a.src = sw(a.src);
+      a.dst = sw(a.dst);
+    }
+    std::map<int32_t, std::tuple<float, float, std::vector<int32_t> > > fin;
+    for (auto& kv : raw->finals) fin[sw(kv.first)] = kv.second;
+    raw->finals.swap(fin);
+  }
+  std::stable_sort(raw->arcs.begin(), raw->arcs.end(), [](const RawArc& x, const RawArc& y) { return x.src < y.src; });
+  lat->nstates = n;
+  const size_t na = raw->arcs.size();
+  lat->src.resize(na);
+  lat->dst.resize(na);
+  lat->label.resize(na);
+  lat->dur.resize(na);
+  lat->graph.resize(na);
+  lat->acoustic.resize(na);
+  lat->tids.resize(na);
+  for (size_t i = 0; i < na; ++i) {
+    RawArc& a = raw->arcs[i];
+    lat->src[i] = a.src;
+    lat->dst[i] = a.dst;
+    lat->label[i] = a.olabel;
+    lat->dur[i] = (int32_t)a.tids.size();
+    lat->graph[i] = a.g;
+    lat->acoustic[i] = a.a;
+    lat->tids[i].swap(a.tids);
+  }
+  const float inf = std::numeric_limits<float>::infinity();
+  lat->fin_graph.assign(n, inf);
+  lat->fin_acoustic.assign(n, inf);
+  lat->fin_dur.assign(n, 0);
+  lat->fin_tids.assign(n, std::vector<int32_t>());
+  for (auto& kv : raw->finals) {
+    lat->fin_graph[kv.first] = std::get<0>(kv.second);
+    lat->fin_acoustic[kv.first] = std::get<1>(kv.second);
+    lat->fin_dur[kv.first] = (int32_t)std::get<2>(kv.second).size();
+    lat->fin_tids[kv.first] = std::get<2>(kv.second);
+  }
+  TopSortIfNeeded(lat);
+}
+
+void ReadText(std::istream& is, CompactLat* lat) {
+  // The text form starts with '\n' after the key and ends with an empty line.
+  RawLat raw;
+  std::string line;
+  std::getline(is, line);  // rest of the key line
+  bool decided = false;
+  int32_t maxs = -1;
+  while (std::getline(is, line)) {
+    size_t a = line.find_first_not_of(" \t\r");
+    if (a == std::string::npos) break;  // blank line terminates the entry
+    std::istringstream ls(line);
+    std::vector<std::string> tok;
+    std::string t;
+    while (ls >> t) tok.push_back(t);
+    if (tok.size() <= 2) {  // final state
+      const int32_t s = atoi(tok[0].c_str());
+      float g = 0, w = 0;
+      std::vector<int32_t> tids;
+      if (tok.size() == 2) ParseWeight(tok[1], true, &g, &w, &tids);
+      raw.finals[s] = std::make_tuple(g, w, tids);
+      maxs = std::max(maxs, s);
+      if (raw.start < 0) raw.start = s;
+      continue;
+    }
+    RawArc arc;
+    arc.src = atoi(tok[0].c_str());
+    arc.dst = atoi(tok[1].c_str());
+    bool is_compact;
+    if (tok.size() == 3) is_compact = true;
+    else if (tok.size() == 5) is_compact = false;
+    else is_compact = tok[3].find(',') != std::string::npos;  // 4 columns: weight or olabel
+    if (!decided) {
+      raw.compact = is_compact;
+      decided = true;
+    } else if (raw.compact != is_compact) {
+      KIO_ERR("Lattice " << lat->key << " mixes CompactLattice and Lattice text lines");
+    }
+    if (is_compact) {
+      arc.ilabel = arc.olabel = atoi(tok[2].c_str());
+      arc.g = arc.a = 0.0f;
+      if (tok.size() == 4) ParseWeight(tok[3], true, &arc.g, &arc.a, &arc.tids);
+    } else {
+      arc.ilabel = atoi(tok[2].c_str());
+      arc.olabel = atoi(tok[3].c_str());
+      arc.g = arc.a = 0.0f;
+      std::vector<int32_t> dummy;
+      if (tok.size() == 5) ParseWeight(tok[4], false, &arc.g, &arc.a, &dummy);
+    }
+    if (raw.start < 0) raw.start = arc.src;
+    maxs = std::max(maxs, std::max(arc.src, arc.dst));
+    raw.arcs.push_back(arc);
+  }
+  raw.nstates = maxs + 1;
+  Finish(&raw, lat);
+}
+
+template <typename T>
+T ReadRaw(std::istream& is) {
+  T v;
+  is.read(reinterpret_cast<char*>(&v), sizeof(T));
+  if (!is) KIO_ERR("Unexpected end of binary lattice stream");
+  return v;
+}
+
+std::string ReadFstString(std::istream& is) {
+  const int32_t n = ReadRaw<int32_t>(is);
+  if (n < 0 || n > (1 << 20)) KIO_ERR("Corrupt FST header");
+  std::string s((size_t)n, '\0');
+  if (n) is.read(&s[0], n);
+  return s;
+}
+
+void ReadBinary(std::istream& is, CompactLat* lat) {
+  // [ext] OpenFst FstHeader + VectorFst body
+  const int32_t magic = ReadRaw<int32_t>(is);
+  if (magic != 2125659606) KIO_ERR("Reading lattice " << lat->key << ": bad FST magic number");
+  const std::string fsttype = ReadFstString(is), arctype = ReadFstString(is);
+  /*version*/ ReadRaw<int32_t>(is);
+  const int32_t flags = ReadRaw<int32_t>(is);
+  /*props*/ ReadRaw<uint64_t>(is);
+  const int64_t start = ReadRaw<int64_t>(is), nstates = ReadRaw<int64_t>(is);
+  /*narcs*/ ReadRaw<int64_t>(is);
+  if (fsttype != "vector") KIO_ERR("Unsupported FST type " << fsttype);
+  if (flags & 3) KIO_ERR("Lattices with symbol tables are not supported");
+  RawLat raw;
+  if (arctype == "compactlattice44") raw.compact = true;
+  else if (arctype == "lattice4") raw.compact = false;
+  else KIO_ERR("Unsupported arc type " << arctype << " (expected compactlattice44 or lattice4)");
+  raw.nstates = (int32_t)nstates;
+  raw.start = (int32_t)start;
+  auto read_weight = [&](float* g, float* a, std::vector<int32_t>* tids) {
+    *g = ReadRaw<float>(is);
+    *a = ReadRaw<float>(is);
+    tids->clear();
+    if (raw.compact) {
+      const int32_t sz = ReadRaw<int32_t>(is);
+      tids->resize(sz);
+      for (int32_t i = 0; i < sz; ++i) (*tids)[i] = ReadRaw<int32_t>(is);
+    }
+  };
+  for (int64_t s = 0; s < nstates; ++s) {
+    float g, a;
+    std::vector<int32_t> tids;
+    read_weight(&g, &a, &tids);
+    if (!(std::isinf(g) && std::isinf(a))) raw.finals[(int32_t)s] = std::make_tuple(g, a, tids);
+    const int64_t na = ReadRaw<int64_t>(is);
+    for (int64_t k = 0; k < na; ++k) {
+      RawArc arc;
+      arc.src = (int32_t)s;
+      arc.ilabel = ReadRaw<int32_t>(is);
+      arc.olabel = ReadRaw<int32_t>(is);
+      read_weight(&arc.g, &arc.a, &arc.tids);
+      arc.dst = ReadRaw<int32_t>(is);
+      raw.arcs.push_back(arc);
+    }
+  }
+  Finish(&raw, lat);
+}
+
+}  // namespace
+
+void ReadCompactLattice(std::istream& is, CompactLat* lat) {
+  int c = is.peek();
+  if (c == '\0') {  // tolerate a Kaldi binary marker "\0B" in front of the FST
+    is.get();
+    if (is.peek() == 'B') is.get();
+    c = is.peek();
+  }
+  if (c == EOF) KIO_ERR("End of stream detected reading CompactLattice " << lat->key);
+  if (isspace(c)) ReadText(is, lat);
+  else if (c == 214) ReadBinary(is, lat);
+  else KIO_ERR("Reading compact lattice " << lat->key << ": does not appear to be an FST");
+}
+
+void TopSortIfNeeded(CompactLat* lat) {
+  const size_t na = lat->src.size();
+  bool sorted = true;
+  for (size_t i = 0; i < na && sorted; ++i) sorted = lat->src[i] < lat->dst[i];
+  if (sorted) return;
+  const int32_t n = lat->nstates;
+  std::vector<int32_t> first(n + 1, 0);
+  for (size_t i = 0; i < na; ++i) first[lat->src[i] + 1]++;
+  for (int32_t s = 0; s < n; ++s) first[s + 1] += first[s];
+  // [ext] fst::TopSort: DFS from the start, then from every unvisited state in id
+  // order; new order = reverse finishing order
+  std::vector<char> color(n, 0);
+  std::vector<int32_t> finish;
+  std::vector<std::pair<int32_t, int32_t> > stack;
+  for (int32_t pass = -1; pass < n; ++pass) {
+    const int32_t root = pass < 0 ? 0 : pass;
+    if (n == 0 || color[root]) continue;
+    color[root] = 1;
+    stack.push_back(std::make_pair(root, first[root]));
+    while (!stack.empty()) {
+      auto& top = stack.back();
+      if (top.second < first[top.first + 1]) {
+        const int32_t d = lat->dst[top.second++];
+        if (color[d] == 1) KIO_ERR("Topological sorting of lattice " << lat->key << " failed (cyclic lattice)");
+        if (color[d] == 0) {
+          color[d] = 1;
+          stack.push_back(std::make_pair(d, first[d]));
+        }
+      } else {
+        color[top.first] = 2;
+        finish.push_back(top.first);
+        stack.pop_back();
+      }
+    }
+  }
+  std::vector<int32_t> order(n);
+  for (int32_t i = 0; i < n; ++i) order[finish[n - 1 - i]] = i;
+  CompactLat out;
+  out.key = lat->key;
+  out.nstates = n;
+  std::vector<size_t> perm(na);
+  for (size_t i = 0; i < na; ++i) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](size_t x, size_t y) { return order[lat->src[x]] < order[lat->src[y]]; });
+  for (size_t p : perm) {
+    out.src.push_back(order[lat->src[p]]);
+    out.dst.push_back(order[lat->dst[p]]);
+    out.label.push_back(lat->label[p]);
+    out.dur.push_back(lat->dur[p]);
+    out.graph.push_back(lat->graph[p]);
+    out.acoustic.push_back(lat->acoustic[p]);
+    out.tids.push_back(lat->tids[p]);
+  }
+  out.fin_graph.resize(n);
+  out.fin_acoustic.resize(n);
+  out.fin_dur.resize(n);
+  out.fin_tids.resize(n);
+  for (int32_t s = 0; s < n; ++s) {
+    out.fin_graph[order[s]] = lat->fin_graph[s];
+    out.fin_acoustic[order[s]] = lat->fin_acoustic[s];
+    out.fin_dur[order[s]] = lat->fin_dur[s];
+    out.fin_tids[order[s]] = lat->fin_tids[s];
+  }
+  *lat = out;
+}
+
+namespace {
+void WriteTextWeight(std::ostream& os, float g, float a, const std::vector<int32_t>& tids) {
+  WriteKaldiFloat(os, g);
+  os << ",";
+  WriteKaldiFloat(os, a);
+  os << ",";
+  for (size_t i = 0; i < tids.size(); ++i) os << (i ? "_" : "") << tids[i];
+}
+template <typename T>
+void WriteRaw(std::ostream& os, T v) {
+  os.write(reinterpret_cast<const char*>(&v), sizeof(T));
+}
+void WriteFstString(std::ostream& os, const std::string& s) {
+  WriteRaw<int32_t>(os, (int32_t)s.size());
+  os.write(s.data(), (std::streamsize)s.size());
+}
+}  // namespace
+
+void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat) {
+  const size_t na = lat.src.size();
+  const float inf = std::numeric_limits<float>::infinity();
+  if (!binary) {
+    // [ext] WriteCompactLattice text: newline after the key, FstPrinter acceptor
+    // format with tabs, final states after a state's arcs, blank line at the end
+    os << '\n';
+    size_t e = 0;
+    for (int32_t s = 0; s < lat.nstates; ++s) {
+      for (; e < na && lat.src[e] == s; ++e) {
+        os << s << '\t' << lat.dst[e] << '\t' << lat.label[e] << '\t';
+        WriteTextWeight(os, lat.graph[e], lat.acoustic[e], lat.tids[e]);
+        os << '\n';
+      }
+      if (!(lat.fin_graph[s] == inf && lat.fin_acoustic[s] == inf)) {
+        os << s << '\t';
+        WriteTextWeight(os, lat.fin_graph[s], lat.fin_acoustic[s], lat.fin_tids[s]);
+        os << '\n';
+      }
+    }
+    os << '\n';
+    return;
+  }
+  WriteRaw<int32_t>(os, 2125659606);
+  WriteFstString(os, "vector");
+  WriteFstString(os, "compactlattice44");
+  WriteRaw<int32_t>(os, 2);                  // file version
+  WriteRaw<int32_t>(os, 0);                  // flags: no symbol tables
+  WriteRaw<uint64_t>(os, 0x3ULL);            // kExpanded | kMutable, everything else unknown
+  WriteRaw<int64_t>(os, lat.nstates ? 0 : -1);
+  WriteRaw<int64_t>(os, lat.nstates);
+  WriteRaw<int64_t>(os, (int64_t)na);
+  size_t e = 0;
+  for (int32_t s = 0; s < lat.nstates; ++s) {
+    WriteRaw<float>(os, lat.fin_graph[s]);
+    WriteRaw<float>(os, lat.fin_acoustic[s]);
+    WriteRaw<int32_t>(os, (int32_t)lat.fin_tids[s].size());
+    for (int32_t t : lat.fin_tids[s]) WriteRaw<int32_t>(os, t);
+    size_t e1 = e;
+    while (e1 < na && lat.src[e1] == s) ++e1;
+    WriteRaw<int64_t>(os, (int64_t)(e1 - e));
+    for (; e < e1; ++e) {
+      WriteRaw<int32_t>(os, lat.label[e]);
+      WriteRaw<int32_t>(os, lat.label[e]);
+      WriteRaw<float>(os, lat.graph[e]);
+      WriteRaw<float>(os, lat.acoustic[e]);
+      WriteRaw<int32_t>(os, (int32_t)lat.tids[e].size());
+      for (int32_t t : lat.tids[e]) WriteRaw<int32_t>(os, t);
+      WriteRaw<int32_t>(os, lat.dst[e]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------- tables ---
+SequentialCompactLatticeReader::SequentialCompactLatticeReader(const std::string& rspecifier) {
+  spec_ = ParseSpecifier(rspecifier, false);
+  in_.reset(new Input(spec_.is_scp ? spec_.scp : spec_.ark));
+  ReadOne();
+}
+
+void SequentialCompactLatticeReader::Next() { ReadOne(); }
+
+void SequentialCompactLatticeReader::ReadOne() {
+  std::istream& is = in_->Stream();
+  cur_ = CompactLat();
+  if (spec_.is_scp) {
+    std::string line;
+    while (std::getline(is, line)) {
+      const size_t a = line.find_first_not_of(" \t\r");
+      if (a == std::string::npos) continue;
+      const size_t sp = line.find_first_of(" \t", a);
+      if (sp == std::string::npos) KIO_ERR("Invalid scp line: " << line);
+      cur_.key = line.substr(a, sp - a);
+      std::string path = line.substr(line.find_first_not_of(" \t", sp));
+      scp_item_.reset(new Input(path));
+      ReadCompactLattice(scp_item_->Stream(), &cur_);
+      return;
+    }
+    done_ = true;
+    return;
+  }
+  // archive: skip whitespace, read the key token, one space, then the object
+  int c;
+  while ((c = is.peek()) != EOF && isspace(c)) is.get();
+  if (c == EOF) {
+    done_ = true;
+    return;
+  }
+  std::string key;
+  while ((c = is.get()) != EOF && !isspace(c)) key += (char)c;
+  if (c == EOF) KIO_ERR("Invalid archive file format: expected space after key " << key);
+  cur_.key = key;
+  if (c == '\n') is.unget();  // text lattices: the newline belongs to the holder
+  ReadCompactLattice(is, &cur_);
+}
+
+TableWriter::TableWriter(const std::string& wspecifier) {
+  if (wspecifier.empty()) return;
+  spec_ = ParseSpecifier(wspecifier, true);
+  if (spec_.is_scp && !spec_.is_ark) KIO_ERR("scp-only wspecifiers are not supported: " << wspecifier);
+  if (spec_.is_scp) KIO_WARN("ark,scp wspecifier: writing the archive only");
+  out_.reset(new Output(spec_.ark));
+}
+
+std::ostream& TableWriter::Begin(const std::string& key) {
+  std::ostream& os = out_->Stream();
+  os << key << ' ';
+  return os;
+}
+
+}  // namespace kio

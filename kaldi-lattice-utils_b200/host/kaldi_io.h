@@ -1,0 +1,190 @@
+// kaldi_io.h -- the slice of Kaldi's command-line and table I/O conventions the
+// seven hot-path tools depend on, re-implemented without Kaldi/OpenFst
+// (Kaldi/OpenFst behaviour marked [ext] is restated from their
+// public formats):
+//   * ParseOptions: --name=value, --config=file, --help, --print-args, --verbose,
+//     positional arguments, usage text; exit codes as the reference's main()s
+//   * rspecifier / wspecifier: ark:file, ark:-, ark:cmd|, ark:|cmd, ark,t:..,
+//     scp:file (sequential reading, "key path[:offset]" lines)
+//   * CompactLattice holder: text (4-column CompactLattice and 5-column Lattice
+//     entries, kwsbin2/egs/lattice.ark.txt / lattice.char.ark.txt) and binary
+//     (OpenFst VectorFst stream, arc types compactlattice44 / lattice4)
+//   * writers: BasicTupleVectorHolder (util/basic-tuple-vector-holder.h:149-181),
+//     Posterior, Int32Vector, CompactLattice
+#ifndef KLU_KALDI_IO_H_
+#define KLU_KALDI_IO_H_
+
+#include <stdint.h>
+#include <stdio.h>
+
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace kio {
+
+struct KaldiError : public std::runtime_error {
+  explicit KaldiError(const std::string& m) : std::runtime_error(m) {}
+};
+#define KIO_ERR(msg)                                   \
+  do {                                                 \
+    std::ostringstream os__;                           \
+    os__ << "ERROR (" << kio::g_program << "): " << msg << "\n"; \
+    throw kio::KaldiError(os__.str());                 \
+  } while (0)
+#define KIO_WARN(msg) (std::cerr << "WARNING (" << kio::g_program << "): " << msg << std::endl)
+#define KIO_LOG(msg) (std::cerr << "LOG (" << kio::g_program << "): " << msg << std::endl)
+#define KIO_VLOG(v, msg) \
+  do {                   \
+    if (kio::g_verbose >= (v)) std::cerr << "VLOG[" << (v) << "] (" << kio::g_program << "): " << msg << std::endl; \
+  } while (0)
+
+extern std::string g_program;
+extern int g_verbose;
+
+// ------------------------------------------------------------ ParseOptions ---
+class ParseOptions {
+ public:
+  explicit ParseOptions(const char* usage) : usage_(usage) {}
+  void Register(const std::string& name, float* p, const std::string& doc) { Add(name, kFloat, p, doc, Str(*p)); }
+  void Register(const std::string& name, int32_t* p, const std::string& doc) { Add(name, kInt, p, doc, Str(*p)); }
+  void Register(const std::string& name, bool* p, const std::string& doc) {
+    Add(name, kBool, p, doc, *p ? "true" : "false");
+  }
+  void Register(const std::string& name, std::string* p, const std::string& doc) { Add(name, kString, p, doc, *p); }
+  // Returns 0, or exits like Kaldi does for --help / bad options.
+  void Read(int argc, const char* const* argv);
+  int NumArgs() const { return (int)args_.size(); }
+  std::string GetArg(int i) const;  // 1-based
+  std::string GetOptArg(int i) const { return i <= NumArgs() ? GetArg(i) : std::string(); }
+  void PrintUsage(bool print_command_line = false) const;
+
+ private:
+  enum Type { kFloat, kInt, kBool, kString };
+  struct Opt {
+    Type type;
+    void* ptr;
+    std::string doc, def;
+  };
+  template <typename T>
+  static std::string Str(T v) {
+    std::ostringstream os;
+    os << v;
+    return os.str();
+  }
+  void Add(const std::string& name, Type t, void* p, const std::string& doc, const std::string& def);
+  static std::string Normalize(const std::string& name);
+  bool SetOption(const std::string& key, const std::string& value, bool has_value);
+  void ReadConfigFile(const std::string& path);
+  std::string usage_;
+  std::map<std::string, Opt> opts_;
+  std::vector<std::string> args_;
+  std::vector<std::string> argv_;
+};
+
+bool SplitStringToIntegers(const std::string& full, const char* delim, bool omit_empty, std::vector<int32_t>* out);
+
+// ------------------------------------------------------------------ lattice ---
+struct CompactLat {
+  std::string key;
+  int32_t nstates = 0;
+  // arcs grouped by ascending src (stored order inside a state)
+  std::vector<int32_t> src, dst, label, dur;
+  std::vector<float> graph, acoustic;
+  std::vector<std::vector<int32_t> > tids;  // transition-id strings (kept for lattice output)
+  std::vector<float> fin_graph, fin_acoustic;  // +inf = not final
+  std::vector<int32_t> fin_dur;
+  std::vector<std::vector<int32_t> > fin_tids;
+};
+
+// Reads one table entry body (after "key ") from `is`: text or binary.
+void ReadCompactLattice(std::istream& is, CompactLat* lat);
+void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat);
+// TopSortCompactLatticeIfNeeded [ext]; throws on cycles.
+void TopSortIfNeeded(CompactLat* lat);
+
+// -------------------------------------------------------------------- tables ---
+struct Specifier {
+  bool is_scp = false, text = false, is_ark = false;
+  std::string ark, scp;  // file names / "-" / "cmd|" / "|cmd"
+};
+Specifier ParseSpecifier(const std::string& spec, bool writing);
+
+class Input {  // file, stdin or pipe opened for reading (binary-safe)
+ public:
+  explicit Input(const std::string& name);
+  ~Input();
+  std::istream& Stream() { return *is_; }
+
+ private:
+  std::unique_ptr<std::istream> owned_;
+  std::istream* is_ = nullptr;
+  FILE* pipe_ = nullptr;
+  std::string buffer_;
+};
+
+class Output {
+ public:
+  explicit Output(const std::string& name);
+  ~Output();
+  std::ostream& Stream() { return *os_; }
+  void Close();
+
+ private:
+  std::unique_ptr<std::ostream> owned_;
+  std::ostream* os_ = nullptr;
+  FILE* pipe_ = nullptr;
+  std::ostringstream pipe_buf_;
+};
+
+class SequentialCompactLatticeReader {
+ public:
+  explicit SequentialCompactLatticeReader(const std::string& rspecifier);
+  bool Done() const { return done_; }
+  void Next();
+  const std::string& Key() const { return cur_.key; }
+  CompactLat& Value() { return cur_; }
+
+ private:
+  void ReadOne();
+  Specifier spec_;
+  std::unique_ptr<Input> in_;       // ark stream, or the scp list
+  std::unique_ptr<Input> scp_item_;
+  CompactLat cur_;
+  bool done_ = false;
+};
+
+class TableWriter {  // archive writer: "key " + payload
+ public:
+  explicit TableWriter(const std::string& wspecifier);
+  bool binary() const { return !spec_.text; }
+  std::ostream& Begin(const std::string& key);  // writes the key, returns the stream
+  void End() {
+    if (spec_.ark == "-" ) out_->Stream().flush();
+  }
+  void Close() { out_->Close(); }
+  bool IsOpen() const { return out_ != nullptr; }
+
+ private:
+  Specifier spec_;
+  std::unique_ptr<Output> out_;
+};
+
+// Kaldi basic types
+void WriteKaldiFloat(std::ostream& os, double v);          // text: precision-7 general format
+void WriteBasicInt32(std::ostream& os, bool binary, int32_t v);
+void WriteBasicFloat(std::ostream& os, bool binary, float v);
+void WriteBasicDouble(std::ostream& os, bool binary, double v);
+void WriteToken(std::ostream& os, bool binary, const std::string& tok);
+
+}  // namespace kio
+
+#endif  // KLU_KALDI_IO_H_

@@ -1,0 +1,535 @@
+// klu_tools.cc -- the seven drop-in command-line tools.  One source, compiled
+// once per tool with -DKLU_TOOL=<enum klu_tool>; each keeps the reference
+// binary's name, flags, positional arguments, output format, stderr logging
+// style and exit codes, and hands the per-lattice work of the
+// reference's functor body to the GPU engine through include/klu.h in batches:
+//
+//   lattice-word-index-position   kwsbin2/lattice-word-index-position.cc:208-297
+//   lattice-word-index-segment    kwsbin2/lattice-word-index-segment.cc:194-282
+//   lattice-word-index-utterance  kwsbin2/lattice-word-index-utterance.cc:194-328
+//   lattice-char-index-position   kwsbin2/lattice-char-index-position.cc:303-409
+//   lattice-to-word-frame-post    latbin/lattice-to-word-frame-post.cc:29-147
+//   lattice-prune-dyn-beam        latbin/lattice-prune-dyn-beam.cc:97-214
+//   lattice-best-path2            latbin/lattice-best-path2.cc:29-221
+//
+// Lattices are independent, so the reader fills a batch (KLU_BATCH_ARCS arcs,
+// default 32M), the batch is packed/uploaded/processed, and entries are written
+// in input order -- the TaskSequencer contract (P9).  --num-threads is accepted
+// and ignored.  KLU_DEVICE selects the GPU (default 0).
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <set>
+
+#include "kaldi_io.h"
+#include "klu.h"
+
+#ifndef KLU_TOOL
+#error "compile with -DKLU_TOOL=<tool id>"
+#endif
+
+using namespace kio;
+
+namespace {
+
+#define KLU_CHECK(call)                                          \
+  do {                                                           \
+    if ((call) != 0) KIO_ERR("GPU engine: " << klu_last_error()); \
+  } while (0)
+
+struct Batch {
+  std::vector<CompactLat> lats;
+  std::vector<int64_t> state_off{0}, arc_off{0};
+  std::vector<int32_t> src, dst, label, dur, fin_dur;
+  std::vector<float> graph, acoustic, fin_graph, fin_acoustic;
+  int64_t arcs() const { return arc_off.back(); }
+  void Add(CompactLat&& l, bool keep_lattice) {
+    src.insert(src.end(), l.src.begin(), l.src.end());
+    dst.insert(dst.end(), l.dst.begin(), l.dst.end());
+    label.insert(label.end(), l.label.begin(), l.label.end());
+    dur.insert(dur.end(), l.dur.begin(), l.dur.end());
+    graph.insert(graph.end(), l.graph.begin(), l.graph.end());
+    acoustic.insert(acoustic.end(), l.acoustic.begin(), l.acoustic.end());
+    fin_graph.insert(fin_graph.end(), l.fin_graph.begin(), l.fin_graph.end());
+    fin_acoustic.insert(fin_acoustic.end(), l.fin_acoustic.begin(), l.fin_acoustic.end());
+    fin_dur.insert(fin_dur.end(), l.fin_dur.begin(), l.fin_dur.end());
+    state_off.push_back(state_off.back() + l.nstates);
+    arc_off.push_back(arc_off.back() + (int64_t)l.src.size());
+    if (!keep_lattice) {  // only prune-dyn-beam writes lattices back
+      CompactLat slim;
+      slim.key = l.key;
+      slim.nstates = l.nstates;
+      lats.push_back(std::move(slim));
+    } else {
+      lats.push_back(std::move(l));
+    }
+  }
+  klu_lattices View() const {
+    klu_lattices v;
+    v.num_lattices = (int32_t)lats.size();
+    v.state_off = state_off.data();
+    v.arc_off = arc_off.data();
+    v.arc_src = src.data();
+    v.arc_dst = dst.data();
+    v.arc_label = label.data();
+    v.arc_dur = dur.data();
+    v.arc_graph = graph.data();
+    v.arc_acoustic = acoustic.data();
+    v.fin_graph = fin_graph.data();
+    v.fin_acoustic = fin_acoustic.data();
+    v.fin_dur = fin_dur.data();
+    return v;
+  }
+};
+
+struct ToolState {
+  klu_ctx* ctx = nullptr;
+  klu_opts opts;
+  std::vector<int32_t> include, exclude, group_labels, group_ids, inc_groups, del_groups;
+  TableWriter* writer = nullptr;
+  double total_cost = 0.0;       // best-path2
+  int64_t total_frames = 0;
+  size_t num_lattices = 0;
+};
+
+[[maybe_unused]] void WriteTupleSep(std::ostream& os, bool binary, size_t i, size_t n) {
+  if (!binary && i + 1 < n) os << "; ";
+}
+
+void ProcessBatch(ToolState* st, Batch* b) {
+  if (b->lats.empty()) return;
+  const int32_t L = (int32_t)b->lats.size();
+  const auto t0 = std::chrono::steady_clock::now();
+  klu_lattices view = b->View();
+  KLU_CHECK(klu_load(st->ctx, &view));
+  KLU_CHECK(klu_run(st->ctx, KLU_TOOL, &st->opts));
+  std::vector<int64_t> off(L + 1);
+  KLU_CHECK(klu_result_offsets(st->ctx, off.data()));
+  const size_t n = (size_t)off[L];
+  TableWriter& w = *st->writer;
+  const bool bin = w.IsOpen() ? w.binary() : false;
+#if KLU_TOOL == 0 /* KLU_SEGMENT */
+  std::vector<int32_t> word(n), t0v(n), t1v(n);
+  std::vector<double> lp(n);
+  KLU_CHECK(klu_fetch_segment(st->ctx, word.data(), t0v.data(), t1v.data(), lp.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    std::ostream& os = w.Begin(b->lats[l].key);
+    const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
+    if (bin) {
+      os.put('\0');
+      os.put('B');
+      WriteBasicInt32(os, true, (int32_t)(e - a));
+    }
+    for (size_t i = a; i < e; ++i) {
+      WriteBasicInt32(os, bin, word[i]);
+      WriteBasicInt32(os, bin, t0v[i]);
+      WriteBasicInt32(os, bin, t1v[i]);
+      WriteBasicDouble(os, bin, lp[i]);
+      WriteTupleSep(os, bin, i - a, e - a);
+    }
+    if (!bin) os << '\n';
+    w.End();
+  }
+#elif KLU_TOOL == 1 /* KLU_POSITION */
+  std::vector<int32_t> word(n), pos(n), t0v(n), t1v(n);
+  std::vector<double> lp(n);
+  KLU_CHECK(klu_fetch_position(st->ctx, word.data(), pos.data(), t0v.data(), t1v.data(), lp.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    std::ostream& os = w.Begin(b->lats[l].key);
+    const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
+    if (bin) {
+      os.put('\0');
+      os.put('B');
+      WriteBasicInt32(os, true, (int32_t)(e - a));
+    }
+    for (size_t i = a; i < e; ++i) {
+      WriteBasicInt32(os, bin, word[i]);
+      WriteBasicInt32(os, bin, pos[i]);
+      WriteBasicInt32(os, bin, t0v[i]);
+      WriteBasicInt32(os, bin, t1v[i]);
+      WriteBasicDouble(os, bin, lp[i]);
+      WriteTupleSep(os, bin, i - a, e - a);
+    }
+    if (!bin) os << '\n';
+    w.End();
+  }
+#elif KLU_TOOL == 2 /* KLU_UTTERANCE */
+  std::vector<int32_t> word(n);
+  std::vector<double> lp(n);
+  KLU_CHECK(klu_fetch_utterance(st->ctx, word.data(), lp.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    std::ostream& os = w.Begin(b->lats[l].key);
+    const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
+    if (bin) {
+      os.put('\0');
+      os.put('B');
+      WriteBasicInt32(os, true, (int32_t)(e - a));
+    }
+    for (size_t i = a; i < e; ++i) {
+      WriteBasicInt32(os, bin, word[i]);
+      WriteBasicDouble(os, bin, lp[i]);
+      WriteTupleSep(os, bin, i - a, e - a);
+    }
+    if (!bin) os << '\n';
+    w.End();
+  }
+#elif KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+  int64_t total_chars = 0;
+  KLU_CHECK(klu_result_char_sizes(st->ctx, &total_chars));
+  std::vector<int64_t> coff(n + 1);
+  std::vector<int32_t> chars((size_t)total_chars), pos(n), t0v(n), t1v(n);
+  std::vector<double> lp(n);
+  KLU_CHECK(klu_fetch_char_position(st->ctx, coff.data(), chars.data(), pos.data(), t0v.data(), t1v.data(), lp.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    std::ostream& os = w.Begin(b->lats[l].key);
+    const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
+    if (bin) {
+      os.put('\0');
+      os.put('B');
+      WriteBasicInt32(os, true, (int32_t)(e - a));
+    }
+    for (size_t i = a; i < e; ++i) {
+      std::string tok;
+      for (int64_t k = coff[i]; k < coff[i + 1]; ++k) {
+        if (k > coff[i]) tok += "_";
+        tok += std::to_string(chars[(size_t)k]);
+      }
+      WriteToken(os, bin, tok);
+      WriteBasicInt32(os, bin, pos[i]);
+      WriteBasicInt32(os, bin, t0v[i]);
+      WriteBasicInt32(os, bin, t1v[i]);
+      WriteBasicDouble(os, bin, lp[i]);
+      WriteTupleSep(os, bin, i - a, e - a);
+    }
+    if (!bin) os << '\n';
+    w.End();
+  }
+#elif KLU_TOOL == 3 /* KLU_FRAME_POST */
+  std::vector<int32_t> nf(L), frame(n), word(n);
+  std::vector<float> lp(n);
+  KLU_CHECK(klu_fetch_frame_post(st->ctx, nf.data(), frame.data(), word.data(), lp.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    std::ostream& os = w.Begin(b->lats[l].key);
+    size_t i = (size_t)off[l];
+    const size_t e = (size_t)off[l + 1];
+    // [ext] PosteriorHolder: text "[ lab p lab p ] [ ... ] \n"; binary "\0B" +
+    // int32 #frames, per frame int32 n then n x (int32, float)
+    if (bin) {
+      os.put('\0');
+      os.put('B');
+      WriteBasicInt32(os, true, nf[l]);
+    }
+    for (int32_t k = 0; k < nf[l]; ++k) {
+      size_t j = i;
+      while (j < e && frame[j] == k) ++j;
+      if (bin) {
+        WriteBasicInt32(os, true, (int32_t)(j - i));
+        for (; i < j; ++i) {
+          WriteBasicInt32(os, true, word[i]);
+          WriteBasicFloat(os, true, lp[i]);
+        }
+      } else {
+        os << "[ ";
+        for (; i < j; ++i) {
+          os << word[i] << ' ';
+          WriteKaldiFloat(os, lp[i]);
+          os << ' ';
+        }
+        os << "] ";
+      }
+    }
+    if (!bin) os << '\n';
+    w.End();
+  }
+#elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
+  std::vector<int32_t> lab(n), nf(L);
+  std::vector<float> cost(L);
+  KLU_CHECK(klu_fetch_best_path2(st->ctx, lab.data(), cost.data(), nf.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    if (w.IsOpen()) {
+      std::ostream& os = w.Begin(b->lats[l].key);
+      const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
+      if (bin) {  // [ext] BasicVectorHolder<int32>
+        os.put('\0');
+        os.put('B');
+        WriteBasicInt32(os, true, (int32_t)(e - a));
+      }
+      for (size_t i = a; i < e; ++i) WriteBasicInt32(os, bin, lab[i]);
+      if (!bin) os << '\n';
+      w.End();
+    }
+    st->total_cost += cost[l];
+    st->total_frames += nf[l];
+    KIO_LOG("For utterance " << b->lats[l].key << ", best cost is " << cost[l] << " over " << nf[l] << " frames.");
+  }
+#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+  const size_t S = (size_t)b->state_off.back();
+  std::vector<int32_t> ai(n), ns(n), nd(n), smap(S);
+  std::vector<float> g(n), a(n), fg(S), fa(S);
+  std::vector<double> beams(2 * (size_t)L);
+  KLU_CHECK(klu_fetch_prune(st->ctx, ai.data(), ns.data(), nd.data(), g.data(), a.data(), smap.data(), fg.data(),
+                            fa.data(), beams.data()));
+  for (int32_t l = 0; l < L; ++l) {
+    const CompactLat& in = b->lats[l];
+    const size_t s0 = (size_t)b->state_off[l];
+    CompactLat out;
+    out.key = in.key;
+    int32_t nstates = 0;
+    for (int32_t s = 0; s < in.nstates; ++s) nstates = std::max(nstates, smap[s0 + s] + 1);
+    out.nstates = nstates;
+    const float inf = std::numeric_limits<float>::infinity();
+    out.fin_graph.assign(nstates, inf);
+    out.fin_acoustic.assign(nstates, inf);
+    out.fin_dur.assign(nstates, 0);
+    out.fin_tids.assign(nstates, std::vector<int32_t>());
+    for (int32_t s = 0; s < in.nstates; ++s) {
+      const int32_t m = smap[s0 + s];
+      if (m < 0) continue;
+      out.fin_graph[m] = fg[s0 + s];
+      out.fin_acoustic[m] = fa[s0 + s];
+      if (!(std::isinf(fg[s0 + s]) && std::isinf(fa[s0 + s]))) out.fin_tids[m] = in.fin_tids[s];
+    }
+    for (size_t i = (size_t)off[l]; i < (size_t)off[l + 1]; ++i) {
+      out.src.push_back(ns[i]);
+      out.dst.push_back(nd[i]);
+      out.label.push_back(in.label[ai[i]]);
+      out.dur.push_back(in.dur[ai[i]]);
+      out.graph.push_back(g[i]);
+      out.acoustic.push_back(a[i]);
+      out.tids.push_back(in.tids[ai[i]]);
+    }
+    std::ostream& os = w.Begin(in.key);
+    WriteCompactLattice(os, bin, out);
+    w.End();
+    const int64_t oa = (int64_t)in.src.size(), na = off[l + 1] - off[l];
+    if (in.nstates == nstates && oa == na) {
+      KIO_LOG("Lattice " << in.key << " was not pruned (beam = " << beams[2 * l] << ", # states = " << in.nstates
+                         << ", # arcs = " << oa << ")");
+    } else {
+      KIO_LOG("Lattice " << in.key << " pruned #states from " << in.nstates << " to " << nstates << " and #arcs from "
+                         << oa << " to " << na << " (beam reduced from " << beams[2 * l] << " to " << beams[2 * l + 1]
+                         << ")");
+    }
+  }
+#endif
+  st->num_lattices += (size_t)L;
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  KIO_VLOG(1, "Batch of " << L << " lattices (" << b->arcs() << " arcs): done in " << sec << " seconds.");
+  *b = Batch();
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+  const int kErrorCode = 1;  // kwsbin2/lattice-char-index-position.cc:405-408
+#else
+  const int kErrorCode = -1;  // e.g. kwsbin2/lattice-word-index-position.cc:293-296
+#endif
+  try {
+    ToolState st;
+    klu_opts_default(&st.opts);
+    float beam = std::numeric_limits<float>::infinity();
+    float acoustic_scale = 1.0f, graph_scale = 1.0f, insertion_penalty = 0.0f;
+    std::string exclude_str, include_str, other_groups_str;
+    int32_t num_threads = 1, num_threads_total = -1;
+    (void)num_threads;
+    (void)num_threads_total;
+#if KLU_TOOL == 1 /* KLU_POSITION */
+    const char* usage =
+        "This tool creates a positional inverted index of the given lattices, in the traditional meaning of "
+        "\"position\" in the context of search engines. That is, the probability that a word appears at some "
+        "position within the transcription, for all possible transcriptions of the utterance.\n\n"
+        "Usage: lattice-word-index-position [options] lat-rspecifier index-wspecifier\n"
+        " e.g.: lattice-word-index-position --acoustic-scale=0.1 ark:1.lats ark:1.word.pos.index\n";
+#elif KLU_TOOL == 0 /* KLU_SEGMENT */
+    const char* usage =
+        "This tool creates a positional inverted index of the given lattices, where the score of each word in a "
+        "segment is the probability that the word occurs in any of the transcriptions of the utterance at that "
+        "specific time segment.\n\n"
+        "Usage: lattice-word-index-segment [options] lat-rspecifier index-wspecifier\n"
+        " e.g.: lattice-word-index-segment --acoustic-scale=0.1 ark:1.lats ark:1.word.seg.index\n";
+#elif KLU_TOOL == 2 /* KLU_UTTERANCE */
+    const char* usage =
+        "This tool creates an inverted index of the given lattices, where the score of each word is the "
+        "probability that the word occurs in any of the transcriptions of the utterance at least once.\n\n"
+        "Usage: lattice-word-index-utterance [options] lat-rspecifier index-wspecifier\n"
+        " e.g.: lattice-word-index-utterance --acoustic-scale=0.1 ark:1.lats ark:1.word.utt.index\n";
+#elif KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+    const char* usage =
+        "Build a position-level word index from character lattices. Characters are grouped (whitespace group, "
+        "optional other groups, default group) and every maximal sub-path of same-group arcs is a pseudo-word.\n\n"
+        "Usage: lattice-char-index-position [options] separator-symbols lat-rspecifier index-wspecifier\n"
+        " e.g.: lattice-char-index-position \"3 4\" ark:1.lats ark:1.index\n";
+#elif KLU_TOOL == 3 /* KLU_FRAME_POST */
+    const char* usage =
+        "Compute the posterior log-probability of each word for each given utterance frame. That is, we compute "
+        "log P(a_i = v | x), for all possible utterance frames i and words v.\n\n"
+        "Usage: lattice-to-word-frame-post [options] lat-rspecifier post-wspecifier\n"
+        " e.g.: lattice-to-word-frame-post --acoustic-scale=0.1 ark:1.lats ark:1.word.pos.post\n";
+#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+    const char* usage =
+        "Iteratively reduce the beam of the lattice until a maximum number of arcs and states is achieved.\n\n"
+        "Usage: lattice-prune-dyn-beam [options] lat-rspecifier lat-wspecifier\n";
+#elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
+    const char* usage =
+        "Generate especial 1-best path through lattices, which minimizes the expected number of position-wise "
+        "errors (an upper bound of the expected Levenshtein distance) instead of the 0-1 sequence loss.\n\n"
+        "Usage: lattice-best-path2 [options] lat-rspecifier [transcriptions-wspecifier]\n";
+#endif
+    ParseOptions po(usage);
+    po.Register("acoustic-scale", &acoustic_scale, "Scaling factor for acoustic likelihoods in the lattices.");
+    po.Register("graph-scale", &graph_scale, "Scaling factor for graph probabilities in the lattices.");
+    po.Register("insertion-penalty", &insertion_penalty,
+                "Add this penalty to the lattice arcs with non-epsilon output label (typically, equivalent to word "
+                "insertion penalty).");
+#if KLU_TOOL == 1 /* KLU_POSITION */ || KLU_TOOL == 0 /* KLU_SEGMENT */ || KLU_TOOL == 2 /* KLU_UTTERANCE */ || KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+    po.Register("beam", &beam, "Pruning beam (applied after acoustic scaling and adding the insertion penalty).");
+    po.Register("num-threads", &num_threads, "Accepted for compatibility; lattices are batched on the GPU instead.");
+    po.Register("num-threads-total", &num_threads_total, "Accepted for compatibility; ignored.");
+#endif
+#if KLU_TOOL == 1 /* KLU_POSITION */ || KLU_TOOL == 0 /* KLU_SEGMENT */ || KLU_TOOL == 2 /* KLU_UTTERANCE */
+    po.Register("exclude-words", &exclude_str,
+                "Space-separated list of integers representing the words to exclude from the index.");
+    po.Register("include-words", &include_str,
+                "Space-separated list of integers representing the words to include in the index.");
+#endif
+#if KLU_TOOL == 2 /* KLU_UTTERANCE */
+    int32_t rho_label = INT_MAX;
+    po.Register("rho-label", &rho_label, "Accepted for compatibility (no composition is materialised).");
+#endif
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+    float determinize_delta = 1.0f / 1024.0f / 8.0f;
+    po.Register("nbest", &st.opts.nbest, "Extract this number of n-best hypothesis.");
+    po.Register("determinize-delta", &determinize_delta,
+                "Accepted for compatibility (sums are exact here, no determinization quantisation).");
+    po.Register("other-groups", &other_groups_str,
+                "Specific labels to group as words. Groups are separated with a semicolon, labels within a group "
+                "with spaces.");
+#endif
+#if KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+    po.Register("beam-ratio", &st.opts.beam_ratio, "Reduce the maximum beam by this ratio at each iteration.");
+    po.Register("min-beam", &st.opts.min_beam, "Minimum beam threshold");
+    po.Register("max-arcs", &st.opts.max_arcs, "Maximum number of arcs of each lattice.");
+    po.Register("max-states", &st.opts.max_states, "Maximum number of states of each lattice.");
+#endif
+    po.Read(argc, argv);
+
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+    if (po.NumArgs() != 3) {
+      po.PrintUsage();
+      exit(1);
+    }
+    const int kLatArg = 2;
+#elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
+    if (po.NumArgs() < 1 || po.NumArgs() > 2) {
+      po.PrintUsage();
+      exit(1);
+    }
+    const int kLatArg = 1;
+#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+    if (po.NumArgs() < 2) {
+      po.PrintUsage();
+      exit(1);
+    }
+    const int kLatArg = 1;
+    if (st.opts.beam_ratio <= 0.0 || st.opts.beam_ratio >= 1.0)
+      KIO_ERR("--beam_ratio must be in the open range (0.0, 1.0).");
+#else
+    if (po.NumArgs() != 2) {
+      po.PrintUsage();
+      exit(1);
+    }
+    const int kLatArg = 1;
+#endif
+    st.opts.acoustic_scale = acoustic_scale;
+    st.opts.graph_scale = graph_scale;
+    st.opts.insertion_penalty = insertion_penalty;
+    st.opts.beam = beam;
+    if (!SplitStringToIntegers(exclude_str, " ", true, &st.exclude)) KIO_ERR("Invalid --exclude-words");
+    if (!SplitStringToIntegers(include_str, " ", true, &st.include)) KIO_ERR("Invalid --include-words");
+    {
+      std::set<int32_t> a(st.exclude.begin(), st.exclude.end()), b(st.include.begin(), st.include.end());
+      st.exclude.assign(a.begin(), a.end());
+      st.include.assign(b.begin(), b.end());
+    }
+    st.opts.include_words = st.include.data();
+    st.opts.num_include = (int32_t)st.include.size();
+    st.opts.exclude_words = st.exclude.data();
+    st.opts.num_exclude = (int32_t)st.exclude.size();
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+    {
+      // kwsbin2/utils.h:41-84 ParseSeparatorGroups
+      std::map<int32_t, int32_t> label_group;
+      label_group[0] = 0;
+      st.inc_groups.push_back(INT_MAX);
+      std::vector<int32_t> ws;
+      if (!SplitStringToIntegers(po.GetArg(1), " ", true, &ws)) KIO_ERR("Invalid whitespace label list");
+      if (ws.empty()) KIO_ERR("At least one label must be specified as a whitespace separator!");
+      auto assign = [&](int32_t group, const std::vector<int32_t>& labels) {
+        for (int32_t lab : labels) {
+          auto r = label_group.emplace(lab, group);
+          if (!r.second)
+            KIO_ERR("Each label must be assigned to one group at most. Label " << lab << " was assigned to both groups "
+                                                                               << r.first->second << " and " << group << ".");
+        }
+      };
+      assign(1, ws);
+      size_t start = 0;
+      int32_t gi = 0;
+      while (start <= other_groups_str.size()) {
+        size_t end = other_groups_str.find(';', start);
+        if (end == std::string::npos) end = other_groups_str.size();
+        const std::string grp = other_groups_str.substr(start, end - start);
+        if (grp.find_first_not_of(" \t") != std::string::npos) {
+          std::vector<int32_t> labs;
+          if (!SplitStringToIntegers(grp, " ", true, &labs)) KIO_ERR("Invalid --other-groups");
+          assign(gi + 2, labs);
+          st.inc_groups.push_back(gi + 2);
+          ++gi;
+        }
+        start = end + 1;
+      }
+      for (auto& kv : label_group) {
+        st.group_labels.push_back(kv.first);
+        st.group_ids.push_back(kv.second);
+      }
+      st.del_groups.push_back(1);
+      st.opts.group_labels = st.group_labels.data();
+      st.opts.group_ids = st.group_ids.data();
+      st.opts.num_group_labels = (int32_t)st.group_labels.size();
+      st.opts.inc_groups = st.inc_groups.data();
+      st.opts.num_inc_groups = (int32_t)st.inc_groups.size();
+      st.opts.del_groups = st.del_groups.data();
+      st.opts.num_del_groups = (int32_t)st.del_groups.size();
+    }
+#endif
+    const char* dev_env = getenv("KLU_DEVICE");
+    KLU_CHECK(klu_create(dev_env ? atoi(dev_env) : 0, &st.ctx));
+    int64_t batch_arcs = (int64_t)32 << 20;
+    if (const char* e = getenv("KLU_BATCH_ARCS")) batch_arcs = std::max<long long>(1, atoll(e));
+
+    const std::string lattice_rspecifier = po.GetArg(kLatArg);
+    TableWriter writer(po.GetOptArg(kLatArg + 1));
+    st.writer = &writer;
+    Batch batch;
+    const bool keep = KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */;
+    for (SequentialCompactLatticeReader reader(lattice_rspecifier); !reader.Done(); reader.Next()) {
+      batch.Add(std::move(reader.Value()), keep);
+      if (batch.arcs() >= batch_arcs) ProcessBatch(&st, &batch);
+    }
+    ProcessBatch(&st, &batch);
+    if (writer.IsOpen()) writer.Close();
+#if KLU_TOOL == 5 /* KLU_BEST_PATH2 */
+    KIO_LOG("Overall cost per frame is " << (st.total_cost / st.total_frames) << " over " << st.total_frames
+                                         << " frames.");
+#endif
+    klu_destroy(st.ctx);
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << e.what();
+    return kErrorCode;
+  }
+}
