@@ -43,6 +43,10 @@ ALGO = {
     "k_reduce": dict(arc=0.0, state=0.0, entry=16.0),
     "k_count_scan": dict(arc=8.0, state=0.0, entry=0.0),
     "k_gather": dict(arc=0.0, state=0.0, entry=16.0),
+    # fused frame-synchronous emit + group-by + order: every arc record read once
+    # (src+dst+label+g+a = 20 B), every (frame, word, logp) row written once (12 B)
+    "k_frame_post": dict(arc=20.0, state=0.0, entry=12.0),
+    "k_frame_compact": dict(arc=0.0, state=0.0, entry=24.0),
 }
 
 

@@ -2,6 +2,7 @@
 // that are not tool specific.  See include/klu.h for the contract.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -138,6 +139,9 @@ klu::BatchView klu_ctx::view() const {
   v.band_lo = d_band_lo.as<int32_t>();
   v.band_off = d_band_off.as<int64_t>();
   v.order = d_order.as<int32_t>();
+  v.fr_base = d_fr_base.as<int32_t>();
+  v.fr_off = d_fr_off.as<int64_t>();
+  v.frame_arc = d_frame_arc.as<int32_t>();
   return v;
 }
 
@@ -203,7 +207,7 @@ int klu_destroy(klu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
                     &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_in2out, &c->d_fin_g, &c->d_fin_a,
-                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_alpha, &c->d_beta,
+                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
   for (DevBuf* b : bufs) b->release();
@@ -255,9 +259,13 @@ int klu_run(klu_ctx* c, int tool, const klu_opts* opts) {
   c->last_tool = -1;
   int rc = 0;
   switch (tool) {
+    case KLU_FRAME_POST:
+      // frame-synchronous kernel; KLU_GENERIC_FRAME_POST=1 selects the generic
+      // emit/sort/reduce pipeline instead (kept as a cross-check)
+      rc = getenv("KLU_GENERIC_FRAME_POST") ? run_index_tool(c, tool, opts) : run_frame_post(c, opts);
+      break;
     case KLU_SEGMENT:
     case KLU_POSITION:
-    case KLU_FRAME_POST:
     case KLU_FWD_BWD:
     case KLU_UTTERANCE:
     case KLU_BEST_PATH2:

@@ -77,12 +77,12 @@ __device__ __forceinline__ bool label_valid(const IndexArgs& a, int label) {
 }
 
 // entries an out-order arc will emit
-__device__ __forceinline__ int arc_entry_count(const IndexArgs& a, int e) {
+__device__ __forceinline__ int arc_entry_count(const IndexArgs& a, int e, int T) {
   const int4 r = a.b.out_rec[e];
   if (a.tool == KLU_FRAME_POST) {
     if (r.w == 0) return 0;
-    const int d = a.b.time[r.x] - a.b.time[a.b.out_src[e]];
-    return d > 0 ? d : 0;
+    const int fa = max(a.b.time[a.b.out_src[e]], 0), fb = min(a.b.time[r.x], T);
+    return fb > fa ? fb - fa : 0;
   }
   if (a.tool == KLU_BEST_PATH2) {
     if (r.w == 0) return 0;
@@ -101,11 +101,12 @@ __global__ void __launch_bounds__(256) k_count_scan(IndexArgs a) {
   const int l = a.l0 + blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = a.b.fr_base[l + 1] - a.b.fr_base[l] - 1;  // frames of the utterance
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (int tile = e0; tile < e1; tile += 256) {
     const int e = tile + tid;
-    const int c = e < e1 ? arc_entry_count(a, e) : 0;
+    const int c = e < e1 ? arc_entry_count(a, e, T) : 0;
     int x = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
       a.idx[base + off] = (unsigned int)off;
     } else if (a.tool == KLU_FRAME_POST) {
       if (r.w == 0) continue;
-      const int t0 = a.b.time[s], t1 = a.b.time[r.x];
+      const int T = a.b.fr_base[l + 1] - a.b.fr_base[l] - 1;
+      const int t0 = max(a.b.time[s], 0), t1 = min(a.b.time[r.x], T);
       if (t1 <= t0) continue;
       // fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-frame-post.cc:102-104
       const double v = __dadd_rn(__dadd_rn(a.alpha[s], a.beta[r.x]), -rec_cost(r, a.cp));

@@ -249,9 +249,10 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
                 cursor[d + 1]++;
                 ++pos;
                 // entry capacity of the arc x frame and arc x length expansions
-                const int32_t dur = in->arc_dur[ge];
                 if (in->arc_label[ge] != 0) {
-                  li.cap_frame += dur > 0 ? dur : 0;
+                  // frames [t(src), t(dst)) of the arc, inside the utterance
+                  const int32_t fa = std::max(times[s], 0), fb = std::min(times[in->arc_dst[ge]], li.num_frames);
+                  li.cap_frame += fb > fa ? fb - fa : 0;
                   li.cap_pos += hi[s] >= 0 ? hi[s] - lo[s] + 1 : 0;
                 }
               }
@@ -289,6 +290,47 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
     c->h_band_off.resize(L + 1);
     for (int32_t l = 0; l <= L; ++l) c->h_band_off[l] = st.band_off[in->state_off[l]];
   }
+  // frame -> arc CSR (the arc x frame expansion of latbin/lattice-to-word-frame-post.cc:110-116
+  // as an index structure): per lattice, per frame, the word arcs alive in it, in arc order
+  std::vector<int32_t> fr_base(L + 1, 0);
+  std::vector<int64_t> fa_base(L + 1, 0);
+  for (int32_t l = 0; l < L; ++l) {
+    fr_base[l + 1] = fr_base[l] + info[l].num_frames + 1;
+    fa_base[l + 1] = fa_base[l] + info[l].cap_frame;
+  }
+  std::vector<int64_t> fr_off((size_t)fr_base[L] + 1, 0);
+  std::vector<int32_t> frame_arc((size_t)std::max<int64_t>(fa_base[L], 1));
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t]() {
+        std::vector<int64_t> cur;
+        for (int32_t l = range[t]; l < range[t + 1]; ++l) {
+          const int32_t T = info[l].num_frames;
+          const int64_t e0 = in->arc_off[l], e1 = in->arc_off[l + 1];
+          int64_t* fo = fr_off.data() + fr_base[l];
+          cur.assign(T + 1, 0);
+          for (int64_t p = e0; p < e1; ++p) {
+            const int4 r = st.out_rec[p];
+            if (r.w == 0) continue;
+            const int32_t fa = std::max(st.time[st.out_src[p]], 0), fb = std::min(st.time[r.x], T);
+            for (int32_t k = fa; k < fb; ++k) cur[k + 1]++;
+          }
+          for (int32_t k = 0; k < T; ++k) cur[k + 1] += cur[k];
+          for (int32_t k = 0; k <= T; ++k) fo[k] = fa_base[l] + cur[k];
+          for (int64_t p = e0; p < e1; ++p) {
+            const int4 r = st.out_rec[p];
+            if (r.w == 0) continue;
+            const int32_t fa = std::max(st.time[st.out_src[p]], 0), fb = std::min(st.time[r.x], T);
+            for (int32_t k = fa; k < fb; ++k) frame_arc[(size_t)(fa_base[l] + cur[k]++)] = (int32_t)p;
+          }
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  c->h_fr_base = fr_base;
+  c->frame_entries = fa_base[L];
+
   // work queue order: lattices by descending arc count
   st.order.resize(L);
   std::iota(st.order.begin(), st.order.end(), 0);
@@ -349,6 +391,9 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(up(c->d_band_lo, st.band_lo.data(), st.band_lo.size() * 4));
   KLU_TRY(up(c->d_band_off, st.band_off.data(), st.band_off.size() * 8));
   KLU_TRY(up(c->d_order, st.order.data(), st.order.size() * 4));
+  KLU_TRY(up(c->d_fr_base, fr_base.data(), fr_base.size() * 4));
+  KLU_TRY(up(c->d_fr_off, fr_off.data(), fr_off.size() * 8));
+  KLU_TRY(up(c->d_frame_arc, frame_arc.data(), frame_arc.size() * 4));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // staging vectors die here
   return 0;
 }

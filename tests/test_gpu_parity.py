@@ -194,3 +194,34 @@ def test_prune_then_best_path_pipeline(klu, ora, engine):
     for l, lat in enumerate(lats2):
         labels, cost = ora.best_path2(lat)
         assert got[l][0] == labels
+
+
+# ---- frame-synchronous kernel vs the generic emit/sort/reduce pipeline ------------
+def test_frame_post_fast_path_equals_generic(klu, engine, monkeypatch):
+    batch = klu.synth_batch("small", 10, seed=4242)
+    engine.load(batch)
+    fast = engine.frame_post(acoustic_scale=0.1)
+    monkeypatch.setenv("KLU_GENERIC_FRAME_POST", "1")
+    generic = engine.frame_post(acoustic_scale=0.1)
+    assert len(fast) == len(generic)
+    for a, b in zip(fast, generic):
+        assert len(a) == len(b)
+        for fa, fb in zip(a, b):
+            assert_rows_match(fa, fb, 1, tol=1e-6)
+
+
+def test_frame_post_many_words_per_frame(klu, ora, engine):
+    # > 256 distinct words alive in one frame: the per-warp hash table overflows and
+    # the kernel falls back to word-hash partitions + a global-memory sort
+    rng = np.random.RandomState(0)
+    n = 900
+    arcs = [(0, 1, 1000 + i, float(rng.uniform(0, 5)), float(rng.uniform(0, 5)), 2) for i in range(n)]
+    arcs += [(0, 1, 1000 + i, float(rng.uniform(0, 5)), 0.25, 2) for i in range(0, n, 3)]   # duplicates to merge
+    arcs += [(1, 2, 7, 0.5, 0.5, 1)]
+    lat = klu.make_lattice("wide", 3, arcs, {2: (0.0, 0.0)})
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    got = engine.frame_post()[0]
+    want = ora.frame_post(lat)
+    assert len(got) == len(want) == 3
+    for g, w in zip(got, want):
+        assert_rows_match(g, w, 1)
