@@ -47,6 +47,7 @@ ALGO = {
     # (src+dst+label+g+a = 20 B), every (frame, word, logp) row written once (12 B)
     "k_frame_post": dict(arc=20.0, state=0.0, entry=12.0),
     "k_frame_compact": dict(arc=0.0, state=0.0, entry=24.0),
+    "k_arc_values": dict(arc=36.0, state=0.0, entry=0.0),
 }
 
 

@@ -27,7 +27,8 @@ namespace klu {
 
 namespace {
 
-constexpr int kFrameWarps = 8;          // warps per CTA
+constexpr int kFrameWarps = 4;          // warps per CTA
+constexpr int kRegInst = 8;             // instances per lane kept in registers (fast path: n <= 256)
 constexpr int kSlots = 256;             // hash slots per warp
 constexpr int kFramesPerItem = 16;      // consecutive frames handled by one warp
 constexpr double kFixScale = 1099511627776.0;  // 2^40
@@ -38,6 +39,7 @@ struct FrameArgs {
   const double* alpha;
   const double* beta;
   const double* total;
+  int4* arcv;                // [E] per out-order arc: {value f64 (2 words), label, 0}
   const int32_t* item_base;  // [L+1] first work item of each lattice
   int num_items;
   // sparse output: frame k of lattice l owns slots [fr_off[k], fr_off[k+1])
@@ -56,37 +58,47 @@ __device__ __forceinline__ unsigned int hash_word(int w) {
   return x ^ (x >> 15);
 }
 
-__device__ __forceinline__ double inv_ord_f64(unsigned long long u) {
-  const unsigned long long b = (u & 0x8000000000000000ULL) ? (u ^ 0x8000000000000000ULL) : ~u;
-  return __longlong_as_double((long long)b);
-}
-
 __device__ __forceinline__ float inv_ord_f32(unsigned int u) {
   const unsigned int b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
   return __uint_as_float(b);
 }
 
-__device__ __forceinline__ double instance_value(const FrameArgs& a, int e, int* word) {
-  const int4 r = __ldg(a.b.out_rec + e);
-  const int s = __ldg(a.b.out_src + e);
-  *word = r.w;
-  // fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-frame-post.cc:102-104
-  return __dadd_rn(__dadd_rn(a.alpha[s], a.beta[r.x]), -rec_cost(r, a.cp));
+// per arc, once: fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-frame-post.cc:102-104
+__global__ void __launch_bounds__(256) k_arc_values(FrameArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.b.E; e += stride) {
+    const int4 r = ld_stream(a.b.out_rec + e);
+    const int s = a.b.out_src[e];
+    const double v = __dadd_rn(__dadd_rn(a.alpha[s], a.beta[r.x]), -rec_cost(r, a.cp));
+    const long long bits = __double_as_longlong(v);
+    a.arcv[e] = make_int4((int)(bits & 0xffffffffLL), (int)(bits >> 32), r.w, 0);
+  }
 }
 
-// warp-wide bitonic sort of n <= 256 keys in shared memory (ascending)
+__device__ __forceinline__ double instance_value(const FrameArgs& a, int e, int* word) {
+  const int4 r = __ldg(a.arcv + e);
+  *word = r.z;
+  return __longlong_as_double(((long long)r.y << 32) | (unsigned int)r.x);
+}
+
+// order-preserving bits of v rounded UP to float: a 32-bit running maximum m' >= v
+// is all the fixed-point sum needs (exp(v - m') <= 1)
+__device__ __forceinline__ unsigned int ord_up_f32(double v) { return ord_f32(__double2float_ru(v)); }
+
+// warp-wide bitonic sort of n_pow2 <= 256 keys in shared memory (ascending); every
+// lane owns whole compare-exchange pairs, so no lane idles inside a stage
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int n_pow2, int lane) {
+  const int half = n_pow2 >> 1;
   for (int k = 2; k <= n_pow2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < n_pow2; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long x = keys[i], y = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) {
-            keys[i] = y;
-            keys[ixj] = x;
-          }
+      for (int p = lane; p < half; p += 32) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const int q = i | j;
+        const unsigned long long x = keys[i], y = keys[q];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) {
+          keys[i] = y;
+          keys[q] = x;
         }
       }
       __syncwarp();
@@ -110,14 +122,24 @@ __device__ void warp_sort_global(unsigned long long* keys, int n, int lane) {
 
 __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(FrameArgs a) {
   __shared__ int s_key[kFrameWarps][kSlots];
-  __shared__ unsigned long long s_max[kFrameWarps][kSlots];
+  __shared__ unsigned int s_max[kFrameWarps][kSlots];
   __shared__ unsigned long long s_sum[kFrameWarps][kSlots];
+  __shared__ unsigned long long s_sort[kFrameWarps][kSlots];
+  __shared__ int s_list[kFrameWarps][kSlots];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* key = s_key[warp];
-  unsigned long long* vmax = s_max[warp];
+  unsigned int* vmax = s_max[warp];
   unsigned long long* vsum = s_sum[warp];
+  unsigned long long* sortbuf = s_sort[warp];
+  int* list = s_list[warp];
   const BatchView& b = a.b;
-  const unsigned long long kNegInfOrd = ord_f64(neg_inf());
+  const unsigned int kEmptyMax = 0u;  // below ord_f32 of every float, -inf included
+  for (int i = lane; i < kSlots; i += 32) {
+    key[i] = -1;
+    vmax[i] = kEmptyMax;
+    vsum[i] = 0ULL;
+  }
+  __syncwarp();
   for (int item = blockIdx.x * kFrameWarps + warp; item < a.num_items; item += gridDim.x * kFrameWarps) {
     // lattice of this item: last l with item_base[l] <= item
     int lo = 0, hi = b.L - 1;
@@ -137,23 +159,110 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(FrameArgs a) {
       const int n = (int)(fo[k + 1] - f0);
       unsigned long long* out = a.ent + f0;
       int written = 0;
-      for (int P = 1;; P <<= 1) {  // word-hash partitions; P = 1 unless the table overflows
+      bool done = false;
+      if (n <= kRegInst * 32) {
+        // ---- fast path: every instance lives in registers between the phases ----
+        double v[kRegInst];
+        int slot[kRegInst];
+        int ovf = 0;
+        int c = 0;  // occupied slots so far (warp-uniform)
+#pragma unroll
+        for (int r = 0; r < kRegInst; ++r) {
+          if (r * 32 < n) {
+            const int i = r * 32 + lane;
+            slot[r] = -1;
+            v[r] = 0.0;
+            bool claimed = false;
+            unsigned int h = 0;
+            if (i < n) {
+              int w;
+              v[r] = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
+              h = hash_word(w) & (kSlots - 1);
+              int probes = 0;
+              for (;; h = (h + 1) & (kSlots - 1)) {
+                const int old = atomicCAS(&key[h], -1, w);
+                if (old == -1) {
+                  claimed = true;
+                  break;
+                }
+                if (old == w) break;
+                if (++probes >= kSlots) {
+                  ovf = 1;
+                  break;
+                }
+              }
+              if (!ovf) {
+                slot[r] = (int)h;
+                atomicMax(&vmax[h], ord_up_f32(v[r]));
+              }
+            }
+            // append the newly claimed slots to the occupied list (no atomics)
+            const unsigned int bal = __ballot_sync(0xffffffffu, claimed);
+            if (claimed) list[c + __popc(bal & ((1u << lane) - 1u))] = (int)h;
+            c += __popc(bal);
+          } else {
+            slot[r] = -1;
+            v[r] = 0.0;
+          }
+        }
+        const bool overflow = __any_sync(0xffffffffu, ovf);
+        __syncwarp();
+        if (!overflow) {
+#pragma unroll
+          for (int r = 0; r < kRegInst; ++r) {
+            if (slot[r] >= 0) {
+              const unsigned int mo = vmax[slot[r]];
+              const float mf = inv_ord_f32(mo);
+              if (mf > -INFINITY) {
+                // v - m' in double, the exponential in float (the output is float32)
+                const float t = __expf((float)(v[r] - (double)mf));
+                atomicAdd(&vsum[slot[r]], (unsigned long long)__float2ll_rn(t * (float)kFixScale));
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (!overflow) {
+          int np2 = 1;
+          while (np2 < c) np2 <<= 1;
+          for (int i = lane; i < np2; i += 32) {
+            unsigned long long sk = ~0ULL;
+            if (i < c) {
+              const int h = list[i];
+              const float mf = inv_ord_f32(vmax[h]);
+              double lse = neg_inf();
+              if (mf > -INFINITY) lse = (double)mf + (double)__logf((float)vsum[h] * (float)(1.0 / kFixScale));
+              const float f = (float)(lse - total) + 0.0f;
+              sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)key[h];
+            }
+            sortbuf[i] = sk;
+          }
+          __syncwarp();
+          warp_bitonic_sort(sortbuf, np2, lane);
+          for (int i = lane; i < c; i += 32) out[i] = sortbuf[i];
+          written = c;
+          done = true;
+        }
+        // reset the touched slots for the next frame
+        for (int i = lane; i < c; i += 32) {
+          const int h = list[i];
+          key[h] = -1;
+          vmax[h] = kEmptyMax;
+          vsum[h] = 0ULL;
+        }
+        __syncwarp();
+      }
+      // ---- slow path: word-hash partitions, values recomputed per phase, global sort ----
+      for (int P = 1; !done; P <<= 1) {
         bool overflow = false;
         written = 0;
         for (int p = 0; p < P && !overflow; ++p) {
-          for (int i = lane; i < kSlots; i += 32) {
-            key[i] = -1;
-            vmax[i] = kNegInfOrd;
-            vsum[i] = 0ULL;
-          }
-          __syncwarp();
-          // pass 1: claim slots, running maximum
           int ovf = 0;
           for (int i = lane; i < n; i += 32) {
             int w;
-            const double v = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
+            const double vv = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
             const unsigned int h0 = hash_word(w);
-            if (P > 1 && (int)((h0 >> 8) & (unsigned)(P - 1)) != p) continue;
+            if ((int)((h0 >> 8) & (unsigned)(P - 1)) != p) continue;
             unsigned int h = h0 & (kSlots - 1);
             int probes = 0;
             for (;; h = (h + 1) & (kSlots - 1)) {
@@ -164,57 +273,50 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(FrameArgs a) {
                 break;
               }
             }
-            if (!ovf) atomicMax(&vmax[h], ord_f64(v));
+            if (!ovf) atomicMax(&vmax[h], ord_up_f32(vv));
           }
           overflow = __any_sync(0xffffffffu, ovf);
           __syncwarp();
-          if (overflow) break;
-          // pass 2: fixed-point sum of exp(v - max)
-          for (int i = lane; i < n; i += 32) {
-            int w;
-            const double v = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
-            const unsigned int h0 = hash_word(w);
-            if (P > 1 && (int)((h0 >> 8) & (unsigned)(P - 1)) != p) continue;
-            unsigned int h = h0 & (kSlots - 1);
-            while (key[h] != w) h = (h + 1) & (kSlots - 1);
-            const double m = inv_ord_f64(vmax[h]);
-            if (m > neg_inf()) {
-              const double t = exp(v - m) * kFixScale;
-              atomicAdd(&vsum[h], (unsigned long long)__double2ll_rn(t));
+          if (!overflow) {
+            for (int i = lane; i < n; i += 32) {
+              int w;
+              const double vv = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
+              const unsigned int h0 = hash_word(w);
+              if ((int)((h0 >> 8) & (unsigned)(P - 1)) != p) continue;
+              unsigned int h = h0 & (kSlots - 1);
+              while (key[h] != w) h = (h + 1) & (kSlots - 1);
+              const float mf = inv_ord_f32(vmax[h]);
+              if (mf > -INFINITY)
+                atomicAdd(&vsum[h], (unsigned long long)__double2ll_rn(exp(vv - (double)mf) * kFixScale));
+            }
+            __syncwarp();
+            for (int base = 0; base < kSlots; base += 32) {
+              const int i = base + lane;
+              const int w = key[i];
+              unsigned long long sk = 0;
+              if (w != -1) {
+                const float mf = inv_ord_f32(vmax[i]);
+                double lse = neg_inf();
+                if (mf > -INFINITY) lse = (double)mf + log((double)vsum[i] * (1.0 / kFixScale));
+                const float f = (float)(lse - total) + 0.0f;
+                sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)w;
+              }
+              const unsigned int bal = __ballot_sync(0xffffffffu, w != -1);
+              if (w != -1) out[written + __popc(bal & ((1u << lane) - 1u))] = sk;
+              written += __popc(bal);
             }
           }
           __syncwarp();
-          // pass 3: normalise, build sort keys, compact
-          for (int base = 0; base < kSlots; base += 32) {
-            const int i = base + lane;
-            const int w = key[i];
-            unsigned long long sk = 0;
-            if (w != -1) {
-              const double m = inv_ord_f64(vmax[i]);
-              double lse = neg_inf();
-              if (m > neg_inf()) lse = m + log((double)vsum[i] * (1.0 / kFixScale));
-              const float f = (float)(lse - total) + 0.0f;
-              sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)w;
-            }
-            const unsigned int bal = __ballot_sync(0xffffffffu, w != -1);
-            if (w != -1) out[written + __popc(bal & ((1u << lane) - 1u))] = sk;
-            written += __popc(bal);
+          for (int i = lane; i < kSlots; i += 32) {
+            key[i] = -1;
+            vmax[i] = kEmptyMax;
+            vsum[i] = 0ULL;
           }
           __syncwarp();
         }
         if (!overflow) {
-          if (P == 1 && written <= kSlots) {
-            // fast path: sort in shared memory (reuse the max array as the key buffer)
-            int np2 = 1;
-            while (np2 < written) np2 <<= 1;
-            for (int i = lane; i < np2; i += 32) vmax[i] = i < written ? out[i] : ~0ULL;
-            __syncwarp();
-            warp_bitonic_sort(vmax, np2, lane);
-            for (int i = lane; i < written; i += 32) out[i] = vmax[i];
-          } else {
-            warp_sort_global(out, written, lane);
-          }
-          break;
+          warp_sort_global(out, written, lane);
+          done = true;
         }
       }
       if (lane == 0) a.frame_cnt[b.fr_base[l] + k] = written;
@@ -330,7 +432,8 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   std::vector<int32_t> item_base(L + 1, 0);
   for (int32_t l = 0; l < L; ++l)
     item_base[l + 1] = item_base[l] + (c->h_num_frames[l] + kFramesPerItem - 1) / kFramesPerItem;
-  enum { F_ITEM = 0, F_ENT, F_CNT, F_FOUT, F_LCNT };
+  enum { F_ITEM = 0, F_ENT, F_CNT, F_FOUT, F_LCNT, F_ARCV };
+  KLU_TRY(c->d_scratch[F_ARCV].reserve(16 * (size_t)std::max<int64_t>(c->E, 1)));
   KLU_TRY(c->d_scratch[F_ITEM].reserve(4 * (size_t)(L + 1)));
   KLU_TRY(c->d_scratch[F_ENT].reserve(8 * (size_t)N));
   KLU_TRY(c->d_scratch[F_CNT].reserve(4 * (size_t)F));
@@ -349,6 +452,7 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   a.alpha = c->d_alpha.as<double>();
   a.beta = c->d_beta.as<double>();
   a.total = c->d_total.as<double>();
+  a.arcv = c->d_scratch[F_ARCV].as<int4>();
   a.item_base = c->d_scratch[F_ITEM].as<int32_t>();
   a.num_items = item_base[L];
   a.ent = c->d_scratch[F_ENT].as<unsigned long long>();
@@ -359,8 +463,13 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   a.o_logp = c->d_res[4].as<float>();
   a.lat_cnt = c->d_scratch[F_LCNT].as<int32_t>();
   a.res_off = c->d_res[5].as<int64_t>();
+  {
+    KLU_LAUNCH(c, "k_arc_values");
+    k_arc_values<<<c->num_sms * 8, 256, 0, c->stream>>>(a);
+  }
+  KLU_TRY(check_launch("k_arc_values"));
   if (a.num_items > 0) {
-    const int grid = std::max(1, std::min((a.num_items + kFrameWarps - 1) / kFrameWarps, c->num_sms * 32));
+    const int grid = std::max(1, std::min((a.num_items + kFrameWarps - 1) / kFrameWarps, c->num_sms * 64));
     {
       KLU_LAUNCH(c, "k_frame_post");
       k_frame_post<<<grid, kFrameWarps * 32, 0, c->stream>>>(a);
