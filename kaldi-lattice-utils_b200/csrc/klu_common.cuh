@@ -69,6 +69,7 @@ struct BatchView {
   const float* fin_a;        // [S]
   const int32_t* time;       // [S] frame of each state (CompactLatticeStateTimes)
   const int32_t* orig;       // [S] lattice-local input id of each state
+  const int32_t* old2new;    // [S] input state (global) -> packed state (global)
   const int32_t* level;      // [S] level index of each state within its lattice
   const int32_t* band_lo;    // [S] min #non-eps labels on paths from the start (-1: unreachable)
   const int64_t* band_off;   // [S+1] offsets into the (state,len) band arrays
@@ -116,7 +117,7 @@ struct klu_ctx {
 
   // ---- device: packed batch ----
   klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
-      d_in2out, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order, d_fr_base, d_fr_off, d_frame_arc;
+      d_in2out, d_old2new, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order, d_fr_base, d_fr_off, d_frame_arc;
   // ---- device: per-run state ----
   klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
   klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps
@@ -150,7 +151,9 @@ struct LaunchScope {
 int check_launch(const char* what);
 
 // klu_pack.cu
-int pack_and_upload(klu_ctx* c, const klu_lattices* lats);
+int pack_and_upload(klu_ctx* c, const klu_lattices* lats);       // host packer (KLU_HOST_PACKER=1)
+// klu_gpack.cu
+int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* lats);   // device packer (default)
 // klu_sweep.cu
 int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam);
 int run_tropical_sweeps(klu_ctx* c, const CostParams& cp);

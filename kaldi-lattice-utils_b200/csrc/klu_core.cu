@@ -135,6 +135,7 @@ klu::BatchView klu_ctx::view() const {
   v.fin_a = d_fin_a.as<float>();
   v.time = d_time.as<int32_t>();
   v.orig = d_orig.as<int32_t>();
+  v.old2new = d_old2new.as<int32_t>();
   v.level = d_level.as<int32_t>();
   v.band_lo = d_band_lo.as<int32_t>();
   v.band_off = d_band_off.as<int64_t>();
@@ -206,7 +207,7 @@ int klu_destroy(klu_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
-                    &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_in2out, &c->d_fin_g, &c->d_fin_a,
+                    &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_in2out, &c->d_old2new, &c->d_fin_g, &c->d_fin_a,
                     &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
@@ -240,7 +241,8 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   KLU_CUDA(cudaSetDevice(c->device));
   c->loaded = false;
   c->last_tool = -1;
-  KLU_TRY(pack_and_upload(c, lats));
+  if (getenv("KLU_HOST_PACKER")) KLU_TRY(pack_and_upload(c, lats));
+  else KLU_TRY(pack_and_upload_gpu(c, lats));
   c->loaded = true;
   return 0;
 }

@@ -895,6 +895,16 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
 
 using namespace klu;
 
+static __global__ void k_unpermute(const double* alpha, const double* beta, const int32_t* old2new, double* oa,
+                                   double* ob, int64_t S) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += stride) {
+    const int n = old2new[s];
+    oa[s] = alpha[n];
+    ob[s] = beta[n];
+  }
+}
+
 // Lazily brings the per-lattice result offsets of the last run to the host.
 static int ensure_offsets(klu_ctx* c) {
   if (c->last_tool < 0) {
@@ -993,17 +1003,20 @@ int klu_fetch_fwd_bwd(klu_ctx* c, double* alpha, double* beta, double* total) {
     return 1;
   }
   KLU_CUDA(cudaSetDevice(c->device));
-  std::vector<double> ha(c->S), hb(c->S);
-  KLU_CUDA(cudaMemcpyAsync(ha.data(), c->d_alpha.p, sizeof(double) * c->S, cudaMemcpyDeviceToHost, c->stream));
-  KLU_CUDA(cudaMemcpyAsync(hb.data(), c->d_beta.p, sizeof(double) * c->S, cudaMemcpyDeviceToHost, c->stream));
-  if (total)
+  // back to the caller's state numbering on the device, then one copy each
+  const size_t S = (size_t)c->S;
+  if (S) {
+    KLU_TRY(c->d_res[6].reserve(16 * S));
+    double* tmp = c->d_res[6].as<double>();
+    k_unpermute<<<c->num_sms * 4, 256, 0, c->stream>>>(c->d_alpha.as<double>(), c->d_beta.as<double>(),
+                                                      c->d_old2new.as<int32_t>(), tmp, tmp + S, (int64_t)S);
+    KLU_TRY(check_launch("k_unpermute"));
+    if (alpha) KLU_CUDA(cudaMemcpyAsync(alpha, tmp, 8 * S, cudaMemcpyDeviceToHost, c->stream));
+    if (beta) KLU_CUDA(cudaMemcpyAsync(beta, tmp + S, 8 * S, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (total && c->L)
     KLU_CUDA(cudaMemcpyAsync(total, c->d_total.p, sizeof(double) * c->L, cudaMemcpyDeviceToHost, c->stream));
   KLU_CUDA(cudaStreamSynchronize(c->stream));
-  for (int64_t s = 0; s < c->S; ++s) {  // back to input numbering
-    const int32_t n = c->h_old2new[s];
-    if (alpha) alpha[s] = ha[n];
-    if (beta) beta[s] = hb[n];
-  }
   return 0;
 }
 

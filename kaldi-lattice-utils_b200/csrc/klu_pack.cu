@@ -387,6 +387,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(up(c->d_fin_a, st.fin_a.data(), st.fin_a.size() * 4));
   KLU_TRY(up(c->d_time, st.time.data(), st.time.size() * 4));
   KLU_TRY(up(c->d_orig, st.orig.data(), st.orig.size() * 4));
+  KLU_TRY(up(c->d_old2new, c->h_old2new.data(), c->h_old2new.size() * 4));
   KLU_TRY(up(c->d_level, st.level.data(), st.level.size() * 4));
   KLU_TRY(up(c->d_band_lo, st.band_lo.data(), st.band_lo.size() * 4));
   KLU_TRY(up(c->d_band_off, st.band_off.data(), st.band_off.size() * 8));

@@ -27,7 +27,7 @@ struct SegSortArgs {
 };
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort(SegSortArgs a) {
+static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort(SegSortArgs a) {
   __shared__ unsigned int hist[8][256];
   __shared__ unsigned int bin_base[256];
   __shared__ unsigned int warp_cnt[kSortWarps][256];

@@ -225,3 +225,25 @@ def test_frame_post_many_words_per_frame(klu, ora, engine):
     assert len(got) == len(want) == 3
     for g, w in zip(got, want):
         assert_rows_match(g, w, 1)
+
+
+# ---- device packer vs host packer ----------------------------------------------
+def test_gpu_packer_equals_host_packer(klu, engine, monkeypatch):
+    lats = klu.synth_batch("small", 9, seed=2024).lattices()
+    lats.insert(3, klu.make_lattice("empty", 0, [], {}))
+    lats.insert(5, klu.make_lattice("single", 1, [], {0: (0.5, 0.25)}))
+    batch = klu.LatticeBatch.from_lattices(lats)
+
+    def run_all():
+        engine.load(batch)
+        engine.run(klu.FWD_BWD)
+        return dict(fb=[x.tolist() for x in engine.fetch_fwd_bwd()], seg=engine.segment(acoustic_scale=0.3),
+                    pos=engine.position(), utt=engine.utterance(), fp=engine.frame_post(),
+                    bp=engine.best_path2(), pr=engine.prune_dyn_beam(max_arcs=150))
+
+    gpu = run_all()
+    monkeypatch.setenv("KLU_HOST_PACKER", "1")
+    host = run_all()
+    assert gpu["seg"] == host["seg"] and gpu["pos"] == host["pos"] and gpu["utt"] == host["utt"]
+    assert gpu["fp"] == host["fp"] and gpu["bp"] == host["bp"] and gpu["pr"] == host["pr"]
+    assert gpu["fb"] == host["fb"]
