@@ -195,12 +195,23 @@ class Engine:
         _chk(self.L.klu_fetch_utterance(self.h, _p(w), _p(lp)))
         return off, w, lp
 
-    def fetch_frame_post(self):
+    def pinned_array(self, dtype, count):
+        """numpy array backed by pinned host memory (klu_host_alloc)."""
+        buf = self.pinned(max(int(count), 1) * np.dtype(dtype).itemsize)
+        self._pinned_keep = getattr(self, "_pinned_keep", [])
+        self._pinned_keep.append(buf)
+        return np.frombuffer(buf, dtype=dtype, count=int(count))
+
+    def fetch_frame_post(self, out=None):
+        """out: optional (frame, word, logp) arrays (e.g. pinned) of sufficient size."""
         off = self.offsets()
         n = int(off[-1])
         nf = np.zeros(len(self.batch), np.int32)
-        fr, w = np.zeros(n, np.int32), np.zeros(n, np.int32)
-        lp = np.zeros(n, np.float32)
+        if out is not None and out[0].size >= n:
+            fr, w, lp = out[0][:n], out[1][:n], out[2][:n]
+        else:
+            fr, w = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            lp = np.zeros(n, np.float32)
         _chk(self.L.klu_fetch_frame_post(self.h, _p(nf), _p(fr), _p(w), _p(lp)))
         return off, nf, fr, w, lp
 
