@@ -52,113 +52,176 @@ __device__ __forceinline__ bool final_pruned(const SweepArgs& a, int l, int s, d
   return __dadd_rn(fcost, a.vfwd[s]) > __dadd_rn(a.best[l], a.beam) && fcost != pos_inf();
 }
 
-template <int G, bool BEAM>
-__device__ void log_forward(const SweepArgs& a, int l, int lane) {
+constexpr int kSweepCap = 256;  // arc terms staged per batch (per warp, in shared memory)
+
+template <bool FWD, bool BEAM>
+__device__ __forceinline__ bool sweep_arc_pruned(const SweepArgs& a, int l, int e, const int4& r) {
+  // FWD walks in-order arcs (r.x = source), BWD out-order arcs (r.x = destination)
+  const int src = FWD ? r.x : a.b.out_src[e];
+  const int dst = FWD ? a.b.out_rec[a.b.in2out[e]].x : r.x;
+  return arc_pruned(a, l, src, dst, r);
+}
+
+// Exact log-sum of the states [sa, sb) of one level, the whole warp on one state at
+// a time: max first, then max + log1p(sum of the other terms) with libm's exp and
+// log1p.  Used for states with more than kSweepCap arcs and whenever the fast
+// path's shared reference point would under- or overflow.
+template <bool FWD, bool BEAM>
+__device__ __noinline__ void sweep_states_exact(const SweepArgs& a, int l, int sa, int sb, int lane) {
+  const BatchView& b = a.b;
+  const int4* rec = FWD ? b.in_rec : b.out_rec;
+  const int* off = FWD ? b.in_off : b.out_off;
+  double* score = FWD ? a.alpha : a.beta;
+  for (int s = sa; s < sb; ++s) {
+    const int e0 = off[s], e1 = off[s + 1];
+    double fin = neg_inf();
+    if (!FWD && lane == 0) {
+      const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
+      if (!(BEAM && final_pruned(a, l, s, fc))) fin = -fc;
+    }
+    double m = fin;
+    int arg = fin > neg_inf() ? -2 : -1;  // -2: the final weight is the local max
+    for (int e = e0 + lane; e < e1; e += 32) {
+      const int4 r = __ldg(rec + e);
+      if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) continue;
+      const double x = score[r.x] - rec_cost(r, a.cp);
+      if (x > m) {
+        m = x;
+        arg = e;
+      }
+    }
+    const double lm = m;
+    m = group_max<32>(m);
+    if (!elect_max_lane<32>(lm, m, lane)) arg = -1;
+    double sum = 0.0;
+    if (m > neg_inf()) {
+      if (fin > neg_inf() && arg != -2) sum = exp(fin - m);
+      for (int e = e0 + lane; e < e1; e += 32) {
+        if (e == arg) continue;
+        const int4 r = __ldg(rec + e);
+        if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) continue;
+        sum += exp(score[r.x] - rec_cost(r, a.cp) - m);
+      }
+    }
+    sum = group_sum<32>(sum);
+    if (lane == 0) score[s] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
+  }
+}
+
+// One (lattice, direction) sweep by one warp.  Inside a level the states are cut
+// into batches of <= 32 states / <= kSweepCap arcs; the arcs of a batch are one
+// contiguous run of 16-byte records (in_rec is sorted by destination, out_rec by
+// source), so the lanes stream them with coalesced loads, each lane turns its arcs
+// into exp(score[other] - cost - ref) and parks the term in shared memory.  `ref`
+// is the score of the previous batch's first state: a point on the frontier, within
+// a few tens of every term, so one shared reference replaces the per-state max of
+// the textbook log-sum-exp (no second pass over the arcs, no arg-max election).
+// A few lanes per state then add the state's terms in arc order and
+// score = ref + log(sum).  A batch whose sums leave [1e-280, 1e280] (reference
+// point too far away, unreachable states, ...) is redone exactly.
+template <bool FWD, bool BEAM>
+__device__ void log_sweep(const SweepArgs& a, int l, int lane, double* xbuf) {
   const BatchView& b = a.b;
   const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
   if (s_begin == s_end) return;
   const int* lv = b.lvl_start + b.lvl_off[l];
   const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
-  double* alpha = a.alpha;
-  for (int s = lv[0] + lane; s < lv[1]; s += 32) alpha[s] = (s == s_begin) ? 0.0 : neg_inf();
-  __syncwarp();
-  constexpr int SPW = 32 / G;
-  const int grp = lane / G, sl = lane % G;
-  for (int j = 1; j < nl; ++j) {
-    const int a0 = lv[j], a1 = lv[j + 1];
-    for (int base = a0; base < a1; base += SPW) {
-      const int s = base + grp;
-      const bool act = s < a1;
-      const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
-      double m = neg_inf();
-      int arg = -1;
-      for (int e = e0 + sl; e < e1; e += G) {
-        const int4 r = __ldg(b.in_rec + e);
-        const double cost = rec_cost(r, a.cp);
-        if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
-        const double x = alpha[r.x] - cost;
-        if (x > m) {
-          m = x;
-          arg = e;
-        }
-      }
-      const double lm = m;
-      m = group_max<G>(m);
-      if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
-      double sum = 0.0;
-      if (m > neg_inf()) {
-        for (int e = e0 + sl; e < e1; e += G) {
-          if (e == arg) continue;
-          const int4 r = __ldg(b.in_rec + e);
-          const double cost = rec_cost(r, a.cp);
-          if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
-          sum += exp(alpha[r.x] - cost - m);
-        }
-      }
-      sum = group_sum<G>(sum);
-      if (act && sl == 0) alpha[s] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
-    }
+  const int4* rec = FWD ? b.in_rec : b.out_rec;
+  const int* off = FWD ? b.in_off : b.out_off;
+  double* score = FWD ? a.alpha : a.beta;
+  double ref = 0.0;
+  if (FWD) {
+    for (int s = lv[0] + lane; s < lv[1]; s += 32) score[s] = (s == s_begin) ? 0.0 : neg_inf();
     __syncwarp();
+  }
+  for (int j = FWD ? 1 : nl - 1; FWD ? (j < nl) : (j >= 0); j += FWD ? 1 : -1) {
+    const int a0 = lv[j], a1 = lv[j + 1];
+    int s0 = a0;
+    while (s0 < a1) {
+      const int idx = s0 + lane;
+      const int o_lo = off[min(idx, a1)], o_hi = off[min(idx + 1, a1)];
+      const int base = __shfl_sync(0xffffffffu, o_lo, 0);
+      // states of the batch: the longest prefix whose arcs fit the staging buffer
+      const int c = __popc(__ballot_sync(0xffffffffu, idx < a1 && o_hi - base <= kSweepCap));
+      if (c == 0) {
+        sweep_states_exact<FWD, BEAM>(a, l, s0, s0 + 1, lane);
+        s0 += 1;
+        continue;
+      }
+      const int nb = __shfl_sync(0xffffffffu, o_hi, c - 1) - base;
+      {  // pull the records a few levels ahead into L2
+        const int pf = base + nb + kSweepCap + lane * 8;
+        if (lane * 8 < nb && pf < b.E) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + pf));
+      }
+      for (int i = lane; i < nb; i += 32) {
+        const int e = base + i;
+        const int4 r = ld_stream(rec + e);
+        double x = score[r.x] - rec_cost(r, a.cp);
+        if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) x = neg_inf();
+        xbuf[i] = fast_exp(x - ref);
+      }
+      __syncwarp();
+      // 32 / pow2ceil(c) lanes per state add its terms, then fold across the lanes
+      const int sh = c <= 1 ? 5 : __clz(c - 1) - 27;  // log2(lanes per state)
+      const int gp = 1 << sh;
+      const int st = lane >> sh, sub = lane & (gp - 1);
+      const int lo = __shfl_sync(0xffffffffu, o_lo, st) - base, hi = __shfl_sync(0xffffffffu, o_hi, st) - base;
+      double sum = 0.0;
+      if (st < c)
+        for (int i = lo + sub; i < hi; i += gp) sum += xbuf[i];
+      for (int o = gp >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      bool bad = false;
+      double val = 0.0;
+      if (st < c && sub == 0) {
+        const int s = s0 + st;
+        double fin = neg_inf();
+        if (!FWD) {
+          const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
+          if (fc < pos_inf() && !(BEAM && final_pruned(a, l, s, fc))) {
+            fin = -fc;
+            sum += fast_exp(fin - ref);
+          }
+        }
+        const int terms = hi - lo + (fin > neg_inf() ? 1 : 0);
+        if (terms <= 2) {
+          // one or two terms: exactly Kaldi's LogAdd (x, or max + log1p(exp(-|d|))), so
+          // chains and diamonds reproduce the reference bit for bit
+          val = fin;
+          for (int i = lo; i < hi; ++i) {
+            const int4 r = __ldg(rec + base + i);
+            double x = score[r.x] - rec_cost(r, a.cp);
+            if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, base + i, r)) x = neg_inf();
+            val = log_add(val, x);
+          }
+          score[s] = val;
+        } else if (sum >= 1e-280 && sum <= 1e280) {
+          val = ref + fast_log(sum);
+          score[s] = val;
+        } else {
+          bad = true;
+        }
+      }
+      if (__any_sync(0xffffffffu, bad)) {
+        sweep_states_exact<FWD, BEAM>(a, l, s0, s0 + c, lane);
+        __syncwarp();
+        double v = (lane < c) ? score[s0 + lane] : neg_inf();
+        v = group_max<32>(v);
+        if (v > neg_inf() && v < pos_inf()) ref = v;
+      } else {
+        const double v0 = __shfl_sync(0xffffffffu, val, 0);
+        if (v0 > neg_inf() && v0 < pos_inf()) ref = v0;
+      }
+      s0 += c;
+      __syncwarp();
+    }
   }
 }
 
-template <int G, bool BEAM>
-__device__ void log_backward(const SweepArgs& a, int l, int lane) {
-  const BatchView& b = a.b;
-  const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
-  if (s_begin == s_end) return;
-  const int* lv = b.lvl_start + b.lvl_off[l];
-  const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
-  double* beta = a.beta;
-  constexpr int SPW = 32 / G;
-  const int grp = lane / G, sl = lane % G;
-  for (int j = nl - 1; j >= 0; --j) {
-    const int a0 = lv[j], a1 = lv[j + 1];
-    for (int base = a0; base < a1; base += SPW) {
-      const int s = base + grp;
-      const bool act = s < a1;
-      const int e0 = act ? b.out_off[s] : 0, e1 = act ? b.out_off[s + 1] : 0;
-      double fin = neg_inf();
-      if (act && sl == 0) {
-        const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
-        if (!(BEAM && final_pruned(a, l, s, fc))) fin = -fc;
-      }
-      double m = fin;
-      int arg = fin > neg_inf() ? -2 : -1;  // -2: the final weight is the local max
-      for (int e = e0 + sl; e < e1; e += G) {
-        const int4 r = __ldg(b.out_rec + e);
-        const double cost = rec_cost(r, a.cp);
-        if (BEAM && arc_pruned(a, l, s, r.x, r)) continue;
-        const double x = beta[r.x] - cost;
-        if (x > m) {
-          m = x;
-          arg = e;
-        }
-      }
-      const double lm = m;
-      m = group_max<G>(m);
-      if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
-      double sum = 0.0;
-      if (m > neg_inf()) {
-        if (fin > neg_inf() && arg != -2) sum = exp(fin - m);
-        for (int e = e0 + sl; e < e1; e += G) {
-          if (e == arg) continue;
-          const int4 r = __ldg(b.out_rec + e);
-          const double cost = rec_cost(r, a.cp);
-          if (BEAM && arc_pruned(a, l, s, r.x, r)) continue;
-          sum += exp(beta[r.x] - cost - m);
-        }
-      }
-      sum = group_sum<G>(sum);
-      if (act && sl == 0) beta[s] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
-    }
-    __syncwarp();
-  }
-}
-
-template <int G, bool BEAM>
-__global__ void __launch_bounds__(128) k_log_sweeps(SweepArgs a) {
+template <bool BEAM>
+__global__ void __launch_bounds__(128) k_log_sweeps(const __grid_constant__ SweepArgs a) {
+  __shared__ double xs[4][kSweepCap];
   const int lane = threadIdx.x & 31;
+  double* xbuf = xs[threadIdx.x >> 5];
   const int ndir = a.do_fwd + a.do_bwd;
   const int nitems = a.b.L * ndir;
   for (;;) {
@@ -168,8 +231,9 @@ __global__ void __launch_bounds__(128) k_log_sweeps(SweepArgs a) {
     if (item >= nitems) break;
     const int l = a.b.order[item / ndir];
     const bool fwd = a.do_fwd && (ndir == 1 || (item % ndir) == 0);
-    if (fwd) log_forward<G, BEAM>(a, l, lane);
-    else log_backward<G, BEAM>(a, l, lane);
+    if (fwd) log_sweep<true, BEAM>(a, l, lane, xbuf);
+    else log_sweep<false, BEAM>(a, l, lane, xbuf);
+    __syncwarp();
   }
 }
 
@@ -411,12 +475,11 @@ int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) 
   if (c->L == 0) return 0;
   KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
   SweepArgs a = make_args(c, cp, use_beam, beam);
-  const int G = pick_group(c->avg_deg);
   const int grid = sweep_grid(c, c->L * 2);
   {
     KLU_LAUNCH(c, "k_log_sweeps");
-    KLU_DISPATCH_G(G, if (use_beam) k_log_sweeps<kG, true><<<grid, 128, 0, c->stream>>>(a);
-                   else k_log_sweeps<kG, false><<<grid, 128, 0, c->stream>>>(a));
+    if (use_beam) k_log_sweeps<true><<<grid, 128, 0, c->stream>>>(a);
+    else k_log_sweeps<false><<<grid, 128, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_log_sweeps"));
   {
