@@ -42,6 +42,7 @@ struct DevBuf {
 // How arc/final weights become costs.
 struct CostParams {
   double gs, as;   // graph / acoustic scale (double products, float storage)
+  float gsf, asf;  // the same scales as the floats the flags are (gs == (double)gsf)
   float pen;       // insertion penalty (float add on arcs with label != 0)
   int scale;       // apply gs/as (either != 1)
   int float_sum;   // cost = (double)(float)(g + a) instead of (double)g + (double)a
@@ -224,8 +225,19 @@ __device__ __forceinline__ double arc_cost(float g, float a, int label, const Co
   return __dadd_rn((double)g2, (double)a2);
 }
 
+// Cost of an arc record.  Arc weights are FINITE (klu_load rejects anything else).
+// ScaleLattice forms (float)(scale * (double)w); the scale is a float-valued double,
+// so that double product is exact (24 + 24 bits) and its rounding to float is the
+// IEEE float product: one FMUL instead of F2F / DMUL / F2F.
 __device__ __forceinline__ double rec_cost(const int4& r, const CostParams& cp) {
-  return arc_cost(__int_as_float(r.y), __int_as_float(r.z), r.w, cp);
+  float g = __int_as_float(r.y), a = __int_as_float(r.z);
+  if (cp.scale) {
+    g = __fmul_rn(cp.gsf, g);
+    a = __fmul_rn(cp.asf, a);
+  }
+  if (r.w != 0) g = __fadd_rn(g, cp.pen);
+  if (cp.float_sum) return (double)__fadd_rn(g, a);
+  return __dadd_rn((double)g, (double)a);
 }
 
 // final weights: no insertion penalty (label 0)
@@ -247,27 +259,32 @@ __device__ __forceinline__ double log_add(double x, double y) {
 }
 
 // ---- cheap f64 exp / log for the level sweeps -------------------------------
+// Taylor coefficients 1/11! .. 1/3! and 2/17 .. 2/3, in constant memory so each DFMA
+// takes its coefficient as a constant-bank operand.
+static __constant__ double kExpPoly[9] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                                   1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,     1.0 / 6.0};
+static __constant__ double kLogPoly[8] = {2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0, 2.0 / 7.0, 2.0 / 5.0, 2.0 / 3.0};
+
 // exp(d) for the terms of a log-sum (relative error < 1e-14, checked on the host
 // against libm over [-700, 700]): round-to-nearest range reduction with the
 // 1.5 * 2^52 trick, degree-11 Taylor polynomial on |r| <= ln2/2, exponent patched
 // in with an integer add.  d < -700 (and NaN) gives 0, d > 700 gives +inf.
 __device__ __forceinline__ double fast_exp(double d) {
-  if (!(d >= -700.0)) return 0.0;
-  if (d > 700.0) return pos_inf();
+  if (!(fabs(d) <= 700.0)) return d < 0.0 ? 0.0 : pos_inf();  // NaN -> +inf (callers treat it as "redo exactly")
   const double t = __fma_rn(d, 1.4426950408889634, 6755399441055744.0);
   const int k = __double2loint(t);
   const double kf = __dadd_rn(t, -6755399441055744.0);
   double r = __fma_rn(kf, -6.93147180369123816490e-01, d);
   r = __fma_rn(kf, -1.90821492927058770002e-10, r);
-  double p = 1.0 / 39916800.0;
-  p = __fma_rn(p, r, 1.0 / 3628800.0);
-  p = __fma_rn(p, r, 1.0 / 362880.0);
-  p = __fma_rn(p, r, 1.0 / 40320.0);
-  p = __fma_rn(p, r, 1.0 / 5040.0);
-  p = __fma_rn(p, r, 1.0 / 720.0);
-  p = __fma_rn(p, r, 1.0 / 120.0);
-  p = __fma_rn(p, r, 1.0 / 24.0);
-  p = __fma_rn(p, r, 1.0 / 6.0);
+  double p = kExpPoly[0];
+  p = __fma_rn(p, r, kExpPoly[1]);
+  p = __fma_rn(p, r, kExpPoly[2]);
+  p = __fma_rn(p, r, kExpPoly[3]);
+  p = __fma_rn(p, r, kExpPoly[4]);
+  p = __fma_rn(p, r, kExpPoly[5]);
+  p = __fma_rn(p, r, kExpPoly[6]);
+  p = __fma_rn(p, r, kExpPoly[7]);
+  p = __fma_rn(p, r, kExpPoly[8]);
   p = __fma_rn(p, r, 0.5);
   p = __fma_rn(p, r, 1.0);
   p = __fma_rn(p, r, 1.0);
@@ -297,14 +314,14 @@ __device__ __forceinline__ double fast_log(double s) {
   double f = __dmul_rn(num, y);
   f = __fma_rn(__fma_rn(-den, f, num), y, f);
   const double f2 = __dmul_rn(f, f);
-  double p = 2.0 / 17.0;
-  p = __fma_rn(p, f2, 2.0 / 15.0);
-  p = __fma_rn(p, f2, 2.0 / 13.0);
-  p = __fma_rn(p, f2, 2.0 / 11.0);
-  p = __fma_rn(p, f2, 2.0 / 9.0);
-  p = __fma_rn(p, f2, 2.0 / 7.0);
-  p = __fma_rn(p, f2, 2.0 / 5.0);
-  p = __fma_rn(p, f2, 2.0 / 3.0);
+  double p = kLogPoly[0];
+  p = __fma_rn(p, f2, kLogPoly[1]);
+  p = __fma_rn(p, f2, kLogPoly[2]);
+  p = __fma_rn(p, f2, kLogPoly[3]);
+  p = __fma_rn(p, f2, kLogPoly[4]);
+  p = __fma_rn(p, f2, kLogPoly[5]);
+  p = __fma_rn(p, f2, kLogPoly[6]);
+  p = __fma_rn(p, f2, kLogPoly[7]);
   p = __dmul_rn(p, f2);
   const double kd = (double)k;
   double res = __fma_rn(kd, 1.90821492927058770002e-10, __dmul_rn(f, p));

@@ -83,6 +83,8 @@ CostParams make_cost_params(const klu_opts* o, bool float_sum) {
   CostParams cp;
   cp.gs = (double)o->graph_scale;
   cp.as = (double)o->acoustic_scale;
+  cp.gsf = o->graph_scale;
+  cp.asf = o->acoustic_scale;
   cp.pen = o->insertion_penalty;
   cp.scale = (o->acoustic_scale != 1.0f || o->graph_scale != 1.0f) ? 1 : 0;
   cp.float_sum = float_sum ? 1 : 0;
