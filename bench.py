@@ -43,11 +43,11 @@ ALGO = {
     "k_reduce": dict(arc=0.0, state=0.0, entry=16.0),
     "k_count_scan": dict(arc=8.0, state=0.0, entry=0.0),
     "k_gather": dict(arc=0.0, state=0.0, entry=16.0),
-    # fused frame-synchronous emit + group-by + order: every arc record read once
-    # (src+dst+label+g+a = 20 B), every (frame, word, logp) row written once (12 B)
-    "k_frame_post": dict(arc=20.0, state=0.0, entry=12.0),
-    "k_frame_compact": dict(arc=0.0, state=0.0, entry=24.0),
-    "k_arc_values": dict(arc=36.0, state=0.0, entry=0.0),
+    # arc posterior pre-pass: record (16) + source id (4) read, posterior (8) written
+    "k_arc_post": dict(arc=28.0, state=16.0, entry=0.0),
+    # frame-synchronous group-by + order: every arc x frame instance reads its arc id (4 B)
+    # and the arc's posterior (8 B); every (frame, word, logp) row is written once (12 B)
+    "k_frame_post": dict(arc=0.0, state=0.0, entry=12.0, inst=12.0),
 }
 
 
@@ -257,7 +257,8 @@ def main():
 
     def algo_bytes(name):
         a = ALGO.get(name, dict(arc=0, state=0, entry=0))
-        return a["arc"] * arcs + a["state"] * states + a["entry"] * entries + a.get("band", 0) * band
+        return (a["arc"] * arcs + a["state"] * states + a["entry"] * entries + a.get("band", 0) * band +
+                a.get("inst", 0) * st.get("frame_instances", 0))
 
     kern = {}
     for k, v in prof.items():

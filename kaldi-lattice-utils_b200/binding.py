@@ -345,7 +345,7 @@ class Engine:
     def stats(self):
         s = (C.c_int64 * 8)()
         _chk(self.L.klu_batch_stats(self.h, s))
-        return dict(lattices=s[0], states=s[1], arcs=s[2], levels=s[3], entries=s[4], band=s[5], max_len=s[6],
+        return dict(lattices=s[0], states=s[1], arcs=s[2], levels=s[3], entries=s[4], band=s[5], frame_instances=s[6],
                     max_time=s[7])
 
     def flush_l2(self):

@@ -77,7 +77,8 @@ struct BatchView {
   const int32_t* order;      // [L] lattices by descending arc count (work queue order)
   const int32_t* fr_base;    // [L+1] first slot of each lattice in fr_off (num_frames + 1 slots per lattice)
   const int64_t* fr_off;     // per (lattice, frame): first entry of the frame in frame_arc
-  const int32_t* frame_arc;  // out-order arc ids (global) of the word arcs alive in each frame
+  const int32_t* frame_arc;  // per frame: out-order arc ids (global) of the word arcs alive in it, sorted by
+                             // (word, arc); bit 31 marks the first arc of every word group
 };
 
 struct KernelStat {
@@ -112,13 +113,16 @@ struct klu_ctx {
   std::vector<int64_t> h_band_off;           // [L+1] first band cell of each lattice
   std::vector<int32_t> h_fr_base;            // [L+1] frame slots
   int64_t frame_entries = 0;                 // sum over lattices of arc x frame instances
+  std::vector<int64_t> h_frame_res_off;      // [L+1] frame-post output rows per lattice (static per batch)
+  int32_t fr_items = 0;                      // frame-post work items (runs of frames)
   int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0, max_states = 0;
   double avg_deg = 0;
   int64_t band_total = 0;
 
   // ---- device: packed batch ----
   klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
-      d_in2out, d_old2new, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order, d_fr_base, d_fr_off, d_frame_arc;
+      d_in2out, d_old2new, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order, d_fr_base, d_fr_off, d_frame_arc,
+      d_fr_item, d_fr_gloc, d_fr_res_off;
   // ---- device: per-run state ----
   klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
   klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps
@@ -162,6 +166,7 @@ int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam
 // klu_index.cu
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o);
 // klu_frame.cu
+int build_frame_groups(klu_ctx* c);  // pack time: (frame, word)-sorted instances, head bits, output offsets
 int run_frame_post(klu_ctx* c, const klu_opts* o);
 // klu_prune.cu
 int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o);

@@ -210,7 +210,7 @@ int klu_destroy(klu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
                     &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_in2out, &c->d_old2new, &c->d_fin_g, &c->d_fin_a,
-                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_alpha, &c->d_beta,
+                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_fr_item, &c->d_fr_gloc, &c->d_fr_res_off, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
   for (DevBuf* b : bufs) b->release();
@@ -243,6 +243,8 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   KLU_CUDA(cudaSetDevice(c->device));
   c->loaded = false;
   c->last_tool = -1;
+  c->h_frame_res_off.assign(1, 0);
+  c->fr_items = 0;
   if (getenv("KLU_HOST_PACKER")) KLU_TRY(pack_and_upload(c, lats));
   else KLU_TRY(pack_and_upload_gpu(c, lats));
   c->loaded = true;
@@ -359,7 +361,7 @@ int klu_batch_stats(klu_ctx* c, int64_t stats[8]) {
   stats[3] = c->NL;
   stats[4] = c->last_entries;
   stats[5] = c->band_total;
-  stats[6] = c->max_len;
+  stats[6] = c->frame_entries;
   stats[7] = c->max_time;
   return 0;
 }

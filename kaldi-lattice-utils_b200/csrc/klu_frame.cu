@@ -5,33 +5,39 @@
 // fw[u] + bw[v] - (float)(g + a); then each frame is normalised, cast to float and
 // sorted by (float log-posterior desc, word asc).
 //
-// Here one warp owns a run of consecutive frames of one lattice.  For a frame it
-// walks the frame -> arc CSR built by the packer (coalesced 4-byte ids, 16-byte arc
-// records and alpha/beta gathers that hit L1/L2 because neighbouring frames share
-// arcs), groups by word in a per-warp shared-memory hash table, and forms each
-// group's log-sum DETERMINISTICALLY: an atomic max over the order-preserving bits
-// of the doubles, then an integer atomic add of exp(v - max) in 2^-40 fixed point
-// (integer addition is associative, so the result does not depend on the order
-// lanes hit the table).  The <= 256 survivors are bitonic-sorted in shared memory
-// on ((~ordered float bits) << 32 | word) and written next to the frame's slot
-// range; a compaction pass produces the dense (frame, word, logp) table.
-// Frames with more distinct words than the table holds are split by word hash
-// into several passes and sorted in global memory (slow path, same results).
+// Which (frame, word) groups exist, which arcs feed each of them and how many rows
+// every frame emits depends only on labels and state times, not on the weights.
+// So klu_load() builds that structure ONCE per batch (build_frame_groups): the
+// arc x frame instances of a lattice sorted by (frame, word, arc), a head bit on
+// the first instance of every group, and the dense output offset of every frame.
+// A run is then two kernels:
+//   k_arc_post    p[e] = exp(fw[u] + bw[v] - cost - total): the arc's posterior,
+//                 once per arc (f64; exp(-700) ~ 1e-304 is the underflow horizon);
+//   k_frame_post  one warp per run of frames: streams the frame's instance list
+//                 (coalesced 4-byte ids, 8-byte gathers of p that hit L1/L2 because
+//                 neighbouring frames share arcs), adds the posteriors of each
+//                 group with a segmented warp scan (fixed shuffle tree, so the sum
+//                 is order-deterministic), takes log(sum) per group, orders the
+//                 frame's rows in shared memory (bitonic, key = ~ordered float
+//                 bits << 32 | word) and writes them straight to their final place
+//                 in the dense (frame, word, logp) table.
+// A group whose sum underflows (or is empty) is redone exactly in the log domain
+// from alpha/beta; frames with more groups than the shared-memory order buffer
+// holds are written unsorted and ordered in global memory (slow, same results).
 #include <math.h>
 
 #include <algorithm>
 
 #include "klu_common.cuh"
+#include "klu_sort.cuh"
 
 namespace klu {
 
 namespace {
 
-constexpr int kFrameWarps = 4;          // warps per CTA
-constexpr int kRegInst = 8;             // instances per lane kept in registers (fast path: n <= 256)
-constexpr int kSlots = 256;             // hash slots per warp
-constexpr int kFramesPerItem = 16;      // consecutive frames handled by one warp
-constexpr double kFixScale = 1099511627776.0;  // 2^40
+constexpr int kFrameWarps = 4;      // warps per CTA
+constexpr int kGroupCap = 256;      // rows of one frame ordered in shared memory
+constexpr int kFramesPerItem = 16;  // consecutive frames handled by one warp
 
 struct FrameArgs {
   BatchView b;
@@ -39,54 +45,64 @@ struct FrameArgs {
   const double* alpha;
   const double* beta;
   const double* total;
-  int4* arcv;                // [E] per out-order arc: {value f64 (2 words), label, 0}
+  double* parc;              // [E] per out-order arc: posterior exp(v - total)
   const int32_t* item_base;  // [L+1] first work item of each lattice
   int num_items;
-  // sparse output: frame k of lattice l owns slots [fr_off[k], fr_off[k+1])
-  unsigned long long* ent;   // sort key per slot: (~ord_f32(logp) << 32) | word
-  int32_t* frame_cnt;        // per frame slot of fr_off: entries written
-  // dense output
-  const int64_t* frame_out;  // per frame: first dense entry
+  const int64_t* gloc;       // per frame slot: lattice-local first output row (T+1 per lattice)
+  const int64_t* res_off;    // [L+1] first output row of each lattice
   int32_t *o_frame, *o_word;
   float* o_logp;
-  int32_t* lat_cnt;          // [L]
-  int64_t* res_off;          // [L+1]
 };
-
-__device__ __forceinline__ unsigned int hash_word(int w) {
-  unsigned int x = (unsigned int)w * 0x9E3779B1u;
-  return x ^ (x >> 15);
-}
 
 __device__ __forceinline__ float inv_ord_f32(unsigned int u) {
   const unsigned int b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
   return __uint_as_float(b);
 }
 
-// per arc, once: fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-frame-post.cc:102-104
-__global__ void __launch_bounds__(256) k_arc_values(FrameArgs a) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.b.E; e += stride) {
+// fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-frame-post.cc:102-104
+__device__ __forceinline__ double arc_value(const FrameArgs& a, int e) {
+  const int4 r = __ldg(a.b.out_rec + e);
+  return __dadd_rn(__dadd_rn(a.alpha[a.b.out_src[e]], a.beta[r.x]), -rec_cost(r, a.cp));
+}
+
+// grid (tiles, L): the posterior of every word arc, once
+__global__ void __launch_bounds__(256) k_arc_post(FrameArgs a) {
+  const int l = blockIdx.y;
+  const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
+  const double total = a.total[l];
+  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
     const int4 r = ld_stream(a.b.out_rec + e);
-    const int s = a.b.out_src[e];
-    const double v = __dadd_rn(__dadd_rn(a.alpha[s], a.beta[r.x]), -rec_cost(r, a.cp));
-    const long long bits = __double_as_longlong(v);
-    a.arcv[e] = make_int4((int)(bits & 0xffffffffLL), (int)(bits >> 32), r.w, 0);
+    double p = 0.0;
+    if (r.w != 0) {
+      const double v = __dadd_rn(__dadd_rn(a.alpha[a.b.out_src[e]], a.beta[r.x]), -rec_cost(r, a.cp));
+      p = fast_exp(v - total);
+    }
+    a.parc[e] = p;
   }
 }
 
-__device__ __forceinline__ double instance_value(const FrameArgs& a, int e, int* word) {
-  const int4 r = __ldg(a.arcv + e);
-  *word = r.z;
-  return __longlong_as_double(((long long)r.y << 32) | (unsigned int)r.x);
+// Exact log-posterior of the group that ENDS at instance `iend` of a frame's list
+// (walks back to the group's head): max first, then libm exp / log.
+__device__ __noinline__ double exact_group_logp(const FrameArgs& a, const int32_t* fa, int iend, double total) {
+  double m = neg_inf();
+  for (int q = iend;; --q) {
+    const unsigned int w = (unsigned int)fa[q];
+    m = fmax(m, arc_value(a, (int)(w & 0x7fffffffu)));
+    if (w >> 31) break;
+  }
+  if (!(m > neg_inf())) return neg_inf();
+  if (m == pos_inf()) return pos_inf();
+  double s = 0.0;
+  for (int q = iend;; --q) {
+    const unsigned int w = (unsigned int)fa[q];
+    s += exp(arc_value(a, (int)(w & 0x7fffffffu)) - m);
+    if (w >> 31) break;
+  }
+  return (m + log(s)) - total;
 }
 
-// order-preserving bits of v rounded UP to float: a 32-bit running maximum m' >= v
-// is all the fixed-point sum needs (exp(v - m') <= 1)
-__device__ __forceinline__ unsigned int ord_up_f32(double v) { return ord_f32(__double2float_ru(v)); }
-
-// warp-wide bitonic sort of n_pow2 <= 256 keys in shared memory (ascending); every
-// lane owns whole compare-exchange pairs, so no lane idles inside a stage
+// warp-wide bitonic sort of n_pow2 <= kGroupCap keys in shared memory (ascending);
+// every lane owns whole compare-exchange pairs, so no lane idles inside a stage
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int n_pow2, int lane) {
   const int half = n_pow2 >> 1;
   for (int k = 2; k <= n_pow2; k <<= 1) {
@@ -106,40 +122,39 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int 
   }
 }
 
-// slow path: odd-even transposition sort of a frame's entries in global memory
-__device__ void warp_sort_global(unsigned long long* keys, int n, int lane) {
+// slow path: odd-even transposition sort of a frame's (logp, word) rows in global memory
+__device__ void warp_sort_rows_global(float* logp, int32_t* word, int n, int lane) {
   for (int round = 0; round < n; ++round) {
     for (int i = (round & 1) + 2 * lane; i + 1 < n; i += 64) {
-      const unsigned long long x = keys[i], y = keys[i + 1];
+      const unsigned long long x = ((unsigned long long)(~ord_f32(logp[i])) << 32) | (unsigned int)word[i];
+      const unsigned long long y = ((unsigned long long)(~ord_f32(logp[i + 1])) << 32) | (unsigned int)word[i + 1];
       if (x > y) {
-        keys[i] = y;
-        keys[i + 1] = x;
+        const float tl = logp[i];
+        logp[i] = logp[i + 1];
+        logp[i + 1] = tl;
+        const int32_t tw = word[i];
+        word[i] = word[i + 1];
+        word[i + 1] = tw;
       }
     }
     __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(FrameArgs a) {
-  __shared__ int s_key[kFrameWarps][kSlots];
-  __shared__ unsigned int s_max[kFrameWarps][kSlots];
-  __shared__ unsigned long long s_sum[kFrameWarps][kSlots];
-  __shared__ unsigned long long s_sort[kFrameWarps][kSlots];
-  __shared__ int s_list[kFrameWarps][kSlots];
+__device__ __forceinline__ float group_logp(double sum_or_logp) {
+  // groups redone exactly carry their (negative) log-posterior instead of a sum
+  const double lp = sum_or_logp < 0.0 ? sum_or_logp : fast_log(sum_or_logp);
+  return (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+}
+
+__global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(const __grid_constant__ FrameArgs a) {
+  __shared__ unsigned long long s_sort[kFrameWarps][kGroupCap];  // group sums (f64 bits), then the order keys
+  __shared__ int s_word[kFrameWarps][kGroupCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int* key = s_key[warp];
-  unsigned int* vmax = s_max[warp];
-  unsigned long long* vsum = s_sum[warp];
   unsigned long long* sortbuf = s_sort[warp];
-  int* list = s_list[warp];
+  int* gword = s_word[warp];
   const BatchView& b = a.b;
-  const unsigned int kEmptyMax = 0u;  // below ord_f32 of every float, -inf included
-  for (int i = lane; i < kSlots; i += 32) {
-    key[i] = -1;
-    vmax[i] = kEmptyMax;
-    vsum[i] = 0ULL;
-  }
-  __syncwarp();
+  const unsigned int lane_le = 0xffffffffu >> (31 - lane);
   for (int item = blockIdx.x * kFrameWarps + warp; item < a.num_items; item += gridDim.x * kFrameWarps) {
     // lattice of this item: last l with item_base[l] <= item
     int lo = 0, hi = b.L - 1;
@@ -153,182 +168,194 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(FrameArgs a) {
     const int k0 = (item - a.item_base[l]) * kFramesPerItem;
     const int k1 = min(T, k0 + kFramesPerItem);
     const int64_t* fo = b.fr_off + b.fr_base[l];
+    const int64_t* gl = a.gloc + b.fr_base[l];
+    const int64_t out0 = a.res_off[l];
     const double total = a.total[l];
     for (int k = k0; k < k1; ++k) {
       const int64_t f0 = fo[k];
       const int n = (int)(fo[k + 1] - f0);
-      unsigned long long* out = a.ent + f0;
-      int written = 0;
-      bool done = false;
-      if (n <= kRegInst * 32) {
-        // ---- fast path: every instance lives in registers between the phases ----
-        double v[kRegInst];
-        int slot[kRegInst];
-        int ovf = 0;
-        int c = 0;  // occupied slots so far (warp-uniform)
+      const int64_t g0 = gl[k];
+      const int c = (int)(gl[k + 1] - g0);
+      if (c == 0) continue;
+      const int64_t dst = out0 + g0;
+      const int32_t* fa = b.frame_arc + f0;
+      const bool small = c <= kGroupCap;
+      int cnt = 0;          // groups opened in earlier chunks
+      double carry = 0.0;   // partial sum of the group left open by the previous chunk
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        // lanes past the end pose as heads so that the last real group closes
+        const unsigned int w = valid ? (unsigned int)__ldg(fa + i) : 0x80000000u;
+        const int e = (int)(w & 0x7fffffffu);
+        const bool head = (w >> 31) != 0;
+        double sum = valid ? __ldg(a.parc + e) : 0.0;
+        const unsigned int hm = __ballot_sync(0xffffffffu, head);
+        const unsigned int below = hm & lane_le;
+        const int seg_lo = below ? 31 - __clz(below) : 0;  // first lane of my group inside this chunk
 #pragma unroll
-        for (int r = 0; r < kRegInst; ++r) {
-          if (r * 32 < n) {
-            const int i = r * 32 + lane;
-            slot[r] = -1;
-            v[r] = 0.0;
-            bool claimed = false;
-            unsigned int h = 0;
-            if (i < n) {
-              int w;
-              v[r] = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
-              h = hash_word(w) & (kSlots - 1);
-              int probes = 0;
-              for (;; h = (h + 1) & (kSlots - 1)) {
-                const int old = atomicCAS(&key[h], -1, w);
-                if (old == -1) {
-                  claimed = true;
-                  break;
-                }
-                if (old == w) break;
-                if (++probes >= kSlots) {
-                  ovf = 1;
-                  break;
-                }
-              }
-              if (!ovf) {
-                slot[r] = (int)h;
-                atomicMax(&vmax[h], ord_up_f32(v[r]));
-              }
-            }
-            // append the newly claimed slots to the occupied list (no atomics)
-            const unsigned int bal = __ballot_sync(0xffffffffu, claimed);
-            if (claimed) list[c + __popc(bal & ((1u << lane) - 1u))] = (int)h;
-            c += __popc(bal);
-          } else {
-            slot[r] = -1;
-            v[r] = 0.0;
-          }
+        for (int d = 1; d < 32; d <<= 1) {
+          const double v = __shfl_up_sync(0xffffffffu, sum, d);
+          if (lane - d >= seg_lo) sum += v;
         }
-        const bool overflow = __any_sync(0xffffffffu, ovf);
-        __syncwarp();
-        if (!overflow) {
-#pragma unroll
-          for (int r = 0; r < kRegInst; ++r) {
-            if (slot[r] >= 0) {
-              const unsigned int mo = vmax[slot[r]];
-              const float mf = inv_ord_f32(mo);
-              if (mf > -INFINITY) {
-                // v - m' in double, the exponential in float (the output is float32)
-                const float t = __expf((float)(v[r] - (double)mf));
-                atomicAdd(&vsum[slot[r]], (unsigned long long)__float2ll_rn(t * (float)kFixScale));
-              }
-            }
-          }
-          __syncwarp();
+        if (!below) sum += carry;
+        // does my group end here?  (the next instance is a head, or the list ends)
+        unsigned int nh = __shfl_down_sync(0xffffffffu, (unsigned int)head, 1);
+        if (lane == 31) nh = (i + 1 < n) ? ((unsigned int)__ldg(fa + i + 1) >> 31) : 1u;
+        const bool is_end = valid && nh;
+        const int rank = cnt + __popc(below) - 1;
+        if (valid && head) {
+          const int word = __ldg(&a.b.out_rec[e].w);
+          if (small) gword[rank] = word;
+          else a.o_word[dst + rank] = word;
         }
-        if (!overflow) {
-          int np2 = 1;
-          while (np2 < c) np2 <<= 1;
-          for (int i = lane; i < np2; i += 32) {
-            unsigned long long sk = ~0ULL;
-            if (i < c) {
-              const int h = list[i];
-              const float mf = inv_ord_f32(vmax[h]);
-              double lse = neg_inf();
-              if (mf > -INFINITY) lse = (double)mf + (double)__logf((float)vsum[h] * (float)(1.0 / kFixScale));
-              const float f = (float)(lse - total) + 0.0f;
-              sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)key[h];
-            }
-            sortbuf[i] = sk;
-          }
-          __syncwarp();
-          warp_bitonic_sort(sortbuf, np2, lane);
-          for (int i = lane; i < c; i += 32) out[i] = sortbuf[i];
-          written = c;
-          done = true;
+        if (is_end) {
+          double r = sum;
+          if (!(sum >= 1e-280)) r = fmin(exact_group_logp(a, fa, i, total), -1e-300);
+          if (small) sortbuf[rank] = (unsigned long long)__double_as_longlong(r);
+          else a.o_logp[dst + rank] = group_logp(r);
         }
-        // reset the touched slots for the next frame
-        for (int i = lane; i < c; i += 32) {
-          const int h = list[i];
-          key[h] = -1;
-          vmax[h] = kEmptyMax;
-          vsum[h] = 0ULL;
-        }
-        __syncwarp();
+        const double last = __shfl_sync(0xffffffffu, sum, 31);
+        carry = (__ballot_sync(0xffffffffu, is_end) >> 31) ? 0.0 : last;
+        cnt += __popc(hm);
       }
-      // ---- slow path: word-hash partitions, values recomputed per phase, global sort ----
-      for (int P = 1; !done; P <<= 1) {
-        bool overflow = false;
-        written = 0;
-        for (int p = 0; p < P && !overflow; ++p) {
-          int ovf = 0;
-          for (int i = lane; i < n; i += 32) {
-            int w;
-            const double vv = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
-            const unsigned int h0 = hash_word(w);
-            if ((int)((h0 >> 8) & (unsigned)(P - 1)) != p) continue;
-            unsigned int h = h0 & (kSlots - 1);
-            int probes = 0;
-            for (;; h = (h + 1) & (kSlots - 1)) {
-              const int old = atomicCAS(&key[h], -1, w);
-              if (old == -1 || old == w) break;
-              if (++probes >= kSlots) {
-                ovf = 1;
-                break;
-              }
-            }
-            if (!ovf) atomicMax(&vmax[h], ord_up_f32(vv));
-          }
-          overflow = __any_sync(0xffffffffu, ovf);
-          __syncwarp();
-          if (!overflow) {
-            for (int i = lane; i < n; i += 32) {
-              int w;
-              const double vv = instance_value(a, __ldg(b.frame_arc + f0 + i), &w);
-              const unsigned int h0 = hash_word(w);
-              if ((int)((h0 >> 8) & (unsigned)(P - 1)) != p) continue;
-              unsigned int h = h0 & (kSlots - 1);
-              while (key[h] != w) h = (h + 1) & (kSlots - 1);
-              const float mf = inv_ord_f32(vmax[h]);
-              if (mf > -INFINITY)
-                atomicAdd(&vsum[h], (unsigned long long)__double2ll_rn(exp(vv - (double)mf) * kFixScale));
-            }
-            __syncwarp();
-            for (int base = 0; base < kSlots; base += 32) {
-              const int i = base + lane;
-              const int w = key[i];
-              unsigned long long sk = 0;
-              if (w != -1) {
-                const float mf = inv_ord_f32(vmax[i]);
-                double lse = neg_inf();
-                if (mf > -INFINITY) lse = (double)mf + log((double)vsum[i] * (1.0 / kFixScale));
-                const float f = (float)(lse - total) + 0.0f;
-                sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)w;
-              }
-              const unsigned int bal = __ballot_sync(0xffffffffu, w != -1);
-              if (w != -1) out[written + __popc(bal & ((1u << lane) - 1u))] = sk;
-              written += __popc(bal);
-            }
-          }
-          __syncwarp();
-          for (int i = lane; i < kSlots; i += 32) {
-            key[i] = -1;
-            vmax[i] = kEmptyMax;
-            vsum[i] = 0ULL;
-          }
-          __syncwarp();
-        }
-        if (!overflow) {
-          warp_sort_global(out, written, lane);
-          done = true;
-        }
-      }
-      if (lane == 0) a.frame_cnt[b.fr_base[l] + k] = written;
       __syncwarp();
+      if (small) {
+        int np2 = 1;
+        while (np2 < c) np2 <<= 1;
+        for (int g = lane; g < np2; g += 32) {
+          unsigned long long sk = ~0ULL;
+          if (g < c) {
+            const float f = group_logp(__longlong_as_double((long long)sortbuf[g]));
+            sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)gword[g];
+          }
+          sortbuf[g] = sk;
+        }
+        __syncwarp();
+        warp_bitonic_sort(sortbuf, np2, lane);
+        for (int g = lane; g < c; g += 32) {
+          const unsigned long long sk = sortbuf[g];
+          a.o_frame[dst + g] = k;
+          a.o_word[dst + g] = (int32_t)(sk & 0xffffffffu);
+          a.o_logp[dst + g] = inv_ord_f32(~(unsigned int)(sk >> 32));
+        }
+        __syncwarp();
+      } else {
+        for (int g = lane; g < c; g += 32) a.o_frame[dst + g] = k;
+        __syncwarp();
+        warp_sort_rows_global(a.o_logp + dst, a.o_word + dst, c, lane);
+      }
     }
   }
 }
 
-// One CTA per lattice: scan the per-frame counts into lattice-local dense offsets.
-__global__ void __launch_bounds__(256) k_frame_scan(FrameArgs a, int64_t* frame_out_local) {
+// ----------------------------------------------------------- pack-time build ---
+struct GroupArgs {
+  BatchView b;
+  int bits_label;
+  const int64_t* inst_base;  // [L+1] first instance of each lattice
+  unsigned long long* key;   // sort input: (frame << bits_label) | word
+  unsigned int* val;         //             out-order arc id
+  const unsigned long long *key_a, *key_b;
+  const unsigned int *val_a, *val_b;
+  const unsigned char* where;
+  int32_t* frame_arc;
+  int32_t* frame_cnt;        // per frame slot: groups in the frame
+  const int32_t* item_base;
+  int num_items;
+  int64_t* gloc;
+  int32_t* lat_cnt;
+};
+
+__device__ __forceinline__ int arc_frames(const BatchView& b, int e, int T, int* first) {
+  const int4 r = b.out_rec[e];
+  if (r.w == 0) return 0;
+  const int fa = max(b.time[b.out_src[e]], 0), fb = min(b.time[r.x], T);
+  *first = fa;
+  return fb > fa ? fb - fa : 0;
+}
+
+// One CTA per lattice: exclusive scan of the arcs' frame counts, then the
+// (frame, word) -> arc instances in arc order (so the stable sort leaves every
+// group in arc order, whatever order the packer's frame CSR was filled in).
+__global__ void __launch_bounds__(256) k_fg_emit(GroupArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
+  const int l = blockIdx.x;
+  const BatchView& b = a.b;
+  const int e0 = b.e_off[l], e1 = b.e_off[l + 1];
+  const int T = b.fr_base[l + 1] - b.fr_base[l] - 1;
+  const int64_t base = a.inst_base[l];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int tile = e0; tile < e1; tile += 256) {
+    const int e = tile + tid;
+    int first = 0;
+    const int cnt = e < e1 ? arc_frames(b, e, T, &first) : 0;
+    int x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    int add = carry_s;
+    for (int w = 0; w < warp; ++w) add += warp_sum[w];
+    const int off = add + x - cnt;
+    if (cnt > 0) {
+      const unsigned long long word = (unsigned long long)(unsigned int)b.out_rec[e].w;
+      for (int q = 0; q < cnt; ++q) {
+        a.key[base + off + q] = ((unsigned long long)(first + q) << a.bits_label) | word;
+        a.val[base + off + q] = (unsigned int)e;
+      }
+    }
+    __syncthreads();
+    if (tid == 255) carry_s = add + x;
+    __syncthreads();
+  }
+}
+
+// one warp per run of frames: sorted instances -> frame_arc with head bits, groups per frame
+__global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BatchView& b = a.b;
+  for (int item = blockIdx.x * 8 + warp; item < a.num_items; item += gridDim.x * 8) {
+    int lo = 0, hi = b.L - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (a.item_base[mid] <= item) lo = mid;
+      else hi = mid - 1;
+    }
+    const int l = lo;
+    const int T = b.fr_base[l + 1] - b.fr_base[l] - 1;
+    const int k0 = (item - a.item_base[l]) * kFramesPerItem;
+    const int k1 = min(T, k0 + kFramesPerItem);
+    const unsigned long long* key = a.where[l] ? a.key_b : a.key_a;
+    const unsigned int* val = a.where[l] ? a.val_b : a.val_a;
+    for (int k = k0; k < k1; ++k) {
+      const int fs = b.fr_base[l] + k;
+      const int64_t f0 = b.fr_off[fs], f1 = b.fr_off[fs + 1];
+      int groups = 0;
+      for (int64_t i = f0 + lane; i < f1; i += 32) {
+        const unsigned long long kk = key[i];
+        const bool head = i == f0 || key[i - 1] != kk;
+        a.frame_arc[i] = (int32_t)(val[i] | (head ? 0x80000000u : 0u));
+        groups += head ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) groups += __shfl_xor_sync(0xffffffffu, groups, o);
+      if (lane == 0) a.frame_cnt[fs] = groups;
+    }
+  }
+}
+
+// One CTA per lattice: scan the per-frame group counts into lattice-local output
+// rows (T + 1 entries: the last one is the lattice's row count).
+__global__ void __launch_bounds__(256) k_fg_scan(GroupArgs a) {
+  __shared__ int warp_sum[8];
+  __shared__ long long carry_s;
   const int l = blockIdx.x;
   const int f0 = a.b.fr_base[l], T = a.b.fr_base[l + 1] - f0 - 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -345,17 +372,20 @@ __global__ void __launch_bounds__(256) k_frame_scan(FrameArgs a, int64_t* frame_
     }
     if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    int add = carry_s;
+    long long add = carry_s;
     for (int w = 0; w < warp; ++w) add += warp_sum[w];
-    if (k < T) frame_out_local[f0 + k] = add + x - c;
+    if (k < T) a.gloc[f0 + k] = add + x - c;
     __syncthreads();
     if (tid == 255) carry_s = add + x;
     __syncthreads();
   }
-  if (tid == 0) a.lat_cnt[l] = carry_s;
+  if (tid == 0) {
+    a.gloc[f0 + T] = carry_s;
+    a.lat_cnt[l] = (int32_t)carry_s;
+  }
 }
 
-__global__ void __launch_bounds__(1024) k_frame_latscan(const int32_t* cnt, int L, int64_t* off) {
+__global__ void __launch_bounds__(1024) k_fg_latscan(const int32_t* cnt, int L, int64_t* off) {
   __shared__ long long warp_sum[32];
   __shared__ long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -382,38 +412,141 @@ __global__ void __launch_bounds__(1024) k_frame_latscan(const int32_t* cnt, int 
   if (tid == 0) off[L] = carry_s;
 }
 
-// dense (frame, word, logp) rows: one warp per (lattice, frame run)
-__global__ void __launch_bounds__(256) k_frame_compact(FrameArgs a, const int64_t* frame_out_local) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const BatchView& b = a.b;
-  for (int item = blockIdx.x * 8 + warp; item < a.num_items; item += gridDim.x * 8) {
-    int lo = 0, hi = b.L - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (a.item_base[mid] <= item) lo = mid;
-      else hi = mid - 1;
-    }
-    const int l = lo;
-    const int T = b.fr_base[l + 1] - b.fr_base[l] - 1;
-    const int k0 = (item - a.item_base[l]) * kFramesPerItem;
-    const int k1 = min(T, k0 + kFramesPerItem);
-    const int64_t base = a.res_off[l];
-    for (int k = k0; k < k1; ++k) {
-      const int fs = b.fr_base[l] + k;
-      const int n = a.frame_cnt[fs];
-      const unsigned long long* src = a.ent + b.fr_off[fs];
-      const int64_t dst = base + frame_out_local[fs];
-      for (int i = lane; i < n; i += 32) {
-        const unsigned long long sk = src[i];
-        a.o_frame[dst + i] = k;
-        a.o_word[dst + i] = (int32_t)(sk & 0xffffffffu);
-        a.o_logp[dst + i] = inv_ord_f32(~(unsigned int)(sk >> 32));
-      }
-    }
-  }
+int bits_for(int64_t maxv) {
+  int b = 1;
+  while (b < 63 && ((int64_t)1 << b) <= maxv) ++b;
+  return b;
 }
 
 }  // namespace
+
+// Called by both packers once the packed arrays, state times and the frame CSR
+// offsets (fr_base, fr_off) are on the device.
+int build_frame_groups(klu_ctx* c) {
+  const int32_t L = c->L;
+  c->h_frame_res_off.assign(L + 1, 0);
+  c->fr_items = 0;
+  if (L == 0) return 0;
+  bool any_bad_times = false;
+  for (int32_t l = 0; l < L; ++l) any_bad_times |= !c->h_times_ok[l];
+  const int64_t N = c->frame_entries;
+  const int64_t F = c->h_fr_base[L];
+  std::vector<int32_t> item_base(L + 1, 0);
+  std::vector<int64_t> inst_base(L + 1, 0);
+  std::vector<int32_t> inst_cnt(L, 0);
+  for (int32_t l = 0; l < L; ++l) {
+    item_base[l + 1] = item_base[l] + (c->h_num_frames[l] + kFramesPerItem - 1) / kFramesPerItem;
+    inst_base[l + 1] = inst_base[l] + c->h_cap_frame[l];
+    if (c->h_cap_frame[l] >= ((int64_t)1 << 31)) {
+      set_error("lattice " + std::to_string(l) + ": more than 2^31 arc x frame instances");
+      return 1;
+    }
+    inst_cnt[l] = (int32_t)c->h_cap_frame[l];
+  }
+  c->fr_items = item_base[L];
+  KLU_TRY(c->d_fr_item.reserve(4 * (size_t)(L + 1)));
+  KLU_TRY(c->d_fr_gloc.reserve(8 * (size_t)std::max<int64_t>(F, 1)));
+  KLU_TRY(c->d_fr_res_off.reserve(8 * (size_t)(L + 1)));
+  KLU_CUDA(cudaMemcpyAsync(c->d_fr_item.p, item_base.data(), 4 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
+  KLU_CUDA(cudaMemsetAsync(c->d_fr_gloc.p, 0, 8 * (size_t)std::max<int64_t>(F, 1), c->stream));
+  KLU_CUDA(cudaMemsetAsync(c->d_fr_res_off.p, 0, 8 * (size_t)(L + 1), c->stream));
+  if (N == 0 || any_bad_times) {  // nothing to index (run_frame_post rejects inconsistent times)
+    KLU_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  const int bits_label = bits_for(c->max_label), bits_time = bits_for(c->max_time);
+  if (bits_label + bits_time > 62) {
+    set_error("frame index key does not fit 62 bits (labels/times too large)");
+    return 1;
+  }
+  // scratch (released afterwards: 28 bytes per instance would otherwise stay resident)
+  DevBuf key_a, key_b, val_a, val_b, misc;
+  auto release_all = [&]() {
+    key_a.release();
+    key_b.release();
+    val_a.release();
+    val_b.release();
+    misc.release();
+  };
+  int rc = 0;
+  do {
+    if ((rc = key_a.reserve(8 * (size_t)N)) || (rc = key_b.reserve(8 * (size_t)N)) ||
+        (rc = val_a.reserve(4 * (size_t)N)) || (rc = val_b.reserve(4 * (size_t)N)) ||
+        (rc = misc.reserve(8 * (size_t)(L + 1) + 4 * (size_t)L + 4 * (size_t)L + (size_t)L + 4 * (size_t)F + 64)))
+      break;
+    char* mp = misc.as<char>();
+    int64_t* d_inst_base = reinterpret_cast<int64_t*>(mp);
+    int32_t* d_inst_cnt = reinterpret_cast<int32_t*>(mp + 8 * (size_t)(L + 1));
+    int32_t* d_lat_cnt = d_inst_cnt + L;
+    int32_t* d_frame_cnt = d_lat_cnt + L;
+    unsigned char* d_where = reinterpret_cast<unsigned char*>(d_frame_cnt + F);
+    cudaMemcpyAsync(d_inst_base, inst_base.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_inst_cnt, inst_cnt.data(), 4 * (size_t)L, cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(d_frame_cnt, 0, 4 * (size_t)F, c->stream);
+    if ((rc = c->d_frame_arc.reserve(4 * (size_t)N))) break;
+    GroupArgs a;
+    a.b = c->view();
+    a.bits_label = bits_label;
+    a.inst_base = d_inst_base;
+    a.key = key_a.as<unsigned long long>();
+    a.val = val_a.as<unsigned int>();
+    a.key_a = key_a.as<unsigned long long>();
+    a.key_b = key_b.as<unsigned long long>();
+    a.val_a = val_a.as<unsigned int>();
+    a.val_b = val_b.as<unsigned int>();
+    a.where = d_where;
+    a.frame_arc = c->d_frame_arc.as<int32_t>();
+    a.frame_cnt = d_frame_cnt;
+    a.item_base = c->d_fr_item.as<int32_t>();
+    a.num_items = c->fr_items;
+    a.gloc = c->d_fr_gloc.as<int64_t>();
+    a.lat_cnt = d_lat_cnt;
+    {
+      KLU_LAUNCH(c, "k_fg_emit");
+      k_fg_emit<<<L, 256, 0, c->stream>>>(a);
+    }
+    if ((rc = check_launch("k_fg_emit"))) break;
+    SegSortArgs ss;
+    ss.seg_base = d_inst_base;
+    ss.seg_cnt = d_inst_cnt;
+    ss.key_a = key_a.as<unsigned long long>();
+    ss.val_a = val_a.as<unsigned int>();
+    ss.key_b = key_b.as<unsigned long long>();
+    ss.val_b = val_b.as<unsigned int>();
+    ss.where = d_where;
+    ss.lo_bit = 0;
+    ss.hi_bit = bits_label + bits_time;
+    {
+      KLU_LAUNCH(c, "k_seg_radix_sort");
+      k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+    }
+    if ((rc = check_launch("k_seg_radix_sort(frame groups)"))) break;
+    if (a.num_items > 0) {
+      KLU_LAUNCH(c, "k_fg_heads");
+      k_fg_heads<<<std::max(1, std::min((a.num_items + 7) / 8, c->num_sms * 32)), 256, 0, c->stream>>>(a);
+    }
+    if ((rc = check_launch("k_fg_heads"))) break;
+    {
+      KLU_LAUNCH(c, "k_fg_scan");
+      k_fg_scan<<<L, 256, 0, c->stream>>>(a);
+    }
+    if ((rc = check_launch("k_fg_scan"))) break;
+    {
+      KLU_LAUNCH(c, "k_fg_latscan");
+      k_fg_latscan<<<1, 1024, 0, c->stream>>>(d_lat_cnt, L, c->d_fr_res_off.as<int64_t>());
+    }
+    if ((rc = check_launch("k_fg_latscan"))) break;
+    if (cudaMemcpyAsync(c->h_frame_res_off.data(), c->d_fr_res_off.p, 8 * (size_t)(L + 1), cudaMemcpyDeviceToHost,
+                        c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error(std::string("build_frame_groups: ") + cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  release_all();
+  return rc;
+}
 
 int run_frame_post(klu_ctx* c, const klu_opts* o) {
   const int32_t L = c->L;
@@ -424,50 +557,40 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
     }
   CostParams cp = make_cost_params(o, false);
   KLU_TRY(run_log_sweeps(c, cp, false, 0.f));
-  c->h_res_off.assign(L + 1, 0);
-  c->last_entries = 0;
+  c->h_res_off = c->h_frame_res_off;
+  c->h_res_off.resize(L + 1, 0);
+  c->last_entries = L ? c->h_res_off[L] : 0;
   if (L == 0) return 0;
-  const int64_t N = std::max<int64_t>(c->frame_entries, 1);
-  const int64_t F = std::max<int64_t>(c->h_fr_base[L], 1);
-  std::vector<int32_t> item_base(L + 1, 0);
-  for (int32_t l = 0; l < L; ++l)
-    item_base[l + 1] = item_base[l] + (c->h_num_frames[l] + kFramesPerItem - 1) / kFramesPerItem;
-  enum { F_ITEM = 0, F_ENT, F_CNT, F_FOUT, F_LCNT, F_ARCV };
-  KLU_TRY(c->d_scratch[F_ARCV].reserve(16 * (size_t)std::max<int64_t>(c->E, 1)));
-  KLU_TRY(c->d_scratch[F_ITEM].reserve(4 * (size_t)(L + 1)));
-  KLU_TRY(c->d_scratch[F_ENT].reserve(8 * (size_t)N));
-  KLU_TRY(c->d_scratch[F_CNT].reserve(4 * (size_t)F));
-  KLU_TRY(c->d_scratch[F_FOUT].reserve(8 * (size_t)F));
-  KLU_TRY(c->d_scratch[F_LCNT].reserve(4 * (size_t)L));
+  const int64_t N = std::max<int64_t>(c->last_entries, 1);
+  KLU_TRY(c->d_scratch[0].reserve(8 * (size_t)std::max<int64_t>(c->E, 1)));
   KLU_TRY(c->d_res[5].reserve(8 * (size_t)(L + 1)));
   KLU_TRY(c->d_res[0].reserve(4 * (size_t)N));
   KLU_TRY(c->d_res[1].reserve(4 * (size_t)N));
   KLU_TRY(c->d_res[4].reserve(4 * (size_t)N));
-  KLU_CUDA(cudaMemcpyAsync(c->d_scratch[F_ITEM].p, item_base.data(), 4 * (size_t)(L + 1), cudaMemcpyHostToDevice,
-                           c->stream));
-  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  KLU_CUDA(cudaMemcpyAsync(c->d_res[5].p, c->d_fr_res_off.p, 8 * (size_t)(L + 1), cudaMemcpyDeviceToDevice, c->stream));
+  if (c->last_entries == 0) return 0;
   FrameArgs a;
   a.b = c->view();
   a.cp = make_cost_params(o, true);  // the arc term is (float)(g + a)
   a.alpha = c->d_alpha.as<double>();
   a.beta = c->d_beta.as<double>();
   a.total = c->d_total.as<double>();
-  a.arcv = c->d_scratch[F_ARCV].as<int4>();
-  a.item_base = c->d_scratch[F_ITEM].as<int32_t>();
-  a.num_items = item_base[L];
-  a.ent = c->d_scratch[F_ENT].as<unsigned long long>();
-  a.frame_cnt = c->d_scratch[F_CNT].as<int32_t>();
-  a.frame_out = nullptr;
+  a.parc = c->d_scratch[0].as<double>();
+  a.item_base = c->d_fr_item.as<int32_t>();
+  a.num_items = c->fr_items;
+  a.gloc = c->d_fr_gloc.as<int64_t>();
+  a.res_off = c->d_fr_res_off.as<int64_t>();
   a.o_frame = c->d_res[0].as<int32_t>();
   a.o_word = c->d_res[1].as<int32_t>();
   a.o_logp = c->d_res[4].as<float>();
-  a.lat_cnt = c->d_scratch[F_LCNT].as<int32_t>();
-  a.res_off = c->d_res[5].as<int64_t>();
   {
-    KLU_LAUNCH(c, "k_arc_values");
-    k_arc_values<<<c->num_sms * 8, 256, 0, c->stream>>>(a);
+    int64_t max_arcs = 0;
+    for (int32_t l = 0; l < L; ++l) max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
+    const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
+    KLU_LAUNCH(c, "k_arc_post");
+    k_arc_post<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
   }
-  KLU_TRY(check_launch("k_arc_values"));
+  KLU_TRY(check_launch("k_arc_post"));
   if (a.num_items > 0) {
     const int grid = std::max(1, std::min((a.num_items + kFrameWarps - 1) / kFrameWarps, c->num_sms * 64));
     {
@@ -476,25 +599,6 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
     }
     KLU_TRY(check_launch("k_frame_post"));
   }
-  {
-    KLU_LAUNCH(c, "k_frame_scan");
-    k_frame_scan<<<L, 256, 0, c->stream>>>(a, c->d_scratch[F_FOUT].as<int64_t>());
-  }
-  KLU_TRY(check_launch("k_frame_scan"));
-  {
-    KLU_LAUNCH(c, "k_scan_counts");
-    k_frame_latscan<<<1, 1024, 0, c->stream>>>(a.lat_cnt, L, a.res_off);
-  }
-  KLU_TRY(check_launch("k_frame_latscan"));
-  if (a.num_items > 0) {
-    const int grid = std::max(1, std::min((a.num_items + 7) / 8, c->num_sms * 32));
-    {
-      KLU_LAUNCH(c, "k_frame_compact");
-      k_frame_compact<<<grid, 256, 0, c->stream>>>(a, c->d_scratch[F_FOUT].as<int64_t>());
-    }
-    KLU_TRY(check_launch("k_frame_compact"));
-  }
-  c->last_entries = -1;
   return 0;
 }
 

@@ -720,14 +720,9 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
                                                             a.fr_off + c->h_fr_base[L]);
   }
   KLU_TRY(check_launch("k_gp_add_base(frames)"));
-  KLU_CUDA(cudaMemsetAsync(a.fr_cnt, 0, 4 * F1, c->stream));
-  {
-    KLU_LAUNCH(c, "k_gp_frames");
-    k_gp_frames<1><<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
-  }
-  KLU_TRY(check_launch("k_gp_frames(fill)"));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // host-side vectors used by async copies die here
-  return 0;
+  // the frame lists themselves (sorted by word, with group heads) are built from the packed arcs
+  return build_frame_groups(c);
 }
 
 }  // namespace klu

@@ -396,7 +396,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(up(c->d_fr_off, fr_off.data(), fr_off.size() * 8));
   KLU_TRY(up(c->d_frame_arc, frame_arc.data(), frame_arc.size() * 4));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // staging vectors die here
-  return 0;
+  return build_frame_groups(c);
 }
 
 }  // namespace klu
