@@ -50,6 +50,7 @@ struct FrameArgs {
   int num_items;
   const int64_t* gloc;       // per frame slot: lattice-local first output row (T+1 per lattice)
   const int64_t* res_off;    // [L+1] first output row of each lattice
+  const int32_t* gwords;     // word of every (frame, word) group, in pre-order row order (static)
   int32_t *o_frame, *o_word;
   float* o_logp;
 };
@@ -101,25 +102,65 @@ __device__ __noinline__ double exact_group_logp(const FrameArgs& a, const int32_
   return (m + log(s)) - total;
 }
 
-// warp-wide bitonic sort of n_pow2 <= kGroupCap keys in shared memory (ascending);
-// every lane owns whole compare-exchange pairs, so no lane idles inside a stage
-__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int n_pow2, int lane) {
-  const int half = n_pow2 >> 1;
-  for (int k = 2; k <= n_pow2; k <<= 1) {
+// Warp-wide bitonic sort of N keys in shared memory (ascending), N a compile-time
+// power of two: every stage is unrolled, so the pair indices are a couple of bit
+// operations on the lane id.  For N >= 128 a lane handles TWO adjacent compare-
+// exchange pairs per step through 16-byte shared-memory accesses.
+template <int N>
+__device__ __forceinline__ void warp_bitonic_fixed(unsigned long long* keys, int lane) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = lane; p < half; p += 32) {
-        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-        const int q = i | j;
-        const unsigned long long x = keys[i], y = keys[q];
-        const bool up = (i & k) == 0;
-        if ((x > y) == up) {
-          keys[i] = y;
-          keys[q] = x;
+      if (N >= 128 && j >= 2) {
+#pragma unroll
+        for (int t = 0; t < N / 128; ++t) {
+          const int p0 = (lane + 32 * t) << 1;  // even pair index: pairs p0 and p0 + 1 sit side by side
+          const int i = ((p0 & ~(j - 1)) << 1) | (p0 & (j - 1));
+          const int q = i | j;
+          const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(keys + i);
+          const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(keys + q);
+          const bool up = (i & k) == 0;
+          if ((x.x > y.x) == up) {
+            keys[i] = y.x;
+            keys[q] = x.x;
+          }
+          if ((x.y > y.y) == up) {
+            keys[i + 1] = y.y;
+            keys[q + 1] = x.y;
+          }
+        }
+      } else if (N >= 128) {  // j == 1: the pair is one aligned 16-byte word
+#pragma unroll
+        for (int t = 0; t < N / 64; ++t) {
+          const int i = (lane + 32 * t) << 1;
+          const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(keys + i);
+          const bool up = (i & k) == 0;
+          if ((x.x > x.y) == up) *reinterpret_cast<ulonglong2*>(keys + i) = make_ulonglong2(x.y, x.x);
+        }
+      } else {
+        if (lane < N / 2) {
+          const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
+          const int q = i | j;
+          const unsigned long long x = keys[i], y = keys[q];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            keys[i] = y;
+            keys[q] = x;
+          }
         }
       }
       __syncwarp();
     }
   }
+}
+
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int n_pow2, int lane) {
+  if (n_pow2 <= 1) return;
+  if (n_pow2 <= 32) warp_bitonic_fixed<32>(keys, lane);  // callers pad to 32 with ~0
+  else if (n_pow2 == 64) warp_bitonic_fixed<64>(keys, lane);
+  else if (n_pow2 == 128) warp_bitonic_fixed<128>(keys, lane);
+  else warp_bitonic_fixed<256>(keys, lane);
 }
 
 // slow path: odd-even transposition sort of a frame's (logp, word) rows in global memory
@@ -147,12 +188,10 @@ __device__ __forceinline__ float group_logp(double sum_or_logp) {
   return (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
 }
 
-__global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(const __grid_constant__ FrameArgs a) {
-  __shared__ unsigned long long s_sort[kFrameWarps][kGroupCap];  // group sums (f64 bits), then the order keys
-  __shared__ int s_word[kFrameWarps][kGroupCap];
+__global__ void __launch_bounds__(kFrameWarps * 32, 8) k_frame_post(const __grid_constant__ FrameArgs a) {
+  __shared__ __align__(16) unsigned long long s_sort[kFrameWarps][kGroupCap];  // group sums (f64 bits), then order keys
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* sortbuf = s_sort[warp];
-  int* gword = s_word[warp];
   const BatchView& b = a.b;
   const unsigned int lane_le = 0xffffffffu >> (31 - lane);
   for (int item = blockIdx.x * kFrameWarps + warp; item < a.num_items; item += gridDim.x * kFrameWarps) {
@@ -182,14 +221,20 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(const __grid_co
       const bool small = c <= kGroupCap;
       int cnt = 0;          // groups opened in earlier chunks
       double carry = 0.0;   // partial sum of the group left open by the previous chunk
+      // lanes past the end pose as heads so that the last real group closes
+      unsigned int w_next = lane < n ? (unsigned int)__ldg(fa + lane) : 0xffffffffu;
+      double p_next = lane < n ? __ldg(a.parc + (w_next & 0x7fffffffu)) : 0.0;
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         const bool valid = i < n;
-        // lanes past the end pose as heads so that the last real group closes
-        const unsigned int w = valid ? (unsigned int)__ldg(fa + i) : 0x80000000u;
-        const int e = (int)(w & 0x7fffffffu);
+        const unsigned int w = w_next;
+        double sum = p_next;
+        {  // the next chunk's loads go out before this chunk's shuffles
+          const int in = i + 32;
+          w_next = in < n ? (unsigned int)__ldg(fa + in) : 0xffffffffu;
+          p_next = in < n ? __ldg(a.parc + (w_next & 0x7fffffffu)) : 0.0;
+        }
         const bool head = (w >> 31) != 0;
-        double sum = valid ? __ldg(a.parc + e) : 0.0;
         const unsigned int hm = __ballot_sync(0xffffffffu, head);
         const unsigned int below = hm & lane_le;
         const int seg_lo = below ? 31 - __clz(below) : 0;  // first lane of my group inside this chunk
@@ -200,15 +245,9 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(const __grid_co
         }
         if (!below) sum += carry;
         // does my group end here?  (the next instance is a head, or the list ends)
-        unsigned int nh = __shfl_down_sync(0xffffffffu, (unsigned int)head, 1);
-        if (lane == 31) nh = (i + 1 < n) ? ((unsigned int)__ldg(fa + i + 1) >> 31) : 1u;
-        const bool is_end = valid && nh;
+        const unsigned int nh0 = __shfl_sync(0xffffffffu, w_next, 0) >> 31;
+        const bool is_end = valid && (lane == 31 ? nh0 != 0 : ((hm >> (lane + 1)) & 1u) != 0);
         const int rank = cnt + __popc(below) - 1;
-        if (valid && head) {
-          const int word = __ldg(&a.b.out_rec[e].w);
-          if (small) gword[rank] = word;
-          else a.o_word[dst + rank] = word;
-        }
         if (is_end) {
           double r = sum;
           if (!(sum >= 1e-280)) r = fmin(exact_group_logp(a, fa, i, total), -1e-300);
@@ -216,18 +255,18 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(const __grid_co
           else a.o_logp[dst + rank] = group_logp(r);
         }
         const double last = __shfl_sync(0xffffffffu, sum, 31);
-        carry = (__ballot_sync(0xffffffffu, is_end) >> 31) ? 0.0 : last;
+        carry = (valid && lane == 31 && !is_end) ? last : 0.0;
+        carry = __shfl_sync(0xffffffffu, carry, 31);
         cnt += __popc(hm);
       }
       __syncwarp();
       if (small) {
-        int np2 = 1;
-        while (np2 < c) np2 <<= 1;
+        const int np2 = c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : 256));
         for (int g = lane; g < np2; g += 32) {
           unsigned long long sk = ~0ULL;
           if (g < c) {
             const float f = group_logp(__longlong_as_double((long long)sortbuf[g]));
-            sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)gword[g];
+            sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)__ldg(a.gwords + dst + g);
           }
           sortbuf[g] = sk;
         }
@@ -241,7 +280,10 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_post(const __grid_co
         }
         __syncwarp();
       } else {
-        for (int g = lane; g < c; g += 32) a.o_frame[dst + g] = k;
+        for (int g = lane; g < c; g += 32) {
+          a.o_frame[dst + g] = k;
+          a.o_word[dst + g] = __ldg(a.gwords + dst + g);
+        }
         __syncwarp();
         warp_sort_rows_global(a.o_logp + dst, a.o_word + dst, c, lane);
       }
@@ -265,6 +307,8 @@ struct GroupArgs {
   int num_items;
   int64_t* gloc;
   int32_t* lat_cnt;
+  const int64_t* res_off;
+  int32_t* gwords;
 };
 
 __device__ __forceinline__ int arc_frames(const BatchView& b, int e, int T, int* first) {
@@ -317,7 +361,10 @@ __global__ void __launch_bounds__(256) k_fg_emit(GroupArgs a) {
   }
 }
 
-// one warp per run of frames: sorted instances -> frame_arc with head bits, groups per frame
+// one warp per run of frames.  WORDS == false: sorted instances -> frame_arc with head
+// bits, groups per frame.  WORDS == true (after the scans): the word of every group,
+// in output-row order.
+template <bool WORDS>
 __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BatchView& b = a.b;
@@ -334,19 +381,28 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
     const int k1 = min(T, k0 + kFramesPerItem);
     const unsigned long long* key = a.where[l] ? a.key_b : a.key_a;
     const unsigned int* val = a.where[l] ? a.val_b : a.val_a;
+    const unsigned long long label_mask = (1ULL << a.bits_label) - 1ULL;
     for (int k = k0; k < k1; ++k) {
       const int fs = b.fr_base[l] + k;
       const int64_t f0 = b.fr_off[fs], f1 = b.fr_off[fs + 1];
       int groups = 0;
-      for (int64_t i = f0 + lane; i < f1; i += 32) {
-        const unsigned long long kk = key[i];
-        const bool head = i == f0 || key[i - 1] != kk;
-        a.frame_arc[i] = (int32_t)(val[i] | (head ? 0x80000000u : 0u));
-        groups += head ? 1 : 0;
+      for (int64_t i0 = f0; i0 < f1; i0 += 32) {
+        const int64_t i = i0 + lane;
+        unsigned long long kk = 0;
+        bool head = false;
+        if (i < f1) {
+          kk = key[i];
+          head = i == f0 || key[i - 1] != kk;
+        }
+        const unsigned int hm = __ballot_sync(0xffffffffu, head);
+        if (!WORDS) {
+          if (i < f1) a.frame_arc[i] = (int32_t)(val[i] | (head ? 0x80000000u : 0u));
+        } else if (head) {
+          a.gwords[a.res_off[l] + a.gloc[fs] + groups + __popc(hm & ((1u << lane) - 1u))] = (int32_t)(kk & label_mask);
+        }
+        groups += __popc(hm);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) groups += __shfl_xor_sync(0xffffffffu, groups, o);
-      if (lane == 0) a.frame_cnt[fs] = groups;
+      if (!WORDS && lane == 0) a.frame_cnt[fs] = groups;
     }
   }
 }
@@ -521,9 +577,12 @@ int build_frame_groups(klu_ctx* c) {
       k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
     }
     if ((rc = check_launch("k_seg_radix_sort(frame groups)"))) break;
+    a.res_off = c->d_fr_res_off.as<int64_t>();
+    a.gwords = nullptr;
+    const int hgrid = std::max(1, std::min((a.num_items + 7) / 8, c->num_sms * 32));
     if (a.num_items > 0) {
       KLU_LAUNCH(c, "k_fg_heads");
-      k_fg_heads<<<std::max(1, std::min((a.num_items + 7) / 8, c->num_sms * 32)), 256, 0, c->stream>>>(a);
+      k_fg_heads<false><<<hgrid, 256, 0, c->stream>>>(a);
     }
     if ((rc = check_launch("k_fg_heads"))) break;
     {
@@ -541,7 +600,15 @@ int build_frame_groups(klu_ctx* c) {
         cudaStreamSynchronize(c->stream) != cudaSuccess) {
       set_error(std::string("build_frame_groups: ") + cudaGetErrorString(cudaGetLastError()));
       rc = 1;
+      break;
     }
+    if ((rc = c->d_fr_gword.reserve(4 * (size_t)std::max<int64_t>(c->h_frame_res_off[L], 1)))) break;
+    a.gwords = c->d_fr_gword.as<int32_t>();
+    if (a.num_items > 0) {
+      KLU_LAUNCH(c, "k_fg_words");
+      k_fg_heads<true><<<hgrid, 256, 0, c->stream>>>(a);
+    }
+    if ((rc = check_launch("k_fg_words"))) break;
   } while (0);
   cudaStreamSynchronize(c->stream);
   release_all();
@@ -580,6 +647,7 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   a.num_items = c->fr_items;
   a.gloc = c->d_fr_gloc.as<int64_t>();
   a.res_off = c->d_fr_res_off.as<int64_t>();
+  a.gwords = c->d_fr_gword.as<int32_t>();
   a.o_frame = c->d_res[0].as<int32_t>();
   a.o_word = c->d_res[1].as<int32_t>();
   a.o_logp = c->d_res[4].as<float>();
