@@ -47,7 +47,11 @@ ALGO = {
     "k_arc_post": dict(arc=28.0, state=16.0, entry=0.0),
     # frame-synchronous group-by + order: every arc x frame instance reads its arc id (4 B)
     # and the arc's posterior (8 B); every (frame, word, logp) row is written once (12 B)
-    "k_frame_post": dict(arc=0.0, state=0.0, entry=12.0, inst=12.0),
+    # group sums: every arc x frame instance reads its arc id (4 B) and the arc's posterior
+    # (8 B); per group 4 B offset read + 4 B log-posterior written
+    "k_group_post": dict(arc=0.0, state=0.0, entry=8.0, inst=12.0),
+    # per-frame ordering: 4 B logp + 4 B word read, (frame, word, logp) row written
+    "k_frame_order": dict(arc=0.0, state=0.0, entry=20.0),
 }
 
 

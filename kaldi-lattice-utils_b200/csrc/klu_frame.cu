@@ -10,20 +10,19 @@
 // So klu_load() builds that structure ONCE per batch (build_frame_groups): the
 // arc x frame instances of a lattice sorted by (frame, word, arc), a head bit on
 // the first instance of every group, and the dense output offset of every frame.
-// A run is then two kernels:
-//   k_arc_post    p[e] = exp(fw[u] + bw[v] - cost - total): the arc's posterior,
-//                 once per arc (f64; exp(-700) ~ 1e-304 is the underflow horizon);
-//   k_frame_post  one warp per run of frames: streams the frame's instance list
-//                 (coalesced 4-byte ids, 8-byte gathers of p that hit L1/L2 because
-//                 neighbouring frames share arcs), adds the posteriors of each
-//                 group with a segmented warp scan (fixed shuffle tree, so the sum
-//                 is order-deterministic), takes log(sum) per group, orders the
-//                 frame's rows in shared memory (bitonic, key = ~ordered float
-//                 bits << 32 | word) and writes them straight to their final place
-//                 in the dense (frame, word, logp) table.
+// A run is then three kernels:
+//   k_arc_post     p[e] = exp(fw[u] + bw[v] - cost - total): the arc's posterior,
+//                  once per arc (f64; exp(-700) ~ 1e-304 is the underflow horizon);
+//   k_group_post   one THREAD per (frame, word) group: adds the posteriors of the
+//                  group's instances in arc order (4-byte ids streamed, 8-byte
+//                  gathers of p that hit L1/L2 because neighbouring frames share
+//                  arcs) and writes (float)log(sum) to the group's pre-order row;
+//   k_frame_order  one warp per run of frames: orders the frame's rows in shared
+//                  memory (bitonic, key = ~ordered float bits << 32 | word) and
+//                  writes (frame, word, logp) to the dense table in place.
 // A group whose sum underflows (or is empty) is redone exactly in the log domain
 // from alpha/beta; frames with more groups than the shared-memory order buffer
-// holds are written unsorted and ordered in global memory (slow, same results).
+// holds are ordered in global memory (slow, same results).
 #include <math.h>
 
 #include <algorithm>
@@ -51,6 +50,8 @@ struct FrameArgs {
   const int64_t* gloc;       // per frame slot: lattice-local first output row (T+1 per lattice)
   const int64_t* res_off;    // [L+1] first output row of each lattice
   const int32_t* gwords;     // word of every (frame, word) group, in pre-order row order (static)
+  const uint32_t* gstart;    // [rows + 1] first instance of every group (static)
+  int64_t rows;
   int32_t *o_frame, *o_word;
   float* o_logp;
 };
@@ -155,13 +156,6 @@ __device__ __forceinline__ void warp_bitonic_fixed(unsigned long long* keys, int
   }
 }
 
-__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int n_pow2, int lane) {
-  if (n_pow2 <= 1) return;
-  if (n_pow2 <= 32) warp_bitonic_fixed<32>(keys, lane);  // callers pad to 32 with ~0
-  else if (n_pow2 == 64) warp_bitonic_fixed<64>(keys, lane);
-  else if (n_pow2 == 128) warp_bitonic_fixed<128>(keys, lane);
-  else warp_bitonic_fixed<256>(keys, lane);
-}
 
 // slow path: odd-even transposition sort of a frame's (logp, word) rows in global memory
 __device__ void warp_sort_rows_global(float* logp, int32_t* word, int n, int lane) {
@@ -182,18 +176,121 @@ __device__ void warp_sort_rows_global(float* logp, int32_t* word, int n, int lan
   }
 }
 
-__device__ __forceinline__ float group_logp(double sum_or_logp) {
-  // groups redone exactly carry their (negative) log-posterior instead of a sum
-  const double lp = sum_or_logp < 0.0 ? sum_or_logp : fast_log(sum_or_logp);
-  return (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+
+// one thread per (frame, word) group
+__global__ void __launch_bounds__(256) k_group_post(const __grid_constant__ FrameArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < a.rows; g += stride) {
+    const uint32_t i0 = __ldg(a.gstart + g), i1 = __ldg(a.gstart + g + 1);
+    double sum = 0.0;
+    for (uint32_t i = i0; i < i1; ++i) sum += __ldg(a.parc + ((unsigned int)__ldg(a.b.frame_arc + i) & 0x7fffffffu));
+    double lp;
+    if (sum >= 1e-280) {
+      lp = fast_log(sum);
+    } else {
+      int lo = 0, hi = a.b.L - 1;  // lattice of this row: last l with res_off[l] <= g
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.res_off[mid] <= g) lo = mid;
+        else hi = mid - 1;
+      }
+      lp = exact_group_logp(a, a.b.frame_arc, i1 - 1, a.total[lo]);
+    }
+    a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+  }
 }
 
-__global__ void __launch_bounds__(kFrameWarps * 32, 8) k_frame_post(const __grid_constant__ FrameArgs a) {
-  __shared__ __align__(16) unsigned long long s_sort[kFrameWarps][kGroupCap];  // group sums (f64 bits), then order keys
+// Bitonic sorting network over 32 * R packed 32-bit keys held in registers, R per
+// lane, position p = lane * R + r (ascending).  Partners closer than R sit in the same
+// lane (two VIMNMX per pair); the others are one shuffle away.
+template <int R>
+__device__ __forceinline__ void bitonic_regs(unsigned int (&v)[R], int lane) {
+  constexpr int N = 32 * R;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < R) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & j) == 0) {
+            const bool up = (k < R) ? ((r & k) == 0) : ((lane & (k / R)) == 0);
+            const unsigned int x = v[r], y = v[r | j];
+            v[r] = up ? min(x, y) : max(x, y);
+            v[r | j] = up ? max(x, y) : min(x, y);
+          }
+        }
+      } else {
+        const int m = j / R;
+        const bool keep_min = ((lane & (k / R)) == 0) == ((lane & m) == 0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned int y = __shfl_xor_sync(0xffffffffu, v[r], m);
+          v[r] = keep_min ? min(v[r], y) : max(v[r], y);
+        }
+      }
+    }
+  }
+}
+
+// Orders the c <= 32 * R rows [dst, dst + c) of frame k by (float logp desc, word asc).
+// The network sorts ONE 32-bit word per row: the ordered bits of the log-posterior
+// with their lowest log2(32 R) bits replaced by the row's pre-order index (rows are
+// stored in ascending word order, so index order = word order).  Rows whose
+// log-posteriors agree in all the kept bits can come out in the wrong order; that is
+// checked against the full keys afterwards and such a frame (a few per cent) is redone
+// with 64-bit keys in shared memory.
+template <int R>
+__device__ __forceinline__ void order_frame(const FrameArgs& a, int64_t dst, int c, int k, int lane,
+                                            unsigned int* s_key, unsigned int* s_sorted,
+                                            unsigned long long* sortbuf) {
+  constexpr unsigned int kMask = 32u * R - 1u;
+  unsigned int v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = lane * R + r;
+    unsigned int ok = 0xffffffffu, pk = 0xffffffffu;
+    if (e < c) {
+      ok = ~ord_f32(a.o_logp[dst + e]);
+      pk = (ok & ~kMask) | (unsigned int)e;
+    }
+    s_key[e] = ok;
+    v[r] = pk;
+  }
+  bitonic_regs<R>(v, lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r) s_sorted[lane * R + r] = v[r];
+  __syncwarp();
+  bool bad = false;
+  for (int g = lane; g < c; g += 32) {
+    const unsigned int idx = s_sorted[g] & kMask;
+    const unsigned int fk = s_key[idx];
+    if (g + 1 < c) bad |= fk > s_key[s_sorted[g + 1] & kMask];
+    a.o_frame[dst + g] = k;
+    a.o_word[dst + g] = __ldg(a.gwords + dst + idx);
+    a.o_logp[dst + g] = inv_ord_f32(~fk);
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    constexpr int N = 32 * R;
+    for (int g = lane; g < N; g += 32)
+      sortbuf[g] = g < c ? (((unsigned long long)s_key[g] << 32) | (unsigned int)__ldg(a.gwords + dst + g)) : ~0ULL;
+    __syncwarp();
+    warp_bitonic_fixed<N>(sortbuf, lane);
+    for (int g = lane; g < c; g += 32) {
+      const unsigned long long sk = sortbuf[g];
+      a.o_word[dst + g] = (int32_t)(sk & 0xffffffffu);
+      a.o_logp[dst + g] = inv_ord_f32(~(unsigned int)(sk >> 32));
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kFrameWarps * 32) k_frame_order(const __grid_constant__ FrameArgs a) {
+  __shared__ __align__(16) unsigned long long s_sort[kFrameWarps][kGroupCap];
+  __shared__ unsigned int s_keys[kFrameWarps][kGroupCap];
+  __shared__ unsigned int s_sorted[kFrameWarps][kGroupCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long* sortbuf = s_sort[warp];
   const BatchView& b = a.b;
-  const unsigned int lane_le = 0xffffffffu >> (31 - lane);
   for (int item = blockIdx.x * kFrameWarps + warp; item < a.num_items; item += gridDim.x * kFrameWarps) {
     // lattice of this item: last l with item_base[l] <= item
     int lo = 0, hi = b.L - 1;
@@ -206,80 +303,20 @@ __global__ void __launch_bounds__(kFrameWarps * 32, 8) k_frame_post(const __grid
     const int T = b.fr_base[l + 1] - b.fr_base[l] - 1;
     const int k0 = (item - a.item_base[l]) * kFramesPerItem;
     const int k1 = min(T, k0 + kFramesPerItem);
-    const int64_t* fo = b.fr_off + b.fr_base[l];
     const int64_t* gl = a.gloc + b.fr_base[l];
     const int64_t out0 = a.res_off[l];
-    const double total = a.total[l];
+    int64_t g_next = gl[k0];
     for (int k = k0; k < k1; ++k) {
-      const int64_t f0 = fo[k];
-      const int n = (int)(fo[k + 1] - f0);
-      const int64_t g0 = gl[k];
-      const int c = (int)(gl[k + 1] - g0);
+      const int64_t g0 = g_next;
+      g_next = gl[k + 1];
+      const int c = (int)(g_next - g0);
       if (c == 0) continue;
       const int64_t dst = out0 + g0;
-      const int32_t* fa = b.frame_arc + f0;
-      const bool small = c <= kGroupCap;
-      int cnt = 0;          // groups opened in earlier chunks
-      double carry = 0.0;   // partial sum of the group left open by the previous chunk
-      // lanes past the end pose as heads so that the last real group closes
-      unsigned int w_next = lane < n ? (unsigned int)__ldg(fa + lane) : 0xffffffffu;
-      double p_next = lane < n ? __ldg(a.parc + (w_next & 0x7fffffffu)) : 0.0;
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < n;
-        const unsigned int w = w_next;
-        double sum = p_next;
-        {  // the next chunk's loads go out before this chunk's shuffles
-          const int in = i + 32;
-          w_next = in < n ? (unsigned int)__ldg(fa + in) : 0xffffffffu;
-          p_next = in < n ? __ldg(a.parc + (w_next & 0x7fffffffu)) : 0.0;
-        }
-        const bool head = (w >> 31) != 0;
-        const unsigned int hm = __ballot_sync(0xffffffffu, head);
-        const unsigned int below = hm & lane_le;
-        const int seg_lo = below ? 31 - __clz(below) : 0;  // first lane of my group inside this chunk
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const double v = __shfl_up_sync(0xffffffffu, sum, d);
-          if (lane - d >= seg_lo) sum += v;
-        }
-        if (!below) sum += carry;
-        // does my group end here?  (the next instance is a head, or the list ends)
-        const unsigned int nh0 = __shfl_sync(0xffffffffu, w_next, 0) >> 31;
-        const bool is_end = valid && (lane == 31 ? nh0 != 0 : ((hm >> (lane + 1)) & 1u) != 0);
-        const int rank = cnt + __popc(below) - 1;
-        if (is_end) {
-          double r = sum;
-          if (!(sum >= 1e-280)) r = fmin(exact_group_logp(a, fa, i, total), -1e-300);
-          if (small) sortbuf[rank] = (unsigned long long)__double_as_longlong(r);
-          else a.o_logp[dst + rank] = group_logp(r);
-        }
-        const double last = __shfl_sync(0xffffffffu, sum, 31);
-        carry = (valid && lane == 31 && !is_end) ? last : 0.0;
-        carry = __shfl_sync(0xffffffffu, carry, 31);
-        cnt += __popc(hm);
-      }
-      __syncwarp();
-      if (small) {
-        const int np2 = c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : 256));
-        for (int g = lane; g < np2; g += 32) {
-          unsigned long long sk = ~0ULL;
-          if (g < c) {
-            const float f = group_logp(__longlong_as_double((long long)sortbuf[g]));
-            sk = ((unsigned long long)(~ord_f32(f)) << 32) | (unsigned int)__ldg(a.gwords + dst + g);
-          }
-          sortbuf[g] = sk;
-        }
-        __syncwarp();
-        warp_bitonic_sort(sortbuf, np2, lane);
-        for (int g = lane; g < c; g += 32) {
-          const unsigned long long sk = sortbuf[g];
-          a.o_frame[dst + g] = k;
-          a.o_word[dst + g] = (int32_t)(sk & 0xffffffffu);
-          a.o_logp[dst + g] = inv_ord_f32(~(unsigned int)(sk >> 32));
-        }
-        __syncwarp();
-      } else {
+      if (c <= 32) order_frame<1>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
+      else if (c <= 64) order_frame<2>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
+      else if (c <= 128) order_frame<4>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
+      else if (c <= 256) order_frame<8>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
+      else {
         for (int g = lane; g < c; g += 32) {
           a.o_frame[dst + g] = k;
           a.o_word[dst + g] = __ldg(a.gwords + dst + g);
@@ -309,6 +346,7 @@ struct GroupArgs {
   int32_t* lat_cnt;
   const int64_t* res_off;
   int32_t* gwords;
+  uint32_t* gstart;
 };
 
 __device__ __forceinline__ int arc_frames(const BatchView& b, int e, int T, int* first) {
@@ -398,7 +436,9 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
         if (!WORDS) {
           if (i < f1) a.frame_arc[i] = (int32_t)(val[i] | (head ? 0x80000000u : 0u));
         } else if (head) {
-          a.gwords[a.res_off[l] + a.gloc[fs] + groups + __popc(hm & ((1u << lane) - 1u))] = (int32_t)(kk & label_mask);
+          const int64_t row = a.res_off[l] + a.gloc[fs] + groups + __popc(hm & ((1u << lane) - 1u));
+          a.gwords[row] = (int32_t)(kk & label_mask);
+          a.gstart[row] = (uint32_t)i;
         }
         groups += __popc(hm);
       }
@@ -511,6 +551,10 @@ int build_frame_groups(klu_ctx* c) {
     return 0;
   }
   const int bits_label = bits_for(c->max_label), bits_time = bits_for(c->max_time);
+  if (N >= ((int64_t)1 << 32) - 1) {
+    set_error("klu_load: more than 2^32 arc x frame instances in one batch; split it");
+    return 1;
+  }
   if (bits_label + bits_time > 62) {
     set_error("frame index key does not fit 62 bits (labels/times too large)");
     return 1;
@@ -603,7 +647,14 @@ int build_frame_groups(klu_ctx* c) {
       break;
     }
     if ((rc = c->d_fr_gword.reserve(4 * (size_t)std::max<int64_t>(c->h_frame_res_off[L], 1)))) break;
+    if ((rc = c->d_fr_gstart.reserve(4 * (size_t)(c->h_frame_res_off[L] + 1)))) break;
     a.gwords = c->d_fr_gword.as<int32_t>();
+    a.gstart = c->d_fr_gstart.as<uint32_t>();
+    {
+      const uint32_t n32 = (uint32_t)N;
+      cudaMemcpyAsync(a.gstart + c->h_frame_res_off[L], &n32, 4, cudaMemcpyHostToDevice, c->stream);
+      cudaStreamSynchronize(c->stream);
+    }
     if (a.num_items > 0) {
       KLU_LAUNCH(c, "k_fg_words");
       k_fg_heads<true><<<hgrid, 256, 0, c->stream>>>(a);
@@ -648,6 +699,8 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   a.gloc = c->d_fr_gloc.as<int64_t>();
   a.res_off = c->d_fr_res_off.as<int64_t>();
   a.gwords = c->d_fr_gword.as<int32_t>();
+  a.gstart = c->d_fr_gstart.as<uint32_t>();
+  a.rows = c->last_entries;
   a.o_frame = c->d_res[0].as<int32_t>();
   a.o_word = c->d_res[1].as<int32_t>();
   a.o_logp = c->d_res[4].as<float>();
@@ -659,13 +712,18 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
     k_arc_post<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_arc_post"));
+  {
+    KLU_LAUNCH(c, "k_group_post");
+    k_group_post<<<c->num_sms * 16, 256, 0, c->stream>>>(a);
+  }
+  KLU_TRY(check_launch("k_group_post"));
   if (a.num_items > 0) {
     const int grid = std::max(1, std::min((a.num_items + kFrameWarps - 1) / kFrameWarps, c->num_sms * 64));
     {
-      KLU_LAUNCH(c, "k_frame_post");
-      k_frame_post<<<grid, kFrameWarps * 32, 0, c->stream>>>(a);
+      KLU_LAUNCH(c, "k_frame_order");
+      k_frame_order<<<grid, kFrameWarps * 32, 0, c->stream>>>(a);
     }
-    KLU_TRY(check_launch("k_frame_post"));
+    KLU_TRY(check_launch("k_frame_order"));
   }
   return 0;
 }
