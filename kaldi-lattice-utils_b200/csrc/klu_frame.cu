@@ -183,7 +183,18 @@ __global__ void __launch_bounds__(256) k_group_post(const __grid_constant__ Fram
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < a.rows; g += stride) {
     const uint32_t i0 = __ldg(a.gstart + g), i1 = __ldg(a.gstart + g + 1);
     double sum = 0.0;
-    for (uint32_t i = i0; i < i1; ++i) sum += __ldg(a.parc + ((unsigned int)__ldg(a.b.frame_arc + i) & 0x7fffffffu));
+    // four instances per trip (most groups have <= 4): the id loads, then the
+    // posterior gathers, go out together; the adds stay in arc order
+    for (uint32_t i = i0; i < i1; i += 4) {
+      unsigned int e[4];
+      double p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = i + u < i1 ? (unsigned int)__ldg(a.b.frame_arc + i + u) & 0x7fffffffu : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = i + u < i1 ? __ldg(a.parc + e[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sum += p[u];
+    }
     double lp;
     if (sum >= 1e-280) {
       lp = fast_log(sum);
