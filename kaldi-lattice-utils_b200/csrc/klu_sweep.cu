@@ -17,6 +17,8 @@
 // with shuffles, and lane 0 of the group writes the f64 score.  State scores live
 // in global memory and are re-read through L1 (same-SM producer/consumer, ordered
 // by __syncwarp between levels).
+#include <stdlib.h>
+
 #include "klu_common.cuh"
 
 namespace klu {
@@ -34,6 +36,7 @@ struct SweepArgs {
   double beam;         // (double)(float)beam
   int* counter;
   int do_fwd, do_bwd;
+  int variant;  // experiment switch (KLU_SWEEP_VARIANT)
 };
 
 // PruneLattice's arc test, evaluated on the fly: the arc is dropped when
@@ -52,7 +55,19 @@ __device__ __forceinline__ bool final_pruned(const SweepArgs& a, int l, int s, d
   return __dadd_rn(fcost, a.vfwd[s]) > __dadd_rn(a.best[l], a.beam) && fcost != pos_inf();
 }
 
-constexpr int kSweepCap = 256;  // arc terms staged per batch (per warp, in shared memory)
+constexpr int kSweepCapPerLane = 8;  // arcs staged per batch = 8 x (lanes of the tile), 16 bytes each
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 template <bool FWD, bool BEAM>
 __device__ __forceinline__ bool sweep_arc_pruned(const SweepArgs& a, int l, int e, const int4& r) {
@@ -62,177 +77,213 @@ __device__ __forceinline__ bool sweep_arc_pruned(const SweepArgs& a, int l, int 
   return arc_pruned(a, l, src, dst, r);
 }
 
-// Exact log-sum of the states [sa, sb) of one level, the whole warp on one state at
-// a time: max first, then max + log1p(sum of the other terms) with libm's exp and
-// log1p.  Used for states with more than kSweepCap arcs and whenever the fast
-// path's shared reference point would under- or overflow.
+// Exact log-sum of ONE state by ONE lane: max first, then max + log1p(sum of the
+// other terms) with libm's exp and log1p (for two terms exactly Kaldi's LogAdd).
+// Used for states with more arcs than a tile stages and whenever the fast path's
+// shared reference point would under- or overflow.
 template <bool FWD, bool BEAM>
-__device__ __noinline__ void sweep_states_exact(const SweepArgs& a, int l, int sa, int sb, int lane) {
+__device__ __noinline__ double sweep_state_exact(const SweepArgs& a, int l, int s) {
   const BatchView& b = a.b;
   const int4* rec = FWD ? b.in_rec : b.out_rec;
   const int* off = FWD ? b.in_off : b.out_off;
-  double* score = FWD ? a.alpha : a.beta;
-  for (int s = sa; s < sb; ++s) {
-    const int e0 = off[s], e1 = off[s + 1];
-    double fin = neg_inf();
-    if (!FWD && lane == 0) {
-      const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
-      if (!(BEAM && final_pruned(a, l, s, fc))) fin = -fc;
-    }
-    double m = fin;
-    int arg = fin > neg_inf() ? -2 : -1;  // -2: the final weight is the local max
-    for (int e = e0 + lane; e < e1; e += 32) {
-      const int4 r = __ldg(rec + e);
-      if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) continue;
-      const double x = score[r.x] - rec_cost(r, a.cp);
-      if (x > m) {
-        m = x;
-        arg = e;
-      }
-    }
-    const double lm = m;
-    m = group_max<32>(m);
-    if (!elect_max_lane<32>(lm, m, lane)) arg = -1;
-    double sum = 0.0;
-    if (m > neg_inf()) {
-      if (fin > neg_inf() && arg != -2) sum = exp(fin - m);
-      for (int e = e0 + lane; e < e1; e += 32) {
-        if (e == arg) continue;
-        const int4 r = __ldg(rec + e);
-        if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) continue;
-        sum += exp(score[r.x] - rec_cost(r, a.cp) - m);
-      }
-    }
-    sum = group_sum<32>(sum);
-    if (lane == 0) score[s] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
+  const double* score = FWD ? a.alpha : a.beta;
+  const int e0 = off[s], e1 = off[s + 1];
+  double fin = neg_inf();
+  if (!FWD) {
+    const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
+    if (!(BEAM && final_pruned(a, l, s, fc))) fin = -fc;
   }
+  double m = fin;
+  int arg = fin > neg_inf() ? -2 : -1;  // -2: the final weight is the max
+  for (int e = e0; e < e1; ++e) {
+    const int4 r = __ldg(rec + e);
+    if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) continue;
+    const double x = score[r.x] - rec_cost(r, a.cp);
+    if (x > m) {
+      m = x;
+      arg = e;
+    }
+  }
+  if (!(m > neg_inf())) return neg_inf();
+  double sum = 0.0;
+  if (fin > neg_inf() && arg != -2) sum = exp(fin - m);
+  for (int e = e0; e < e1; ++e) {
+    if (e == arg) continue;
+    const int4 r = __ldg(rec + e);
+    if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) continue;
+    sum += exp(score[r.x] - rec_cost(r, a.cp) - m);
+  }
+  return m + log1p(sum);
 }
 
-// One (lattice, direction) sweep by one warp.  Inside a level the states are cut
-// into batches of <= 32 states / <= kSweepCap arcs; the arcs of a batch are one
-// contiguous run of 16-byte records (in_rec is sorted by destination, out_rec by
-// source), so the lanes stream them with coalesced loads, each lane turns its arcs
-// into exp(score[other] - cost - ref) and parks the term in shared memory.  `ref`
-// is the score of the previous batch's first state: a point on the frontier, within
-// a few tens of every term, so one shared reference replaces the per-state max of
-// the textbook log-sum-exp (no second pass over the arcs, no arg-max election).
-// A few lanes per state then add the state's terms in arc order and
-// score = ref + log(sum).  A batch whose sums leave [1e-280, 1e280] (reference
-// point too far away, unreachable states, ...) is redone exactly.
-template <bool FWD, bool BEAM>
-__device__ void log_sweep(const SweepArgs& a, int l, int lane, double* xbuf) {
+// Level-synchronous sweep of 32 / G (lattice, direction) items by one warp: a tile
+// of G lanes owns one lattice, and the 32 / G tiles run in lockstep so that every
+// issued instruction works for all of them (the level loop of a lattice is a long
+// dependent chain; what the machine can overlap is OTHER lattices).
+//
+// Inside a level a tile cuts the states into batches of <= G states and
+// <= 16 G arcs.  The arcs of a batch are one contiguous run of 16-byte records
+// (in_rec is sorted by destination, out_rec by source): the tile's lanes stream
+// them, each lane turns its arcs into exp(score[other] - cost - ref) and parks the
+// term in shared memory.  `ref` is the score of the previous batch's first state: a
+// point on the frontier, within a few tens of every term, so one shared reference
+// replaces the per-state max of the textbook log-sum-exp (no second pass over the
+// arcs).  A few lanes per state then add the state's terms in arc order and
+// score = ref + log(sum).  States with one or two terms use Kaldi's LogAdd form
+// exactly; sums that leave [1e-280, 1e280] (reference point too far, unreachable
+// states, ...) are redone exactly.
+template <int G, bool FWD, bool BEAM>
+__device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2* xwarp) {
+  constexpr int kCap = kSweepCapPerLane * G;
+  constexpr int kLog2G = G == 32 ? 5 : G == 16 ? 4 : G == 8 ? 3 : G == 4 ? 2 : 1;
   const BatchView& b = a.b;
-  const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
-  if (s_begin == s_end) return;
+  const int gi = lane / G, sl = lane % G;
+  const unsigned int gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (gi * G);
+  double2* xbuf = xwarp + gi * kCap;  // per arc: the record, then {cost, score}, then {exp term, -}
+  const int4* rec = FWD ? b.in_rec : b.out_rec;
+  const int* off = FWD ? b.in_off : b.out_off;
+  double* score = FWD ? a.alpha : a.beta;
+  bool done = first + gi >= b.L;
+  const int l = done ? 0 : b.order[first + gi];
+  const int s_begin = b.s_off[l];
+  if (!done && s_begin == b.s_off[l + 1]) done = true;
   const int* lv = b.lvl_start + b.lvl_off[l];
   const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
-  const int4* rec = FWD ? b.in_rec : b.out_rec;
-  const int* off = FWD ? b.in_off : b.out_off;
-  double* score = FWD ? a.alpha : a.beta;
   double ref = 0.0;
-  if (FWD) {
-    for (int s = lv[0] + lane; s < lv[1]; s += 32) score[s] = (s == s_begin) ? 0.0 : neg_inf();
-    __syncwarp();
+  int j = FWD ? 1 : nl - 1;
+  if (FWD && !done)
+    for (int s = lv[0] + sl; s < lv[1]; s += G) score[s] = (s == s_begin) ? 0.0 : neg_inf();
+  if (!done && (FWD ? j >= nl : j < 0)) done = true;
+  int a1 = 0, s0 = 0;
+  if (!done) {
+    s0 = lv[j];
+    a1 = lv[j + 1];
   }
-  for (int j = FWD ? 1 : nl - 1; FWD ? (j < nl) : (j >= 0); j += FWD ? 1 : -1) {
-    const int a0 = lv[j], a1 = lv[j + 1];
-    int s0 = a0;
-    while (s0 < a1) {
-      const int idx = s0 + lane;
-      const int o_lo = off[min(idx, a1)], o_hi = off[min(idx + 1, a1)];
-      const int base = __shfl_sync(0xffffffffu, o_lo, 0);
-      // states of the batch: the longest prefix whose arcs fit the staging buffer
-      const int c = __popc(__ballot_sync(0xffffffffu, idx < a1 && o_hi - base <= kSweepCap));
-      if (c == 0) {
-        sweep_states_exact<FWD, BEAM>(a, l, s0, s0 + 1, lane);
-        s0 += 1;
-        continue;
-      }
-      const int nb = __shfl_sync(0xffffffffu, o_hi, c - 1) - base;
-      {  // pull the records a few levels ahead into L2
-        const int pf = base + nb + kSweepCap + lane * 8;
-        if (lane * 8 < nb && pf < b.E) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + pf));
-      }
-      for (int i = lane; i < nb; i += 32) {
-        const int e = base + i;
-        const int4 r = ld_stream(rec + e);
-        double x = score[r.x] - rec_cost(r, a.cp);
-        if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, e, r)) x = neg_inf();
-        xbuf[i] = fast_exp(x - ref);
-      }
-      __syncwarp();
-      // 32 / pow2ceil(c) lanes per state add its terms, then fold across the lanes
-      const int sh = c <= 1 ? 5 : __clz(c - 1) - 27;  // log2(lanes per state)
-      const int gp = 1 << sh;
-      const int st = lane >> sh, sub = lane & (gp - 1);
-      const int lo = __shfl_sync(0xffffffffu, o_lo, st) - base, hi = __shfl_sync(0xffffffffu, o_hi, st) - base;
-      double sum = 0.0;
-      if (st < c)
-        for (int i = lo + sub; i < hi; i += gp) sum += xbuf[i];
-      for (int o = gp >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      bool bad = false;
-      double val = 0.0;
-      if (st < c && sub == 0) {
-        const int s = s0 + st;
-        double fin = neg_inf();
-        if (!FWD) {
-          const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
-          if (fc < pos_inf() && !(BEAM && final_pruned(a, l, s, fc))) {
-            fin = -fc;
-            sum += fast_exp(fin - ref);
-          }
-        }
-        const int terms = hi - lo + (fin > neg_inf() ? 1 : 0);
-        if (terms <= 2) {
-          // one or two terms: exactly Kaldi's LogAdd (x, or max + log1p(exp(-|d|))), so
-          // chains and diamonds reproduce the reference bit for bit
-          val = fin;
-          for (int i = lo; i < hi; ++i) {
-            const int4 r = __ldg(rec + base + i);
-            double x = score[r.x] - rec_cost(r, a.cp);
-            if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, base + i, r)) x = neg_inf();
-            val = log_add(val, x);
-          }
-          score[s] = val;
-        } else if (sum >= 1e-280 && sum <= 1e280) {
-          val = ref + fast_log(sum);
-          score[s] = val;
-        } else {
-          bad = true;
-        }
-      }
-      if (__any_sync(0xffffffffu, bad)) {
-        sweep_states_exact<FWD, BEAM>(a, l, s0, s0 + c, lane);
-        __syncwarp();
-        double v = (lane < c) ? score[s0 + lane] : neg_inf();
-        v = group_max<32>(v);
-        if (v > neg_inf() && v < pos_inf()) ref = v;
-      } else {
-        const double v0 = __shfl_sync(0xffffffffu, val, 0);
-        if (v0 > neg_inf() && v0 < pos_inf()) ref = v0;
-      }
-      s0 += c;
-      __syncwarp();
+  __syncwarp();
+  while (!__all_sync(0xffffffffu, done)) {
+    // ---- the next batch of this tile's current level
+    const int idx = s0 + sl;
+    int o_lo = 0, o_hi = 0;
+    if (!done) {
+      o_lo = off[min(idx, a1)];
+      o_hi = off[min(idx + 1, a1)];
     }
+    const int base = __shfl_sync(0xffffffffu, o_lo, 0, G);
+    const unsigned int fit = __ballot_sync(0xffffffffu, !done && idx < a1 && o_hi - base <= kCap) & gmask;
+    const int c = __popc(fit);  // states of the batch: the longest prefix whose arcs fit the staging buffer
+    const int o_last = __shfl_sync(0xffffffffu, o_hi, max(c - 1, 0), G);
+    const int nb = c > 0 ? o_last - base : 0;
+    if (!done && c > 0) {  // pull the records a few levels ahead into L2
+      const int pf = base + nb + kCap + sl * 8;
+      if (sl * 8 < nb && pf < b.E) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + pf));
+    }
+    // Three passes over the lane's own arcs, each a batch of independent memory
+    // operations: (1) the 16-byte records, global -> shared, asynchronously;
+    // (2) cost from the record, and the other end's score gathered asynchronously into
+    // the same slot; (3) the exp terms.  One memory latency per pass, not per arc.
+    for (int i = sl; i < nb; i += G) cp_async16(xbuf + i, rec + base + i);
+    cp_async_wait_all();
+    for (int i = sl; i < nb; i += G) {
+      const int4 r = *reinterpret_cast<const int4*>(xbuf + i);
+      double cost = rec_cost(r, a.cp);
+      if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, base + i, r)) cost = pos_inf();
+      xbuf[i].x = cost;
+      cp_async8(&xbuf[i].y, score + r.x);
+    }
+    cp_async_wait_all();
+    for (int i = sl; i < nb; i += G) {
+      const double2 v = xbuf[i];
+      xbuf[i].x = fast_exp(v.y - v.x - ref);
+    }
+    __syncwarp();
+    // ---- G / pow2ceil(c) lanes per state add its terms, then fold across those lanes
+    const int sh = c <= 1 ? kLog2G : kLog2G - (32 - __clz(c - 1));  // log2(lanes per state)
+    const int gp = 1 << sh;
+    const int st = sl >> sh, sub = sl & (gp - 1);
+    const int lo = __shfl_sync(0xffffffffu, o_lo, st, G) - base, hi = __shfl_sync(0xffffffffu, o_hi, st, G) - base;
+    double sum = 0.0;
+    if (st < c)
+      for (int i = lo + sub; i < hi; i += gp) sum += xbuf[i].x;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double v = __shfl_xor_sync(0xffffffffu, sum, o, G);
+      if (o < gp) sum += v;
+    }
+    bool bad = false;
+    double val = 0.0;
+    if (st < c && sub == 0) {
+      const int s = s0 + st;
+      double fin = neg_inf();
+      if (!FWD) {
+        const double fc = final_cost(b.fin_g[s], b.fin_a[s], a.cp);
+        if (fc < pos_inf() && !(BEAM && final_pruned(a, l, s, fc))) {
+          fin = -fc;
+          sum += fast_exp(fin - ref);
+        }
+      }
+      const int terms = hi - lo + (fin > neg_inf() ? 1 : 0);
+      if (terms <= 2) {
+        // one or two terms: exactly Kaldi's LogAdd (x, or max + log1p(exp(-|d|))), so
+        // chains and diamonds reproduce the reference bit for bit
+        val = fin;
+        for (int i = lo; i < hi; ++i) {
+          const int4 r = __ldg(rec + base + i);
+          double x = score[r.x] - rec_cost(r, a.cp);
+          if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, base + i, r)) x = neg_inf();
+          val = log_add(val, x);
+        }
+      } else if (sum >= 1e-280 && sum <= 1e280) {
+        val = ref + fast_log(sum);
+      } else {
+        bad = true;
+      }
+      if (bad) val = sweep_state_exact<FWD, BEAM>(a, l, s);
+      score[s] = val;
+    }
+    if (!done && c == 0 && sl == 0) {  // a single state with more arcs than the tile stages
+      val = sweep_state_exact<FWD, BEAM>(a, l, s0);
+      score[s0] = val;
+    }
+    // the next reference point: this batch's first state (lane 0 of the tile holds it)
+    const double v0 = __shfl_sync(0xffffffffu, val, 0, G);
+    if (!done && v0 > neg_inf() && v0 < pos_inf()) ref = v0;
+    // ---- advance: next batch, next level, or finished
+    if (!done) {
+      s0 += c > 0 ? c : 1;
+      if (s0 >= a1) {
+        j += FWD ? 1 : -1;
+        if (FWD ? j >= nl : j < 0) {
+          done = true;
+        } else {
+          s0 = lv[j];
+          a1 = lv[j + 1];
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
-template <bool BEAM>
+// Work queue: unit t < ceil(L / NG) sweeps lattices order[t*NG .. t*NG+NG) forward,
+// the following units sweep them backward (a warp's tiles share the direction, so
+// they share the code path).
+template <int G, bool BEAM>
 __global__ void __launch_bounds__(128) k_log_sweeps(const __grid_constant__ SweepArgs a) {
-  __shared__ double xs[4][kSweepCap];
+  constexpr int NG = 32 / G;
+  __shared__ double2 xs[4][kSweepCapPerLane * 32];
   const int lane = threadIdx.x & 31;
-  double* xbuf = xs[threadIdx.x >> 5];
-  const int ndir = a.do_fwd + a.do_bwd;
-  const int nitems = a.b.L * ndir;
+  double2* xwarp = xs[threadIdx.x >> 5];
+  const int per_dir = (a.b.L + NG - 1) / NG;
+  const int nunits = per_dir * (a.do_fwd + a.do_bwd);
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(a.counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= nitems) break;
-    const int l = a.b.order[item / ndir];
-    const bool fwd = a.do_fwd && (ndir == 1 || (item % ndir) == 0);
-    if (fwd) log_sweep<true, BEAM>(a, l, lane, xbuf);
-    else log_sweep<false, BEAM>(a, l, lane, xbuf);
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(a.counter, 1);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= nunits) break;
+    const bool fwd = a.do_fwd && unit < per_dir;
+    const int first = (unit - (fwd || !a.do_fwd ? 0 : per_dir)) * NG;
+    if (fwd) log_sweep_tiles<G, true, BEAM>(a, first, lane, xwarp);
+    else log_sweep_tiles<G, false, BEAM>(a, first, lane, xwarp);
     __syncwarp();
   }
 }
@@ -453,6 +504,7 @@ SweepArgs make_args(klu_ctx* c, const CostParams& cp, bool use_beam, float beam)
   a.counter = c->d_counter.as<int>();
   a.do_fwd = 1;
   a.do_bwd = 1;
+  a.variant = getenv("KLU_SWEEP_VARIANT") ? atoi(getenv("KLU_SWEEP_VARIANT")) : 0;
   return a;
 }
 
@@ -475,11 +527,21 @@ int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) 
   if (c->L == 0) return 0;
   KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
   SweepArgs a = make_args(c, cp, use_beam, beam);
-  const int grid = sweep_grid(c, c->L * 2);
+  // lanes per lattice: enough to stream a level's arcs in ~10 trips, more when there
+  // are too few lattices to fill the machine otherwise
+  int G = 4;
+  {
+    const double arcs_per_level = c->NL > 0 ? (double)c->E / (double)c->NL : 1.0;
+    while (G < 32 && G * 12 < arcs_per_level) G <<= 1;
+    while (G < 32 && (int64_t)2 * c->L * G / 32 < (int64_t)c->num_sms * 8) G <<= 1;
+    if (const char* env = getenv("KLU_SWEEP_LANES")) G = atoi(env);
+  }
+  const int units = 2 * ((c->L + 32 / G - 1) / (32 / G));
+  const int grid = sweep_grid(c, units);
   {
     KLU_LAUNCH(c, "k_log_sweeps");
-    if (use_beam) k_log_sweeps<true><<<grid, 128, 0, c->stream>>>(a);
-    else k_log_sweeps<false><<<grid, 128, 0, c->stream>>>(a);
+    KLU_DISPATCH_G(G, if (use_beam) k_log_sweeps<kG, true><<<grid, 128, 0, c->stream>>>(a);
+                   else k_log_sweeps<kG, false><<<grid, 128, 0, c->stream>>>(a));
   }
   KLU_TRY(check_launch("k_log_sweeps"));
   {
