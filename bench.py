@@ -63,31 +63,60 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons DURING the timed region: NVML in-process
+    (a few ms per sample); nvidia-smi subprocesses only if NVML is unavailable."""
+
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.stop_flag, self.samples, self.reasons, self.max_mhz = gpu, False, [], set(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(
+            n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5)
+        f = [x.strip() for x in out.stdout.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for n, v in zip(names, f[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                if self.nvml is not None:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.005 if self.nvml is not None else 0.2)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def dist_setup(n):
@@ -165,7 +194,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "lattice arcs/sec (fwd-bwd + word-position index)", "value": v,
         "unit": "arcs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, n),
+        "data": "synthetic", "config": workload_config(args, args.lattices),
         "cpu_baseline": {"value": v, "unit": "arcs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "arcs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -184,7 +213,7 @@ def workload_config(args, nlat):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tool", default="frame_post", choices=sorted(TOOLS))

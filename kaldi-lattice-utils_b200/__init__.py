@@ -11,8 +11,9 @@ import it through `__graft_entry__.load_package()` / importlib, e.g.
     klu = importlib.util.module_from_spec(spec); sys.modules["klu_b200"] = klu
     spec.loader.exec_module(klu)
 """
-from . import binding, lattice  # noqa: F401
+from . import binding, lattice, shard  # noqa: F401
 from .binding import (BEST_PATH2, CHAR_POSITION, FRAME_POST, FWD_BWD, POSITION, PRUNE_DYN_BEAM, SEGMENT,  # noqa: F401
                       UTTERANCE, Engine, KluError)
 from .lattice import (Lattice, LatticeBatch, format_tuples, kaldi_float, make_lattice, read_text_ark,  # noqa: F401
                       synth_batch, topsort)
+from .shard import partition_by_arcs, run_sharded  # noqa: F401,E402

@@ -22,6 +22,7 @@
 
 #include <chrono>
 #include <set>
+#include <thread>
 
 #include "kaldi_io.h"
 #include "klu.h"
@@ -85,7 +86,7 @@ struct Batch {
 };
 
 struct ToolState {
-  klu_ctx* ctx = nullptr;
+  std::vector<klu_ctx*> ctxs;  // one per GPU (KLU_DEVICES)
   klu_opts opts;
   std::vector<int32_t> include, exclude, group_labels, group_ids, inc_groups, del_groups;
   TableWriter* writer = nullptr;
@@ -98,22 +99,71 @@ struct ToolState {
   if (!binary && i + 1 < n) os << "; ";
 }
 
-void ProcessBatch(ToolState* st, Batch* b) {
-  if (b->lats.empty()) return;
+// Everything klu_fetch_* returns for one batch (which fields are used depends on the tool).
+struct Results {
+  std::vector<int64_t> off, coff;
+  std::vector<int32_t> i0, i1, i2, i3, chars, smap;
+  std::vector<double> d0, beams;
+  std::vector<float> f0, f1, f2, f3;
+  std::string error;
+  double sec = 0.0;
+};
+
+// GPU part of a batch: pack + upload, run the tool, bring the results to the host.
+// Runs on the worker thread that owns `ctx` (one context per GPU).
+void ComputeBatch(klu_ctx* ctx, const klu_opts* opts, const Batch* b, Results* r) {
+  try {
+    const int32_t L = (int32_t)b->lats.size();
+    const auto t0 = std::chrono::steady_clock::now();
+    klu_lattices view = b->View();
+    KLU_CHECK(klu_load(ctx, &view));
+    KLU_CHECK(klu_run(ctx, KLU_TOOL, opts));
+    r->off.resize(L + 1);
+    KLU_CHECK(klu_result_offsets(ctx, r->off.data()));
+    const size_t n = (size_t)r->off[L];
+#if KLU_TOOL == 0 /* KLU_SEGMENT */
+    r->i0.resize(n), r->i1.resize(n), r->i2.resize(n), r->d0.resize(n);
+    KLU_CHECK(klu_fetch_segment(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->d0.data()));
+#elif KLU_TOOL == 1 /* KLU_POSITION */
+    r->i0.resize(n), r->i1.resize(n), r->i2.resize(n), r->i3.resize(n), r->d0.resize(n);
+    KLU_CHECK(klu_fetch_position(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->i3.data(), r->d0.data()));
+#elif KLU_TOOL == 2 /* KLU_UTTERANCE */
+    r->i0.resize(n), r->d0.resize(n);
+    KLU_CHECK(klu_fetch_utterance(ctx, r->i0.data(), r->d0.data()));
+#elif KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+    int64_t total_chars = 0;
+    KLU_CHECK(klu_result_char_sizes(ctx, &total_chars));
+    r->coff.resize(n + 1), r->chars.resize((size_t)total_chars);
+    r->i1.resize(n), r->i2.resize(n), r->i3.resize(n), r->d0.resize(n);
+    KLU_CHECK(klu_fetch_char_position(ctx, r->coff.data(), r->chars.data(), r->i1.data(), r->i2.data(), r->i3.data(),
+                                      r->d0.data()));
+#elif KLU_TOOL == 3 /* KLU_FRAME_POST */
+    r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
+    KLU_CHECK(klu_fetch_frame_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
+#elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
+    r->i0.resize(n), r->i1.resize(L), r->f0.resize(L);
+    KLU_CHECK(klu_fetch_best_path2(ctx, r->i0.data(), r->f0.data(), r->i1.data()));
+#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+    const size_t S = (size_t)b->state_off.back();
+    r->i0.resize(n), r->i1.resize(n), r->i2.resize(n), r->smap.resize(S);
+    r->f0.resize(n), r->f1.resize(n), r->f2.resize(S), r->f3.resize(S), r->beams.resize(2 * (size_t)L);
+    KLU_CHECK(klu_fetch_prune(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data(), r->f1.data(), r->smap.data(),
+                              r->f2.data(), r->f3.data(), r->beams.data()));
+#endif
+    r->sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  } catch (const std::exception& e) {
+    r->error = e.what();
+  }
+}
+
+// Host part: writes the batch's entries in input order (TaskSequencer contract, P9).
+void EmitBatch(ToolState* st, Batch* b, Results* r) {
+  if (!r->error.empty()) throw std::runtime_error(r->error);
   const int32_t L = (int32_t)b->lats.size();
-  const auto t0 = std::chrono::steady_clock::now();
-  klu_lattices view = b->View();
-  KLU_CHECK(klu_load(st->ctx, &view));
-  KLU_CHECK(klu_run(st->ctx, KLU_TOOL, &st->opts));
-  std::vector<int64_t> off(L + 1);
-  KLU_CHECK(klu_result_offsets(st->ctx, off.data()));
-  const size_t n = (size_t)off[L];
+  const std::vector<int64_t>& off = r->off;
   TableWriter& w = *st->writer;
   const bool bin = w.IsOpen() ? w.binary() : false;
 #if KLU_TOOL == 0 /* KLU_SEGMENT */
-  std::vector<int32_t> word(n), t0v(n), t1v(n);
-  std::vector<double> lp(n);
-  KLU_CHECK(klu_fetch_segment(st->ctx, word.data(), t0v.data(), t1v.data(), lp.data()));
   for (int32_t l = 0; l < L; ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
@@ -123,19 +173,16 @@ void ProcessBatch(ToolState* st, Batch* b) {
       WriteBasicInt32(os, true, (int32_t)(e - a));
     }
     for (size_t i = a; i < e; ++i) {
-      WriteBasicInt32(os, bin, word[i]);
-      WriteBasicInt32(os, bin, t0v[i]);
-      WriteBasicInt32(os, bin, t1v[i]);
-      WriteBasicDouble(os, bin, lp[i]);
+      WriteBasicInt32(os, bin, r->i0[i]);
+      WriteBasicInt32(os, bin, r->i1[i]);
+      WriteBasicInt32(os, bin, r->i2[i]);
+      WriteBasicDouble(os, bin, r->d0[i]);
       WriteTupleSep(os, bin, i - a, e - a);
     }
     if (!bin) os << '\n';
     w.End();
   }
 #elif KLU_TOOL == 1 /* KLU_POSITION */
-  std::vector<int32_t> word(n), pos(n), t0v(n), t1v(n);
-  std::vector<double> lp(n);
-  KLU_CHECK(klu_fetch_position(st->ctx, word.data(), pos.data(), t0v.data(), t1v.data(), lp.data()));
   for (int32_t l = 0; l < L; ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
@@ -145,20 +192,17 @@ void ProcessBatch(ToolState* st, Batch* b) {
       WriteBasicInt32(os, true, (int32_t)(e - a));
     }
     for (size_t i = a; i < e; ++i) {
-      WriteBasicInt32(os, bin, word[i]);
-      WriteBasicInt32(os, bin, pos[i]);
-      WriteBasicInt32(os, bin, t0v[i]);
-      WriteBasicInt32(os, bin, t1v[i]);
-      WriteBasicDouble(os, bin, lp[i]);
+      WriteBasicInt32(os, bin, r->i0[i]);
+      WriteBasicInt32(os, bin, r->i1[i]);
+      WriteBasicInt32(os, bin, r->i2[i]);
+      WriteBasicInt32(os, bin, r->i3[i]);
+      WriteBasicDouble(os, bin, r->d0[i]);
       WriteTupleSep(os, bin, i - a, e - a);
     }
     if (!bin) os << '\n';
     w.End();
   }
 #elif KLU_TOOL == 2 /* KLU_UTTERANCE */
-  std::vector<int32_t> word(n);
-  std::vector<double> lp(n);
-  KLU_CHECK(klu_fetch_utterance(st->ctx, word.data(), lp.data()));
   for (int32_t l = 0; l < L; ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
@@ -168,20 +212,14 @@ void ProcessBatch(ToolState* st, Batch* b) {
       WriteBasicInt32(os, true, (int32_t)(e - a));
     }
     for (size_t i = a; i < e; ++i) {
-      WriteBasicInt32(os, bin, word[i]);
-      WriteBasicDouble(os, bin, lp[i]);
+      WriteBasicInt32(os, bin, r->i0[i]);
+      WriteBasicDouble(os, bin, r->d0[i]);
       WriteTupleSep(os, bin, i - a, e - a);
     }
     if (!bin) os << '\n';
     w.End();
   }
 #elif KLU_TOOL == 6 /* KLU_CHAR_POSITION */
-  int64_t total_chars = 0;
-  KLU_CHECK(klu_result_char_sizes(st->ctx, &total_chars));
-  std::vector<int64_t> coff(n + 1);
-  std::vector<int32_t> chars((size_t)total_chars), pos(n), t0v(n), t1v(n);
-  std::vector<double> lp(n);
-  KLU_CHECK(klu_fetch_char_position(st->ctx, coff.data(), chars.data(), pos.data(), t0v.data(), t1v.data(), lp.data()));
   for (int32_t l = 0; l < L; ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
@@ -192,24 +230,23 @@ void ProcessBatch(ToolState* st, Batch* b) {
     }
     for (size_t i = a; i < e; ++i) {
       std::string tok;
-      for (int64_t k = coff[i]; k < coff[i + 1]; ++k) {
-        if (k > coff[i]) tok += "_";
-        tok += std::to_string(chars[(size_t)k]);
+      for (int64_t k = r->coff[i]; k < r->coff[i + 1]; ++k) {
+        if (k > r->coff[i]) tok += "_";
+        tok += std::to_string(r->chars[(size_t)k]);
       }
       WriteToken(os, bin, tok);
-      WriteBasicInt32(os, bin, pos[i]);
-      WriteBasicInt32(os, bin, t0v[i]);
-      WriteBasicInt32(os, bin, t1v[i]);
-      WriteBasicDouble(os, bin, lp[i]);
+      WriteBasicInt32(os, bin, r->i1[i]);
+      WriteBasicInt32(os, bin, r->i2[i]);
+      WriteBasicInt32(os, bin, r->i3[i]);
+      WriteBasicDouble(os, bin, r->d0[i]);
       WriteTupleSep(os, bin, i - a, e - a);
     }
     if (!bin) os << '\n';
     w.End();
   }
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */
-  std::vector<int32_t> nf(L), frame(n), word(n);
-  std::vector<float> lp(n);
-  KLU_CHECK(klu_fetch_frame_post(st->ctx, nf.data(), frame.data(), word.data(), lp.data()));
+  const std::vector<int32_t>&nf = r->i0, &frame = r->i1, &word = r->i2;
+  const std::vector<float>& lp = r->f0;
   for (int32_t l = 0; l < L; ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     size_t i = (size_t)off[l];
@@ -244,9 +281,8 @@ void ProcessBatch(ToolState* st, Batch* b) {
     w.End();
   }
 #elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
-  std::vector<int32_t> lab(n), nf(L);
-  std::vector<float> cost(L);
-  KLU_CHECK(klu_fetch_best_path2(st->ctx, lab.data(), cost.data(), nf.data()));
+  const std::vector<int32_t>&lab = r->i0, &nf = r->i1;
+  const std::vector<float>& cost = r->f0;
   for (int32_t l = 0; l < L; ++l) {
     if (w.IsOpen()) {
       std::ostream& os = w.Begin(b->lats[l].key);
@@ -265,12 +301,9 @@ void ProcessBatch(ToolState* st, Batch* b) {
     KIO_LOG("For utterance " << b->lats[l].key << ", best cost is " << cost[l] << " over " << nf[l] << " frames.");
   }
 #elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
-  const size_t S = (size_t)b->state_off.back();
-  std::vector<int32_t> ai(n), ns(n), nd(n), smap(S);
-  std::vector<float> g(n), a(n), fg(S), fa(S);
-  std::vector<double> beams(2 * (size_t)L);
-  KLU_CHECK(klu_fetch_prune(st->ctx, ai.data(), ns.data(), nd.data(), g.data(), a.data(), smap.data(), fg.data(),
-                            fa.data(), beams.data()));
+  const std::vector<int32_t>&ai = r->i0, &ns = r->i1, &nd = r->i2, &smap = r->smap;
+  const std::vector<float>&g = r->f0, &a = r->f1, &fg = r->f2, &fa = r->f3;
+  const std::vector<double>& beams = r->beams;
   for (int32_t l = 0; l < L; ++l) {
     const CompactLat& in = b->lats[l];
     const size_t s0 = (size_t)b->state_off[l];
@@ -315,9 +348,26 @@ void ProcessBatch(ToolState* st, Batch* b) {
   }
 #endif
   st->num_lattices += (size_t)L;
-  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  KIO_VLOG(1, "Batch of " << L << " lattices (" << b->arcs() << " arcs): done in " << sec << " seconds.");
-  *b = Batch();
+  KIO_VLOG(1, "Batch of " << L << " lattices (" << b->arcs() << " arcs): done in " << r->sec << " seconds.");
+}
+
+// A wave = up to one batch per GPU, computed concurrently (one host thread + one
+// CUDA stream per GPU, no shared mutable state between contexts), then written in
+// input order.
+void ProcessWave(ToolState* st, std::vector<Batch>* wave) {
+  const size_t nb = wave->size();
+  if (nb == 0) return;
+  std::vector<Results> res(nb);
+  if (nb == 1) {
+    ComputeBatch(st->ctxs[0], &st->opts, &(*wave)[0], &res[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < nb; ++i)
+      th.emplace_back(ComputeBatch, st->ctxs[i], &st->opts, &(*wave)[i], &res[i]);
+    for (auto& t : th) t.join();
+  }
+  for (size_t i = 0; i < nb; ++i) EmitBatch(st, &(*wave)[i], &res[i]);
+  wave->clear();
 }
 
 }  // namespace
@@ -506,27 +556,47 @@ int main(int argc, char* argv[]) {
       st.opts.num_del_groups = (int32_t)st.del_groups.size();
     }
 #endif
-    const char* dev_env = getenv("KLU_DEVICE");
-    KLU_CHECK(klu_create(dev_env ? atoi(dev_env) : 0, &st.ctx));
+    // KLU_DEVICES=0,1,... : one context (stream, buffers) per listed GPU; KLU_DEVICE=n for one
+    {
+      std::vector<int32_t> devs;
+      if (const char* e = getenv("KLU_DEVICES")) {
+        std::string str(e);
+        for (char& ch : str)
+          if (ch == ',') ch = ' ';
+        if (!SplitStringToIntegers(str, " ", true, &devs) || devs.empty()) KIO_ERR("Invalid KLU_DEVICES");
+      } else {
+        const char* dev_env = getenv("KLU_DEVICE");
+        devs.push_back(dev_env ? atoi(dev_env) : 0);
+      }
+      for (int32_t d : devs) {
+        klu_ctx* ctx = nullptr;
+        KLU_CHECK(klu_create(d, &ctx));
+        st.ctxs.push_back(ctx);
+      }
+    }
     int64_t batch_arcs = (int64_t)32 << 20;
     if (const char* e = getenv("KLU_BATCH_ARCS")) batch_arcs = std::max<long long>(1, atoll(e));
 
     const std::string lattice_rspecifier = po.GetArg(kLatArg);
     TableWriter writer(po.GetOptArg(kLatArg + 1));
     st.writer = &writer;
-    Batch batch;
+    std::vector<Batch> wave(1);
     const bool keep = KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */;
     for (SequentialCompactLatticeReader reader(lattice_rspecifier); !reader.Done(); reader.Next()) {
-      batch.Add(std::move(reader.Value()), keep);
-      if (batch.arcs() >= batch_arcs) ProcessBatch(&st, &batch);
+      wave.back().Add(std::move(reader.Value()), keep);
+      if (wave.back().arcs() >= batch_arcs) {
+        if (wave.size() == st.ctxs.size()) ProcessWave(&st, &wave);
+        wave.emplace_back();
+      }
     }
-    ProcessBatch(&st, &batch);
+    if (wave.back().lats.empty()) wave.pop_back();
+    ProcessWave(&st, &wave);
     if (writer.IsOpen()) writer.Close();
 #if KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     KIO_LOG("Overall cost per frame is " << (st.total_cost / st.total_frames) << " over " << st.total_frames
                                          << " frames.");
 #endif
-    klu_destroy(st.ctx);
+    for (klu_ctx* ctx : st.ctxs) klu_destroy(ctx);
     return 0;
   } catch (const std::exception& e) {
     std::cerr << e.what();

@@ -109,6 +109,20 @@ def test_stdin_pipe_scp_and_batching(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tool", ["lattice-word-index-position", "lattice-to-word-frame-post"])
+def test_multi_context_waves_keep_input_order(tool):
+    # KLU_DEVICES: one worker thread + context per listed GPU (here the same GPU
+    # twice), one lattice per batch, three waves: output must equal the single-context run
+    text = open(os.path.join(GOLD, "lattice.ark.txt"), "rb").read()
+    five = b"\n".join(text.replace(b"lat1", b"lat%d" % i) for i in range(1, 6))
+    one = run(tool, "ark:-", "ark,t:-", stdin=five)
+    multi = run(tool, "ark:-", "ark,t:-", stdin=five, env={"KLU_DEVICES": "0,0", "KLU_BATCH_ARCS": "1"})
+    assert one.returncode == 0 and multi.returncode == 0, multi.stderr.decode()
+    assert multi.stdout == one.stdout
+    assert [x.split()[0] for x in multi.stdout.decode().strip("\n").split("\n")] == ["lat%d" % i for i in range(1, 6)]
+
+
+@pytest.mark.gpu
 def test_frame_post_and_best_path_text():
     r = run("lattice-to-word-frame-post", WORD, "ark,t:-")
     assert r.returncode == 0, r.stderr.decode()
