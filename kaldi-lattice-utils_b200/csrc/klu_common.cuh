@@ -136,6 +136,7 @@ struct klu_ctx {
   std::vector<int64_t> h_res_off;  // [L+1] entries per lattice of the last run
   int64_t last_entries = 0;
   int64_t last_chars = 0;
+  void* char_state = nullptr;  // host-side rows of the last char-index run (klu_char.cu)
 
   klu::BatchView view() const;
 };
@@ -184,6 +185,7 @@ struct BestPathChunk {
 int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch);
 // klu_char.cu
 int run_char_position(klu_ctx* c, const klu_opts* o);
+void char_release(klu_ctx* c);
 
 CostParams make_cost_params(const klu_opts* o, bool float_sum);
 int pick_group(double avg_deg);  // lanes cooperating on one state, from the mean degree

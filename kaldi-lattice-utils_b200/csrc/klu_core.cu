@@ -213,6 +213,7 @@ int klu_destroy(klu_ctx* c) {
                     &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_fr_item, &c->d_fr_gloc, &c->d_fr_res_off, &c->d_fr_gword, &c->d_fr_gstart, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
+  char_release(c);
   for (DevBuf* b : bufs) b->release();
   for (auto& b : c->d_scratch) b.release();
   for (auto& b : c->d_res) b.release();

@@ -38,3 +38,53 @@ def assert_rows_match(got, want, nkey, tol=TOL, what=""):
     for i, (g, w) in enumerate(zip(got, want)):
         if g[:nkey] != w[:nkey]:
             assert close(g[-1], w[-1], tol), what + ": order differs beyond tolerance at %d: %r vs %r" % (i, g, w)
+
+
+def char_lattice(klu, rng, key, nwords=4, alphabet=5, punct=(), eps_prob=0.0):
+    """Synthetic HTR-like character lattice: a time-layered DAG, one frame per arc,
+    1-2 states per frame and 1-2 labels per state pair; label 1 is the whitespace
+    delimiter.  Every few frames ALL arcs carry a delimiter (so same-group runs stay
+    short enough for the oracle's explicit sub-path enumeration), elsewhere a delimiter
+    is one of the alternatives now and then (so word counts differ between paths)."""
+    layers = [[0]]
+    nstates = 1
+    arcs = []
+    t = 0
+    for w in range(nwords):
+        wlen = int(rng.randint(1, 5))
+        for k in range(wlen + 1):
+            forced_space = k == wlen and w + 1 < nwords
+            if k == wlen and w + 1 == nwords:
+                break
+            nxt = [nstates + i for i in range(int(rng.randint(1, 3)))]
+            nstates += len(nxt)
+            for u in layers[-1]:
+                for v in nxt:
+                    if len(nxt) > 1 and len(layers[-1]) > 1 and rng.rand() < 0.3:
+                        continue
+                    for _ in range(int(rng.randint(1, 3))):
+                        if forced_space:
+                            lab = 1
+                        else:
+                            x = rng.rand()
+                            if x < 0.12:
+                                lab = 1
+                            elif x < 0.12 + eps_prob:
+                                lab = 0
+                            elif punct and x < 0.25 + eps_prob:
+                                lab = int(punct[rng.randint(len(punct))])
+                            else:
+                                lab = 2 + int(rng.randint(alphabet))
+                        arcs.append((u, v, lab, float(rng.uniform(0, 4)), float(rng.uniform(0, 4)), 1))
+            # every state of the new layer must be reachable, every old one must continue
+            for v in nxt:
+                if not any(a[1] == v for a in arcs):
+                    arcs.append((layers[-1][0], v, 2, 1.0, 1.0, 1))
+            for u in layers[-1]:
+                if not any(a[0] == u for a in arcs):
+                    arcs.append((u, nxt[0], 2, 1.0, 1.0, 1))
+            layers.append(nxt)
+            t += 1
+    finals = {s: (float(rng.uniform(0, 1)), 0.0) for s in layers[-1]}
+    arcs.sort(key=lambda a: a[0])
+    return klu.make_lattice(key, nstates, arcs, finals)
