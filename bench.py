@@ -37,6 +37,9 @@ TOOLS = {"frame_post": 3, "segment": 0, "position": 1, "utterance": 2, "fwd_bwd"
 ALGO = {
     # alpha sweep src+g+a (12) + beta sweep dst+g+a (12); alpha+beta written once (16/state)
     "k_log_sweeps": dict(arc=24.0, state=16.0, entry=0.0),
+    "k_log_sweeps(fwd)": dict(arc=12.0, state=8.0, entry=0.0),
+    # backward sweep + arc posteriors: record read (12 B of it algorithmic) + posterior written (8 B)
+    "k_log_sweeps(bwd+post)": dict(arc=20.0, state=16.0, entry=0.0),
     "k_banded_alpha": dict(arc=12.0, state=0.0, entry=0.0, band=8.0),
     "k_emit": dict(arc=20.0, state=0.0, entry=16.0),
     "k_seg_radix_sort": dict(arc=0.0, state=0.0, entry=16.0),
@@ -50,8 +53,8 @@ ALGO = {
     # group sums: every arc x frame instance reads its arc id (4 B) and the arc's posterior
     # (8 B); per group 4 B offset read + 4 B log-posterior written
     "k_group_post": dict(arc=0.0, state=0.0, entry=8.0, inst=12.0),
-    # per-frame ordering: 4 B logp + 4 B word read, (frame, word, logp) row written
-    "k_frame_order": dict(arc=0.0, state=0.0, entry=20.0),
+    # per-frame ordering: 4 B logp + 4 B word read, (word, logp) written in order (the frame column is static)
+    "k_frame_order": dict(arc=0.0, state=0.0, entry=16.0),
 }
 
 
@@ -320,19 +323,26 @@ def main():
     if args.tool == "frame_post":  # results land in pinned host buffers
         out = (eng.pinned_array(np.int32, entries), eng.pinned_array(np.int32, entries),
                eng.pinned_array(np.float32, entries))
+    parts = []
     for i in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
         eng.load(batch)
+        t1 = time.perf_counter()
         eng.run(tool, **flags)
+        eng.sync()
+        t2 = time.perf_counter()
         _, d2h = fetch_for(eng, klu, args.tool, out)
         eng.sync()
         dt = time.perf_counter() - t0
         if i > 0:
             e2e_ms.append(1e3 * dt)
+            parts.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t0 + dt - t2)))
     e2e_step = reduce_max(sum(e2e_ms) / len(e2e_ms)) if e2e_ms else None
     e2e = {"value": world * arcs / (e2e_step * 1e-3) if e2e_step else None, "unit": "arcs/s",
            "ms_per_step": e2e_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_load_run_fetch": [round(float(np.mean([p[k] for p in parts])), 2) for k in range(3)] if parts else None,
+           "ms_load_run_fetch_each": [[round(x, 1) for x in p] for p in parts],
            "note": "klu_load (H2D of the caller's pinned SoA arrays + device packer) + klu_run + klu_fetch "
                    "(D2H of the full index into pinned buffers), wall clock, max over ranks"}
 

@@ -180,8 +180,12 @@ __device__ void warp_sort_rows_global(float* logp, int32_t* word, int n, int lan
 // one thread per (frame, word) group
 __global__ void __launch_bounds__(256) k_group_post(const __grid_constant__ FrameArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < a.rows; g += stride) {
-    const uint32_t i0 = __ldg(a.gstart + g), i1 = __ldg(a.gstart + g + 1);
+  const int lane = threadIdx.x & 31;
+  // the loop condition is warp-uniform: lanes past the last row idle inside the body
+  for (int64_t gw = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); gw < a.rows; gw += stride) {
+    const int64_t g = gw + lane;
+    const bool live = g < a.rows;
+    const uint32_t i0 = live ? __ldg(a.gstart + g) : 0u, i1 = live ? __ldg(a.gstart + g + 1) : 0u;
     double sum = 0.0;
     // four instances per trip (most groups have <= 4): the id loads, then the
     // posterior gathers, go out together; the adds stay in arc order
@@ -195,8 +199,9 @@ __global__ void __launch_bounds__(256) k_group_post(const __grid_constant__ Fram
 #pragma unroll
       for (int u = 0; u < 4; ++u) sum += p[u];
     }
-    double lp;
-    if (sum >= 1e-280) {
+    double lp = 0.0;
+    if (!live) {
+    } else if (sum >= 1e-280) {
       lp = fast_log(sum);
     } else {
       int lo = 0, hi = a.b.L - 1;  // lattice of this row: last l with res_off[l] <= g
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(256) k_group_post(const __grid_constant__ Fram
       }
       lp = exact_group_logp(a, a.b.frame_arc, i1 - 1, a.total[lo]);
     }
-    a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+    if (live) a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
   }
 }
 
@@ -277,7 +282,6 @@ __device__ __forceinline__ void order_frame(const FrameArgs& a, int64_t dst, int
     const unsigned int idx = s_sorted[g] & kMask;
     const unsigned int fk = s_key[idx];
     if (g + 1 < c) bad |= fk > s_key[s_sorted[g + 1] & kMask];
-    a.o_frame[dst + g] = k;
     a.o_word[dst + g] = __ldg(a.gwords + dst + idx);
     a.o_logp[dst + g] = inv_ord_f32(~fk);
   }
@@ -328,10 +332,7 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_order(const __grid_c
       else if (c <= 128) order_frame<4>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
       else if (c <= 256) order_frame<8>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
       else {
-        for (int g = lane; g < c; g += 32) {
-          a.o_frame[dst + g] = k;
-          a.o_word[dst + g] = __ldg(a.gwords + dst + g);
-        }
+        for (int g = lane; g < c; g += 32) a.o_word[dst + g] = __ldg(a.gwords + dst + g);
         __syncwarp();
         warp_sort_rows_global(a.o_logp + dst, a.o_word + dst, c, lane);
       }
@@ -357,6 +358,7 @@ struct GroupArgs {
   int32_t* lat_cnt;
   const int64_t* res_off;
   int32_t* gwords;
+  int32_t* gframe;
   uint32_t* gstart;
 };
 
@@ -449,6 +451,7 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
         } else if (head) {
           const int64_t row = a.res_off[l] + a.gloc[fs] + groups + __popc(hm & ((1u << lane) - 1u));
           a.gwords[row] = (int32_t)(kk & label_mask);
+          a.gframe[row] = k;
           a.gstart[row] = (uint32_t)i;
         }
         groups += __popc(hm);
@@ -570,15 +573,11 @@ int build_frame_groups(klu_ctx* c) {
     set_error("frame index key does not fit 62 bits (labels/times too large)");
     return 1;
   }
-  // scratch (released afterwards: 28 bytes per instance would otherwise stay resident)
-  DevBuf key_a, key_b, val_a, val_b, misc;
-  auto release_all = [&]() {
-    key_a.release();
-    key_b.release();
-    val_a.release();
-    val_b.release();
-    misc.release();
-  };
+  // scratch: the context's tool-scratch slots (free while loading; they stay allocated, so
+  // repeated loads do not go through cudaMalloc / cudaFree again)
+  DevBuf &key_a = c->d_scratch[6], &key_b = c->d_scratch[7], &val_a = c->d_scratch[8], &val_b = c->d_scratch[9],
+         &misc = c->d_scratch[10];
+  auto release_all = [&]() {};
   int rc = 0;
   do {
     if ((rc = key_a.reserve(8 * (size_t)N)) || (rc = key_b.reserve(8 * (size_t)N)) ||
@@ -659,7 +658,9 @@ int build_frame_groups(klu_ctx* c) {
     }
     if ((rc = c->d_fr_gword.reserve(4 * (size_t)std::max<int64_t>(c->h_frame_res_off[L], 1)))) break;
     if ((rc = c->d_fr_gstart.reserve(4 * (size_t)(c->h_frame_res_off[L] + 1)))) break;
+    if ((rc = c->d_fr_gframe.reserve(4 * (size_t)std::max<int64_t>(c->h_frame_res_off[L], 1)))) break;
     a.gwords = c->d_fr_gword.as<int32_t>();
+    a.gframe = c->d_fr_gframe.as<int32_t>();
     a.gstart = c->d_fr_gstart.as<uint32_t>();
     {
       const uint32_t n32 = (uint32_t)N;
@@ -687,13 +688,13 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   CostParams cp = make_cost_params(o, false);
   KLU_TRY(run_log_sweeps(c, cp, false, 0.f));
   c->h_res_off = c->h_frame_res_off;
+  c->frame_col_static = true;
   c->h_res_off.resize(L + 1, 0);
   c->last_entries = L ? c->h_res_off[L] : 0;
   if (L == 0) return 0;
   const int64_t N = std::max<int64_t>(c->last_entries, 1);
   KLU_TRY(c->d_scratch[0].reserve(8 * (size_t)std::max<int64_t>(c->E, 1)));
   KLU_TRY(c->d_res[5].reserve(8 * (size_t)(L + 1)));
-  KLU_TRY(c->d_res[0].reserve(4 * (size_t)N));
   KLU_TRY(c->d_res[1].reserve(4 * (size_t)N));
   KLU_TRY(c->d_res[4].reserve(4 * (size_t)N));
   KLU_CUDA(cudaMemcpyAsync(c->d_res[5].p, c->d_fr_res_off.p, 8 * (size_t)(L + 1), cudaMemcpyDeviceToDevice, c->stream));
@@ -712,7 +713,7 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   a.gwords = c->d_fr_gword.as<int32_t>();
   a.gstart = c->d_fr_gstart.as<uint32_t>();
   a.rows = c->last_entries;
-  a.o_frame = c->d_res[0].as<int32_t>();
+  a.o_frame = nullptr;  // the frame column is static per batch (d_fr_gframe)
   a.o_word = c->d_res[1].as<int32_t>();
   a.o_logp = c->d_res[4].as<float>();
   {

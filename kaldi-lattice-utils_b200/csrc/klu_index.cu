@@ -990,7 +990,9 @@ int klu_fetch_frame_post(klu_ctx* c, int32_t* num_frames, int32_t* frame, int32_
   KLU_TRY(ensure_offsets(c));
   const size_t n = (size_t)c->last_entries;
   if (num_frames) memcpy(num_frames, c->h_num_frames.data(), sizeof(int32_t) * c->L);
-  KLU_TRY(d2h(c, frame, c->d_res[0].p, n * 4));
+  // the frame column of the frame-synchronous path is static per batch (klu_frame.cu);
+  // the generic pipeline (KLU_GENERIC_FRAME_POST) writes its own
+  KLU_TRY(d2h(c, frame, c->frame_col_static ? c->d_fr_gframe.p : c->d_res[0].p, n * 4));
   KLU_TRY(d2h(c, word, c->d_res[1].p, n * 4));
   KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 4));
   KLU_CUDA(cudaStreamSynchronize(c->stream));
