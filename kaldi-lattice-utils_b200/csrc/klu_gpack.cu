@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <numeric>
 
 #include "klu_common.cuh"
@@ -425,6 +426,12 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   });
   DevBuf* sc = c->d_scratch;
   enum { R_SRC = 0, R_DST, R_LABEL, R_DUR, R_G, R_A, R_KEYA, R_KEYB, R_VALA, R_VALB, R_MISC, R_MISC2 };
+  // Host-to-device copies of different contexts take turns (one process-wide lock held
+  // until this batch's copies have landed): with several contexts on one GPU -- the
+  // tools' worker threads, a pipelined caller -- the next batch's upload then overlaps
+  // this batch's packing, run and result download instead of interleaving with its upload.
+  static std::mutex h2d_turn;
+  std::unique_lock<std::mutex> h2d_lock(h2d_turn);
   KLU_TRY(upload(c, c->d_s_off, s_off.data(), 4 * (size_t)(L + 1)));
   KLU_TRY(upload(c, c->d_e_off, e_off.data(), 4 * (size_t)(L + 1)));
   KLU_TRY(upload(c, c->d_order, order.data(), 4 * (size_t)L));
@@ -446,6 +453,8 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
     KLU_CUDA(cudaMemcpyAsync(r_fa, in->fin_acoustic, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
     if (in->fin_dur) KLU_CUDA(cudaMemcpyAsync(r_fdur, in->fin_dur, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
   }
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  h2d_lock.unlock();
   // per-lattice metadata: meta (L x 8 int), cap (2L int64), lat_tot (L+1 int64), where flags
   KLU_TRY(sc[R_MISC2].reserve(4 * (size_t)M_STRIDE * (L + 1) + 8 * (size_t)(3 * L + 4) + 2 * (size_t)L + 64));
   char* m2 = sc[R_MISC2].as<char>();
