@@ -147,6 +147,8 @@ def dist_setup(n):
 
 
 def flags_for(tool):
+    if tool == "prune_dyn_beam":  # BASELINE.json configs[2]
+        return dict(max_arcs=20000, max_states=1500, beam_ratio=0.9)
     return dict(acoustic_scale=0.1)
 
 
@@ -167,6 +169,12 @@ def fetch_for(eng, klu, tool, out=None):
     if t == klu.FWD_BWD:
         r = eng.fetch_fwd_bwd()
         return 0, sum(int(x.nbytes) for x in r)
+    if t == klu.PRUNE_DYN_BEAM:
+        r = eng.fetch_prune()
+        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
+    if t == klu.BEST_PATH2:
+        r = eng.fetch_best_path2()
+        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
     raise ValueError(tool)
 
 
