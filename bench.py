@@ -316,8 +316,14 @@ def main():
     achieved = algo_bytes(dom) / (dom_ms * 1e-3) / 1e9
     # whole-pipeline algorithmic model of SURVEY.md 8d: 76 B/arc + 28 B/state
     pipe_bytes = 76.0 * arcs + 28.0 * states
+    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if dom in tj:
+            traffic = tj[dom]["dram_bytes_per_arc"] * arcs
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes(dom),
                 "pipeline_frac_76B_per_arc": pipe_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "kernels": kern}
