@@ -257,8 +257,7 @@ __device__ __forceinline__ void bitonic_regs(unsigned int (&v)[R], int lane) {
 // checked against the full keys afterwards and such a frame (a few per cent) is redone
 // with 64-bit keys in shared memory.
 template <int R>
-__device__ __forceinline__ void order_frame(const FrameArgs& a, int64_t dst, int c, int k, int lane,
-                                            unsigned int* s_key, unsigned int* s_sorted,
+__device__ __forceinline__ void order_frame(const FrameArgs& a, int64_t dst, int c, int lane, unsigned int* s_key,
                                             unsigned long long* sortbuf) {
   constexpr unsigned int kMask = 32u * R - 1u;
   unsigned int v[R];
@@ -274,16 +273,23 @@ __device__ __forceinline__ void order_frame(const FrameArgs& a, int64_t dst, int
     v[r] = pk;
   }
   bitonic_regs<R>(v, lane);
+  __syncwarp();  // s_key is complete
+  // rows leave straight from the registers (position p = lane * R + r); the order is
+  // checked against the full keys on the way
+  unsigned int fk[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) s_sorted[lane * R + r] = v[r];
-  __syncwarp();
+  for (int r = 0; r < R; ++r) fk[r] = s_key[v[r] & kMask];
+  const unsigned int next0 = __shfl_down_sync(0xffffffffu, fk[0], 1);
   bool bad = false;
-  for (int g = lane; g < c; g += 32) {
-    const unsigned int idx = s_sorted[g] & kMask;
-    const unsigned int fk = s_key[idx];
-    if (g + 1 < c) bad |= fk > s_key[s_sorted[g + 1] & kMask];
-    a.o_word[dst + g] = __ldg(a.gwords + dst + idx);
-    a.o_logp[dst + g] = inv_ord_f32(~fk);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int p = lane * R + r;
+    if (p < c) {
+      const unsigned int nx = r + 1 < R ? fk[r + 1 < R ? r + 1 : r] : next0;
+      if (p + 1 < c) bad |= fk[r] > nx;
+      a.o_word[dst + p] = __ldg(a.gwords + dst + (v[r] & kMask));
+      a.o_logp[dst + p] = inv_ord_f32(~fk[r]);
+    }
   }
   if (__any_sync(0xffffffffu, bad)) {
     constexpr int N = 32 * R;
@@ -300,10 +306,9 @@ __device__ __forceinline__ void order_frame(const FrameArgs& a, int64_t dst, int
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kFrameWarps * 32) k_frame_order(const __grid_constant__ FrameArgs a) {
+__global__ void __launch_bounds__(kFrameWarps * 32, 8) k_frame_order(const __grid_constant__ FrameArgs a) {
   __shared__ __align__(16) unsigned long long s_sort[kFrameWarps][kGroupCap];
   __shared__ unsigned int s_keys[kFrameWarps][kGroupCap];
-  __shared__ unsigned int s_sorted[kFrameWarps][kGroupCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BatchView& b = a.b;
   for (int item = blockIdx.x * kFrameWarps + warp; item < a.num_items; item += gridDim.x * kFrameWarps) {
@@ -327,10 +332,10 @@ __global__ void __launch_bounds__(kFrameWarps * 32) k_frame_order(const __grid_c
       const int c = (int)(g_next - g0);
       if (c == 0) continue;
       const int64_t dst = out0 + g0;
-      if (c <= 32) order_frame<1>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
-      else if (c <= 64) order_frame<2>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
-      else if (c <= 128) order_frame<4>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
-      else if (c <= 256) order_frame<8>(a, dst, c, k, lane, s_keys[warp], s_sorted[warp], s_sort[warp]);
+      if (c <= 32) order_frame<1>(a, dst, c, lane, s_keys[warp], s_sort[warp]);
+      else if (c <= 64) order_frame<2>(a, dst, c, lane, s_keys[warp], s_sort[warp]);
+      else if (c <= 128) order_frame<4>(a, dst, c, lane, s_keys[warp], s_sort[warp]);
+      else if (c <= 256) order_frame<8>(a, dst, c, lane, s_keys[warp], s_sort[warp]);
       else {
         for (int g = lane; g < c; g += 32) a.o_word[dst + g] = __ldg(a.gwords + dst + g);
         __syncwarp();
