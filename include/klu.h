@@ -16,6 +16,7 @@
  *                      (+ fstext/fstext-utils2.h:109-271)
  *   KLU_CHAR_POSITION  kwsbin2/lattice-char-index-position.cc:137-284
  *                      (+ kwsbin2/utils.h:41-303, fstext/fstext-utils2.h:278-603)
+ *   KLU_POSITION_POST  latbin/lattice-to-word-position-post.cc:70-141
  *
  * Plain pointers and sizes only; all pointers are HOST pointers.  Every function
  * returns 0 on success; on failure klu_last_error() (thread-local) explains.
@@ -51,7 +52,8 @@ enum klu_tool {
   KLU_PRUNE_DYN_BEAM = 4,
   KLU_BEST_PATH2 = 5,
   KLU_CHAR_POSITION = 6,
-  KLU_FWD_BWD = 7 /* alpha/beta only (ComputeLatticeAlphasAndBetas [ext]) */
+  KLU_FWD_BWD = 7, /* alpha/beta only (ComputeLatticeAlphasAndBetas [ext]) */
+  KLU_POSITION_POST = 8
 };
 
 /* A batch of lattices as concatenated SoA arrays.  state_off/arc_off have
@@ -141,6 +143,9 @@ int klu_fetch_utterance(klu_ctx* ctx, int32_t* word, double* logp);
 /* frame-post: num_frames[num_lattices] (Posterior length incl. empty frames);
  * entries carry their frame index. */
 int klu_fetch_frame_post(klu_ctx* ctx, int32_t* num_frames, int32_t* frame, int32_t* word, float* logp);
+/* position-post: num_positions[num_lattices] (Posterior length = longest label sequence);
+ * entries carry their 0-based position index. */
+int klu_fetch_position_post(klu_ctx* ctx, int32_t* num_positions, int32_t* position, int32_t* word, float* logp);
 /* best-path2: entries are the transcript labels; cost[num_lattices] (float path
  * cost, latbin/lattice-best-path2.cc:192), num_frames[num_lattices]. */
 int klu_fetch_best_path2(klu_ctx* ctx, int32_t* label, float* cost, int32_t* num_frames);

@@ -12,17 +12,18 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD = range(8)
+SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST = range(9)
 TOOL_NAMES = {SEGMENT: "lattice-word-index-segment", POSITION: "lattice-word-index-position",
               UTTERANCE: "lattice-word-index-utterance", FRAME_POST: "lattice-to-word-frame-post",
               PRUNE_DYN_BEAM: "lattice-prune-dyn-beam", BEST_PATH2: "lattice-best-path2",
-              CHAR_POSITION: "lattice-char-index-position", FWD_BWD: "fwd-bwd"}
+              CHAR_POSITION: "lattice-char-index-position", FWD_BWD: "fwd-bwd",
+              POSITION_POST: "lattice-to-word-position-post"}
 INT_MAX = 2**31 - 1
 
 # every symbol include/klu.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["klu_last_error", "klu_version", "klu_opts_default", "klu_device_count", "klu_create", "klu_destroy",
            "klu_host_alloc", "klu_host_free", "klu_topsort", "klu_load", "klu_run", "klu_sync", "klu_result_offsets",
-           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post",
+           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_position_post",
            "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position",
            "klu_fetch_fwd_bwd", "klu_timer_start", "klu_timer_stop", "klu_launch_count", "klu_profile_enable",
            "klu_profile_json", "klu_batch_stats", "klu_flush_l2"]
@@ -215,6 +216,15 @@ class Engine:
         _chk(self.L.klu_fetch_frame_post(self.h, _p(nf), _p(fr), _p(w), _p(lp)))
         return off, nf, fr, w, lp
 
+    def fetch_position_post(self):
+        off = self.offsets()
+        n = int(off[-1])
+        npos = np.zeros(len(self.batch), np.int32)
+        pos, w = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lp = np.zeros(n, np.float32)
+        _chk(self.L.klu_fetch_position_post(self.h, _p(npos), _p(pos), _p(w), _p(lp)))
+        return off, npos, pos, w, lp
+
     def fetch_best_path2(self):
         off = self.offsets()
         n = int(off[-1])
@@ -283,6 +293,18 @@ class Engine:
             for k, ww, p in zip(fr[a:b].tolist(), w[a:b].tolist(), lp[a:b].tolist()):
                 frames[k].append((ww, p))
             res.append(frames)
+        return res
+
+    def position_post(self, **o):
+        """Per lattice: list (one per transcript position) of lists of (word, float32 logp)."""
+        self.run(POSITION_POST, **o)
+        off, npos, pos, w, lp = self.fetch_position_post()
+        res = []
+        for l, (a, b) in enumerate(zip(off[:-1], off[1:])):
+            rows = [[] for _ in range(int(npos[l]))]
+            for k, ww, p in zip(pos[a:b].tolist(), w[a:b].tolist(), lp[a:b].tolist()):
+                rows[k].append((ww, p))
+            res.append(rows)
         return res
 
     def best_path2(self, **o):

@@ -277,6 +277,7 @@ int klu_run(klu_ctx* c, int tool, const klu_opts* opts) {
     case KLU_FWD_BWD:
     case KLU_UTTERANCE:
     case KLU_BEST_PATH2:
+    case KLU_POSITION_POST:
       rc = run_index_tool(c, tool, opts);
       break;
     case KLU_PRUNE_DYN_BEAM:

@@ -84,7 +84,7 @@ __device__ __forceinline__ int arc_entry_count(const IndexArgs& a, int e, int T)
     const int fa = max(a.b.time[a.b.out_src[e]], 0), fb = min(a.b.time[r.x], T);
     return fb > fa ? fb - fa : 0;
   }
-  if (a.tool == KLU_BEST_PATH2) {
+  if (a.tool == KLU_BEST_PATH2 || a.tool == KLU_POSITION_POST) {
     if (r.w == 0) return 0;
   } else if (!label_valid(a, r.w)) {
     return 0;
@@ -177,8 +177,9 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
         a.aux[base + o] = arc_local;
         a.idx[base + o] = (unsigned int)o;
       }
-    } else {  // KLU_POSITION, KLU_BEST_PATH2: one entry per (arc, #labels before it)
-      if (a.tool == KLU_BEST_PATH2 ? (r.w == 0) : !label_valid(a, r.w)) continue;
+    } else {  // KLU_POSITION, KLU_BEST_PATH2, KLU_POSITION_POST: one entry per (arc, #labels before it)
+      const bool plain = a.tool == KLU_BEST_PATH2 || a.tool == KLU_POSITION_POST;
+      if (plain ? (r.w == 0) : !label_valid(a, r.w)) continue;
       const int w = (int)(a.b.band_off[s + 1] - a.b.band_off[s]);
       if (w <= 0) continue;
       const bool dead = a.use_beam && emit_arc_pruned(a, l, s, r);
@@ -188,9 +189,13 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
         const double al = a.alpha2[a.b.band_off[s] - a.band_base + i];
         // fw[(len,s)] + arc_lkh + bw[next] (position tool, :162-163) or
         // fw[u] + bw[v] - cost (best-path2, :134); beta of the unfolded lattice = beta[next]
-        const double v = a.tool == KLU_BEST_PATH2 ? __dadd_rn(__dadd_rn(al, a.beta[r.x]), tail)
-                                                  : __dadd_rn(__dadd_rn(al, tail), a.beta[r.x]);
-        const unsigned long long k = ((unsigned long long)r.w << a.bits_len) | (unsigned long long)(lo + i);
+        // position-post: fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-position-post.cc:111-113
+        const double v = plain ? __dadd_rn(__dadd_rn(al, a.beta[r.x]), tail)
+                               : __dadd_rn(__dadd_rn(al, tail), a.beta[r.x]);
+        // position-post groups by position first: key = (state_len[next] = lo + i + 1, word)
+        const unsigned long long k = a.tool == KLU_POSITION_POST
+                                         ? (((unsigned long long)(lo + i + 1) << a.bits_label) | (unsigned long long)r.w)
+                                         : (((unsigned long long)r.w << a.bits_len) | (unsigned long long)(lo + i));
         const int o = off + i;
         a.key[base + o] = (dead || !(al > neg_inf())) ? a.drop_key : k;
         a.val[base + o] = v;
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       a.rval[base + slot] = logp;
       a.raux[base + slot] = besta;
       logp = logp + 0.0;  // -0.0 and +0.0 compare equal in the reference's sort
-      if (a.tool == KLU_FRAME_POST) {
+      if (a.tool == KLU_FRAME_POST || a.tool == KLU_POSITION_POST) {
         const float f = (float)logp + 0.0f;
         a.key2[base + slot] = ((k >> a.bits_label) << 32) | (unsigned long long)(~ord_f32(f));
       } else {
@@ -412,9 +417,9 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
       a.c2[out + i] = a.b.time[a.b.out_src[e]];
       a.c3[out + i] = a.b.time[a.b.out_rec[e].x];
       a.v[out + i] = logp;
-    } else {  // frame post
+    } else {  // frame post / position post (0-based position index)
       const unsigned long long lm = (1ULL << a.bits_label) - 1ULL;
-      a.c0[out + i] = (int32_t)(k >> a.bits_label);
+      a.c0[out + i] = (int32_t)(k >> a.bits_label) - (a.tool == KLU_POSITION_POST ? 1 : 0);
       a.c1[out + i] = (int32_t)(k & lm);
       a.vf[out + i] = (float)logp;
     }
@@ -560,7 +565,7 @@ int bits_for(int64_t maxv) {
 
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   const int32_t L = c->L;
-  const bool needs_times = tool != KLU_FWD_BWD && tool != KLU_UTTERANCE;  // best-path2 reports frames (:102)
+  const bool needs_times = tool != KLU_FWD_BWD && tool != KLU_UTTERANCE && tool != KLU_POSITION_POST;  // best-path2 reports frames (:102)
   if (needs_times)
     for (int32_t l = 0; l < L; ++l)
       if (!c->h_times_ok[l]) {
@@ -568,7 +573,8 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
         set_error("lattice " + std::to_string(l) + ": inconsistent state times (lattice is not aligned)");
         return 1;
       }
-  const bool use_beam = tool != KLU_FRAME_POST && tool != KLU_FWD_BWD && tool != KLU_BEST_PATH2 && o->beam != INFINITY;
+  const bool use_beam = tool != KLU_FRAME_POST && tool != KLU_FWD_BWD && tool != KLU_BEST_PATH2 &&
+                        tool != KLU_POSITION_POST && o->beam != INFINITY;
   if (use_beam && !(o->beam > 0.0f)) {
     set_error("--beam must be positive");  // KALDI_ASSERT(beam > 0.0) in PruneLattice [ext]
     return 1;
@@ -594,7 +600,8 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     for (int32_t l = 0; l < L; ++l) {
       const int64_t cap = (tool == KLU_SEGMENT || tool == KLU_UTTERANCE) ? (c->h_e_off[l + 1] - c->h_e_off[l])
                           : tool == KLU_FRAME_POST ? c->h_cap_frame[l] : c->h_cap_pos[l];
-      const int64_t band = (tool == KLU_POSITION || tool == KLU_BEST_PATH2) ? c->h_band_off[l + 1] - c->h_band_off[l] : 0;
+      const int64_t band = (tool == KLU_POSITION || tool == KLU_BEST_PATH2 || tool == KLU_POSITION_POST)
+                               ? c->h_band_off[l + 1] - c->h_band_off[l] : 0;
       if (cap >= ((int64_t)1 << 31)) {
         set_error("lattice " + std::to_string(l) + ": more than 2^31 index entries");
         return 1;
@@ -641,11 +648,12 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // ent_base is a stack object
 
   int fmode = 0, fn = 0;
-  if (tool != KLU_FRAME_POST && tool != KLU_BEST_PATH2) KLU_TRY(upload_filter(c, o, &fmode, &fn));
+  if (tool != KLU_FRAME_POST && tool != KLU_BEST_PATH2 && tool != KLU_POSITION_POST)
+    KLU_TRY(upload_filter(c, o, &fmode, &fn));
 
   IndexArgs a;
   a.b = c->view();
-  a.cp = make_cost_params(o, tool == KLU_FRAME_POST);  // F1 adds g + a in float
+  a.cp = make_cost_params(o, tool == KLU_FRAME_POST || tool == KLU_POSITION_POST);  // these add g + a in float
   a.tool = tool;
   a.filter_mode = fmode;
   a.filter_n = fn;
@@ -671,9 +679,10 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   int key_bits = 0;
   if (tool == KLU_UTTERANCE) key_bits = a.bits_label;
   else if (tool == KLU_SEGMENT) key_bits = a.bits_label + 2 * a.bits_time;
-  else if (tool == KLU_POSITION || tool == KLU_BEST_PATH2) key_bits = a.bits_label + a.bits_len;
+  else if (tool == KLU_POSITION || tool == KLU_BEST_PATH2 || tool == KLU_POSITION_POST)
+    key_bits = a.bits_label + a.bits_len + (tool == KLU_POSITION_POST ? 1 : 0);  // positions run to max_len inclusive
   else key_bits = a.bits_time + a.bits_label;
-  if (key_bits > 62 || (tool == KLU_FRAME_POST && a.bits_time > 31)) {
+  if (key_bits > 62 || (tool == KLU_FRAME_POST && a.bits_time > 31) || (tool == KLU_POSITION_POST && a.bits_len > 30)) {
     set_error("index key does not fit 62 bits (labels/times too large)");
     return 1;
   }
@@ -704,7 +713,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     if (nl <= 0) continue;
     a.l0 = l0;
     a.band_base = 0;
-    if (tool == KLU_POSITION || tool == KLU_BEST_PATH2) {
+    if (tool == KLU_POSITION || tool == KLU_BEST_PATH2 || tool == KLU_POSITION_POST) {
       KLU_TRY(run_banded_alpha(c, cp, use_beam, o->beam, l0, l1));
       a.band_base = c->h_band_off[l0];
     }
@@ -993,6 +1002,21 @@ int klu_fetch_frame_post(klu_ctx* c, int32_t* num_frames, int32_t* frame, int32_
   // the frame column of the frame-synchronous path is static per batch (klu_frame.cu);
   // the generic pipeline (KLU_GENERIC_FRAME_POST) writes its own
   KLU_TRY(d2h(c, frame, c->frame_col_static ? c->d_fr_gframe.p : c->d_res[0].p, n * 4));
+  KLU_TRY(d2h(c, word, c->d_res[1].p, n * 4));
+  KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 4));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int klu_fetch_position_post(klu_ctx* c, int32_t* num_positions, int32_t* position, int32_t* word, float* logp) {
+  if (c->last_tool != KLU_POSITION_POST) {
+    set_error("klu_fetch_position_post: last run was not KLU_POSITION_POST");
+    return 1;
+  }
+  KLU_TRY(ensure_offsets(c));
+  const size_t n = (size_t)c->last_entries;
+  if (num_positions) memcpy(num_positions, c->h_maxlen.data(), sizeof(int32_t) * c->L);
+  KLU_TRY(d2h(c, position, c->d_res[0].p, n * 4));
   KLU_TRY(d2h(c, word, c->d_res[1].p, n * 4));
   KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 4));
   KLU_CUDA(cudaStreamSynchronize(c->stream));

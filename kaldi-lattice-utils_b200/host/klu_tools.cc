@@ -11,6 +11,7 @@
 //   lattice-to-word-frame-post    latbin/lattice-to-word-frame-post.cc:29-147
 //   lattice-prune-dyn-beam        latbin/lattice-prune-dyn-beam.cc:97-214
 //   lattice-best-path2            latbin/lattice-best-path2.cc:29-221
+//   lattice-to-word-position-post latbin/lattice-to-word-position-post.cc:28-147
 //
 // Lattices are independent, so the reader fills a batch (KLU_BATCH_ARCS arcs,
 // default 32M), the batch is packed/uploaded/processed, and entries are written
@@ -140,6 +141,9 @@ void ComputeBatch(klu_ctx* ctx, const klu_opts* opts, const Batch* b, Results* r
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */
     r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
     KLU_CHECK(klu_fetch_frame_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
+#elif KLU_TOOL == 8 /* KLU_POSITION_POST */
+    r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
+    KLU_CHECK(klu_fetch_position_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
 #elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     r->i0.resize(n), r->i1.resize(L), r->f0.resize(L);
     KLU_CHECK(klu_fetch_best_path2(ctx, r->i0.data(), r->f0.data(), r->i1.data()));
@@ -244,7 +248,7 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
     if (!bin) os << '\n';
     w.End();
   }
-#elif KLU_TOOL == 3 /* KLU_FRAME_POST */
+#elif KLU_TOOL == 3 /* KLU_FRAME_POST */ || KLU_TOOL == 8 /* KLU_POSITION_POST */
   const std::vector<int32_t>&nf = r->i0, &frame = r->i1, &word = r->i2;
   const std::vector<float>& lp = r->f0;
   for (int32_t l = 0; l < L; ++l) {
@@ -419,6 +423,13 @@ int main(int argc, char* argv[]) {
         "log P(a_i = v | x), for all possible utterance frames i and words v.\n\n"
         "Usage: lattice-to-word-frame-post [options] lat-rspecifier post-wspecifier\n"
         " e.g.: lattice-to-word-frame-post --acoustic-scale=0.1 ark:1.lats ark:1.word.pos.post\n";
+#elif KLU_TOOL == 8 /* KLU_POSITION_POST */
+    const char* usage =
+        "Compute the posterior log-probability of each word for each given transcription position. That is, we "
+        "compute log P(w_k = v | x), for all possible transcript position k, and words v.\n\n"
+        "Usage: lattice-to-word-position-post [options] lat-rspecifier post-wspecifier [segm-wspecifier]\n"
+        " e.g.: lattice-to-word-position-post --acoustic-scale=0.1 ark:1.lats ark:1.word.pos.post\n"
+        "See also: lattice-to-word-frame-post\n";
 #elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
     const char* usage =
         "Iteratively reduce the beam of the lattice until a maximum number of arcs and states is achieved.\n\n"
@@ -473,6 +484,12 @@ int main(int argc, char* argv[]) {
       exit(1);
     }
     const int kLatArg = 2;
+#elif KLU_TOOL == 8 /* KLU_POSITION_POST */
+    if (po.NumArgs() != 2 && po.NumArgs() != 3) {  // latbin/lattice-to-word-position-post.cc:60-63
+      po.PrintUsage();
+      exit(1);
+    }
+    const int kLatArg = 1;
 #elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     if (po.NumArgs() < 1 || po.NumArgs() > 2) {
       po.PrintUsage();

@@ -715,6 +715,45 @@ void WordFramePost(Lat lat, const Opts& o, Result* r) {
   r->ds0 = total;
 }
 
+// latbin/lattice-to-word-position-post.cc:70-141: the position
+// tool's math with pos = state_len[next], the arc term -(g + a) added in FLOAT (:111-113),
+// no label filter / beam, a Posterior (one frame per position) as output: per position
+// the (word, float logp) pairs sorted by (float logp desc, word asc) (:128-134).
+void WordPositionPost(Lat lat0, const Opts& o, Result* r) {
+  Prologue(&lat0, o, false);
+  if (lat0.Empty()) { r->s0 = 0; return; }
+  Lat lat;
+  std::vector<int32> state_len;
+  const int32 max_len = DisambiguateLength(lat0, &lat, &state_len);
+  std::vector<double> fw, bw;
+  const double total = AlphasAndBetas(lat, &fw, &bw);
+  std::vector<std::map<int32, double> > acc(max_len + 1);  // acc[0] is not used
+  for (int32 u = 0; u < lat.NumStates(); ++u) {
+    for (const auto& arc : lat.out[u]) {
+      if (arc.label == 0) continue;
+      const int32 pos = state_len[arc.next];
+      const double through = fw[u] + bw[arc.next] - (arc.g + arc.a);  // float add, :113
+      auto rr = acc[pos].emplace(arc.label, through);
+      if (!rr.second) rr.first->second = LogAdd(rr.first->second, through);
+    }
+  }
+  for (int32 n = 1; n <= max_len; ++n) {
+    std::vector<std::pair<int32, float> > post;
+    for (const auto& kv : acc[n]) post.emplace_back(kv.first, (float)(kv.second - total));
+    std::sort(post.begin(), post.end(), [](const std::pair<int32, float>& a, const std::pair<int32, float>& b) -> bool {
+      if (a.second != b.second) return b.second < a.second;
+      else return a.first < b.first;
+    });
+    for (const auto& p : post) {
+      r->i0.push_back(n - 1);
+      r->i1.push_back(p.first);
+      r->f0.push_back(p.second);
+    }
+  }
+  r->s0 = max_len;
+  r->ds0 = total;
+}
+
 // latbin/lattice-prune-dyn-beam.cc:27-90
 double ComputeLatticeBeam(const Lat& lat) {
   const int32 num_states = lat.NumStates();
@@ -1236,7 +1275,7 @@ typedef struct ora_opts {
 } ora_opts;
 
 enum { ORA_SEGMENT = 0, ORA_POSITION = 1, ORA_UTTERANCE = 2, ORA_FRAME_POST = 3, ORA_PRUNE_DYN_BEAM = 4,
-       ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
+       ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
        ORA_BRUTE_FRAME = 12, ORA_BRUTE_UTTERANCE = 13 };
 
 static Opts ConvertOpts(const ora_opts* o) {
@@ -1271,6 +1310,7 @@ static void RunTool(int tool, const ora_lat* l, const Opts& o, Result* r) {
     case ORA_PRUNE_DYN_BEAM: PruneDynBeam(lat, o, r); break;
     case ORA_BEST_PATH2: BestPath2(lat, o, r); break;
     case ORA_CHAR_POSITION: CharIndexPosition(lat, o, r); break;
+    case ORA_POSITION_POST: WordPositionPost(lat, o, r); break;
     case ORA_BRUTE_SEGMENT: BruteForce(lat, 0, r); break;
     case ORA_BRUTE_POSITION: BruteForce(lat, 1, r); break;
     case ORA_BRUTE_FRAME: BruteForce(lat, 2, r); break;

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION = range(7)
+POSITION_POST = 8
 BRUTE_SEGMENT, BRUTE_POSITION, BRUTE_FRAME, BRUTE_UTTERANCE = 10, 11, 12, 13
 
 INT_MAX = 2**31 - 1
@@ -185,6 +186,16 @@ def frame_post(lat, **o):
     for k, w, p in zip(r.i[0].tolist(), r.i[1].tolist(), r.f[0].tolist()):
         frames[k].append((w, p))
     return frames
+
+
+def position_post(lat, **o):
+    """latbin/lattice-to-word-position-post: list (one per transcript position) of lists of
+    (word, float32 logp)."""
+    r = run(POSITION_POST, lat, **o)
+    pos = [[] for _ in range(r.s0)]
+    for k, w, p in zip(r.i[0].tolist(), r.i[1].tolist(), r.f[0].tolist()):
+        pos[k].append((w, p))
+    return pos
 
 
 def best_path2(lat, **o):

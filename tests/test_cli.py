@@ -11,7 +11,8 @@ from util import GOLD, goldens
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "kaldi-lattice-utils_b200", "bin")
 TOOLS = ["lattice-word-index-segment", "lattice-word-index-position", "lattice-word-index-utterance",
-         "lattice-to-word-frame-post", "lattice-prune-dyn-beam", "lattice-best-path2", "lattice-char-index-position"]
+         "lattice-to-word-frame-post", "lattice-prune-dyn-beam", "lattice-best-path2", "lattice-char-index-position",
+         "lattice-to-word-position-post"]
 
 
 def run(tool, *args, env=None, stdin=None):
@@ -120,6 +121,15 @@ def test_multi_context_waves_keep_input_order(tool):
     assert one.returncode == 0 and multi.returncode == 0, multi.stderr.decode()
     assert multi.stdout == one.stdout
     assert [x.split()[0] for x in multi.stdout.decode().strip("\n").split("\n")] == ["lat%d" % i for i in range(1, 6)]
+
+
+@pytest.mark.gpu
+def test_position_post_text():
+    r = run("lattice-to-word-position-post", WORD, "ark,t:-")
+    assert r.returncode == 0, r.stderr.decode()
+    # Posterior text form: one [ word logp ... ] block per transcript position
+    assert r.stdout.decode() == ("lat1 [ 2 -0.2231435 1 -1.609438 ] [ 3 -0.2231435 4 -1.609438 ] [ 5 0 ] [ 2 0 ] "
+                                 "[ 6 0 ] [ 7 0 ] [ 8 0 ] \n")
 
 
 @pytest.mark.gpu

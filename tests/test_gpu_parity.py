@@ -155,6 +155,30 @@ def test_best_path2_parity(klu, ora, engine, shape, n, seed, flags):
         assert abs(got[l][1] - cost) <= 1e-4 * max(1.0, abs(cost))
 
 
+# ---- lattice-to-word-position-post ---------------------------
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", [dict(), dict(acoustic_scale=0.1), dict(graph_scale=0.7, insertion_penalty=0.5)])
+def test_position_post_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 77)
+    engine.load(batch)
+    got = engine.position_post(**flags)
+    for l, lat in enumerate(batch.lattices()):
+        want = ora.position_post(lat, **flags)
+        assert len(got[l]) == len(want), "number of positions, lattice %d" % l
+        for k, (g, w) in enumerate(zip(got[l], want)):
+            assert_rows_match(g, w, 1, what="position-post lat %d pos %d" % (l, k))
+
+
+def test_position_post_readme_lattice(klu, ora, engine, word_lat):
+    _load(klu, engine, [word_lat])
+    got = engine.position_post()[0]
+    want = ora.position_post(word_lat)
+    assert [[w for w, _ in pos] for pos in got] == [[w for w, _ in pos] for pos in want]
+    for g, w in zip(got, want):
+        for (_, a), (_, b) in zip(g, w):
+            assert a == b  # float32 values, bit-identical on this chain/diamond lattice
+
+
 # ---- lattice-prune-dyn-beam -----------------------------------------------------
 def _check_prune(got, want, lat):
     assert got["nstates"] == want["nstates"]
