@@ -334,7 +334,13 @@ def main():
     #     cut into slices by arc count, two contexts on this GPU taking slices in turn from
     #     two host threads, so that the upload of one slice overlaps packing, run and result
     #     download of the previous one.  `e2e.value` is (b); (a) is reported beside it.
-    h2d = sum(int(x.nbytes) for x in (batch.state_off, batch.arc_off, batch.src, batch.dst, batch.label, batch.dur,
+    # the caller hands over per-state arc counts instead of a per-arc source array
+    # (klu_lattices.state_num_arcs; OpenFst stores arcs grouped by state)
+    narcs = batch.state_num_arcs()
+    narcs_pinned = eng.pinned_array(np.int32, max(narcs.size, 1))
+    narcs_pinned[:narcs.size] = narcs
+    narcs = narcs_pinned[:narcs.size]
+    h2d = sum(int(x.nbytes) for x in (batch.state_off, batch.arc_off, narcs, batch.dst, batch.label, batch.dur,
                                       batch.graph, batch.acoustic, batch.fin_graph, batch.fin_acoustic,
                                       batch.fin_dur))
     d2h = 0
@@ -346,7 +352,7 @@ def main():
     for i in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
-        eng.load(batch)
+        eng.load(batch, state_num_arcs=narcs)
         t1 = time.perf_counter()
         eng.run(tool, **flags)
         eng.sync()
@@ -365,6 +371,7 @@ def main():
         cuts = np.searchsorted(batch.arc_off, np.linspace(0, batch.arc_off[-1], nsl + 1)[1:-1]).tolist()
         cuts = [0] + [int(x) for x in cuts] + [nlat]
         subs = [batch.slice(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        sub_narcs = [narcs[int(batch.state_off[a]):int(batch.state_off[b])] for a, b in zip(cuts[:-1], cuts[1:])]
         engines = [klu.Engine(local) for _ in range(min(2, nsl))]
         row_off = np.concatenate([[0], np.cumsum([0] * nsl)])  # filled by the first pass
         sub_rows = [0] * nsl
@@ -372,7 +379,7 @@ def main():
         def work(k, record):
             e = engines[k]
             for j in range(k, nsl, len(engines)):
-                e.load(subs[j])
+                e.load(subs[j], state_num_arcs=sub_narcs[j])
                 e.run(tool, **flags)
                 if record:
                     sub_rows[j] = int(e.offsets()[-1])

@@ -71,6 +71,11 @@ typedef struct klu_lattices {
   const float* fin_graph;    /* per state; +inf = not final */
   const float* fin_acoustic; /* per state; +inf = not final */
   const int32_t* fin_dur;    /* per state; may be NULL (all 0) */
+  /* Optional: arcs leaving each state (fst NumArcs(s)), concatenated like fin_graph.  When
+   * given, arc_src may be NULL -- the arcs of a lattice are then taken to be grouped by
+   * source state in state order (how OpenFst stores them), which saves a sixth of the
+   * host-to-device traffic. */
+  const int32_t* state_num_arcs;
 } klu_lattices;
 
 /* Command-line flags of the tools.  klu_opts_default() fills the

@@ -33,7 +33,7 @@ class KluLattices(C.Structure):
     _fields_ = [("num_lattices", C.c_int32), ("state_off", C.c_void_p), ("arc_off", C.c_void_p),
                 ("arc_src", C.c_void_p), ("arc_dst", C.c_void_p), ("arc_label", C.c_void_p), ("arc_dur", C.c_void_p),
                 ("arc_graph", C.c_void_p), ("arc_acoustic", C.c_void_p), ("fin_graph", C.c_void_p),
-                ("fin_acoustic", C.c_void_p), ("fin_dur", C.c_void_p)]
+                ("fin_acoustic", C.c_void_p), ("fin_dur", C.c_void_p), ("state_num_arcs", C.c_void_p)]
 
 
 class KluOpts(C.Structure):
@@ -149,10 +149,12 @@ class Engine:
         return buf
 
     # -- data -----------------------------------------------------------------
-    def load(self, batch):
-        kl = KluLattices(len(batch), _p(batch.state_off), _p(batch.arc_off), _p(batch.src), _p(batch.dst),
+    def load(self, batch, state_num_arcs=None):
+        """state_num_arcs (optional, int32 per state): upload without the per-arc source array."""
+        kl = KluLattices(len(batch), _p(batch.state_off), _p(batch.arc_off),
+                         None if state_num_arcs is not None else _p(batch.src), _p(batch.dst),
                          _p(batch.label), _p(batch.dur), _p(batch.graph), _p(batch.acoustic), _p(batch.fin_graph),
-                         _p(batch.fin_acoustic), _p(batch.fin_dur))
+                         _p(batch.fin_acoustic), _p(batch.fin_dur), _p(state_num_arcs))
         _chk(self.L.klu_load(self.h, C.byref(kl)))
         self.batch = batch
 

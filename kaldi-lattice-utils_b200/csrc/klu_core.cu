@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <string>
+#include <vector>
 
 #include "klu_common.cuh"
 
@@ -246,6 +247,37 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   c->last_tool = -1;
   c->h_frame_res_off.assign(1, 0);
   c->fr_items = 0;
+  klu_lattices with_src;
+  std::vector<int32_t> src_tmp;
+  if (!lats->arc_src) {
+    if (!lats->state_num_arcs) {
+      set_error("klu_load: arc_src and state_num_arcs are both NULL");
+      return 1;
+    }
+    for (int32_t l = 0; l < lats->num_lattices; ++l) {  // the counts must tile each lattice's arc range
+      int64_t sum = 0;
+      for (int64_t s = lats->state_off[l]; s < lats->state_off[l + 1]; ++s) {
+        if (lats->state_num_arcs[s] < 0) sum = -1;
+        if (sum < 0) break;
+        sum += lats->state_num_arcs[s];
+      }
+      if (sum != lats->arc_off[l + 1] - lats->arc_off[l]) {
+        set_error("klu_load: lattice " + std::to_string(l) + ": state_num_arcs does not add up to its arc count");
+        return 1;
+      }
+    }
+    if (getenv("KLU_HOST_PACKER")) {  // the host twin wants explicit sources
+      src_tmp.resize((size_t)lats->arc_off[lats->num_lattices]);
+      for (int32_t l = 0; l < lats->num_lattices; ++l) {
+        int64_t e = lats->arc_off[l];
+        for (int64_t s = lats->state_off[l]; s < lats->state_off[l + 1]; ++s)
+          for (int32_t k = 0; k < lats->state_num_arcs[s]; ++k) src_tmp[(size_t)e++] = (int32_t)(s - lats->state_off[l]);
+      }
+      with_src = *lats;
+      with_src.arc_src = src_tmp.data();
+      lats = &with_src;
+    }
+  }
   if (getenv("KLU_HOST_PACKER")) KLU_TRY(pack_and_upload(c, lats));
   else KLU_TRY(pack_and_upload_gpu(c, lats));
   c->loaded = true;

@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(256) k_gp_first_arc(GP a) {
   if (bad) atomicMax(&a.meta[l * M_STRIDE + M_ERR], bad);
 }
 
+// grid (tiles, L): source state of every arc from the per-state first-arc offsets (input
+// without arc_src)
+__global__ void __launch_bounds__(256) k_gp_expand_src(GP a, int32_t* src_out) {
+  const int l = blockIdx.y;
+  const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
+  const int e_end = a.e_off[l + 1];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+    const int f0 = a.first_arc[s0 + s];
+    const int f1 = s + 1 < ns ? a.first_arc[s0 + s + 1] : e_end;
+    for (int e = f0; e < f1; ++e) src_out[e] = s;
+  }
+}
+
 // one warp per lattice: levels, state times, label-count bands, per-lattice stats
 __global__ void __launch_bounds__(128) k_gp_levels(GP a, int* counter) {
   const int lane = threadIdx.x & 31;
@@ -435,7 +448,8 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(upload(c, c->d_s_off, s_off.data(), 4 * (size_t)(L + 1)));
   KLU_TRY(upload(c, c->d_e_off, e_off.data(), 4 * (size_t)(L + 1)));
   KLU_TRY(upload(c, c->d_order, order.data(), 4 * (size_t)L));
-  KLU_TRY(upload(c, sc[R_SRC], in->arc_src, 4 * (size_t)E));
+  if (in->arc_src) KLU_TRY(upload(c, sc[R_SRC], in->arc_src, 4 * (size_t)E));
+  else KLU_TRY(sc[R_SRC].reserve(4 * E1));
   KLU_TRY(upload(c, sc[R_DST], in->arc_dst, 4 * (size_t)E));
   KLU_TRY(upload(c, sc[R_LABEL], in->arc_label, 4 * (size_t)E));
   KLU_TRY(upload(c, sc[R_DUR], in->arc_dur, 4 * (size_t)E));
@@ -539,6 +553,19 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   c->max_states = (int32_t)max_states;
   const int arc_tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
   const int st_tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_states + 255) / 256, 16));
+  if (!in->arc_src) {  // arcs grouped by source state: expand the sources from the per-state arc counts
+    KLU_CUDA(cudaMemcpyAsync(a.counts, in->state_num_arcs, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
+    {
+      KLU_LAUNCH(c, "k_gp_lat_scan");
+      k_gp_lat_scan<0><<<L, 256, 0, c->stream>>>(a.counts, a.s_off, a.e_off, a.first_arc, nullptr, nullptr);
+    }
+    KLU_TRY(check_launch("k_gp_lat_scan(src)"));
+    {
+      KLU_LAUNCH(c, "k_gp_expand_src");
+      k_gp_expand_src<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a, sc[R_SRC].as<int32_t>());
+    }
+    KLU_TRY(check_launch("k_gp_expand_src"));
+  }
   {
     KLU_LAUNCH(c, "k_gp_first_arc");
     k_gp_first_arc<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);

@@ -82,6 +82,7 @@ struct Batch {
     v.fin_graph = fin_graph.data();
     v.fin_acoustic = fin_acoustic.data();
     v.fin_dur = fin_dur.data();
+    v.state_num_arcs = nullptr;
     return v;
   }
 };

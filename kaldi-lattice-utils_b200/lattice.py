@@ -72,6 +72,17 @@ class LatticeBatch:
     def lattices(self):
         return [self[i] for i in range(len(self))]
 
+    def state_num_arcs(self):
+        """Arcs leaving each state (int32, concatenated over the batch): the optional
+        klu_lattices.state_num_arcs input that replaces the per-arc source array."""
+        out = np.zeros(int(self.state_off[-1]), np.int32)
+        for l in range(len(self)):
+            s0, s1 = int(self.state_off[l]), int(self.state_off[l + 1])
+            e0, e1 = int(self.arc_off[l]), int(self.arc_off[l + 1])
+            if e1 > e0:
+                out[s0:s1] = np.bincount(self.src[e0:e1], minlength=s1 - s0)
+        return out
+
     def slice(self, lo, hi):
         s0, s1 = int(self.state_off[lo]), int(self.state_off[hi])
         e0, e1 = int(self.arc_off[lo]), int(self.arc_off[hi])

@@ -251,6 +251,24 @@ def test_frame_post_many_words_per_frame(klu, ora, engine):
         assert_rows_match(g, w, 1)
 
 
+# ---- input without the per-arc source array ---------------------------------------
+def test_load_from_state_arc_counts(klu, engine, monkeypatch):
+    batch = klu.synth_batch("small", 7, seed=31)
+    engine.load(batch)
+    want = dict(seg=engine.segment(acoustic_scale=0.3), fp=engine.frame_post(), pr=engine.prune_dyn_beam(max_arcs=150))
+    counts = batch.state_num_arcs()
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("KLU_HOST_PACKER", "1")
+        engine.load(batch, state_num_arcs=counts)
+        got = dict(seg=engine.segment(acoustic_scale=0.3), fp=engine.frame_post(), pr=engine.prune_dyn_beam(max_arcs=150))
+        assert got == want
+    bad = counts.copy()
+    bad[0] += 1
+    with pytest.raises(klu.KluError):
+        engine.load(batch, state_num_arcs=bad)
+
+
 # ---- device packer vs host packer ----------------------------------------------
 def test_gpu_packer_equals_host_packer(klu, engine, monkeypatch):
     lats = klu.synth_batch("small", 9, seed=2024).lattices()
