@@ -17,6 +17,7 @@
  *   KLU_CHAR_POSITION  kwsbin2/lattice-char-index-position.cc:137-284
  *                      (+ kwsbin2/utils.h:41-303, fstext/fstext-utils2.h:278-603)
  *   KLU_POSITION_POST  latbin/lattice-to-word-position-post.cc:70-141
+ *   KLU_CHAR_SEGMENT   kwsbin2/lattice-char-index-segment.cc:93-223
  *
  * Plain pointers and sizes only; all pointers are HOST pointers.  Every function
  * returns 0 on success; on failure klu_last_error() (thread-local) explains.
@@ -53,7 +54,8 @@ enum klu_tool {
   KLU_BEST_PATH2 = 5,
   KLU_CHAR_POSITION = 6,
   KLU_FWD_BWD = 7, /* alpha/beta only (ComputeLatticeAlphasAndBetas [ext]) */
-  KLU_POSITION_POST = 8
+  KLU_POSITION_POST = 8,
+  KLU_CHAR_SEGMENT = 9
 };
 
 /* A batch of lattices as concatenated SoA arrays.  state_off/arc_off have
@@ -167,6 +169,8 @@ int klu_fetch_prune(klu_ctx* ctx, int32_t* arc_index, int32_t* new_src, int32_t*
 int klu_result_char_sizes(klu_ctx* ctx, int64_t* total_chars);
 int klu_fetch_char_position(klu_ctx* ctx, int64_t* char_off, int32_t* chars, int32_t* pos, int32_t* t0,
                             int32_t* t1, double* logp);
+/* char segment index (KLU_CHAR_SEGMENT): same layout, rows carry (t0, t1) only. */
+int klu_fetch_char_segment(klu_ctx* ctx, int64_t* char_off, int32_t* chars, int32_t* t0, int32_t* t1, double* logp);
 /* KLU_FWD_BWD / any run: per-state alpha, beta (input state numbering) and
  * per-lattice total = 0.5*(tot_fwd + beta[0]) */
 int klu_fetch_fwd_bwd(klu_ctx* ctx, double* alpha, double* beta, double* total);

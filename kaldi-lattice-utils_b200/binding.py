@@ -12,19 +12,19 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST = range(9)
+SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST, CHAR_SEGMENT = range(10)
 TOOL_NAMES = {SEGMENT: "lattice-word-index-segment", POSITION: "lattice-word-index-position",
               UTTERANCE: "lattice-word-index-utterance", FRAME_POST: "lattice-to-word-frame-post",
               PRUNE_DYN_BEAM: "lattice-prune-dyn-beam", BEST_PATH2: "lattice-best-path2",
               CHAR_POSITION: "lattice-char-index-position", FWD_BWD: "fwd-bwd",
-              POSITION_POST: "lattice-to-word-position-post"}
+              POSITION_POST: "lattice-to-word-position-post", CHAR_SEGMENT: "lattice-char-index-segment"}
 INT_MAX = 2**31 - 1
 
 # every symbol include/klu.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["klu_last_error", "klu_version", "klu_opts_default", "klu_device_count", "klu_create", "klu_destroy",
            "klu_host_alloc", "klu_host_free", "klu_topsort", "klu_load", "klu_run", "klu_sync", "klu_result_offsets",
            "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_position_post",
-           "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position",
+           "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position", "klu_fetch_char_segment",
            "klu_fetch_fwd_bwd", "klu_timer_start", "klu_timer_stop", "klu_launch_count", "klu_profile_enable",
            "klu_profile_json", "klu_batch_stats", "klu_flush_l2"]
 
@@ -342,6 +342,25 @@ class Engine:
                 s = "_".join(str(c) for c in chars[coff[i]:coff[i + 1]].tolist())
                 rows.append((s, int(pos[i]), int(t0[i]), int(t1[i]), float(lp[i])))
             res.append(rows)
+        return res
+
+    def char_segment(self, wspace, other_groups=(), **o):
+        """lattice-char-index-segment rows per lattice: (string, t0, t1, logp)."""
+        lg, inc, dele = char_groups(wspace, other_groups)
+        self.run(CHAR_SEGMENT, label_group=lg, inc_groups=inc, del_groups=dele, **o)
+        off = self.offsets()
+        n = int(off[-1])
+        tot = C.c_int64()
+        _chk(self.L.klu_result_char_sizes(self.h, C.byref(tot)))
+        coff = np.zeros(n + 1, np.int64)
+        chars = np.zeros(tot.value, np.int32)
+        t0, t1 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lp = np.zeros(n, np.float64)
+        _chk(self.L.klu_fetch_char_segment(self.h, _p(coff), _p(chars), _p(t0), _p(t1), _p(lp)))
+        res = []
+        for a, b in zip(off[:-1], off[1:]):
+            res.append([("_".join(str(c) for c in chars[coff[i]:coff[i + 1]].tolist()), int(t0[i]), int(t1[i]),
+                         float(lp[i])) for i in range(a, b)])
         return res
 
     # -- measurement ------------------------------------------------------------

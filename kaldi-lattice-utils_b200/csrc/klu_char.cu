@@ -47,6 +47,7 @@ struct CharArgs {
   int ngl, NG, dflt;       // #explicit labels, #dense groups, dense index of the default group
   unsigned int inc_mask, del_mask;
   int eps;                 // dense index of group 0 (epsilon)
+  int segment;             // lattice-char-index-segment: keys carry frame tags instead of word counts
   int use_beam;
   const double *vfwd, *vbwd, *best;
   double beam;
@@ -277,6 +278,8 @@ struct Frontier {
   unsigned int* cval;
   double *c_wsum, *c_wmax;
   int32_t* c_t0;
+  int32_t* c_state;            // segment mode: lattice-local destination state of every candidate
+  unsigned long long* c_main;  // segment mode: (parent | label | frame tag) of every candidate
   // sorted candidates
   const unsigned long long *key_a, *key_b;
   const unsigned int *val_a, *val_b;
@@ -289,6 +292,13 @@ struct Frontier {
   int64_t parent_pool_base; // first pool slot of the current depth (parents)
   int depth;
 };
+
+// lattice-char-index-segment: SymbolToPathSegmentationFst (kwsbin2/utils.h:251-303) keeps
+// an output label on every arc that enters a state where the sub-path may stop (a final
+// state of the factor FST = a state with an exit): the end frame of that arc, + 1.
+__device__ __forceinline__ unsigned long long frame_tag(const CharArgs& a, int x, int g) {
+  return a.exitw[(long long)x * a.NG + g] > neg_inf() ? (unsigned long long)(a.b.time[x] + 1) : 0ULL;
+}
 
 // depth 0: candidates per out-order arc = cells of the source whose group differs
 __global__ void __launch_bounds__(256) k_char_count0(CharArgs a, Frontier f) {
@@ -329,9 +339,16 @@ __global__ void __launch_bounds__(256) k_char_emit0(CharArgs a, Frontier f) {
       if (q % a.NG == g) continue;
       const double x = a.A[uc + q];
       if (!(x > neg_inf())) continue;
-      const unsigned long long count = (unsigned long long)(a.nlo[u] + q / a.NG + inc);
-      f.ckey[o] = (count << (kKeyCharBits + kKeyStateBits)) | ((unsigned long long)(unsigned int)r.w << kKeyStateBits) |
-                  (unsigned long long)(r.x - b.s_off[l]);
+      if (a.segment) {  // root = the sub-path's first frame; merged only with equal frame tags
+        f.c_main[o] = ((unsigned long long)b.time[u] << (kKeyCharBits + kKeyStateBits)) |
+                      ((unsigned long long)(unsigned int)r.w << kKeyStateBits) | frame_tag(a, r.x, g);
+        f.c_state[o] = r.x - b.s_off[l];
+        f.ckey[o] = (unsigned long long)(r.x - b.s_off[l]);
+      } else {
+        const unsigned long long count = (unsigned long long)(a.nlo[u] + q / a.NG + inc);
+        f.ckey[o] = (count << (kKeyCharBits + kKeyStateBits)) | ((unsigned long long)(unsigned int)r.w << kKeyStateBits) |
+                    (unsigned long long)(r.x - b.s_off[l]);
+      }
       f.cval[o] = (unsigned int)(o - base);
       f.c_wsum[o] = x - cost;
       f.c_wmax[o] = x - cost;
@@ -407,14 +424,35 @@ __global__ void __launch_bounds__(256) k_char_expand(CharArgs a, Frontier f) {
       const int4 r = b.out_rec[k];
       if (group_of(a, r.w) != g || char_arc_pruned(a, l, x, r.x, r)) continue;
       const double cost = rec_cost(r, a.cp);
-      f.ckey[o] = (parent << (kKeyCharBits + kKeyStateBits)) | ((unsigned long long)(unsigned int)r.w << kKeyStateBits) |
-                  (unsigned long long)(r.x - b.s_off[l]);
+      if (a.segment) {
+        f.c_main[o] = (parent << (kKeyCharBits + kKeyStateBits)) | ((unsigned long long)(unsigned int)r.w << kKeyStateBits) |
+                      frame_tag(a, r.x, g);
+        f.c_state[o] = r.x - b.s_off[l];
+        f.ckey[o] = (unsigned long long)(r.x - b.s_off[l]);
+      } else {
+        f.ckey[o] = (parent << (kKeyCharBits + kKeyStateBits)) | ((unsigned long long)(unsigned int)r.w << kKeyStateBits) |
+                    (unsigned long long)(r.x - b.s_off[l]);
+      }
       f.cval[o] = (unsigned int)(o - cb);
       f.c_wsum[o] = f.it_wsum[base + i] - cost;
       f.c_wmax[o] = f.it_wmax[base + i] - cost;
       f.c_t0[o] = f.it_t0[base + i];
       ++o;
     }
+  }
+}
+
+// segment mode, between the two stable sorts: candidates are ordered by destination
+// state; give them their main key (always in buffer A) for the second sort
+__global__ void __launch_bounds__(256) k_char_rekey(Frontier f, unsigned long long* key_a, unsigned int* val_a) {
+  const int l = blockIdx.y;
+  const int n = f.ccnt[l];
+  const int64_t cb = f.cbase[l];
+  const unsigned int* val = (f.where[l] ? f.val_b : f.val_a) + cb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int j = val[i];
+    key_a[cb + i] = f.c_main[cb + j];
+    val_a[cb + i] = j;
   }
 }
 
@@ -435,10 +473,18 @@ __global__ void __launch_bounds__(256) k_char_reduce(CharArgs a, Frontier f) {
     const int i = tile + tid;
     unsigned long long k = 0;
     bool ihead = false, nhead = false;
+    int st_i = 0;  // lattice-local destination state of candidate i
     if (i < n) {
       k = key[i];
-      ihead = i == 0 || key[i - 1] != k;
-      nhead = i == 0 || (key[i - 1] >> kKeyStateBits) != (k >> kKeyStateBits);
+      if (a.segment) {  // key = (parent, label, frame tag); the state rides beside it
+        st_i = f.c_state[cb + val[i]];
+        nhead = i == 0 || key[i - 1] != k;
+        ihead = nhead || f.c_state[cb + val[i - 1]] != st_i;
+      } else {
+        st_i = (int)(k & ((1ULL << kKeyStateBits) - 1ULL));
+        ihead = i == 0 || key[i - 1] != k;
+        nhead = i == 0 || (key[i - 1] >> kKeyStateBits) != (k >> kKeyStateBits);
+      }
     }
     int xi = ihead ? 1 : 0, xn = nhead ? 1 : 0;
 #pragma unroll
@@ -466,7 +512,7 @@ __global__ void __launch_bounds__(256) k_char_reduce(CharArgs a, Frontier f) {
       unsigned int j = val[i];
       double wsum = f.c_wsum[cb + j], wmax = f.c_wmax[cb + j];
       int t0 = f.c_t0[cb + j];
-      for (int q = i + 1; q < n && key[q] == k; ++q) {
+      for (int q = i + 1; q < n && key[q] == k && (!a.segment || f.c_state[cb + val[q]] == st_i); ++q) {
         j = val[q];
         wsum = log_add(wsum, f.c_wsum[cb + j]);
         const double v = f.c_wmax[cb + j];
@@ -477,7 +523,7 @@ __global__ void __launch_bounds__(256) k_char_reduce(CharArgs a, Frontier f) {
         }
       }
       f.n_node[cb + slot] = (int32_t)node;
-      f.n_state[cb + slot] = a.b.s_off[l] + (int)(k & ((1ULL << kKeyStateBits) - 1ULL));
+      f.n_state[cb + slot] = a.b.s_off[l] + st_i;
       f.n_wsum[cb + slot] = wsum;
       f.n_wmax[cb + slot] = wmax;
       f.n_t0[cb + slot] = t0;
@@ -623,7 +669,7 @@ CharState& char_state(klu_ctx* c) {
 
 }  // namespace
 
-int run_char_position(klu_ctx* c, const klu_opts* o) {
+int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   const int32_t L = c->L;
   for (int32_t l = 0; l < L; ++l)
     if (!c->h_times_ok[l]) {
@@ -650,8 +696,9 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
   c->last_entries = 0;
   c->last_chars = 0;
   if (L == 0 || c->S == 0) return 0;
-  if (c->max_states >= (1 << kKeyStateBits) || c->max_label >= (1 << kKeyCharBits)) {
-    set_error("char index: more than 2^20 states per lattice or labels above 2^20 are not supported");
+  if (c->max_states >= (1 << kKeyStateBits) || c->max_label >= (1 << kKeyCharBits) ||
+      (segment && c->max_time + 1 >= (1 << kKeyStateBits))) {
+    set_error("char index: more than 2^20 states (or frames) per lattice or labels above 2^20 are not supported");
     return 1;
   }
   // ---- dense label groups (kwsbin2/utils.h:41-84) ----
@@ -704,7 +751,9 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
   a.NG = (int)gids.size();
   a.dflt = dense(INT_MAX);
   a.eps = dense(0);
-  for (int32_t i = 0; i < o->num_inc_groups; ++i) a.inc_mask |= 1u << dense(o->inc_groups[i]);
+  a.segment = segment ? 1 : 0;
+  // the segment tool has no word-count split (kwsbin2/lattice-char-index-segment.cc:113-117)
+  for (int32_t i = 0; !segment && i < o->num_inc_groups; ++i) a.inc_mask |= 1u << dense(o->inc_groups[i]);
   for (int32_t i = 0; i < o->num_del_groups; ++i) a.del_mask |= 1u << dense(o->del_groups[i]);
   a.use_beam = use_beam ? 1 : 0;
   a.vfwd = c->d_vfwd.as<double>();
@@ -771,11 +820,12 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
   // ---- frontier buffers (grown as needed) ----
   DevBuf it_node, it_state, it_t0, it_wsum, it_wmax;       // current items
   DevBuf n_node, n_state, n_t0, n_wsum, n_wmax;             // next items
-  DevBuf ckey_a, ckey_b, cval_a, cval_b, c_wsum, c_wmax, c_t0, cand_cnt, cand_loc, where;
+  DevBuf ckey_a, ckey_b, cval_a, cval_b, c_wsum, c_wmax, c_t0, c_state, c_main, cand_cnt, cand_loc, where;
   DevBuf nd_parent, nd_chr, nd_cnt, nd_grp, nd_lat, nd_t0, nd_t1, nd_len, nd_total, nd_best;
   DevBuf d_ibase, d_icnt, d_cbase, d_ccnt, d_ncnt;
   std::vector<DevBuf*> all = {&it_node, &it_state, &it_t0, &it_wsum, &it_wmax, &n_node, &n_state, &n_t0, &n_wsum, &n_wmax,
-                              &ckey_a, &ckey_b, &cval_a, &cval_b, &c_wsum, &c_wmax, &c_t0, &cand_cnt, &cand_loc, &where,
+                              &ckey_a, &ckey_b, &cval_a, &cval_b, &c_wsum, &c_wmax, &c_t0, &c_state, &c_main, &cand_cnt,
+                              &cand_loc, &where,
                               &nd_parent, &nd_chr, &nd_cnt, &nd_grp, &nd_lat, &nd_t0, &nd_t1, &nd_len, &nd_total, &nd_best,
                               &d_ibase, &d_icnt, &d_cbase, &d_ccnt, &d_ncnt};
   struct Releaser {
@@ -853,6 +903,10 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
     KLU_TRY(c_wsum.reserve(8 * (size_t)ncand));
     KLU_TRY(c_wmax.reserve(8 * (size_t)ncand));
     KLU_TRY(c_t0.reserve(4 * (size_t)ncand));
+    if (segment) {
+      KLU_TRY(c_state.reserve(4 * (size_t)ncand));
+      KLU_TRY(c_main.reserve(8 * (size_t)ncand));
+    }
     KLU_TRY(n_node.reserve(4 * (size_t)ncand));
     KLU_TRY(n_state.reserve(4 * (size_t)ncand));
     KLU_TRY(n_t0.reserve(4 * (size_t)ncand));
@@ -881,6 +935,8 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
     f.c_wsum = c_wsum.as<double>();
     f.c_wmax = c_wmax.as<double>();
     f.c_t0 = c_t0.as<int32_t>();
+    f.c_state = c_state.as<int32_t>();
+    f.c_main = c_main.as<unsigned long long>();
     f.depth = depth;
     f.parent_pool_base = parent_pool_base;
     f.node_pool_base = pool;
@@ -901,12 +957,33 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
     ss.val_b = cval_b.as<unsigned int>();
     ss.where = where.as<unsigned char>();
     ss.lo_bit = 0;
-    ss.hi_bit = 64;
+    ss.hi_bit = segment ? kKeyStateBits : 64;  // segment mode: by destination state first ...
     {
       KLU_LAUNCH(c, "k_seg_radix_sort");
       k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
     }
     KLU_TRY(check_launch("k_seg_radix_sort(char)"));
+    if (segment) {  // ... then, stably, by (parent, label, frame tag)
+      f.key_a = ss.key_a;
+      f.key_b = ss.key_b;
+      f.val_a = ss.val_a;
+      f.val_b = ss.val_b;
+      f.where = ss.where;
+      int64_t max_c = 0;
+      for (int32_t l = 0; l < L; ++l) max_c = std::max<int64_t>(max_c, h_cnt[l]);
+      {
+        KLU_LAUNCH(c, "k_char_rekey");
+        k_char_rekey<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_c + 255) / 256, 64)), L), 256, 0,
+                       c->stream>>>(f, ss.key_a, ss.val_a);
+      }
+      KLU_TRY(check_launch("k_char_rekey"));
+      ss.hi_bit = 64;
+      {
+        KLU_LAUNCH(c, "k_seg_radix_sort");
+        k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+      }
+      KLU_TRY(check_launch("k_seg_radix_sort(char keys)"));
+    }
     f.key_a = ss.key_a;
     f.key_b = ss.key_b;
     f.val_a = ss.val_a;
@@ -1120,7 +1197,10 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
       std::sort(perm.begin() + h_obase[l], perm.begin() + h_obase[l + 1], [&](int64_t x, int64_t y) {
         if (out.logp[x] != out.logp[y]) return out.logp[x] > out.logp[y];
         if (str[x] != str[y]) return str[x] < str[y];
-        return out.pos[x] < out.pos[y];
+        if (!segment) return out.pos[x] < out.pos[y];
+        // kwsbin2/lattice-char-index-segment.cc:205-219: then initial frame, then final frame
+        if (out.t0[x] != out.t0[y]) return out.t0[x] < out.t0[y];
+        return out.t1[x] < out.t1[y];
       });
     CharState s2;
     s2.row_off = out.row_off;
@@ -1140,6 +1220,9 @@ int run_char_position(klu_ctx* c, const klu_opts* o) {
   return 0;
 }
 
+int run_char_position(klu_ctx* c, const klu_opts* o) { return run_char_index(c, o, false); }
+int run_char_segment(klu_ctx* c, const klu_opts* o) { return run_char_index(c, o, true); }
+
 void char_release(klu_ctx* c) {
   delete static_cast<CharState*>(c->char_state);
   c->char_state = nullptr;
@@ -1152,8 +1235,8 @@ using namespace klu;
 extern "C" {
 
 int klu_result_char_sizes(klu_ctx* c, int64_t* total_chars) {
-  if (c->last_tool != KLU_CHAR_POSITION) {
-    set_error("klu_result_char_sizes: last run was not KLU_CHAR_POSITION");
+  if (c->last_tool != KLU_CHAR_POSITION && c->last_tool != KLU_CHAR_SEGMENT) {
+    set_error("klu_result_char_sizes: last run was not a char index tool");
     return 1;
   }
   *total_chars = c->last_chars;
@@ -1179,6 +1262,17 @@ int klu_fetch_char_position(klu_ctx* c, int64_t* char_off, int32_t* chars, int32
   if (t1 && n) memcpy(t1, s.t1.data(), 4 * n);
   if (logp && n) memcpy(logp, s.logp.data(), 8 * n);
   return 0;
+}
+
+int klu_fetch_char_segment(klu_ctx* c, int64_t* char_off, int32_t* chars, int32_t* t0, int32_t* t1, double* logp) {
+  if (c->last_tool != KLU_CHAR_SEGMENT) {
+    set_error("klu_fetch_char_segment: last run was not KLU_CHAR_SEGMENT");
+    return 1;
+  }
+  c->last_tool = KLU_CHAR_POSITION;  // same row store
+  const int rc = klu_fetch_char_position(c, char_off, chars, nullptr, t0, t1, logp);
+  c->last_tool = KLU_CHAR_SEGMENT;
+  return rc;
 }
 
 }  // extern "C"

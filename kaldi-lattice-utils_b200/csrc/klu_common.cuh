@@ -186,6 +186,7 @@ struct BestPathChunk {
 int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch);
 // klu_char.cu
 int run_char_position(klu_ctx* c, const klu_opts* o);
+int run_char_segment(klu_ctx* c, const klu_opts* o);
 void char_release(klu_ctx* c);
 
 CostParams make_cost_params(const klu_opts* o, bool float_sum);

@@ -12,6 +12,7 @@
 //   lattice-prune-dyn-beam        latbin/lattice-prune-dyn-beam.cc:97-214
 //   lattice-best-path2            latbin/lattice-best-path2.cc:29-221
 //   lattice-to-word-position-post latbin/lattice-to-word-position-post.cc:28-147
+//   lattice-char-index-segment    kwsbin2/lattice-char-index-segment.cc:249-349
 //
 // Lattices are independent, so the reader fills a batch (KLU_BATCH_ARCS arcs,
 // default 32M), the batch is packed/uploaded/processed, and entries are written
@@ -139,6 +140,12 @@ void ComputeBatch(klu_ctx* ctx, const klu_opts* opts, const Batch* b, Results* r
     r->i1.resize(n), r->i2.resize(n), r->i3.resize(n), r->d0.resize(n);
     KLU_CHECK(klu_fetch_char_position(ctx, r->coff.data(), r->chars.data(), r->i1.data(), r->i2.data(), r->i3.data(),
                                       r->d0.data()));
+#elif KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
+    int64_t total_chars = 0;
+    KLU_CHECK(klu_result_char_sizes(ctx, &total_chars));
+    r->coff.resize(n + 1), r->chars.resize((size_t)total_chars);
+    r->i2.resize(n), r->i3.resize(n), r->d0.resize(n);
+    KLU_CHECK(klu_fetch_char_segment(ctx, r->coff.data(), r->chars.data(), r->i2.data(), r->i3.data(), r->d0.data()));
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */
     r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
     KLU_CHECK(klu_fetch_frame_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
@@ -224,7 +231,7 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
     if (!bin) os << '\n';
     w.End();
   }
-#elif KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+#elif KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
   for (int32_t l = 0; l < L; ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
@@ -240,7 +247,9 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
         tok += std::to_string(r->chars[(size_t)k]);
       }
       WriteToken(os, bin, tok);
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
       WriteBasicInt32(os, bin, r->i1[i]);
+#endif
       WriteBasicInt32(os, bin, r->i2[i]);
       WriteBasicInt32(os, bin, r->i3[i]);
       WriteBasicDouble(os, bin, r->d0[i]);
@@ -378,7 +387,7 @@ void ProcessWave(ToolState* st, std::vector<Batch>* wave) {
 }  // namespace
 
 int main(int argc, char* argv[]) {
-#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
   const int kErrorCode = 1;  // kwsbin2/lattice-char-index-position.cc:405-408
 #else
   const int kErrorCode = -1;  // e.g. kwsbin2/lattice-word-index-position.cc:293-296
@@ -418,6 +427,12 @@ int main(int argc, char* argv[]) {
         "optional other groups, default group) and every maximal sub-path of same-group arcs is a pseudo-word.\n\n"
         "Usage: lattice-char-index-position [options] separator-symbols lat-rspecifier index-wspecifier\n"
         " e.g.: lattice-char-index-position \"3 4\" ark:1.lats ark:1.index\n";
+#elif KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
+    const char* usage =
+        "Build a segment-level word index from character lattices. Characters are grouped (whitespace group, "
+        "optional other groups, default group) and every maximal sub-path of same-group arcs is a pseudo-word.\n\n"
+        "Usage: lattice-char-index-segment [options] separator-symbols lat-rspecifier index-wspecifier\n"
+        " e.g.: lattice-char-index-segment \"3 4\" ark:1.lats ark:1.index\n";
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */
     const char* usage =
         "Compute the posterior log-probability of each word for each given utterance frame. That is, we compute "
@@ -447,7 +462,7 @@ int main(int argc, char* argv[]) {
     po.Register("insertion-penalty", &insertion_penalty,
                 "Add this penalty to the lattice arcs with non-epsilon output label (typically, equivalent to word "
                 "insertion penalty).");
-#if KLU_TOOL == 1 /* KLU_POSITION */ || KLU_TOOL == 0 /* KLU_SEGMENT */ || KLU_TOOL == 2 /* KLU_UTTERANCE */ || KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+#if KLU_TOOL == 1 /* KLU_POSITION */ || KLU_TOOL == 0 /* KLU_SEGMENT */ || KLU_TOOL == 2 /* KLU_UTTERANCE */ || KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
     po.Register("beam", &beam, "Pruning beam (applied after acoustic scaling and adding the insertion penalty).");
     po.Register("num-threads", &num_threads, "Accepted for compatibility; lattices are batched on the GPU instead.");
     po.Register("num-threads-total", &num_threads_total, "Accepted for compatibility; ignored.");
@@ -462,7 +477,7 @@ int main(int argc, char* argv[]) {
     int32_t rho_label = INT_MAX;
     po.Register("rho-label", &rho_label, "Accepted for compatibility (no composition is materialised).");
 #endif
-#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
     float determinize_delta = 1.0f / 1024.0f / 8.0f;
     po.Register("nbest", &st.opts.nbest, "Extract this number of n-best hypothesis.");
     po.Register("determinize-delta", &determinize_delta,
@@ -479,7 +494,7 @@ int main(int argc, char* argv[]) {
 #endif
     po.Read(argc, argv);
 
-#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
     if (po.NumArgs() != 3) {
       po.PrintUsage();
       exit(1);
@@ -527,7 +542,7 @@ int main(int argc, char* argv[]) {
     st.opts.num_include = (int32_t)st.include.size();
     st.opts.exclude_words = st.exclude.data();
     st.opts.num_exclude = (int32_t)st.exclude.size();
-#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
     {
       // kwsbin2/utils.h:41-84 ParseSeparatorGroups
       std::map<int32_t, int32_t> label_group;

@@ -1161,6 +1161,151 @@ void CharIndexPosition(Lat lat0, const Opts& o, Result* r) {
 }
 
 // ---------------------------------------------------------------------------
+// lattice-char-index-segment: kwsbin2/lattice-char-index-segment.cc:93-223.
+// Same GroupFactorFst construction as the position tool but WITHOUT the word-count
+// split (DisambiguateStatesByInputLabelGroup only, :113-117), and the paths that the
+// log-semiring determinisation (:158-164) merges are those with the same sequence of
+// ENCODED (ilabel, olabel) pairs, where SymbolToPathSegmentationFst
+// (kwsbin2/utils.h:251-303) keeps an output label only on the arcs leaving the start
+// state (t0 + 1 of the sub-path) and on EVERY arc entering a final state of the
+// factor FST (t_end_of_that_arc + 1) -- a state is final there iff it has an exit
+// (a final weight or an arc into another group).  Hence sub-paths with the same
+// characters and the same (t0, t1) are NOT merged when the frames at which they pass
+// through intermediate "could stop here" states differ (SURVEY.md 8c hazard 9).
+// Row = (string, t0, t1, logp); n-best by logp, then sorted by (logp desc, string asc,
+// t0 asc, t1 asc) (:205-219).
+void CharIndexSegment(Lat lat0, const Opts& o0, Result* r) {
+  Opts o = o0;
+  o.group_inc.clear();  // no word-count dimension: every split state has count 0
+  Prologue(&lat0, o, true);
+  if (lat0.Empty()) return;
+  SplitLat sp;
+  SplitByGroupAndCount(lat0, o, &sp);
+  const Lat& lat = sp.lat;
+  const int32 n = lat.NumStates();
+  std::vector<int32> indeg(n, 0), order;
+  for (int32 s = 0; s < n; ++s)
+    for (const auto& arc : lat.out[s]) indeg[arc.next]++;
+  {
+    std::vector<int32> st;
+    for (int32 s = n - 1; s >= 0; --s)
+      if (indeg[s] == 0) st.push_back(s);
+    while (!st.empty()) {
+      int32 s = st.back();
+      st.pop_back();
+      order.push_back(s);
+      for (const auto& arc : lat.out[s])
+        if (--indeg[arc.next] == 0) st.push_back(arc.next);
+    }
+  }
+  std::vector<double> fw(n, kLogZeroDouble), bw(n, kLogZeroDouble);
+  fw[0] = 0.0;
+  for (int32 s : order)
+    for (const auto& arc : lat.out[s]) fw[arc.next] = LogAdd(fw[arc.next], fw[s] - Cost(arc.g, arc.a));
+  for (auto it = order.rbegin(); it != order.rend(); ++it) {
+    const int32 s = *it;
+    double b = -Cost(lat.fg[s], lat.fa[s]);
+    for (const auto& arc : lat.out[s]) b = LogAdd(b, bw[arc.next] - Cost(arc.g, arc.a));
+    bw[s] = b;
+  }
+  const double total = bw[0];
+  std::vector<int32> times(n, -1);
+  times[0] = 0;
+  for (int32 s : order)
+    for (const auto& arc : lat.out[s]) {
+      const int32 t = times[s] + arc.dur;
+      if (times[arc.next] == -1) times[arc.next] = t;
+      else if (times[arc.next] != t) { r->error = "inconsistent state times"; return; }
+    }
+  std::vector<double> exitw(n, kLogZeroDouble);
+  for (int32 u = 0; u < n; ++u) {
+    double e = -Cost(lat.fg[u], lat.fa[u]);
+    for (const auto& arc : lat.out[u])
+      if (sp.group[arc.next] != sp.group[u]) e = LogAdd(e, -Cost(arc.g, arc.a) + bw[arc.next]);
+    exitw[u] = e;
+  }
+  // key: t0, then one (char, otag) pair per arc; otag = t_end + 1 on arcs entering a
+  // state with an exit, 0 elsewhere
+  typedef std::vector<int32> Key;
+  std::map<Key, double> acc;
+  struct Frame { int32 state; size_t arc; };
+  for (int32 u = 0; u < n; ++u) {
+    for (const auto& first : lat.out[u]) {
+      const int32 v1 = first.next;
+      if (!(u == 0 || sp.group[u] != sp.group[v1])) continue;
+      const int32 g = sp.group[v1];
+      if (o.delete_groups.count(g)) continue;
+      if (g == 0) continue;
+      Key key;
+      key.push_back(times[u]);
+      auto push = [&](int32 label, int32 x) {
+        key.push_back(label);
+        key.push_back(exitw[x] != kLogZeroDouble ? times[x] + 1 : 0);
+      };
+      auto visit = [&](int32 x, double w) {
+        if (exitw[x] == kLogZeroDouble) return;
+        const double val = w + exitw[x];
+        auto it = acc.find(key);
+        if (it == acc.end()) acc.emplace(key, val);
+        else it->second = LogAdd(it->second, val);
+      };
+      std::vector<Frame> stack;
+      std::vector<double> wstack;
+      const double w0 = fw[u] - Cost(first.g, first.a);
+      push(first.label, v1);
+      stack.push_back(Frame{v1, 0});
+      wstack.push_back(w0);
+      visit(v1, w0);
+      while (!stack.empty()) {
+        Frame& f = stack.back();
+        if (f.arc >= lat.out[f.state].size()) {
+          stack.pop_back();
+          wstack.pop_back();
+          key.pop_back();
+          key.pop_back();
+          continue;
+        }
+        const Arc& arc = lat.out[f.state][f.arc++];
+        if (sp.group[arc.next] != g || f.state == 0) continue;
+        const double w = wstack.back() - Cost(arc.g, arc.a);
+        push(arc.label, arc.next);
+        stack.push_back(Frame{arc.next, 0});
+        wstack.push_back(w);
+        visit(arc.next, w);
+      }
+    }
+  }
+  struct Row { std::string s; int32 t0, t1; double logp; };
+  std::vector<Row> rows;
+  for (const auto& kv : acc) {
+    const Key& k = kv.first;
+    std::string s;
+    for (size_t i = 1; i + 1 < k.size(); i += 2) {
+      if (k[i] == 0) continue;  // LabelSequenceToString(skip_epsilon = true)
+      if (!s.empty()) s += "_";
+      s += std::to_string(k[i]);
+    }
+    if (s.empty()) continue;
+    rows.push_back(Row{s, k[0], k.back() - 1, kv.second - total});
+  }
+  std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.logp > b.logp; });
+  if ((int64_t)rows.size() > (int64_t)o.nbest) rows.resize(o.nbest);
+  std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) -> bool {
+    if (a.logp != b.logp) return a.logp > b.logp;
+    else if (a.s != b.s) return a.s < b.s;
+    else if (a.t0 != b.t0) return a.t0 < b.t0;
+    else return a.t1 < b.t1;
+  });
+  for (const auto& row : rows) {
+    r->str.push_back(row.s);
+    r->i0.push_back(row.t0);
+    r->i1.push_back(row.t1);
+    r->d0.push_back(row.logp);
+  }
+  r->ds0 = total;
+}
+
+// ---------------------------------------------------------------------------
 // Brute force: enumerate every complete path of a (tiny) lattice.  Used by the
 // tests to pin the oracle itself for the tools the reference has no golden for.
 // mode 0: segment keys (word,t0,t1); 1: position keys (word,pos,0); 2: frame
@@ -1275,7 +1420,7 @@ typedef struct ora_opts {
 } ora_opts;
 
 enum { ORA_SEGMENT = 0, ORA_POSITION = 1, ORA_UTTERANCE = 2, ORA_FRAME_POST = 3, ORA_PRUNE_DYN_BEAM = 4,
-       ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
+       ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_CHAR_SEGMENT = 9, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
        ORA_BRUTE_FRAME = 12, ORA_BRUTE_UTTERANCE = 13 };
 
 static Opts ConvertOpts(const ora_opts* o) {
@@ -1311,6 +1456,7 @@ static void RunTool(int tool, const ora_lat* l, const Opts& o, Result* r) {
     case ORA_BEST_PATH2: BestPath2(lat, o, r); break;
     case ORA_CHAR_POSITION: CharIndexPosition(lat, o, r); break;
     case ORA_POSITION_POST: WordPositionPost(lat, o, r); break;
+    case ORA_CHAR_SEGMENT: CharIndexSegment(lat, o, r); break;
     case ORA_BRUTE_SEGMENT: BruteForce(lat, 0, r); break;
     case ORA_BRUTE_POSITION: BruteForce(lat, 1, r); break;
     case ORA_BRUTE_FRAME: BruteForce(lat, 2, r); break;

@@ -15,6 +15,7 @@ _LIB = None
 
 SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION = range(7)
 POSITION_POST = 8
+CHAR_SEGMENT = 9
 BRUTE_SEGMENT, BRUTE_POSITION, BRUTE_FRAME, BRUTE_UTTERANCE = 10, 11, 12, 13
 
 INT_MAX = 2**31 - 1
@@ -226,6 +227,20 @@ def char_position(lat, wspace, other_groups=(), **o):
         inc.append(gi + 2)
     r = run(CHAR_POSITION, lat, label_group=label_group, inc_groups=inc, del_groups=[1], **o)
     return list(zip(r.s, r.i[0].tolist(), r.i[1].tolist(), r.i[2].tolist(), r.d.tolist()))
+
+
+def char_segment(lat, wspace, other_groups=(), **o):
+    """kwsbin2/lattice-char-index-segment: rows (string, t0, t1, logp)."""
+    label_group = {0: 0}
+    for w in wspace:
+        label_group[w] = 1
+    inc = [INT_MAX]
+    for gi, grp in enumerate(other_groups):
+        for lab in grp:
+            label_group[lab] = gi + 2
+        inc.append(gi + 2)
+    r = run(CHAR_SEGMENT, lat, label_group=label_group, inc_groups=inc, del_groups=[1], **o)
+    return list(zip(r.s, r.i[0].tolist(), r.i[1].tolist(), r.d.tolist()))
 
 
 def brute(tool, lat):

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "kaldi-lattice-utils_b200", "bin")
 TOOLS = ["lattice-word-index-segment", "lattice-word-index-position", "lattice-word-index-utterance",
          "lattice-to-word-frame-post", "lattice-prune-dyn-beam", "lattice-best-path2", "lattice-char-index-position",
-         "lattice-to-word-position-post"]
+         "lattice-to-word-position-post", "lattice-char-index-segment"]
 
 
 def run(tool, *args, env=None, stdin=None):

@@ -79,3 +79,64 @@ def test_char_position_other_groups_and_epsilons(klu, ora, engine):
     got = engine.char_position([1], other_groups=[[40, 41]], nbest=100000)
     for l, lat in enumerate(lats):
         _check(got[l], ora.char_position(lat, [1], other_groups=[[40, 41]], nbest=100000), "punct2 lat %d" % l)
+
+
+# ---- lattice-char-index-segment ----------------------------------
+def _check_seg(got, want, what):
+    # rows (string, t0, t1, logp).  Sub-paths with the same string and (t0, t1) but
+    # different intermediate frame tags are separate rows (SURVEY.md 8c hazard 9), so
+    # rows are compared as sorted multisets: keys exact, values within TOL
+    assert len(got) == len(want), what
+    for g, w in zip(sorted(got, key=lambda r: (r[:3], -r[3])), sorted(want, key=lambda r: (r[:3], -r[3]))):
+        assert g[:3] == w[:3], what
+        assert abs(g[3] - w[3]) <= TOL, what
+    for a, b in zip(got[:-1], got[1:]):
+        assert a[3] >= b[3]
+
+
+def test_readme_char_segment(klu, ora, engine):
+    lat = klu.read_text_ark(os.path.join(GOLD, "lattice.char.ark.txt"))[0]
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    got = engine.char_segment([28])[0]
+    want = ora.char_segment(lat, [28])
+    _check_seg(got, want, "README char lattice")
+    assert [r[:3] for r in got] == [r[:3] for r in want]
+
+
+def test_readme_char_segment_cli():
+    tool = os.path.join(ROOT, "kaldi-lattice-utils_b200", "bin", "lattice-char-index-segment")
+    r = subprocess.run([tool, "28", "ark:" + os.path.join(GOLD, "lattice.char.ark.txt"), "ark,t:-"],
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+
+    def parse(line):
+        key, rest = line.strip().split(" ", 1)
+        rows = []
+        for ent in rest.split(";"):
+            f = ent.split()
+            if f:
+                rows.append((f[0], int(f[1]), int(f[2]), float(f[3])))
+        return key, rows
+    gk, got = parse(r.stdout.decode())
+    wk, want = parse(goldens()["char_segment"])
+    assert gk == wk and [x[:3] for x in got] == [x[:3] for x in want]
+    assert max(abs(a[3] - b[3]) for a, b in zip(got, want)) <= TOL
+
+
+@pytest.mark.parametrize("flags", [dict(nbest=100000), dict(acoustic_scale=0.5, nbest=100000), dict(beam=4.0, nbest=100000)])
+def test_char_segment_parity_random(klu, ora, engine, flags):
+    rng = np.random.RandomState(4321)
+    lats = [char_lattice(klu, rng, "s%d" % i, nwords=int(rng.randint(1, 5)), punct=(40,), eps_prob=0.05)
+            for i in range(12)]
+    engine.load(klu.LatticeBatch.from_lattices(lats))
+    got = engine.char_segment([1], other_groups=[[40]], **flags)
+    for l, lat in enumerate(lats):
+        _check_seg(got[l], ora.char_segment(lat, [1], other_groups=[[40]], **flags), "seg lat %d %r" % (l, flags))
+
+
+def test_char_segment_c5(klu, ora, engine):
+    batch = klu.synth_batch("c5", 2, seed=9)
+    engine.load(batch)
+    got = engine.char_segment([1], nbest=100000)
+    for l, lat in enumerate(batch.lattices()):
+        _check_seg(got[l], ora.char_segment(lat, [1], nbest=100000), "c5 seg lat %d" % l)

@@ -51,6 +51,20 @@ def test_readme_char_position(ora, char_lat):
         assert abs(g[4] - w[4]) <= TOL
 
 
+def test_readme_char_segment(ora, char_lat):
+    # kwsbin2/README.md:182 (lattice-char-index-segment): strings,
+    # segments and order exact; values within the reference's float32 noise
+    body = goldens()["char_segment"].split(" ", 1)[1]
+    want = []
+    for t in body.split(";"):
+        f = t.split()
+        want.append((f[0], int(f[1]), int(f[2]), float(f[3])))
+    got = ora.char_segment(char_lat, [28])
+    assert [r[:3] for r in got] == [r[:3] for r in want]
+    for g, w in zip(got, want):
+        assert abs(g[3] - w[3]) <= TOL
+
+
 def test_readme_state_times(klu, ora, word_lat):
     # kwsbin2/README.md:61-64; times come out of the segment keys
     times = goldens()["state_times"]
