@@ -288,7 +288,10 @@ Input::Input(const std::string& name_in) {
       off = (size_t)strtoull(name.c_str() + colon + 1, nullptr, 10);
       name = name.substr(0, colon);
     }
-    auto* f = new std::ifstream(name, std::ios::in | std::ios::binary);
+    auto* f = new std::ifstream();
+    filebuf_.resize(4 << 20);  // large reads: table entries are parsed straight off the stream buffer
+    f->rdbuf()->pubsetbuf(&filebuf_[0], (std::streamsize)filebuf_.size());
+    f->open(name, std::ios::in | std::ios::binary);
     owned_.reset(f);
     if (!*f) KIO_ERR("Error opening input stream " << name);
     if (off) f->seekg((std::streamoff)off);
@@ -552,7 +555,79 @@ std::string ReadFstString(std::istream& is) {
   return s;
 }
 
-void ReadBinary(std::istream& is, CompactLat* lat) {
+// Bulk reads straight from the stream buffer (no sentry / formatting layer per field).
+inline void GetBytes(std::streambuf* sb, void* p, std::streamsize n) {
+  if (n > 0 && sb->sgetn(reinterpret_cast<char*>(p), n) != n) KIO_ERR("Unexpected end of binary lattice stream");
+}
+
+// Fast path for the common case -- a binary CompactLattice whose start state is 0:
+// the OpenFst body lists the arcs state by state, i.e. already grouped by source, so
+// the SoA arrays are filled directly (one read for the fixed part of every arc, one
+// for its transition ids, which are kept only for the tool that writes lattices back).
+void ReadBinaryCompactFast(std::istream& is, int64_t nstates, int64_t narcs_hint, bool keep_tids, CompactLat* lat) {
+  std::streambuf* sb = is.rdbuf();
+  struct FinalHead { float g, a; int32_t sz; };
+  struct ArcHead { int32_t ilabel, olabel; float g, a; int32_t sz; };
+  static_assert(sizeof(FinalHead) == 12 && sizeof(ArcHead) == 20, "packed layout");
+  const int32_t n = (int32_t)nstates;
+  lat->nstates = n;
+  const float inf = std::numeric_limits<float>::infinity();
+  lat->fin_graph.assign(n, inf);
+  lat->fin_acoustic.assign(n, inf);
+  lat->fin_dur.assign(n, 0);
+  if (keep_tids) lat->fin_tids.assign(n, std::vector<int32_t>());
+  if (narcs_hint > 0 && narcs_hint < ((int64_t)1 << 31)) {
+    const size_t r = (size_t)narcs_hint;
+    lat->src.reserve(r);
+    lat->dst.reserve(r);
+    lat->label.reserve(r);
+    lat->dur.reserve(r);
+    lat->graph.reserve(r);
+    lat->acoustic.reserve(r);
+    if (keep_tids) lat->tids.reserve(r);
+  }
+  std::vector<int32_t> scratch;
+  for (int32_t s = 0; s < n; ++s) {
+    FinalHead fh;
+    GetBytes(sb, &fh, sizeof(fh));
+    if (fh.sz < 0) KIO_ERR("Corrupt binary lattice " << lat->key);
+    scratch.resize((size_t)fh.sz);
+    GetBytes(sb, scratch.data(), 4 * (std::streamsize)fh.sz);
+    if (!(std::isinf(fh.g) && std::isinf(fh.a))) {
+      lat->fin_graph[s] = fh.g;
+      lat->fin_acoustic[s] = fh.a;
+      lat->fin_dur[s] = fh.sz;
+      if (keep_tids) lat->fin_tids[s] = scratch;
+    }
+    int64_t na;
+    GetBytes(sb, &na, 8);
+    if (na < 0) KIO_ERR("Corrupt binary lattice " << lat->key);
+    for (int64_t k = 0; k < na; ++k) {
+      ArcHead ah;
+      GetBytes(sb, &ah, sizeof(ah));
+      if (ah.sz < 0) KIO_ERR("Corrupt binary lattice " << lat->key);
+      scratch.resize((size_t)ah.sz);
+      GetBytes(sb, scratch.data(), 4 * (std::streamsize)ah.sz);
+      int32_t dst;
+      GetBytes(sb, &dst, 4);
+      lat->src.push_back(s);
+      lat->dst.push_back(dst);
+      lat->label.push_back(ah.olabel);
+      lat->dur.push_back(ah.sz);
+      lat->graph.push_back(ah.g);
+      lat->acoustic.push_back(ah.a);
+      if (keep_tids) lat->tids.push_back(scratch);
+    }
+  }
+  if (!keep_tids) {
+    lat->tids.clear();
+    lat->fin_tids.clear();
+  }
+  // the stream position moved underneath the istream: nothing is buffered above the streambuf
+  TopSortIfNeeded(lat);
+}
+
+void ReadBinary(std::istream& is, CompactLat* lat, bool keep_tids) {
   // [ext] OpenFst FstHeader + VectorFst body
   const int32_t magic = ReadRaw<int32_t>(is);
   if (magic != 2125659606) KIO_ERR("Reading lattice " << lat->key << ": bad FST magic number");
@@ -561,9 +636,13 @@ void ReadBinary(std::istream& is, CompactLat* lat) {
   const int32_t flags = ReadRaw<int32_t>(is);
   /*props*/ ReadRaw<uint64_t>(is);
   const int64_t start = ReadRaw<int64_t>(is), nstates = ReadRaw<int64_t>(is);
-  /*narcs*/ ReadRaw<int64_t>(is);
+  const int64_t narcs = ReadRaw<int64_t>(is);
   if (fsttype != "vector") KIO_ERR("Unsupported FST type " << fsttype);
   if (flags & 3) KIO_ERR("Lattices with symbol tables are not supported");
+  if (arctype == "compactlattice44" && start == 0 && nstates > 0 && nstates < ((int64_t)1 << 31)) {
+    ReadBinaryCompactFast(is, nstates, narcs, keep_tids, lat);
+    return;
+  }
   RawLat raw;
   if (arctype == "compactlattice44") raw.compact = true;
   else if (arctype == "lattice4") raw.compact = false;
@@ -601,7 +680,7 @@ void ReadBinary(std::istream& is, CompactLat* lat) {
 
 }  // namespace
 
-void ReadCompactLattice(std::istream& is, CompactLat* lat) {
+void ReadCompactLattice(std::istream& is, CompactLat* lat, bool keep_tids) {
   int c = is.peek();
   if (c == '\0') {  // tolerate a Kaldi binary marker "\0B" in front of the FST
     is.get();
@@ -610,7 +689,7 @@ void ReadCompactLattice(std::istream& is, CompactLat* lat) {
   }
   if (c == EOF) KIO_ERR("End of stream detected reading CompactLattice " << lat->key);
   if (isspace(c)) ReadText(is, lat);
-  else if (c == 214) ReadBinary(is, lat);
+  else if (c == 214) ReadBinary(is, lat, keep_tids);
   else KIO_ERR("Reading compact lattice " << lat->key << ": does not appear to be an FST");
 }
 
@@ -751,7 +830,8 @@ void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat) {
 }
 
 // ------------------------------------------------------------------- tables ---
-SequentialCompactLatticeReader::SequentialCompactLatticeReader(const std::string& rspecifier) {
+SequentialCompactLatticeReader::SequentialCompactLatticeReader(const std::string& rspecifier, bool keep_tids)
+    : keep_tids_(keep_tids) {
   spec_ = ParseSpecifier(rspecifier, false);
   in_.reset(new Input(spec_.is_scp ? spec_.scp : spec_.ark));
   ReadOne();
@@ -772,7 +852,7 @@ void SequentialCompactLatticeReader::ReadOne() {
       cur_.key = line.substr(a, sp - a);
       std::string path = line.substr(line.find_first_not_of(" \t", sp));
       scp_item_.reset(new Input(path));
-      ReadCompactLattice(scp_item_->Stream(), &cur_);
+      ReadCompactLattice(scp_item_->Stream(), &cur_, keep_tids_);
       return;
     }
     done_ = true;
@@ -790,7 +870,7 @@ void SequentialCompactLatticeReader::ReadOne() {
   if (c == EOF) KIO_ERR("Invalid archive file format: expected space after key " << key);
   cur_.key = key;
   if (c == '\n') is.unget();  // text lattices: the newline belongs to the holder
-  ReadCompactLattice(is, &cur_);
+  ReadCompactLattice(is, &cur_, keep_tids_);
 }
 
 TableWriter::TableWriter(const std::string& wspecifier) {

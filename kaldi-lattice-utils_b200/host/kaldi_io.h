@@ -106,7 +106,9 @@ struct CompactLat {
 };
 
 // Reads one table entry body (after "key ") from `is`: text or binary.
-void ReadCompactLattice(std::istream& is, CompactLat* lat);
+// keep_tids = false drops the transition-id strings (only their lengths, the arc
+// durations, are needed unless the lattice is written back).
+void ReadCompactLattice(std::istream& is, CompactLat* lat, bool keep_tids = true);
 void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat);
 // TopSortCompactLatticeIfNeeded [ext]; throws on cycles.
 void TopSortIfNeeded(CompactLat* lat);
@@ -125,6 +127,7 @@ class Input {  // file, stdin or pipe opened for reading (binary-safe)
   std::istream& Stream() { return *is_; }
 
  private:
+  std::string filebuf_;  // stream buffer of a file input (declared first: destroyed after owned_)
   std::unique_ptr<std::istream> owned_;
   std::istream* is_ = nullptr;
   FILE* pipe_ = nullptr;
@@ -147,7 +150,7 @@ class Output {
 
 class SequentialCompactLatticeReader {
  public:
-  explicit SequentialCompactLatticeReader(const std::string& rspecifier);
+  explicit SequentialCompactLatticeReader(const std::string& rspecifier, bool keep_tids = true);
   bool Done() const { return done_; }
   void Next();
   const std::string& Key() const { return cur_.key; }
@@ -155,6 +158,7 @@ class SequentialCompactLatticeReader {
 
  private:
   void ReadOne();
+  bool keep_tids_ = true;
   Specifier spec_;
   std::unique_ptr<Input> in_;       // ark stream, or the scp list
   std::unique_ptr<Input> scp_item_;

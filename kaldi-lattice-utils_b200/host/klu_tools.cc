@@ -615,7 +615,7 @@ int main(int argc, char* argv[]) {
     st.writer = &writer;
     std::vector<Batch> wave(1);
     const bool keep = KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */;
-    for (SequentialCompactLatticeReader reader(lattice_rspecifier); !reader.Done(); reader.Next()) {
+    for (SequentialCompactLatticeReader reader(lattice_rspecifier, keep); !reader.Done(); reader.Next()) {
       wave.back().Add(std::move(reader.Value()), keep);
       if (wave.back().arcs() >= batch_arcs) {
         if (wave.size() == st.ctxs.size()) ProcessWave(&st, &wave);
