@@ -1,6 +1,11 @@
 // kaldi_io.cc -- see kaldi_io.h.
 #include "kaldi_io.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <string.h>
 
 #include <algorithm>
@@ -196,9 +201,11 @@ void WriteKaldiFloat(std::ostream& os, double v) {
 }
 
 void WriteBasicInt32(std::ostream& os, bool binary, int32_t v) {
-  if (binary) {
-    os.put((char)4);
-    os.write(reinterpret_cast<const char*>(&v), 4);
+  if (binary) {  // straight into the stream buffer: no sentry per field
+    char b[5];
+    b[0] = 4;
+    memcpy(b + 1, &v, 4);
+    if (os.rdbuf()->sputn(b, 5) != 5) os.setstate(std::ios::badbit);
   } else {
     os << v << " ";
   }
@@ -206,8 +213,10 @@ void WriteBasicInt32(std::ostream& os, bool binary, int32_t v) {
 
 void WriteBasicFloat(std::ostream& os, bool binary, float v) {
   if (binary) {
-    os.put((char)4);
-    os.write(reinterpret_cast<const char*>(&v), 4);
+    char b[5];
+    b[0] = 4;
+    memcpy(b + 1, &v, 4);
+    if (os.rdbuf()->sputn(b, 5) != 5) os.setstate(std::ios::badbit);
   } else {
     WriteKaldiFloat(os, v);
     os << " ";
@@ -216,8 +225,10 @@ void WriteBasicFloat(std::ostream& os, bool binary, float v) {
 
 void WriteBasicDouble(std::ostream& os, bool binary, double v) {
   if (binary) {
-    os.put((char)8);
-    os.write(reinterpret_cast<const char*>(&v), 8);
+    char b[9];
+    b[0] = 8;
+    memcpy(b + 1, &v, 8);
+    if (os.rdbuf()->sputn(b, 9) != 9) os.setstate(std::ios::badbit);
   } else {
     WriteKaldiFloat(os, v);
     os << " ";
@@ -277,7 +288,8 @@ Input::Input(const std::string& name_in) {
     while ((n = fread(buf, 1, sizeof(buf), pipe_)) > 0) buffer_.append(buf, n);
     pclose(pipe_);
     pipe_ = nullptr;
-    owned_.reset(new std::istringstream(buffer_, std::ios::in | std::ios::binary));
+    membuf_.reset(new MemBuf(buffer_.data(), buffer_.size()));
+    owned_.reset(new std::istream(membuf_.get()));
     is_ = owned_.get();
   } else {
     // "path:offset" (scp entries)
@@ -287,6 +299,27 @@ Input::Input(const std::string& name_in) {
         name.find_first_not_of("0123456789", colon + 1) == std::string::npos) {
       off = (size_t)strtoull(name.c_str() + colon + 1, nullptr, 10);
       name = name.substr(0, colon);
+    }
+    // regular files are memory-mapped: entries are parsed in place
+    {
+      const int fd = open(name.c_str(), O_RDONLY);
+      struct stat st;
+      if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 && (size_t)st.st_size >= off) {
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+          madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+          map_ = m;
+          map_len_ = (size_t)st.st_size;
+        }
+      }
+      if (fd >= 0) close(fd);
+      if (map_) {
+        membuf_.reset(new MemBuf(static_cast<const char*>(map_), map_len_));
+        membuf_->advance(off);
+        owned_.reset(new std::istream(membuf_.get()));
+        is_ = owned_.get();
+        return;
+      }
     }
     auto* f = new std::ifstream();
     filebuf_.resize(4 << 20);  // large reads: table entries are parsed straight off the stream buffer
@@ -299,7 +332,11 @@ Input::Input(const std::string& name_in) {
   }
 }
 
-Input::~Input() {}
+Input::~Input() {
+  owned_.reset();
+  membuf_.reset();
+  if (map_) munmap(map_, map_len_);
+}
 
 Output::Output(const std::string& name) {
   if (name == "-" || name.empty()) {
@@ -564,7 +601,86 @@ inline void GetBytes(std::streambuf* sb, void* p, std::streamsize n) {
 // the OpenFst body lists the arcs state by state, i.e. already grouped by source, so
 // the SoA arrays are filled directly (one read for the fixed part of every arc, one
 // for its transition ids, which are kept only for the tool that writes lattices back).
+// The same over a memory block: no copies except into the SoA arrays.
+bool ReadBinaryCompactMem(MemBuf* mb, int64_t nstates, int64_t narcs, bool keep_tids, CompactLat* lat) {
+  if (narcs < 0 || narcs >= ((int64_t)1 << 31)) return false;  // header without an arc count: generic path
+  const char* p = mb->cur();
+  const char* const end = mb->end();
+  const int32_t n = (int32_t)nstates;
+  const size_t na_total = (size_t)narcs;
+  lat->nstates = n;
+  const float inf = std::numeric_limits<float>::infinity();
+  lat->fin_graph.assign(n, inf);
+  lat->fin_acoustic.assign(n, inf);
+  lat->fin_dur.assign(n, 0);
+  if (keep_tids) lat->fin_tids.assign(n, std::vector<int32_t>());
+  lat->src.resize(na_total);
+  lat->dst.resize(na_total);
+  lat->label.resize(na_total);
+  lat->dur.resize(na_total);
+  lat->graph.resize(na_total);
+  lat->acoustic.resize(na_total);
+  if (keep_tids) lat->tids.resize(na_total);
+  size_t e = 0;
+  auto need = [&](size_t bytes) {
+    if ((size_t)(end - p) < bytes) KIO_ERR("Unexpected end of binary lattice " << lat->key);
+  };
+  for (int32_t s = 0; s < n; ++s) {
+    need(12);
+    float g, a;
+    int32_t sz;
+    memcpy(&g, p, 4);
+    memcpy(&a, p + 4, 4);
+    memcpy(&sz, p + 8, 4);
+    p += 12;
+    if (sz < 0) KIO_ERR("Corrupt binary lattice " << lat->key);
+    need(4 * (size_t)sz + 8);
+    if (!(std::isinf(g) && std::isinf(a))) {
+      lat->fin_graph[s] = g;
+      lat->fin_acoustic[s] = a;
+      lat->fin_dur[s] = sz;
+      if (keep_tids) {
+        lat->fin_tids[s].resize((size_t)sz);
+        if (sz) memcpy(lat->fin_tids[s].data(), p, 4 * (size_t)sz);
+      }
+    }
+    p += 4 * (size_t)sz;
+    int64_t na;
+    memcpy(&na, p, 8);
+    p += 8;
+    if (na < 0 || e + (size_t)na > na_total) KIO_ERR("Corrupt binary lattice " << lat->key << ": arc counts disagree");
+    for (int64_t k = 0; k < na; ++k, ++e) {
+      need(24);
+      int32_t olabel, asz, dst;
+      memcpy(&olabel, p + 4, 4);
+      memcpy(&lat->graph[e], p + 8, 4);
+      memcpy(&lat->acoustic[e], p + 12, 4);
+      memcpy(&asz, p + 16, 4);
+      p += 20;
+      if (asz < 0) KIO_ERR("Corrupt binary lattice " << lat->key);
+      need(4 * (size_t)asz + 4);
+      if (keep_tids) {
+        lat->tids[e].resize((size_t)asz);
+        if (asz) memcpy(lat->tids[e].data(), p, 4 * (size_t)asz);
+      }
+      p += 4 * (size_t)asz;
+      memcpy(&dst, p, 4);
+      p += 4;
+      lat->src[e] = s;
+      lat->dst[e] = dst;
+      lat->label[e] = olabel;
+      lat->dur[e] = asz;
+    }
+  }
+  if (e != na_total) KIO_ERR("Corrupt binary lattice " << lat->key << ": arc counts disagree");
+  mb->advance((size_t)(p - mb->cur()));
+  TopSortIfNeeded(lat);
+  return true;
+}
+
 void ReadBinaryCompactFast(std::istream& is, int64_t nstates, int64_t narcs_hint, bool keep_tids, CompactLat* lat) {
+  if (MemBuf* mb = dynamic_cast<MemBuf*>(is.rdbuf()))
+    if (ReadBinaryCompactMem(mb, nstates, narcs_hint, keep_tids, lat)) return;
   std::streambuf* sb = is.rdbuf();
   struct FinalHead { float g, a; int32_t sz; };
   struct ArcHead { int32_t ilabel, olabel; float g, a; int32_t sz; };

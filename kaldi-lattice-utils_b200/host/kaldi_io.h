@@ -25,6 +25,7 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <streambuf>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -120,6 +121,31 @@ struct Specifier {
 };
 Specifier ParseSpecifier(const std::string& spec, bool writing);
 
+// Read-only stream buffer over a block of memory (a memory-mapped archive, or the
+// collected output of an input pipe).  Table entries can be parsed straight from
+// cur() .. end() and the position moved with advance(); the std::istream layered on
+// top sees the same position.
+class MemBuf : public std::streambuf {
+ public:
+  MemBuf(const char* begin, size_t n) {
+    char* b = const_cast<char*>(begin);
+    setg(b, b, b + n);
+  }
+  const char* cur() const { return gptr(); }
+  const char* end() const { return egptr(); }
+  void advance(size_t n) { setg(eback(), gptr() + n, egptr()); }
+
+ protected:
+  pos_type seekoff(off_type off, std::ios_base::seekdir dir, std::ios_base::openmode) override {
+    char* base = dir == std::ios_base::beg ? eback() : dir == std::ios_base::cur ? gptr() : egptr();
+    char* p = base + off;
+    if (p < eback() || p > egptr()) return pos_type(off_type(-1));
+    setg(eback(), p, egptr());
+    return pos_type(p - eback());
+  }
+  pos_type seekpos(pos_type pos, std::ios_base::openmode m) override { return seekoff(off_type(pos), std::ios_base::beg, m); }
+};
+
 class Input {  // file, stdin or pipe opened for reading (binary-safe)
  public:
   explicit Input(const std::string& name);
@@ -128,6 +154,9 @@ class Input {  // file, stdin or pipe opened for reading (binary-safe)
 
  private:
   std::string filebuf_;  // stream buffer of a file input (declared first: destroyed after owned_)
+  std::unique_ptr<MemBuf> membuf_;
+  void* map_ = nullptr;  // memory-mapped regular file
+  size_t map_len_ = 0;
   std::unique_ptr<std::istream> owned_;
   std::istream* is_ = nullptr;
   FILE* pipe_ = nullptr;
