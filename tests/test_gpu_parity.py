@@ -289,3 +289,58 @@ def test_gpu_packer_equals_host_packer(klu, engine, monkeypatch):
     assert gpu["seg"] == host["seg"] and gpu["pos"] == host["pos"] and gpu["utt"] == host["utt"]
     assert gpu["fp"] == host["fp"] and gpu["bp"] == host["bp"] and gpu["pr"] == host["pr"]
     assert gpu["fb"] == host["fb"]
+
+
+# ---- edge cases of the frame-synchronous path --------------------------------------
+def test_frame_post_underflowing_group_is_redone_exactly(klu, ora, engine):
+    # word 9 only occurs on an arc 2000 nats worse than the best path: exp(-2000) underflows
+    # the f64 posterior, so its group goes through the exact log-domain path
+    arcs = [(0, 1, 5, 1.0, 0.5, 2), (0, 1, 9, 2000.0, 0.5, 2), (0, 1, 6, 1.5, 0.25, 2), (1, 2, 7, 0.5, 0.5, 3),
+            (1, 2, 9, 2500.0, 0.0, 3)]
+    lat = klu.make_lattice("under", 3, arcs, {2: (0.0, 0.0)})
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    got = engine.frame_post()[0]
+    want = ora.frame_post(lat)
+    assert len(got) == len(want) == 5
+    for g, w in zip(got, want):
+        assert [x[0] for x in g] == [x[0] for x in w]
+        for (_, a), (_, b) in zip(g, w):
+            assert abs(a - b) <= 1e-4 * max(1.0, abs(b))
+    assert got[0][-1][0] == 9 and -2001.0 < got[0][-1][1] < -1997.0
+
+
+def test_frame_post_ties_and_near_ties(klu, ora, engine):
+    # exact ties (identical weights, different words) order by word; values that differ only in
+    # the low mantissa bits of the float log-posterior exercise the 64-bit re-sort
+    rng = np.random.RandomState(3)
+    arcs = []
+    for w in range(40):
+        arcs.append((0, 1, 100 + w, 1.0, 0.5, 1))                       # 40-way exact tie
+    for w in range(40):
+        arcs.append((0, 1, 200 + w, 3.0 + 1e-7 * rng.randint(0, 50), 0.5, 1))  # near-ties
+    arcs.append((1, 2, 7, 0.5, 0.5, 1))
+    lat = klu.make_lattice("ties", 3, arcs, {2: (0.0, 0.0)})
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    got = engine.frame_post()[0]
+    want = ora.frame_post(lat)
+    assert [x[0] for x in got[0][:40]] == list(range(100, 140))
+    for g, w in zip(got, want):
+        assert_rows_match(g, w, 1, what="ties")
+        for a, b in zip(g[:-1], g[1:]):  # strictly the reference's comparator on OUR floats
+            assert a[1] > b[1] or (a[1] == b[1] and a[0] < b[0])
+
+
+def test_unreachable_and_dead_end_states(klu, ora, engine):
+    # state 2 cannot be reached from the start (and has no arcs: CompactLatticeStateTimes
+    # asserts otherwise), state 3 cannot reach a final state
+    arcs = [(0, 1, 5, 1.0, 0.5, 1), (0, 3, 8, 0.5, 0.5, 1), (1, 4, 6, 0.5, 0.5, 1)]
+    lat = klu.make_lattice("holes", 5, arcs, {4: (0.0, 0.0)})
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    engine.run(klu.FWD_BWD)
+    al, be, tot = engine.fetch_fwd_bwd()
+    assert al[2] == -np.inf and be[3] == -np.inf and np.isfinite(al[[0, 1, 3, 4]]).all()
+    assert_rows_match(engine.segment()[0], ora.segment(lat), 3, what="holes segment")
+    got, want = engine.frame_post()[0], ora.frame_post(lat)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert_rows_match(g, w, 1, what="holes frame-post")
