@@ -18,6 +18,7 @@
  *                      (+ kwsbin2/utils.h:41-303, fstext/fstext-utils2.h:278-603)
  *   KLU_POSITION_POST  latbin/lattice-to-word-position-post.cc:70-141
  *   KLU_CHAR_SEGMENT   kwsbin2/lattice-char-index-segment.cc:93-223
+ *   KLU_LENGTH_DIST    latbin/lattice-to-transcript-length-dist.cc:64-125
  *
  * Plain pointers and sizes only; all pointers are HOST pointers.  Every function
  * returns 0 on success; on failure klu_last_error() (thread-local) explains.
@@ -55,7 +56,8 @@ enum klu_tool {
   KLU_CHAR_POSITION = 6,
   KLU_FWD_BWD = 7, /* alpha/beta only (ComputeLatticeAlphasAndBetas [ext]) */
   KLU_POSITION_POST = 8,
-  KLU_CHAR_SEGMENT = 9
+  KLU_CHAR_SEGMENT = 9,
+  KLU_LENGTH_DIST = 10
 };
 
 /* A batch of lattices as concatenated SoA arrays.  state_off/arc_off have
@@ -153,6 +155,8 @@ int klu_fetch_frame_post(klu_ctx* ctx, int32_t* num_frames, int32_t* frame, int3
 /* position-post: num_positions[num_lattices] (Posterior length = longest label sequence);
  * entries carry their 0-based position index. */
 int klu_fetch_position_post(klu_ctx* ctx, int32_t* num_positions, int32_t* position, int32_t* word, float* logp);
+/* length-dist: entries are (transcript length, float log-posterior), one Posterior frame per lattice. */
+int klu_fetch_length_dist(klu_ctx* ctx, int32_t* length, float* logp);
 /* best-path2: entries are the transcript labels; cost[num_lattices] (float path
  * cost, latbin/lattice-best-path2.cc:192), num_frames[num_lattices]. */
 int klu_fetch_best_path2(klu_ctx* ctx, int32_t* label, float* cost, int32_t* num_frames);

@@ -12,18 +12,19 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST, CHAR_SEGMENT = range(10)
+SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST, CHAR_SEGMENT, LENGTH_DIST = range(11)
 TOOL_NAMES = {SEGMENT: "lattice-word-index-segment", POSITION: "lattice-word-index-position",
               UTTERANCE: "lattice-word-index-utterance", FRAME_POST: "lattice-to-word-frame-post",
               PRUNE_DYN_BEAM: "lattice-prune-dyn-beam", BEST_PATH2: "lattice-best-path2",
               CHAR_POSITION: "lattice-char-index-position", FWD_BWD: "fwd-bwd",
-              POSITION_POST: "lattice-to-word-position-post", CHAR_SEGMENT: "lattice-char-index-segment"}
+              POSITION_POST: "lattice-to-word-position-post", CHAR_SEGMENT: "lattice-char-index-segment",
+              LENGTH_DIST: "lattice-to-transcript-length-dist"}
 INT_MAX = 2**31 - 1
 
 # every symbol include/klu.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["klu_last_error", "klu_version", "klu_opts_default", "klu_device_count", "klu_create", "klu_destroy",
            "klu_host_alloc", "klu_host_free", "klu_topsort", "klu_load", "klu_run", "klu_sync", "klu_result_offsets",
-           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_position_post",
+           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_position_post", "klu_fetch_length_dist",
            "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position", "klu_fetch_char_segment",
            "klu_fetch_fwd_bwd", "klu_timer_start", "klu_timer_stop", "klu_launch_count", "klu_profile_enable",
            "klu_profile_json", "klu_batch_stats", "klu_flush_l2"]
@@ -308,6 +309,15 @@ class Engine:
                 rows[k].append((ww, p))
             res.append(rows)
         return res
+
+    def length_dist(self, **o):
+        """Per lattice: [(length, float32 logp)] in the reference's output order."""
+        self.run(LENGTH_DIST, **o)
+        off = self.offsets()
+        n = int(off[-1])
+        ln, lp = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        _chk(self.L.klu_fetch_length_dist(self.h, _p(ln), _p(lp)))
+        return [list(zip(ln[a:b].tolist(), lp[a:b].tolist())) for a, b in zip(off[:-1], off[1:])]
 
     def best_path2(self, **o):
         self.run(BEST_PATH2, **o)

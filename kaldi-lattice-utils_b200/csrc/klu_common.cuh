@@ -184,6 +184,8 @@ struct BestPathChunk {
   bool first_chunk;
 };
 int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch);
+// klu_lendist.cu
+int run_length_dist(klu_ctx* c, const klu_opts* o);
 // klu_char.cu
 int run_char_position(klu_ctx* c, const klu_opts* o);
 int run_char_segment(klu_ctx* c, const klu_opts* o);

@@ -1008,6 +1008,19 @@ int klu_fetch_frame_post(klu_ctx* c, int32_t* num_frames, int32_t* frame, int32_
   return 0;
 }
 
+int klu_fetch_length_dist(klu_ctx* c, int32_t* length, float* logp) {
+  if (c->last_tool != KLU_LENGTH_DIST) {
+    set_error("klu_fetch_length_dist: last run was not KLU_LENGTH_DIST");
+    return 1;
+  }
+  KLU_TRY(ensure_offsets(c));
+  const size_t n = (size_t)c->last_entries;
+  KLU_TRY(d2h(c, length, c->d_res[0].p, n * 4));
+  KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 4));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int klu_fetch_position_post(klu_ctx* c, int32_t* num_positions, int32_t* position, int32_t* word, float* logp) {
   if (c->last_tool != KLU_POSITION_POST) {
     set_error("klu_fetch_position_post: last run was not KLU_POSITION_POST");

@@ -13,6 +13,7 @@
 //   lattice-best-path2            latbin/lattice-best-path2.cc:29-221
 //   lattice-to-word-position-post latbin/lattice-to-word-position-post.cc:28-147
 //   lattice-char-index-segment    kwsbin2/lattice-char-index-segment.cc:249-349
+//   lattice-to-transcript-length-dist latbin/lattice-to-transcript-length-dist.cc:28-131
 //
 // Lattices are independent, so the reader fills a batch (KLU_BATCH_ARCS arcs,
 // default 32M), the batch is packed/uploaded/processed, and entries are written
@@ -149,6 +150,10 @@ void ComputeBatch(klu_ctx* ctx, const klu_opts* opts, const Batch* b, Results* r
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */
     r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
     KLU_CHECK(klu_fetch_frame_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
+#elif KLU_TOOL == 10 /* KLU_LENGTH_DIST */
+    // one Posterior frame per lattice (latbin/lattice-to-transcript-length-dist.cc:111)
+    r->i0.assign(L, 1), r->i1.assign(n, 0), r->i2.resize(n), r->f0.resize(n);
+    KLU_CHECK(klu_fetch_length_dist(ctx, r->i2.data(), r->f0.data()));
 #elif KLU_TOOL == 8 /* KLU_POSITION_POST */
     r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
     KLU_CHECK(klu_fetch_position_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
@@ -258,7 +263,7 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
     if (!bin) os << '\n';
     w.End();
   }
-#elif KLU_TOOL == 3 /* KLU_FRAME_POST */ || KLU_TOOL == 8 /* KLU_POSITION_POST */
+#elif KLU_TOOL == 3 /* KLU_FRAME_POST */ || KLU_TOOL == 8 /* KLU_POSITION_POST */ || KLU_TOOL == 10 /* KLU_LENGTH_DIST */
   const std::vector<int32_t>&nf = r->i0, &frame = r->i1, &word = r->i2;
   const std::vector<float>& lp = r->f0;
   for (int32_t l = 0; l < L; ++l) {
@@ -439,6 +444,11 @@ int main(int argc, char* argv[]) {
         "log P(a_i = v | x), for all possible utterance frames i and words v.\n\n"
         "Usage: lattice-to-word-frame-post [options] lat-rspecifier post-wspecifier\n"
         " e.g.: lattice-to-word-frame-post --acoustic-scale=0.1 ark:1.lats ark:1.word.pos.post\n";
+#elif KLU_TOOL == 10 /* KLU_LENGTH_DIST */
+    const char* usage =
+        "Compute the distribution of the length of the transcriptions in a lattice.\n\n"
+        "Usage: lattice-to-transcript-length-dist [options] lattice-rspecifier1 posterior-wspecifier\n"
+        " e.g.: lattice-to-transcript-length-dist ark:1.lats ark:1.posts\n";
 #elif KLU_TOOL == 8 /* KLU_POSITION_POST */
     const char* usage =
         "Compute the posterior log-probability of each word for each given transcription position. That is, we "

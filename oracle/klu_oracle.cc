@@ -754,6 +754,39 @@ void WordPositionPost(Lat lat0, const Opts& o, Result* r) {
   r->ds0 = total;
 }
 
+// latbin/lattice-to-transcript-length-dist.cc:64-125: posterior of
+// the transcript length.  In the length-unfolded lattice every final state (len, u) adds
+// fw[(len, u)] - cost(final(u)) to acc[len] (:97-108, states in id order); output = ONE
+// Posterior frame of (length, float logp) sorted by (float logp desc, length asc) (:111-123).
+void TranscriptLengthDist(Lat lat0, const Opts& o, Result* r) {
+  Prologue(&lat0, o, false);
+  if (lat0.Empty()) { r->s0 = 1; return; }
+  Lat lat;
+  std::vector<int32> state_len;
+  DisambiguateLength(lat0, &lat, &state_len);
+  std::vector<double> fw, bw;
+  const double total = AlphasAndBetas(lat, &fw, &bw);
+  std::map<int32, double> acc;
+  for (int32 u = 0; u < lat.NumStates(); ++u) {
+    if (std::isinf(lat.fg[u]) && std::isinf(lat.fa[u])) continue;
+    const double end = fw[u] - Cost(lat.fg[u], lat.fa[u]);
+    auto rr = acc.emplace(state_len[u], end);
+    if (!rr.second) rr.first->second = LogAdd(rr.first->second, end);
+  }
+  std::vector<std::pair<int32, float> > post;
+  for (const auto& kv : acc) post.emplace_back(kv.first, (float)(kv.second - total));
+  std::sort(post.begin(), post.end(), [](const std::pair<int32, float>& a, const std::pair<int32, float>& b) -> bool {
+    if (a.second != b.second) return b.second < a.second;
+    else return a.first < b.first;
+  });
+  for (const auto& p : post) {
+    r->i0.push_back(p.first);
+    r->f0.push_back(p.second);
+  }
+  r->s0 = 1;
+  r->ds0 = total;
+}
+
 // latbin/lattice-prune-dyn-beam.cc:27-90
 double ComputeLatticeBeam(const Lat& lat) {
   const int32 num_states = lat.NumStates();
@@ -1420,7 +1453,7 @@ typedef struct ora_opts {
 } ora_opts;
 
 enum { ORA_SEGMENT = 0, ORA_POSITION = 1, ORA_UTTERANCE = 2, ORA_FRAME_POST = 3, ORA_PRUNE_DYN_BEAM = 4,
-       ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_CHAR_SEGMENT = 9, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
+       ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_CHAR_SEGMENT = 9, ORA_LENGTH_DIST = 14, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
        ORA_BRUTE_FRAME = 12, ORA_BRUTE_UTTERANCE = 13 };
 
 static Opts ConvertOpts(const ora_opts* o) {
@@ -1457,6 +1490,7 @@ static void RunTool(int tool, const ora_lat* l, const Opts& o, Result* r) {
     case ORA_CHAR_POSITION: CharIndexPosition(lat, o, r); break;
     case ORA_POSITION_POST: WordPositionPost(lat, o, r); break;
     case ORA_CHAR_SEGMENT: CharIndexSegment(lat, o, r); break;
+    case ORA_LENGTH_DIST: TranscriptLengthDist(lat, o, r); break;
     case ORA_BRUTE_SEGMENT: BruteForce(lat, 0, r); break;
     case ORA_BRUTE_POSITION: BruteForce(lat, 1, r); break;
     case ORA_BRUTE_FRAME: BruteForce(lat, 2, r); break;

@@ -16,6 +16,7 @@ _LIB = None
 SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION = range(7)
 POSITION_POST = 8
 CHAR_SEGMENT = 9
+LENGTH_DIST = 14
 BRUTE_SEGMENT, BRUTE_POSITION, BRUTE_FRAME, BRUTE_UTTERANCE = 10, 11, 12, 13
 
 INT_MAX = 2**31 - 1
@@ -197,6 +198,12 @@ def position_post(lat, **o):
     for k, w, p in zip(r.i[0].tolist(), r.i[1].tolist(), r.f[0].tolist()):
         pos[k].append((w, p))
     return pos
+
+
+def length_dist(lat, **o):
+    """latbin/lattice-to-transcript-length-dist: [(length, float32 logp)] in output order."""
+    r = run(LENGTH_DIST, lat, **o)
+    return list(zip(r.i[0].tolist(), r.f[0].tolist()))
 
 
 def best_path2(lat, **o):

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "kaldi-lattice-utils_b200", "bin")
 TOOLS = ["lattice-word-index-segment", "lattice-word-index-position", "lattice-word-index-utterance",
          "lattice-to-word-frame-post", "lattice-prune-dyn-beam", "lattice-best-path2", "lattice-char-index-position",
-         "lattice-to-word-position-post", "lattice-char-index-segment"]
+         "lattice-to-word-position-post", "lattice-char-index-segment",
+         "lattice-to-transcript-length-dist"]
 
 
 def run(tool, *args, env=None, stdin=None):
@@ -121,6 +122,13 @@ def test_multi_context_waves_keep_input_order(tool):
     assert one.returncode == 0 and multi.returncode == 0, multi.stderr.decode()
     assert multi.stdout == one.stdout
     assert [x.split()[0] for x in multi.stdout.decode().strip("\n").split("\n")] == ["lat%d" % i for i in range(1, 6)]
+
+
+@pytest.mark.gpu
+def test_length_dist_text():
+    r = run("lattice-to-transcript-length-dist", WORD, "ark,t:-")
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout.decode() == "lat1 [ 7 0 ] \n"
 
 
 @pytest.mark.gpu

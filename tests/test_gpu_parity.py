@@ -179,6 +179,23 @@ def test_position_post_readme_lattice(klu, ora, engine, word_lat):
             assert a == b  # float32 values, bit-identical on this chain/diamond lattice
 
 
+# ---- lattice-to-transcript-length-dist -----------------------
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", [dict(), dict(acoustic_scale=0.1, insertion_penalty=0.5)])
+def test_length_dist_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 5)
+    lats = batch.lattices() + [klu.make_lattice("empty", 0, [], {})]
+    engine.load(klu.LatticeBatch.from_lattices(lats))
+    got = engine.length_dist(**flags)
+    for l, lat in enumerate(lats):
+        assert_rows_match(got[l], ora.length_dist(lat, **flags), 1, what="length-dist lat %d" % l)
+
+
+def test_length_dist_readme_lattice(klu, engine, word_lat):
+    _load(klu, engine, [word_lat])
+    assert engine.length_dist()[0] == [(7, 0.0)]
+
+
 # ---- lattice-prune-dyn-beam -----------------------------------------------------
 def _check_prune(got, want, lat):
     assert got["nstates"] == want["nstates"]
