@@ -55,6 +55,9 @@ ALGO = {
     "k_group_post": dict(arc=0.0, state=0.0, entry=8.0, inst=12.0),
     # per-frame ordering: 4 B logp + 4 B word read, (word, logp) written in order (the frame column is static)
     "k_frame_order": dict(arc=0.0, state=0.0, entry=16.0),
+    # fused window kernel: record + source id per arc (20 B), arc id per instance (4 B), offset read +
+    # log-posterior written per group (8 B)
+    "k_frame_groups": dict(arc=20.0, state=16.0, entry=8.0, inst=4.0),
 }
 
 

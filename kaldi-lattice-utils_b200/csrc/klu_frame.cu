@@ -24,6 +24,8 @@
 // from alpha/beta; frames with more groups than the shared-memory order buffer
 // holds are ordered in global memory (slow, same results).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -52,6 +54,11 @@ struct FrameArgs {
   const int32_t* gwords;     // word of every (frame, word) group, in pre-order row order (static)
   const uint32_t* gstart;    // [rows + 1] first instance of every group (static)
   int64_t rows;
+  const int4* tarc;          // [E] arcs in START-TIME order: {src, dst, graph bits, acoustic bits} (static)
+  const int32_t* tlabel;     // [E] their labels; frame_arc holds indices into this order
+  const int32_t* run_lo;     // per work item (run of frames): smallest / largest time-order arc index among
+  const int32_t* run_hi;     // its instances (static); the arcs in between are the run's "window"
+  int win_cap;               // window entries that fit the dynamic shared memory
   int32_t *o_frame, *o_word;
   float* o_logp;
 };
@@ -62,25 +69,19 @@ __device__ __forceinline__ float inv_ord_f32(unsigned int u) {
 }
 
 // fw[u] + bw[next] - (float)(g + a), latbin/lattice-to-word-frame-post.cc:102-104
-__device__ __forceinline__ double arc_value(const FrameArgs& a, int e) {
-  const int4 r = __ldg(a.b.out_rec + e);
-  return __dadd_rn(__dadd_rn(a.alpha[a.b.out_src[e]], a.beta[r.x]), -rec_cost(r, a.cp));
+__device__ __forceinline__ double arc_value(const FrameArgs& a, int j) {  // j: time-order arc index
+  const int4 t = __ldg(a.tarc + j);
+  const int4 r = make_int4(t.y, t.z, t.w, __ldg(a.tlabel + j));
+  return __dadd_rn(__dadd_rn(a.alpha[t.x], a.beta[t.y]), -rec_cost(r, a.cp));
 }
 
-// grid (tiles, L): the posterior of every word arc, once
+// grid (tiles, L): the posterior of every word arc, once (cross-check path KLU_FRAME_UNFUSED)
 __global__ void __launch_bounds__(256) k_arc_post(FrameArgs a) {
   const int l = blockIdx.y;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const double total = a.total[l];
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
-    const int4 r = ld_stream(a.b.out_rec + e);
-    double p = 0.0;
-    if (r.w != 0) {
-      const double v = __dadd_rn(__dadd_rn(a.alpha[a.b.out_src[e]], a.beta[r.x]), -rec_cost(r, a.cp));
-      p = fast_exp(v - total);
-    }
-    a.parc[e] = p;
-  }
+  for (int j = e0 + blockIdx.x * blockDim.x + threadIdx.x; j < e1; j += gridDim.x * blockDim.x)
+    a.parc[j] = __ldg(a.tlabel + j) != 0 ? fast_exp(arc_value(a, j) - total) : 0.0;
 }
 
 // Exact log-posterior of the group that ENDS at instance `iend` of a frame's list
@@ -213,6 +214,87 @@ __global__ void __launch_bounds__(256) k_group_post(const __grid_constant__ Fram
       lp = exact_group_logp(a, a.b.frame_arc, i1 - 1, a.total[lo]);
     }
     if (live) a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+  }
+}
+
+// Fused arc posteriors + group sums for one run of kFramesPerItem frames per CTA.
+// With the arcs numbered by start time (a copy made at pack time), the word arcs alive
+// in a run of frames are a contiguous index range -- the run's window.  Phase 1 computes the posterior of
+// every arc of the window into shared memory (coalesced record reads, one exp per arc;
+// windows of neighbouring runs overlap by the arcs that span the boundary, ~1/8 extra);
+// phase 2 is k_group_post with its gathers served from shared memory.  No per-arc
+// posterior array in HBM, no dependent global gathers.  Runs whose window does not fit
+// (very long arcs) take the posteriors from alpha/beta directly, instance by instance.
+__global__ void __launch_bounds__(128) k_frame_groups(const __grid_constant__ FrameArgs a) {
+  extern __shared__ double s_post[];
+  const BatchView& b = a.b;
+  const int item = blockIdx.x;
+  int lo = 0, hi = b.L - 1;  // lattice of this item: last l with item_base[l] <= item
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.item_base[mid] <= item) lo = mid;
+    else hi = mid - 1;
+  }
+  const int l = lo;
+  const int T = b.fr_base[l + 1] - b.fr_base[l] - 1;
+  const int k0 = (item - a.item_base[l]) * kFramesPerItem;
+  const int k1 = min(T, k0 + kFramesPerItem);
+  const int64_t* gl = a.gloc + b.fr_base[l];
+  const int64_t row0 = a.res_off[l] + gl[k0], row1 = a.res_off[l] + gl[k1];
+  if (row0 == row1) return;
+  const int wlo = a.run_lo[item], whi = a.run_hi[item];
+  const bool windowed = whi - wlo < a.win_cap;
+  const double total = a.total[l];
+  if (windowed) {
+    // four arcs per thread and trip: their record, label and score loads go out together
+    for (int j0 = wlo + threadIdx.x; j0 <= whi; j0 += 4 * blockDim.x) {
+      int4 t[4];
+      int lab[4];
+      double al[4], be[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * blockDim.x;
+        if (j <= whi) {
+          t[u] = __ldg(a.tarc + j);
+          lab[u] = __ldg(a.tlabel + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * blockDim.x;
+        if (j <= whi) {
+          al[u] = a.alpha[t[u].x];
+          be[u] = a.beta[t[u].y];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * blockDim.x;
+        if (j <= whi) {
+          const int4 r = make_int4(t[u].y, t[u].z, t[u].w, lab[u]);
+          s_post[j - wlo] = lab[u] != 0 ? fast_exp(__dadd_rn(__dadd_rn(al[u], be[u]), -rec_cost(r, a.cp)) - total) : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int64_t g = row0 + threadIdx.x; g < row1; g += blockDim.x) {
+    const uint32_t i0 = __ldg(a.gstart + g), i1 = __ldg(a.gstart + g + 1);
+    double sum = 0.0;
+    if (windowed) {
+      for (uint32_t i = i0; i < i1; i += 4) {  // four instance ids in flight, the adds stay in order
+        int e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = i + u < i1 ? (int)((unsigned int)__ldg(b.frame_arc + i + u) & 0x7fffffffu) - wlo : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sum += i + u < i1 ? s_post[e[u]] : 0.0;
+      }
+    } else {
+      for (uint32_t i = i0; i < i1; ++i)
+        sum += fast_exp(arc_value(a, (int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu)) - total);
+    }
+    const double lp = sum >= 1e-280 ? fast_log(sum) : exact_group_logp(a, b.frame_arc, i1 - 1, total);
+    a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
   }
 }
 
@@ -365,7 +447,37 @@ struct GroupArgs {
   int32_t* gwords;
   int32_t* gframe;
   uint32_t* gstart;
+  int32_t *run_lo, *run_hi;
+  int32_t* max_window;       // largest window of the batch
+  const int64_t* arc_base;   // [L] = e_off as 64-bit segment bases
+  int32_t* rank_of;          // [E] out-order arc -> time-order index (global)
+  int4* tarc;
+  int32_t* tlabel;
 };
+
+// grid (tiles, L): sort input for the time order: key = start frame, val = out-order arc (lattice-local)
+__global__ void __launch_bounds__(256) k_fg_time_keys(GroupArgs a) {
+  const int l = blockIdx.y;
+  const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
+  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+    a.key[e] = (unsigned long long)max(a.b.time[a.b.out_src[e]], 0);
+    a.val[e] = (unsigned int)(e - e0);
+  }
+}
+
+// grid (tiles, L): the time-ordered arc copy and the inverse permutation
+__global__ void __launch_bounds__(256) k_fg_time_copy(GroupArgs a) {
+  const int l = blockIdx.y;
+  const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
+  const unsigned int* val = (a.where[l] ? a.val_b : a.val_a) + e0;
+  for (int j = e0 + blockIdx.x * blockDim.x + threadIdx.x; j < e1; j += gridDim.x * blockDim.x) {
+    const int e = e0 + (int)val[j - e0];
+    const int4 r = a.b.out_rec[e];
+    a.tarc[j] = make_int4(a.b.out_src[e], r.x, r.y, r.z);
+    a.tlabel[j] = r.w;
+    a.rank_of[e] = j;
+  }
+}
 
 __device__ __forceinline__ int arc_frames(const BatchView& b, int e, int T, int* first) {
   const int4 r = b.out_rec[e];
@@ -376,8 +488,8 @@ __device__ __forceinline__ int arc_frames(const BatchView& b, int e, int T, int*
 }
 
 // One CTA per lattice: exclusive scan of the arcs' frame counts, then the
-// (frame, word) -> arc instances in arc order (so the stable sort leaves every
-// group in arc order, whatever order the packer's frame CSR was filled in).
+// (frame, word) -> arc instances in arc order, each carrying the arc's TIME-ORDER index
+// (the stable sort then leaves every group in a fixed order).
 __global__ void __launch_bounds__(256) k_fg_emit(GroupArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
@@ -408,7 +520,7 @@ __global__ void __launch_bounds__(256) k_fg_emit(GroupArgs a) {
       const unsigned long long word = (unsigned long long)(unsigned int)b.out_rec[e].w;
       for (int q = 0; q < cnt; ++q) {
         a.key[base + off + q] = ((unsigned long long)(first + q) << a.bits_label) | word;
-        a.val[base + off + q] = (unsigned int)e;
+        a.val[base + off + q] = (unsigned int)a.rank_of[e];
       }
     }
     __syncthreads();
@@ -438,6 +550,7 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
     const unsigned long long* key = a.where[l] ? a.key_b : a.key_a;
     const unsigned int* val = a.where[l] ? a.val_b : a.val_a;
     const unsigned long long label_mask = (1ULL << a.bits_label) - 1ULL;
+    int wlo = 0x7fffffff, whi = -1;  // arc id window of the run
     for (int k = k0; k < k1; ++k) {
       const int fs = b.fr_base[l] + k;
       const int64_t f0 = b.fr_off[fs], f1 = b.fr_off[fs + 1];
@@ -452,7 +565,12 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
         }
         const unsigned int hm = __ballot_sync(0xffffffffu, head);
         if (!WORDS) {
-          if (i < f1) a.frame_arc[i] = (int32_t)(val[i] | (head ? 0x80000000u : 0u));
+          if (i < f1) {
+            const unsigned int e = val[i];
+            a.frame_arc[i] = (int32_t)(e | (head ? 0x80000000u : 0u));
+            wlo = min(wlo, (int)e);
+            whi = max(whi, (int)e);
+          }
         } else if (head) {
           const int64_t row = a.res_off[l] + a.gloc[fs] + groups + __popc(hm & ((1u << lane) - 1u));
           a.gwords[row] = (int32_t)(kk & label_mask);
@@ -462,6 +580,18 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
         groups += __popc(hm);
       }
       if (!WORDS && lane == 0) a.frame_cnt[fs] = groups;
+    }
+    if (!WORDS) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+        whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+      }
+      if (lane == 0) {
+        a.run_lo[item] = wlo;
+        a.run_hi[item] = whi;
+        if (whi >= wlo) atomicMax(a.max_window, whi - wlo + 1);
+      }
     }
   }
 }
@@ -587,7 +717,7 @@ int build_frame_groups(klu_ctx* c) {
   do {
     if ((rc = key_a.reserve(8 * (size_t)N)) || (rc = key_b.reserve(8 * (size_t)N)) ||
         (rc = val_a.reserve(4 * (size_t)N)) || (rc = val_b.reserve(4 * (size_t)N)) ||
-        (rc = misc.reserve(8 * (size_t)(L + 1) + 4 * (size_t)L + 4 * (size_t)L + (size_t)L + 4 * (size_t)F + 64)))
+        (rc = misc.reserve(8 * (size_t)(L + 1) + 4 * (size_t)L + 4 * (size_t)L + (size_t)L + 4 * (size_t)F + 256)))
       break;
     char* mp = misc.as<char>();
     int64_t* d_inst_base = reinterpret_cast<int64_t*>(mp);
@@ -616,6 +746,69 @@ int build_frame_groups(klu_ctx* c) {
     a.num_items = c->fr_items;
     a.gloc = c->d_fr_gloc.as<int64_t>();
     a.lat_cnt = d_lat_cnt;
+    // ---- arcs by start time: a copy the frame kernels index (a run of frames then touches
+    //      one contiguous range of it), and the out-order -> time-order map for the instances
+    {
+      const size_t E1 = (size_t)std::max<int64_t>(c->E, 1);
+      if ((rc = key_a.reserve(8 * std::max<size_t>((size_t)N, E1))) || (rc = key_b.reserve(8 * std::max<size_t>((size_t)N, E1))) ||
+          (rc = val_a.reserve(4 * std::max<size_t>((size_t)N, E1))) || (rc = val_b.reserve(4 * std::max<size_t>((size_t)N, E1))) ||
+          (rc = c->d_scratch[11].reserve(4 * E1)) || (rc = c->d_fr_tarc.reserve(16 * E1)) ||
+          (rc = c->d_fr_tlabel.reserve(4 * E1)))
+        break;
+      a.key = key_a.as<unsigned long long>();
+      a.val = val_a.as<unsigned int>();
+      a.key_a = key_a.as<unsigned long long>();
+      a.key_b = key_b.as<unsigned long long>();
+      a.val_a = val_a.as<unsigned int>();
+      a.val_b = val_b.as<unsigned int>();
+      a.rank_of = c->d_scratch[11].as<int32_t>();
+      a.tarc = c->d_fr_tarc.as<int4>();
+      a.tlabel = c->d_fr_tlabel.as<int32_t>();
+      int64_t max_arcs = 0;
+      std::vector<int64_t> arc_base(L + 1);
+      std::vector<int32_t> arc_cnt(L);
+      for (int32_t l = 0; l < L; ++l) {
+        max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
+        arc_base[l] = c->h_e_off[l];
+        arc_cnt[l] = (int32_t)(c->h_e_off[l + 1] - c->h_e_off[l]);
+      }
+      arc_base[L] = c->h_e_off[L];
+      const int arc_tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
+      DevBuf seg;
+      if ((rc = seg.reserve(8 * (size_t)(L + 1) + 4 * (size_t)L))) break;
+      cudaMemcpyAsync(seg.p, arc_base.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream);
+      cudaMemcpyAsync(seg.as<char>() + 8 * (size_t)(L + 1), arc_cnt.data(), 4 * (size_t)L, cudaMemcpyHostToDevice, c->stream);
+      {
+        KLU_LAUNCH(c, "k_fg_time_keys");
+        k_fg_time_keys<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
+      }
+      rc = check_launch("k_fg_time_keys");
+      if (!rc) {
+        SegSortArgs st;
+        st.seg_base = seg.as<int64_t>();
+        st.seg_cnt = reinterpret_cast<const int32_t*>(seg.as<char>() + 8 * (size_t)(L + 1));
+        st.key_a = a.key_a ? key_a.as<unsigned long long>() : nullptr;
+        st.val_a = val_a.as<unsigned int>();
+        st.key_b = key_b.as<unsigned long long>();
+        st.val_b = val_b.as<unsigned int>();
+        st.where = d_where;
+        st.lo_bit = 0;
+        st.hi_bit = bits_time;
+        {
+          KLU_LAUNCH(c, "k_seg_radix_sort");
+          k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(st);
+        }
+        rc = check_launch("k_seg_radix_sort(arc start times)");
+      }
+      if (!rc) {
+        KLU_LAUNCH(c, "k_fg_time_copy");
+        k_fg_time_copy<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
+        rc = check_launch("k_fg_time_copy");
+      }
+      cudaStreamSynchronize(c->stream);
+      seg.release();
+      if (rc) break;
+    }
     {
       KLU_LAUNCH(c, "k_fg_emit");
       k_fg_emit<<<L, 256, 0, c->stream>>>(a);
@@ -638,12 +831,32 @@ int build_frame_groups(klu_ctx* c) {
     if ((rc = check_launch("k_seg_radix_sort(frame groups)"))) break;
     a.res_off = c->d_fr_res_off.as<int64_t>();
     a.gwords = nullptr;
+    if ((rc = c->d_fr_run_lo.reserve(4 * (size_t)std::max(a.num_items, 1)))) break;
+    if ((rc = c->d_fr_run_hi.reserve(4 * (size_t)std::max(a.num_items, 1)))) break;
+    a.run_lo = c->d_fr_run_lo.as<int32_t>();
+    a.run_hi = c->d_fr_run_hi.as<int32_t>();
+    a.max_window = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_where) + (((size_t)L + 3) & ~(size_t)3));  // spare int of the misc block
+    cudaMemsetAsync(a.max_window, 0, 4, c->stream);
     const int hgrid = std::max(1, std::min((a.num_items + 7) / 8, c->num_sms * 32));
     if (a.num_items > 0) {
       KLU_LAUNCH(c, "k_fg_heads");
       k_fg_heads<false><<<hgrid, 256, 0, c->stream>>>(a);
     }
     if ((rc = check_launch("k_fg_heads"))) break;
+    if (getenv("KLU_DEBUG_WINDOWS") && a.num_items > 0) {
+      std::vector<int32_t> lo(a.num_items), hi(a.num_items);
+      cudaMemcpyAsync(lo.data(), a.run_lo, 4 * (size_t)a.num_items, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemcpyAsync(hi.data(), a.run_hi, 4 * (size_t)a.num_items, cudaMemcpyDeviceToHost, c->stream);
+      cudaStreamSynchronize(c->stream);
+      long long sum = 0, mx = 0, big = 0;
+      for (int i = 0; i < a.num_items; ++i) {
+        const long long w = hi[i] >= lo[i] ? (long long)hi[i] - lo[i] + 1 : 0;
+        sum += w;
+        mx = std::max(mx, w);
+        big += w > 5120;
+      }
+      fprintf(stderr, "frame windows: items %d mean %.1f max %lld over-cap %lld\n", a.num_items, (double)sum / a.num_items, mx, big);
+    }
     {
       KLU_LAUNCH(c, "k_fg_scan");
       k_fg_scan<<<L, 256, 0, c->stream>>>(a);
@@ -654,6 +867,7 @@ int build_frame_groups(klu_ctx* c) {
       k_fg_latscan<<<1, 1024, 0, c->stream>>>(d_lat_cnt, L, c->d_fr_res_off.as<int64_t>());
     }
     if ((rc = check_launch("k_fg_latscan"))) break;
+    cudaMemcpyAsync(&c->fr_max_window, a.max_window, 4, cudaMemcpyDeviceToHost, c->stream);
     if (cudaMemcpyAsync(c->h_frame_res_off.data(), c->d_fr_res_off.p, 8 * (size_t)(L + 1), cudaMemcpyDeviceToHost,
                         c->stream) != cudaSuccess ||
         cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -698,7 +912,7 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   c->last_entries = L ? c->h_res_off[L] : 0;
   if (L == 0) return 0;
   const int64_t N = std::max<int64_t>(c->last_entries, 1);
-  KLU_TRY(c->d_scratch[0].reserve(8 * (size_t)std::max<int64_t>(c->E, 1)));
+  if (getenv("KLU_FRAME_UNFUSED")) KLU_TRY(c->d_scratch[0].reserve(8 * (size_t)std::max<int64_t>(c->E, 1)));
   KLU_TRY(c->d_res[5].reserve(8 * (size_t)(L + 1)));
   KLU_TRY(c->d_res[1].reserve(4 * (size_t)N));
   KLU_TRY(c->d_res[4].reserve(4 * (size_t)N));
@@ -721,19 +935,39 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   a.o_frame = nullptr;  // the frame column is static per batch (d_fr_gframe)
   a.o_word = c->d_res[1].as<int32_t>();
   a.o_logp = c->d_res[4].as<float>();
-  {
-    int64_t max_arcs = 0;
-    for (int32_t l = 0; l < L; ++l) max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
-    const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
-    KLU_LAUNCH(c, "k_arc_post");
-    k_arc_post<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
+  a.run_lo = c->d_fr_run_lo.as<int32_t>();
+  a.run_hi = c->d_fr_run_hi.as<int32_t>();
+  a.tarc = c->d_fr_tarc.as<int4>();
+  a.tlabel = c->d_fr_tlabel.as<int32_t>();
+  static const bool unfused = getenv("KLU_FRAME_UNFUSED") != nullptr;  // cross-check path: posteriors through HBM
+  if (unfused) {
+    {
+      int64_t max_arcs = 0;
+      for (int32_t l = 0; l < L; ++l) max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
+      const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
+      KLU_LAUNCH(c, "k_arc_post");
+      k_arc_post<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
+    }
+    KLU_TRY(check_launch("k_arc_post"));
+    {
+      KLU_LAUNCH(c, "k_group_post");
+      k_group_post<<<c->num_sms * 16, 256, 0, c->stream>>>(a);
+    }
+    KLU_TRY(check_launch("k_group_post"));
+  } else if (a.num_items > 0) {
+    // shared memory: the largest window of the batch, capped (runs beyond the cap take the slow path)
+    const int kMaxWinBytes = 64 << 10;
+    static bool attr_set = false;
+    if (!attr_set) {
+      KLU_CUDA(cudaFuncSetAttribute(k_frame_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxWinBytes));
+      attr_set = true;
+    }
+    const int kWinBytes = std::min(kMaxWinBytes, std::max(1024, (c->fr_max_window * 8 + 1023) & ~1023));
+    a.win_cap = kWinBytes / 8;
+    KLU_LAUNCH(c, "k_frame_groups");
+    k_frame_groups<<<a.num_items, 128, kWinBytes, c->stream>>>(a);
+    KLU_TRY(check_launch("k_frame_groups"));
   }
-  KLU_TRY(check_launch("k_arc_post"));
-  {
-    KLU_LAUNCH(c, "k_group_post");
-    k_group_post<<<c->num_sms * 16, 256, 0, c->stream>>>(a);
-  }
-  KLU_TRY(check_launch("k_group_post"));
   if (a.num_items > 0) {
     const int grid = std::max(1, std::min((a.num_items + kFrameWarps - 1) / kFrameWarps, c->num_sms * 64));
     {
