@@ -278,23 +278,44 @@ __global__ void __launch_bounds__(128) k_frame_groups(const __grid_constant__ Fr
     }
     __syncthreads();
   }
-  for (int64_t g = row0 + threadIdx.x; g < row1; g += blockDim.x) {
-    const uint32_t i0 = __ldg(a.gstart + g), i1 = __ldg(a.gstart + g + 1);
-    double sum = 0.0;
+  // two groups per thread and trip: both offset pairs, then both first id quads, are in flight together
+  for (int64_t g0 = row0 + threadIdx.x; g0 < row1; g0 += 2 * blockDim.x) {
+    uint32_t i0[2], i1[2];
+    double sum[2] = {0.0, 0.0};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int64_t g = g0 + v * blockDim.x;
+      i0[v] = g < row1 ? __ldg(a.gstart + g) : 0u;
+      i1[v] = g < row1 ? __ldg(a.gstart + g + 1) : 0u;
+    }
     if (windowed) {
-      for (uint32_t i = i0; i < i1; i += 4) {  // four instance ids in flight, the adds stay in order
-        int e[4];
+      int e[2][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) e[u] = i + u < i1 ? (int)((unsigned int)__ldg(b.frame_arc + i + u) & 0x7fffffffu) - wlo : 0;
+      for (int v = 0; v < 2; ++v)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) sum += i + u < i1 ? s_post[e[u]] : 0.0;
+        for (int u = 0; u < 4; ++u)
+          e[v][u] = i0[v] + u < i1[v] ? (int)((unsigned int)__ldg(b.frame_arc + i0[v] + u) & 0x7fffffffu) - wlo : -1;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sum[v] += e[v][u] >= 0 ? s_post[e[v][u]] : 0.0;
+        for (uint32_t i = i0[v] + 4; i < i1[v]; ++i)  // the rare long groups
+          sum[v] += s_post[(int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu) - wlo];
       }
     } else {
-      for (uint32_t i = i0; i < i1; ++i)
-        sum += fast_exp(arc_value(a, (int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu)) - total);
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+        for (uint32_t i = i0[v]; i < i1[v]; ++i)
+          sum[v] += fast_exp(arc_value(a, (int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu)) - total);
     }
-    const double lp = sum >= 1e-280 ? fast_log(sum) : exact_group_logp(a, b.frame_arc, i1 - 1, total);
-    a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int64_t g = g0 + v * blockDim.x;
+      if (g < row1) {
+        const double lp = sum[v] >= 1e-280 ? fast_log(sum[v]) : exact_group_logp(a, b.frame_arc, i1[v] - 1, total);
+        a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+      }
+    }
   }
 }
 
