@@ -54,6 +54,8 @@ __device__ __forceinline__ bool final_pruned(const SweepArgs& a, int l, int s, d
   return __dadd_rn(fcost, a.vfwd[s]) > __dadd_rn(a.best[l], a.beam) && fcost != pos_inf();
 }
 
+// most recent state scores of a tile kept in shared memory (a ring indexed by state id)
+__host__ __device__ constexpr int sweep_ring(int G) { return G >= 8 ? 128 : 32; }
 constexpr int kSweepCapPerLane = 8;  // arcs staged per batch = 8 x (lanes of the tile), 16 bytes each
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -132,13 +134,15 @@ __device__ __noinline__ double sweep_state_exact(const SweepArgs& a, int l, int 
 // exactly; sums that leave [1e-280, 1e280] (reference point too far, unreachable
 // states, ...) are redone exactly.
 template <int G, bool FWD, bool BEAM>
-__device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2* xwarp) {
+__device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2* xwarp, double* rwarp) {
   constexpr int kCap = kSweepCapPerLane * G;
+  constexpr int kRing = sweep_ring(G);
   constexpr int kLog2G = G == 32 ? 5 : G == 16 ? 4 : G == 8 ? 3 : G == 4 ? 2 : 1;
   const BatchView& b = a.b;
   const int gi = lane / G, sl = lane % G;
   const unsigned int gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (gi * G);
   double2* xbuf = xwarp + gi * kCap;  // per arc: the record, then {cost, score}, then {exp term, -}
+  double* ring = rwarp + gi * kRing;
   const int4* rec = FWD ? b.in_rec : b.out_rec;
   const int* off = FWD ? b.in_off : b.out_off;
   double* score = FWD ? a.alpha : a.beta;
@@ -151,11 +155,15 @@ __device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2
   double ref = 0.0;
   int j = FWD ? 1 : nl - 1;
   if (FWD && !done)
-    for (int s = lv[0] + sl; s < lv[1]; s += G) score[s] = (s == s_begin) ? 0.0 : neg_inf();
+    for (int s = lv[0] + sl; s < lv[1]; s += G) {
+      const double v = (s == s_begin) ? 0.0 : neg_inf();
+      score[s] = v;
+      ring[s & (kRing - 1)] = v;
+    }
   if (!done && (FWD ? j >= nl : j < 0)) done = true;
-  int a1 = 0, s0 = 0;
+  int a0 = 0, a1 = 0, s0 = 0;
   if (!done) {
-    s0 = lv[j];
+    s0 = a0 = lv[j];
     a1 = lv[j + 1];
   }
   __syncwarp();
@@ -176,23 +184,40 @@ __device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2
       const int pf = base + nb + kCap + sl * 8;
       if (sl * 8 < nb && pf < b.E) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + pf));
     }
-    // Three passes over the lane's own arcs, each a batch of independent memory
-    // operations: (1) the 16-byte records, global -> shared, asynchronously;
-    // (2) cost from the record, and the other end's score gathered asynchronously into
-    // the same slot; (3) the exp terms.  One memory latency per pass, not per arc.
+    // Passes over the lane's own arcs, each a batch of independent memory operations:
+    // (1) the 16-byte records, global -> shared, asynchronously; (2) cost from the record
+    // and the other end's score -- from the tile's shared-memory ring of recent scores
+    // when it is still there (a level [a0, a1) overwrites the ring slots of the states
+    // kRing below a0.. / above ..a1, everything nearer is intact), else gathered
+    // asynchronously into the slot -- and the exp term; (3) the exp terms of the gathered ones.
     for (int i = sl; i < nb; i += G) cp_async16(xbuf + i, rec + base + i);
     cp_async_wait_all();
-    for (int i = sl; i < nb; i += G) {
-      const int4 r = *reinterpret_cast<const int4*>(xbuf + i);
-      double cost = rec_cost(r, a.cp);
-      if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, base + i, r)) cost = pos_inf();
-      xbuf[i].x = cost;
-      cp_async8(&xbuf[i].y, score + r.x);
+    unsigned int pending = 0;
+    {
+      int it = 0;
+      for (int i = sl; i < nb; i += G, ++it) {
+        const int4 r = *reinterpret_cast<const int4*>(xbuf + i);
+        double cost = rec_cost(r, a.cp);
+        if (BEAM && sweep_arc_pruned<FWD, BEAM>(a, l, base + i, r)) cost = pos_inf();
+        const int t = r.x;
+        if (FWD ? (t >= a1 - kRing) : (t < a0 + kRing)) {
+          xbuf[i].x = fast_exp(ring[t & (kRing - 1)] - cost - ref);
+        } else {
+          xbuf[i].x = cost;
+          cp_async8(&xbuf[i].y, score + t);
+          pending |= 1u << it;
+        }
+      }
     }
-    cp_async_wait_all();
-    for (int i = sl; i < nb; i += G) {
-      const double2 v = xbuf[i];
-      xbuf[i].x = fast_exp(v.y - v.x - ref);
+    if (__any_sync(0xffffffffu, pending != 0)) {
+      cp_async_wait_all();
+      int it = 0;
+      for (int i = sl; i < nb; i += G, ++it) {
+        if ((pending >> it) & 1u) {
+          const double2 v = xbuf[i];
+          xbuf[i].x = fast_exp(v.y - v.x - ref);
+        }
+      }
     }
     __syncwarp();
     // ---- G / pow2ceil(c) lanes per state add its terms, then fold across those lanes
@@ -238,10 +263,12 @@ __device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2
       }
       if (bad) val = sweep_state_exact<FWD, BEAM>(a, l, s);
       score[s] = val;
+      ring[s & (kRing - 1)] = val;
     }
     if (!done && c == 0 && sl == 0) {  // a single state with more arcs than the tile stages
       val = sweep_state_exact<FWD, BEAM>(a, l, s0);
       score[s0] = val;
+      ring[s0 & (kRing - 1)] = val;
     }
     // the next reference point: this batch's first state (lane 0 of the tile holds it)
     const double v0 = __shfl_sync(0xffffffffu, val, 0, G);
@@ -254,7 +281,7 @@ __device__ void log_sweep_tiles(const SweepArgs& a, int first, int lane, double2
         if (FWD ? j >= nl : j < 0) {
           done = true;
         } else {
-          s0 = lv[j];
+          s0 = a0 = lv[j];
           a1 = lv[j + 1];
         }
       }
@@ -270,8 +297,10 @@ template <int G, bool BEAM>
 __global__ void __launch_bounds__(128) k_log_sweeps(const __grid_constant__ SweepArgs a) {
   constexpr int NG = 32 / G;
   __shared__ double2 xs[4][kSweepCapPerLane * 32];
+  __shared__ double rings[4][NG * sweep_ring(G)];
   const int lane = threadIdx.x & 31;
   double2* xwarp = xs[threadIdx.x >> 5];
+  double* rwarp = rings[threadIdx.x >> 5];
   const int per_dir = (a.b.L + NG - 1) / NG;
   const int nunits = per_dir * (a.do_fwd + a.do_bwd);
   for (;;) {
@@ -281,8 +310,8 @@ __global__ void __launch_bounds__(128) k_log_sweeps(const __grid_constant__ Swee
     if (unit >= nunits) break;
     const bool fwd = a.do_fwd && unit < per_dir;
     const int first = (unit - (fwd || !a.do_fwd ? 0 : per_dir)) * NG;
-    if (fwd) log_sweep_tiles<G, true, BEAM>(a, first, lane, xwarp);
-    else log_sweep_tiles<G, false, BEAM>(a, first, lane, xwarp);
+    if (fwd) log_sweep_tiles<G, true, BEAM>(a, first, lane, xwarp, rwarp);
+    else log_sweep_tiles<G, false, BEAM>(a, first, lane, xwarp, rwarp);
     __syncwarp();
   }
 }
