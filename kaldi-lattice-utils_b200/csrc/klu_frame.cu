@@ -39,6 +39,8 @@ namespace {
 constexpr int kFrameWarps = 4;      // warps per CTA
 constexpr int kGroupCap = 256;      // rows of one frame ordered in shared memory
 constexpr int kFramesPerItem = 16;  // consecutive frames handled by one warp
+constexpr int kDeferMin = 4;        // groups longer than this are summed in a second pass
+constexpr int kLongCap = 1024;      // ... at most this many per run of frames (the rest are summed in place)
 
 struct FrameArgs {
   BatchView b;
@@ -245,6 +247,22 @@ __global__ void __launch_bounds__(128) k_frame_groups(const __grid_constant__ Fr
   const int wlo = a.run_lo[item], whi = a.run_hi[item];
   const bool windowed = whi - wlo < a.win_cap;
   const double total = a.total[l];
+  __shared__ int s_long[kLongCap];
+  __shared__ int s_nlong;
+  if (threadIdx.x == 0) s_nlong = 0;  // ordered before its first use by the barrier after phase 1
+  if (windowed && threadIdx.x >= 96) {
+    // the last warp first asks L2 for what phase 2 will read -- the run's group offsets
+    // and instance ids, two contiguous ranges -- so that those loads, which sit on a
+    // dependent chain (offset -> id -> shared-memory posterior), find them there
+    const int pl = threadIdx.x - 96;
+    const char* q = reinterpret_cast<const char*>(a.gstart + row0);
+    const int64_t qb = (row1 - row0 + 1) * 4;
+    for (int64_t off = pl * 128; off < qb; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + off));
+    const uint32_t ilo = __ldg(a.gstart + row0), ihi = __ldg(a.gstart + row1);
+    q = reinterpret_cast<const char*>(b.frame_arc + ilo);
+    const int64_t ib = (int64_t)(ihi - ilo) * 4;
+    for (int64_t off = pl * 128; off < ib; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + off));
+  }
   if (windowed) {
     // four arcs per thread and trip: their record, label and score loads go out together
     for (int j0 = wlo + threadIdx.x; j0 <= whi; j0 += 4 * blockDim.x) {
@@ -278,10 +296,16 @@ __global__ void __launch_bounds__(128) k_frame_groups(const __grid_constant__ Fr
     }
     __syncthreads();
   }
-  // two groups per thread and trip: both offset pairs, then both first id quads, are in flight together
-  for (int64_t g0 = row0 + threadIdx.x; g0 < row1; g0 += 2 * blockDim.x) {
+  // two groups per thread and trip: both offset pairs, then both first id quads, are in flight together.
+  // Groups of more than four instances (one in ten) would hold the other 31 lanes of
+  // their warp in a long loop: they are put on a list in shared memory instead and
+  // summed afterwards, long ones side by side.  A group is always added up by one
+  // thread in instance order, so which thread does it cannot change the result.
+  // (trip count uniform across a warp: the list push below is a warp-wide ballot)
+  for (int64_t g0 = row0 + threadIdx.x; g0 - (threadIdx.x & 31) < row1; g0 += 2 * blockDim.x) {
     uint32_t i0[2], i1[2];
     double sum[2] = {0.0, 0.0};
+    bool defer[2] = {false, false};
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int64_t g = g0 + v * blockDim.x;
@@ -299,8 +323,22 @@ __global__ void __launch_bounds__(128) k_frame_groups(const __grid_constant__ Fr
       for (int v = 0; v < 2; ++v) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) sum[v] += e[v][u] >= 0 ? s_post[e[v][u]] : 0.0;
-        for (uint32_t i = i0[v] + 4; i < i1[v]; ++i)  // the rare long groups
-          sum[v] += s_post[(int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu) - wlo];
+        const bool is_long = i1[v] - i0[v] > (unsigned int)kDeferMin;
+        const unsigned int m = __ballot_sync(0xffffffffu, is_long);
+        if (m) {
+          const int lane = threadIdx.x & 31;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_nlong, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int slot = base + __popc(m & ((1u << lane) - 1u));
+          if (is_long && slot < kLongCap) {
+            s_long[slot] = (int)(g0 + v * blockDim.x - row0);
+            defer[v] = true;
+          }
+        }
+        if (!defer[v])
+          for (uint32_t i = i0[v] + 4; i < i1[v]; ++i)
+            sum[v] += s_post[(int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu) - wlo];
       }
     } else {
 #pragma unroll
@@ -311,11 +349,30 @@ __global__ void __launch_bounds__(128) k_frame_groups(const __grid_constant__ Fr
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int64_t g = g0 + v * blockDim.x;
-      if (g < row1) {
+      if (g < row1 && !defer[v]) {
         const double lp = sum[v] >= 1e-280 ? fast_log(sum[v]) : exact_group_logp(a, b.frame_arc, i1[v] - 1, total);
         a.o_logp[g] = (float)lp + 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
       }
     }
+  }
+  if (!windowed) return;
+  __syncthreads();
+  const int nlong = min(s_nlong, kLongCap);
+  for (int k = threadIdx.x; k < nlong; k += blockDim.x) {
+    const int64_t g = row0 + s_long[k];
+    const uint32_t i0 = __ldg(a.gstart + g), i1 = __ldg(a.gstart + g + 1);
+    double sum = 0.0;
+    uint32_t i = i0;
+    for (; i + 4 <= i1; i += 4) {  // four ids in flight
+      int e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = (int)((unsigned int)__ldg(b.frame_arc + i + u) & 0x7fffffffu) - wlo;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sum += s_post[e[u]];
+    }
+    for (; i < i1; ++i) sum += s_post[(int)((unsigned int)__ldg(b.frame_arc + i) & 0x7fffffffu) - wlo];
+    const double lp = sum >= 1e-280 ? fast_log(sum) : exact_group_logp(a, b.frame_arc, i1 - 1, total);
+    a.o_logp[g] = (float)lp + 0.0f;
   }
 }
 
@@ -429,6 +486,17 @@ __global__ void __launch_bounds__(kFrameWarps * 32, 8) k_frame_order(const __gri
     const int64_t* gl = a.gloc + b.fr_base[l];
     const int64_t out0 = a.res_off[l];
     int64_t g_next = gl[k0];
+    {
+      // the run's rows are two contiguous ranges (log-posteriors, words): ask L2 for them
+      // now, the frames below then wait on L2 rather than on HBM, one after the other
+      const int64_t nb = (gl[k1] - g_next) * 4;
+      const char* q0 = reinterpret_cast<const char*>(a.o_logp + out0 + g_next);
+      const char* q1 = reinterpret_cast<const char*>(a.gwords + out0 + g_next);
+      for (int64_t off = lane * 128; off < nb; off += 32 * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + off));
+      }
+    }
     for (int k = k0; k < k1; ++k) {
       const int64_t g0 = g_next;
       g_next = gl[k + 1];
@@ -978,11 +1046,7 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
   } else if (a.num_items > 0) {
     // shared memory: the largest window of the batch, capped (runs beyond the cap take the slow path)
     const int kMaxWinBytes = 64 << 10;
-    static bool attr_set = false;
-    if (!attr_set) {
-      KLU_CUDA(cudaFuncSetAttribute(k_frame_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxWinBytes));
-      attr_set = true;
-    }
+    KLU_CUDA(cudaFuncSetAttribute(k_frame_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxWinBytes));  // per device
     const int kWinBytes = std::min(kMaxWinBytes, std::max(1024, (c->fr_max_window * 8 + 1023) & ~1023));
     a.win_cap = kWinBytes / 8;
     KLU_LAUNCH(c, "k_frame_groups");
