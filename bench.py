@@ -236,7 +236,8 @@ def main():
     ap.add_argument("--ref-lattices", type=int, default=2500, help="bounded CPU sample (lattices) per step")
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-slices", type=int, default=4, help="slices of the pipelined end-to-end run (1 = off)")
+    ap.add_argument("--e2e-slices", type=int, default=8, help="slices of the pipelined end-to-end run (1 = off)")
+    ap.add_argument("--e2e-contexts", type=int, default=3, help="contexts (host threads) of the pipelined run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -334,8 +335,8 @@ def main():
     # ---- end to end through the C ABI: host arrays -> index on the host ----
     # (a) one klu_load + klu_run + klu_fetch call sequence over the whole shard;
     # (b) the same calls pipelined the way the drop-in tools do it (KLU_DEVICES): the shard
-    #     cut into slices by arc count, two contexts on this GPU taking slices in turn from
-    #     two host threads, so that the upload of one slice overlaps packing, run and result
+    #     cut into slices by arc count, a few contexts on this GPU taking slices in turn, one
+    #     host thread each, so that the upload of one slice overlaps packing, run and result
     #     download of the previous one.  `e2e.value` is (b); (a) is reported beside it.
     # the caller hands over per-state arc counts instead of a per-arc source array
     # (klu_lattices.state_num_arcs; OpenFst stores arcs grouped by state)
@@ -369,13 +370,13 @@ def main():
     single_step = reduce_max(sum(e2e_ms) / len(e2e_ms)) if e2e_ms else None
     pipe_step = None
     if args.e2e_steps > 0 and args.e2e_slices > 1 and args.tool == "frame_post":
-        eng.close()  # its device memory goes to the two pipeline contexts
+        eng.close()  # its device memory goes to the pipeline contexts
         nsl = min(args.e2e_slices, nlat)
         cuts = np.searchsorted(batch.arc_off, np.linspace(0, batch.arc_off[-1], nsl + 1)[1:-1]).tolist()
         cuts = [0] + [int(x) for x in cuts] + [nlat]
         subs = [batch.slice(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
         sub_narcs = [narcs[int(batch.state_off[a]):int(batch.state_off[b])] for a, b in zip(cuts[:-1], cuts[1:])]
-        engines = [klu.Engine(local) for _ in range(min(2, nsl))]
+        engines = [klu.Engine(local) for _ in range(min(args.e2e_contexts, nsl))]
         row_off = np.concatenate([[0], np.cumsum([0] * nsl)])  # filled by the first pass
         sub_rows = [0] * nsl
 
@@ -415,7 +416,7 @@ def main():
            "single_call_ms_per_step": single_step,
            "single_call_ms_load_run_fetch": [round(float(np.mean([p[k] for p in parts])), 2) for k in range(3)]
            if parts else None,
-           "pipeline": {"slices": args.e2e_slices, "contexts": 2} if pipe_step else None,
+           "pipeline": {"slices": args.e2e_slices, "contexts": args.e2e_contexts} if pipe_step else None,
            "note": "klu_load (H2D of the caller's pinned SoA arrays + device packer) + klu_run + klu_fetch "
                    "(D2H of the full index into pinned buffers), wall clock, max over ranks; value = the "
                    "pipelined call sequence when `pipeline` is set, else the single call sequence"}

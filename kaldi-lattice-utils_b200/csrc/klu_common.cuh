@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <map>
 #include <string>
@@ -38,6 +41,29 @@ struct DevBuf {
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// KLU_TRACE=1: wall-clock marks of the host-side phases on stderr (pipelining diagnostics).
+inline void klu_trace(const void* c, const char* what) {
+  static const bool on = getenv("KLU_TRACE") != nullptr;
+  if (!on) return;
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  fprintf(stderr, "[klu %p] %.3f %s\n", c, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6, what);
+}
+
+// The packer's metadata transfers (per-lattice arrays, KBs) do not use the copy engines:
+// those are shared by all contexts of the device, and a small copy queued behind another
+// context's multi-hundred-MB upload or result download waits for all of it -- with the
+// packing kernels of this context behind it.  They go through a pinned staging area
+// instead, which a one-line kernel reads or writes over PCIe directly.
+//   small_h2d: stream-ordered copy of `bytes` (multiple of 4) to the device; src may be reused at return.
+//   small_d2h: queues a read; dst_host is filled by the next small_sync().
+//   small_sync: cudaStreamSynchronize + delivery of the queued reads.
+// stage_begin() (start of klu_load) sizes the area for L lattices and recycles it.
+int stage_begin(klu_ctx* c, size_t L);
+int small_h2d(klu_ctx* c, void* dst_dev, const void* src_host, size_t bytes);
+int small_d2h(klu_ctx* c, void* dst_host, const void* src_dev, size_t bytes);
+int small_sync(klu_ctx* c);
 
 // How arc/final weights become costs.
 struct CostParams {
@@ -91,6 +117,14 @@ struct KernelStat {
 struct klu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // small_h2d / small_d2h: pinned staging area read / written by kernels (no copy engine)
+  char* h_stage = nullptr;
+  size_t stage_cap = 0, stage_used = 0;
+  struct StagedRead {
+    void* dst;
+    size_t off, bytes;
+  };
+  std::vector<StagedRead> stage_reads;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 148;
   int64_t launches = 0;
@@ -123,7 +157,7 @@ struct klu_ctx {
   // ---- device: packed batch ----
   klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
       d_in2out, d_old2new, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order, d_fr_base, d_fr_off, d_frame_arc,
-      d_fr_item, d_fr_gloc, d_fr_res_off, d_fr_gword, d_fr_gstart, d_fr_gframe, d_fr_run_lo, d_fr_run_hi, d_fr_tarc, d_fr_tlabel;
+      d_fr_item, d_fr_gloc, d_fr_res_off, d_fr_gword, d_fr_gstart, d_fr_gframe, d_fr_run_lo, d_fr_run_hi, d_fr_tarc, d_fr_tlabel, d_fr_seg;
   // ---- device: per-run state ----
   klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
   klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps

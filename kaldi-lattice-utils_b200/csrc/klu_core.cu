@@ -13,6 +13,69 @@
 
 namespace klu {
 
+namespace {
+__global__ void k_stage_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void stage_launch(klu_ctx* c, void* dst, const void* src, size_t bytes) {
+  const size_t n = bytes / 4;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 64));
+  k_stage_words<<<grid, 256, 0, c->stream>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src), n);
+}
+}  // namespace
+
+int stage_begin(klu_ctx* c, size_t L) {
+  KLU_CUDA(cudaStreamSynchronize(c->stream));  // nothing in flight reads the area any more
+  c->stage_used = 0;
+  c->stage_reads.clear();
+  const size_t want = 256 * (L + 64) + (64u << 10);
+  if (want > c->stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->stage_cap = 0;
+    KLU_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage), want + want / 4, cudaHostAllocDefault));
+    c->stage_cap = want + want / 4;
+  }
+  return 0;
+}
+
+int small_h2d(klu_ctx* c, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!bytes) return 0;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if ((bytes & 3) || c->stage_used + need > c->stage_cap) {
+    KLU_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+  }
+  char* st = c->h_stage + c->stage_used;
+  c->stage_used += need;
+  memcpy(st, src_host, bytes);
+  stage_launch(c, dst_dev, st, bytes);
+  KLU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int small_d2h(klu_ctx* c, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!bytes) return 0;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if ((bytes & 3) || c->stage_used + need > c->stage_cap) {
+    KLU_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+  }
+  const size_t off = c->stage_used;
+  c->stage_used += need;
+  stage_launch(c, c->h_stage + off, src_dev, bytes);
+  KLU_CUDA(cudaGetLastError());
+  c->stage_reads.push_back({dst_host, off, bytes});
+  return 0;
+}
+
+int small_sync(klu_ctx* c) {
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  for (const auto& r : c->stage_reads) memcpy(r.dst, c->h_stage + r.off, r.bytes);
+  c->stage_reads.clear();
+  return 0;
+}
+
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
@@ -211,7 +274,7 @@ int klu_destroy(klu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_s_off, &c->d_e_off, &c->d_lvl_off, &c->d_lvl_start, &c->d_in_rec, &c->d_out_rec,
                     &c->d_in_off, &c->d_out_off, &c->d_out_src, &c->d_out_orig, &c->d_in2out, &c->d_old2new, &c->d_fin_g, &c->d_fin_a,
-                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_fr_item, &c->d_fr_gloc, &c->d_fr_res_off, &c->d_fr_gword, &c->d_fr_gstart, &c->d_fr_gframe, &c->d_fr_run_lo, &c->d_fr_run_hi, &c->d_fr_tarc, &c->d_fr_tlabel, &c->d_alpha, &c->d_beta,
+                    &c->d_time, &c->d_orig, &c->d_level, &c->d_band_lo, &c->d_band_off, &c->d_order, &c->d_fr_base, &c->d_fr_off, &c->d_frame_arc, &c->d_fr_item, &c->d_fr_gloc, &c->d_fr_res_off, &c->d_fr_gword, &c->d_fr_gstart, &c->d_fr_gframe, &c->d_fr_run_lo, &c->d_fr_run_hi, &c->d_fr_tarc, &c->d_fr_tlabel, &c->d_fr_seg, &c->d_alpha, &c->d_beta,
                     &c->d_total, &c->d_totfwd, &c->d_counter, &c->d_filter, &c->d_vfwd, &c->d_vbwd, &c->d_best,
                     &c->d_alpha2, &c->d_flush};
   char_release(c);
@@ -225,6 +288,7 @@ int klu_destroy(klu_ctx* c) {
   }
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -281,6 +345,7 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   if (getenv("KLU_HOST_PACKER")) KLU_TRY(pack_and_upload(c, lats));
   else KLU_TRY(pack_and_upload_gpu(c, lats));
   c->loaded = true;
+  klu_trace(c, "load: done");
   return 0;
 }
 

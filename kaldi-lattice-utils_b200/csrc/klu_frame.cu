@@ -781,7 +781,7 @@ int build_frame_groups(klu_ctx* c) {
   KLU_TRY(c->d_fr_item.reserve(4 * (size_t)(L + 1)));
   KLU_TRY(c->d_fr_gloc.reserve(8 * (size_t)std::max<int64_t>(F, 1)));
   KLU_TRY(c->d_fr_res_off.reserve(8 * (size_t)(L + 1)));
-  KLU_CUDA(cudaMemcpyAsync(c->d_fr_item.p, item_base.data(), 4 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
+  KLU_TRY(small_h2d(c, c->d_fr_item.p, item_base.data(), 4 * (size_t)(L + 1)));
   KLU_CUDA(cudaMemsetAsync(c->d_fr_gloc.p, 0, 8 * (size_t)std::max<int64_t>(F, 1), c->stream));
   KLU_CUDA(cudaMemsetAsync(c->d_fr_res_off.p, 0, 8 * (size_t)(L + 1), c->stream));
   if (N == 0 || any_bad_times) {  // nothing to index (run_frame_post rejects inconsistent times)
@@ -814,8 +814,8 @@ int build_frame_groups(klu_ctx* c) {
     int32_t* d_lat_cnt = d_inst_cnt + L;
     int32_t* d_frame_cnt = d_lat_cnt + L;
     unsigned char* d_where = reinterpret_cast<unsigned char*>(d_frame_cnt + F);
-    cudaMemcpyAsync(d_inst_base, inst_base.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(d_inst_cnt, inst_cnt.data(), 4 * (size_t)L, cudaMemcpyHostToDevice, c->stream);
+    if ((rc = small_h2d(c, d_inst_base, inst_base.data(), 8 * (size_t)(L + 1)))) break;
+    if ((rc = small_h2d(c, d_inst_cnt, inst_cnt.data(), 4 * (size_t)L))) break;
     cudaMemsetAsync(d_frame_cnt, 0, 4 * (size_t)F, c->stream);
     if ((rc = c->d_frame_arc.reserve(4 * (size_t)N))) break;
     GroupArgs a;
@@ -863,10 +863,10 @@ int build_frame_groups(klu_ctx* c) {
       }
       arc_base[L] = c->h_e_off[L];
       const int arc_tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
-      DevBuf seg;
+      DevBuf& seg = c->d_fr_seg;  // persistent: a cudaFree here would stall the other contexts of the device
       if ((rc = seg.reserve(8 * (size_t)(L + 1) + 4 * (size_t)L))) break;
-      cudaMemcpyAsync(seg.p, arc_base.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream);
-      cudaMemcpyAsync(seg.as<char>() + 8 * (size_t)(L + 1), arc_cnt.data(), 4 * (size_t)L, cudaMemcpyHostToDevice, c->stream);
+      if ((rc = small_h2d(c, seg.p, arc_base.data(), 8 * (size_t)(L + 1)))) break;
+      if ((rc = small_h2d(c, seg.as<char>() + 8 * (size_t)(L + 1), arc_cnt.data(), 4 * (size_t)L))) break;
       {
         KLU_LAUNCH(c, "k_fg_time_keys");
         k_fg_time_keys<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
@@ -894,8 +894,7 @@ int build_frame_groups(klu_ctx* c) {
         k_fg_time_copy<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
         rc = check_launch("k_fg_time_copy");
       }
-      cudaStreamSynchronize(c->stream);
-      seg.release();
+      cudaStreamSynchronize(c->stream);  // arc_base / arc_cnt go out of scope
       if (rc) break;
     }
     {
@@ -956,14 +955,9 @@ int build_frame_groups(klu_ctx* c) {
       k_fg_latscan<<<1, 1024, 0, c->stream>>>(d_lat_cnt, L, c->d_fr_res_off.as<int64_t>());
     }
     if ((rc = check_launch("k_fg_latscan"))) break;
-    cudaMemcpyAsync(&c->fr_max_window, a.max_window, 4, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaMemcpyAsync(c->h_frame_res_off.data(), c->d_fr_res_off.p, 8 * (size_t)(L + 1), cudaMemcpyDeviceToHost,
-                        c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess) {
-      set_error(std::string("build_frame_groups: ") + cudaGetErrorString(cudaGetLastError()));
-      rc = 1;
-      break;
-    }
+    if ((rc = small_d2h(c, &c->fr_max_window, a.max_window, 4))) break;
+    if ((rc = small_d2h(c, c->h_frame_res_off.data(), c->d_fr_res_off.p, 8 * (size_t)(L + 1)))) break;
+    if ((rc = small_sync(c))) break;
     if ((rc = c->d_fr_gword.reserve(4 * (size_t)std::max<int64_t>(c->h_frame_res_off[L], 1)))) break;
     if ((rc = c->d_fr_gstart.reserve(4 * (size_t)(c->h_frame_res_off[L] + 1)))) break;
     if ((rc = c->d_fr_gframe.reserve(4 * (size_t)std::max<int64_t>(c->h_frame_res_off[L], 1)))) break;
@@ -972,8 +966,7 @@ int build_frame_groups(klu_ctx* c) {
     a.gstart = c->d_fr_gstart.as<uint32_t>();
     {
       const uint32_t n32 = (uint32_t)N;
-      cudaMemcpyAsync(a.gstart + c->h_frame_res_off[L], &n32, 4, cudaMemcpyHostToDevice, c->stream);
-      cudaStreamSynchronize(c->stream);
+      if ((rc = small_h2d(c, a.gstart + c->h_frame_res_off[L], &n32, 4))) break;
     }
     if (a.num_items > 0) {
       KLU_LAUNCH(c, "k_fg_words");

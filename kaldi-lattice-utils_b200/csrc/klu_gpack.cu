@@ -403,10 +403,14 @@ __global__ void __launch_bounds__(256) k_gp_frames(GP a) {
   }
 }
 
+int h2d(klu_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (bytes) KLU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
 int upload(klu_ctx* c, DevBuf& b, const void* src, size_t bytes) {
   KLU_TRY(b.reserve(bytes ? bytes : 16));
-  if (bytes) KLU_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  return 0;
+  return h2d(c, b.p, src, bytes);
 }
 
 }  // namespace
@@ -444,7 +448,10 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   // tools' worker threads, a pipelined caller -- the next batch's upload then overlaps
   // this batch's packing, run and result download instead of interleaving with its upload.
   static std::mutex h2d_turn;
+  KLU_TRY(stage_begin(c, (size_t)L));
+  klu_trace(c, "load: waiting for the upload turn");
   std::unique_lock<std::mutex> h2d_lock(h2d_turn);
+  klu_trace(c, "load: upload begins");
   KLU_TRY(upload(c, c->d_s_off, s_off.data(), 4 * (size_t)(L + 1)));
   KLU_TRY(upload(c, c->d_e_off, e_off.data(), 4 * (size_t)(L + 1)));
   KLU_TRY(upload(c, c->d_order, order.data(), 4 * (size_t)L));
@@ -463,12 +470,15 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   float* r_fa = reinterpret_cast<float*>(misc + S1);
   int32_t* r_fdur = misc + 2 * S1;
   if (S) {
-    KLU_CUDA(cudaMemcpyAsync(r_fg, in->fin_graph, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
-    KLU_CUDA(cudaMemcpyAsync(r_fa, in->fin_acoustic, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
-    if (in->fin_dur) KLU_CUDA(cudaMemcpyAsync(r_fdur, in->fin_dur, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
+    KLU_TRY(h2d(c, r_fg, in->fin_graph, 4 * (size_t)S));
+    KLU_TRY(h2d(c, r_fa, in->fin_acoustic, 4 * (size_t)S));
+    if (in->fin_dur) KLU_TRY(h2d(c, r_fdur, in->fin_dur, 4 * (size_t)S));
   }
+  // (per-state arc counts, when the caller gave those instead of arc sources: counts slot of misc)
+  if (!in->arc_src) KLU_TRY(h2d(c, misc + 8 * S1 + 8, in->state_num_arcs, 4 * (size_t)S));
   KLU_CUDA(cudaStreamSynchronize(c->stream));
   h2d_lock.unlock();
+  klu_trace(c, "load: upload done, packing");
   // per-lattice metadata: meta (L x 8 int), cap (2L int64), lat_tot (L+1 int64), where flags
   KLU_TRY(sc[R_MISC2].reserve(4 * (size_t)M_STRIDE * (L + 1) + 8 * (size_t)(3 * L + 4) + 2 * (size_t)L + 64));
   char* m2 = sc[R_MISC2].as<char>();
@@ -554,7 +564,6 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   const int arc_tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
   const int st_tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_states + 255) / 256, 16));
   if (!in->arc_src) {  // arcs grouped by source state: expand the sources from the per-state arc counts
-    KLU_CUDA(cudaMemcpyAsync(a.counts, in->state_num_arcs, 4 * (size_t)S, cudaMemcpyHostToDevice, c->stream));
     {
       KLU_LAUNCH(c, "k_gp_lat_scan");
       k_gp_lat_scan<0><<<L, 256, 0, c->stream>>>(a.counts, a.s_off, a.e_off, a.first_arc, nullptr, nullptr);
@@ -579,8 +588,9 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_gp_levels"));
   // ---- host round trip 1: per-lattice metadata ----
   std::vector<int32_t> meta((size_t)M_STRIDE * L);
-  KLU_CUDA(cudaMemcpyAsync(meta.data(), a.meta, 4 * meta.size(), cudaMemcpyDeviceToHost, c->stream));
-  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  KLU_TRY(small_d2h(c, meta.data(), a.meta, 4 * meta.size()));
+  KLU_TRY(small_sync(c));
+  klu_trace(c, "load: levels known");
   std::vector<int32_t> lvl_off(L + 1, 0);
   for (int32_t l = 0; l < L; ++l) {
     const int32_t* m = meta.data() + (size_t)M_STRIDE * l;
@@ -635,15 +645,15 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   // 64-bit segment bases for the sort
   KLU_TRY(c->d_res[6].reserve(8 * (size_t)(2 * L + 2)));
   int64_t* seg64 = c->d_res[6].as<int64_t>();
-  KLU_CUDA(cudaMemcpyAsync(seg64, in->state_off, 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
-  KLU_CUDA(cudaMemcpyAsync(seg64 + L + 1, in->arc_off, 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
+  KLU_TRY(small_h2d(c, seg64, in->state_off, 8 * (size_t)(L + 1)));
+  KLU_TRY(small_h2d(c, seg64 + L + 1, in->arc_off, 8 * (size_t)(L + 1)));
   KLU_TRY(c->d_res[7].reserve(4 * (size_t)(2 * L + 2)));
   std::vector<int32_t> seg_cnt(2 * (size_t)L);
   for (int32_t l = 0; l < L; ++l) {
     seg_cnt[l] = (int32_t)(in->state_off[l + 1] - in->state_off[l]);
     seg_cnt[L + l] = (int32_t)(in->arc_off[l + 1] - in->arc_off[l]);
   }
-  KLU_CUDA(cudaMemcpyAsync(c->d_res[7].p, seg_cnt.data(), 4 * seg_cnt.size(), cudaMemcpyHostToDevice, c->stream));
+  KLU_TRY(small_h2d(c, c->d_res[7].p, seg_cnt.data(), 4 * seg_cnt.size()));
   unsigned long long* key_a = sc[R_KEYA].as<unsigned long long>();
   unsigned long long* key_b = sc[R_KEYB].as<unsigned long long>();
   unsigned int* val_a = sc[R_VALA].as<unsigned int>();
@@ -720,9 +730,10 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_gp_add_base(band)"));
   // ---- host round trip 2: band bases and expansion capacities ----
   std::vector<long long> h_tot(L + 1), h_cap(2 * (size_t)L);
-  KLU_CUDA(cudaMemcpyAsync(h_tot.data(), a.lat_tot, 8 * (size_t)(L + 1), cudaMemcpyDeviceToHost, c->stream));
-  KLU_CUDA(cudaMemcpyAsync(h_cap.data(), a.cap, 16 * (size_t)L, cudaMemcpyDeviceToHost, c->stream));
-  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  KLU_TRY(small_d2h(c, h_tot.data(), a.lat_tot, 8 * (size_t)(L + 1)));
+  KLU_TRY(small_d2h(c, h_cap.data(), a.cap, 16 * (size_t)L));
+  KLU_TRY(small_sync(c));
+  klu_trace(c, "load: bands known");
   for (int32_t l = 0; l <= L; ++l) c->h_band_off[l] = h_tot[l];
   c->band_total = h_tot[L];
   std::vector<long long> fa_base(L + 1, 0);
@@ -738,7 +749,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(sc[R_VALB].reserve(4 * F1));  // frame counters (the sort buffers are free again)
   a.fr_cnt = sc[R_VALB].as<int32_t>();
   KLU_CUDA(cudaMemsetAsync(a.fr_cnt, 0, 4 * F1, c->stream));
-  KLU_CUDA(cudaMemcpyAsync(a.lat_tot, fa_base.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
+  KLU_TRY(small_h2d(c, a.lat_tot, fa_base.data(), 8 * (size_t)(L + 1)));
   {
     KLU_LAUNCH(c, "k_gp_frames");
     k_gp_frames<0><<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
@@ -758,6 +769,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_gp_add_base(frames)"));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // host-side vectors used by async copies die here
   // the frame lists themselves (sorted by word, with group heads) are built from the packed arcs
+  klu_trace(c, "load: packed, building frame groups");
   return build_frame_groups(c);
 }
 

@@ -996,7 +996,9 @@ int klu_fetch_frame_post(klu_ctx* c, int32_t* num_frames, int32_t* frame, int32_
     set_error("klu_fetch_frame_post: last run was not KLU_FRAME_POST");
     return 1;
   }
+  klu_trace(c, "fetch: waiting for the run");
   KLU_TRY(ensure_offsets(c));
+  klu_trace(c, "fetch: download begins");
   const size_t n = (size_t)c->last_entries;
   if (num_frames) memcpy(num_frames, c->h_num_frames.data(), sizeof(int32_t) * c->L);
   // the frame column of the frame-synchronous path is static per batch (klu_frame.cu);
@@ -1005,6 +1007,7 @@ int klu_fetch_frame_post(klu_ctx* c, int32_t* num_frames, int32_t* frame, int32_
   KLU_TRY(d2h(c, word, c->d_res[1].p, n * 4));
   KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 4));
   KLU_CUDA(cudaStreamSynchronize(c->stream));
+  klu_trace(c, "fetch: done");
   return 0;
 }
 
