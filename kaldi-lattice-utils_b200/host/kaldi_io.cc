@@ -9,6 +9,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 
 namespace kio {
@@ -597,13 +603,50 @@ inline void GetBytes(std::streambuf* sb, void* p, std::streamsize n) {
   if (n > 0 && sb->sgetn(reinterpret_cast<char*>(p), n) != n) KIO_ERR("Unexpected end of binary lattice stream");
 }
 
+// Walks the length fields of a binary CompactLattice body (nstates states from p) without
+// reading anything else: the number of arcs and the end of the body.  OpenFst's VectorFst
+// writer leaves the header's arc count at zero, so this walk is how the arcs are counted.
+// False if the body is truncated or a length is negative.
+bool CountBinaryCompactArcs(const char* p, const char* end, int64_t nstates, int64_t* narcs, const char** body_end) {
+  int64_t total = 0;
+  for (int64_t s = 0; s < nstates; ++s) {
+    if (end - p < 12) return false;
+    int32_t sz;
+    memcpy(&sz, p + 8, 4);
+    if (sz < 0 || (end - p - 12) / 4 < sz) return false;
+    p += 12 + 4 * (size_t)sz;
+    if (end - p < 8) return false;
+    int64_t na;
+    memcpy(&na, p, 8);
+    p += 8;
+    if (na < 0 || na > (end - p) / 24) return false;
+    for (int64_t k = 0; k < na; ++k) {
+      if (end - p < 24) return false;
+      int32_t asz;
+      memcpy(&asz, p + 16, 4);
+      if (asz < 0 || (end - p - 24) / 4 < asz) return false;
+      p += 24 + 4 * (size_t)asz;
+    }
+    total += na;
+  }
+  *narcs = total;
+  *body_end = p;
+  return true;
+}
+
 // Fast path for the common case -- a binary CompactLattice whose start state is 0:
 // the OpenFst body lists the arcs state by state, i.e. already grouped by source, so
 // the SoA arrays are filled directly (one read for the fixed part of every arc, one
 // for its transition ids, which are kept only for the tool that writes lattices back).
 // The same over a memory block: no copies except into the SoA arrays.
+// narcs < 0: not counted yet.
 bool ReadBinaryCompactMem(MemBuf* mb, int64_t nstates, int64_t narcs, bool keep_tids, CompactLat* lat) {
-  if (narcs < 0 || narcs >= ((int64_t)1 << 31)) return false;  // header without an arc count: generic path
+  if (narcs < 0) {
+    const char* body_end;
+    if (!CountBinaryCompactArcs(mb->cur(), mb->end(), nstates, &narcs, &body_end))
+      KIO_ERR("Unexpected end of binary lattice " << lat->key << " (or corrupt length field)");
+  }
+  if (narcs >= ((int64_t)1 << 31)) KIO_ERR("Lattice " << lat->key << " has too many arcs");
   const char* p = mb->cur();
   const char* const end = mb->end();
   const int32_t n = (int32_t)nstates;
@@ -680,7 +723,7 @@ bool ReadBinaryCompactMem(MemBuf* mb, int64_t nstates, int64_t narcs, bool keep_
 
 void ReadBinaryCompactFast(std::istream& is, int64_t nstates, int64_t narcs_hint, bool keep_tids, CompactLat* lat) {
   if (MemBuf* mb = dynamic_cast<MemBuf*>(is.rdbuf()))
-    if (ReadBinaryCompactMem(mb, nstates, narcs_hint, keep_tids, lat)) return;
+    if (ReadBinaryCompactMem(mb, nstates, -1, keep_tids, lat)) return;  // the header's count is only a hint
   std::streambuf* sb = is.rdbuf();
   struct FinalHead { float g, a; int32_t sz; };
   struct ArcHead { int32_t ilabel, olabel; float g, a; int32_t sz; };
@@ -915,6 +958,8 @@ void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat) {
     os << '\n';
     return;
   }
+  os.put('\0');  // Kaldi's binary-mode marker (CompactLatticeHolder::Write -> InitKaldiOutputStream) [ext]
+  os.put('B');
   WriteRaw<int32_t>(os, 2125659606);
   WriteFstString(os, "vector");
   WriteFstString(os, "compactlattice44");
@@ -923,7 +968,7 @@ void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat) {
   WriteRaw<uint64_t>(os, 0x3ULL);            // kExpanded | kMutable, everything else unknown
   WriteRaw<int64_t>(os, lat.nstates ? 0 : -1);
   WriteRaw<int64_t>(os, lat.nstates);
-  WriteRaw<int64_t>(os, (int64_t)na);
+  WriteRaw<int64_t>(os, 0);                  // arc count: left at zero by OpenFst's VectorFst writer
   size_t e = 0;
   for (int32_t s = 0; s < lat.nstates; ++s) {
     WriteRaw<float>(os, lat.fin_graph[s]);
@@ -987,6 +1032,169 @@ void SequentialCompactLatticeReader::ReadOne() {
   cur_.key = key;
   if (c == '\n') is.unget();  // text lattices: the newline belongs to the holder
   ReadCompactLattice(is, &cur_, keep_tids_);
+}
+
+namespace {
+int IoThreads() {
+  const char* e = getenv("KLU_IO_THREADS");
+  return std::max(1, e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+}
+}  // namespace
+
+void ParallelFor(size_t n, const std::function<void(size_t)>& fn, int threads) {
+  if (threads <= 0) threads = IoThreads();
+  threads = (int)std::min<size_t>((size_t)std::max(threads, 1), n);
+  if (threads <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next(0);
+  std::mutex mu;
+  std::exception_ptr failure;
+  auto work = [&] {
+    try {
+      for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+    } catch (...) {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!failure) failure = std::current_exception();
+      next.store(n);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (failure) std::rethrow_exception(failure);
+}
+
+namespace {
+// One archive entry located but not parsed: "key \0B" + FstHeader + body, a binary
+// CompactLattice with start state 0 (what ReadBinary's fast path takes).
+struct EntrySpan {
+  std::string key;
+  const char* body = nullptr;
+  size_t len = 0;
+  int64_t nstates = 0, narcs = 0;
+};
+
+// Locates the entry at the buffer's position and moves past it.  False -- nothing
+// consumed -- at the end of the archive and for anything the fast path does not take
+// (text entries, other FST types, a truncated body): the sequential reader then deals
+// with the entry, error messages included.
+bool ScanEntry(MemBuf* mb, EntrySpan* sp) {
+  const char* p = mb->cur();
+  const char* const end = mb->end();
+  while (p < end && isspace((unsigned char)*p)) ++p;
+  const char* k0 = p;
+  while (p < end && !isspace((unsigned char)*p)) ++p;
+  if (p == k0 || p == end || *p != ' ') return false;
+  sp->key.assign(k0, p);
+  ++p;
+  if (end - p >= 2 && p[0] == '\0' && p[1] == 'B') p += 2;  // Kaldi's binary-mode marker (tolerated when absent)
+  auto rd32 = [&](int32_t* v) {
+    if (end - p < 4) return false;
+    memcpy(v, p, 4);
+    p += 4;
+    return true;
+  };
+  auto rd64 = [&](int64_t* v) {
+    if (end - p < 8) return false;
+    memcpy(v, p, 8);
+    p += 8;
+    return true;
+  };
+  auto rdstr = [&](std::string* str) {
+    int32_t n;
+    if (!rd32(&n) || n < 0 || end - p < n) return false;
+    str->assign(p, (size_t)n);
+    p += n;
+    return true;
+  };
+  int32_t magic, version, flags;
+  int64_t props, start, nstates, hdr_arcs;
+  std::string fsttype, arctype;
+  if (!rd32(&magic) || magic != 2125659606 || !rdstr(&fsttype) || !rdstr(&arctype) || !rd32(&version) || !rd32(&flags) ||
+      !rd64(&props) || !rd64(&start) || !rd64(&nstates) || !rd64(&hdr_arcs))
+    return false;
+  if (fsttype != "vector" || (flags & 3) || arctype != "compactlattice44" || start != 0 || nstates <= 0 ||
+      nstates >= ((int64_t)1 << 31))
+    return false;
+  const char* body_end;
+  int64_t narcs;
+  if (!CountBinaryCompactArcs(p, end, nstates, &narcs, &body_end) || narcs >= ((int64_t)1 << 31)) return false;
+  sp->body = p;
+  sp->len = (size_t)(body_end - p);
+  sp->nstates = nstates;
+  sp->narcs = narcs;
+  mb->advance((size_t)(body_end - mb->cur()));
+  return true;
+}
+}  // namespace
+
+bool SequentialCompactLatticeReader::ReadBlock(int64_t max_arcs, std::vector<CompactLat>* out) {
+  out->clear();
+  if (done_ || spec_.is_scp) return false;
+  MemBuf* mb = dynamic_cast<MemBuf*>(in_->Stream().rdbuf());
+  if (!mb) return false;
+  int64_t arcs = (int64_t)cur_.src.size();
+  out->push_back(std::move(cur_));
+  // This thread walks the archive from entry to entry; the others parse what it has
+  // found so far (deques: elements stay put while more are appended).
+  std::deque<EntrySpan> spans;
+  std::deque<CompactLat> lats;
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t next = 0;
+  bool finished = false;
+  std::exception_ptr failure;
+  const bool keep = keep_tids_;
+  auto parse = [&] {
+    for (;;) {
+      EntrySpan* sp;
+      CompactLat* lat;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return next < spans.size() || finished; });
+        if (next >= spans.size()) return;
+        sp = &spans[next];
+        lat = &lats[next];
+        ++next;
+      }
+      try {
+        lat->key = sp->key;
+        MemBuf body(sp->body, sp->len);
+        ReadBinaryCompactMem(&body, sp->nstates, sp->narcs, keep, lat);
+      } catch (...) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failure) failure = std::current_exception();
+      }
+    }
+  };
+  std::vector<std::thread> helpers;
+  for (int t = 1, n = IoThreads(); t < n; ++t) helpers.emplace_back(parse);
+  while (arcs < max_arcs) {
+    EntrySpan sp;
+    if (!ScanEntry(mb, &sp)) break;
+    arcs += sp.narcs;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      spans.push_back(std::move(sp));
+      lats.emplace_back();
+    }
+    cv.notify_one();
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    finished = true;
+  }
+  cv.notify_all();
+  parse();
+  for (auto& t : helpers) t.join();
+  if (failure) std::rethrow_exception(failure);
+  out->reserve(1 + lats.size());
+  for (CompactLat& l : lats) out->push_back(std::move(l));
+  ReadOne();  // the entry after the block (or the end of the archive)
+  return true;
 }
 
 TableWriter::TableWriter(const std::string& wspecifier) {

@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <limits>
 #include <map>
@@ -177,6 +178,10 @@ class Output {
   std::ostringstream pipe_buf_;
 };
 
+// fn(i) for every i in [0, n) on up to `threads` threads (0 = $KLU_IO_THREADS, else the
+// hardware's, at most 16); the first exception thrown by any of them is rethrown.
+void ParallelFor(size_t n, const std::function<void(size_t)>& fn, int threads = 0);
+
 class SequentialCompactLatticeReader {
  public:
   explicit SequentialCompactLatticeReader(const std::string& rspecifier, bool keep_tids = true);
@@ -184,6 +189,13 @@ class SequentialCompactLatticeReader {
   void Next();
   const std::string& Key() const { return cur_.key; }
   CompactLat& Value() { return cur_; }
+  // Block mode, for archives held in memory (memory-mapped files, collected pipes): moves
+  // the current entry and the following ones into `out` until they hold `max_arcs` arcs
+  // (the entry that crosses the mark included, as a sequential reader filling a batch
+  // would), and leaves the reader on the entry after them.  The binary entries are located
+  // by walking their length fields and parsed on several threads.  False, with nothing
+  // consumed, when the archive is not a memory block (or Done()).
+  bool ReadBlock(int64_t max_arcs, std::vector<CompactLat>* out);
 
  private:
   void ReadOne();

@@ -17,13 +17,20 @@
 //
 // Lattices are independent, so the reader fills a batch (KLU_BATCH_ARCS arcs,
 // default 32M), the batch is packed/uploaded/processed, and entries are written
-// in input order -- the TaskSequencer contract (P9).  --num-threads is accepted
-// and ignored.  KLU_DEVICE selects the GPU (default 0).
+// in input order -- the TaskSequencer contract (P9); parsing, GPU work and writing
+// of successive batches overlap (class Pipeline).  --num-threads is accepted
+// and ignored.  KLU_DEVICE selects the GPU (default 0), KLU_DEVICES=a,b,... several contexts.
 #include <limits.h>
+#include <malloc.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <memory>
+#include <mutex>
 #include <set>
 #include <thread>
 
@@ -69,6 +76,40 @@ struct Batch {
     } else {
       lats.push_back(std::move(l));
     }
+  }
+  // A block of lattices at once: the arrays grow once and the lattices are copied in by
+  // several threads (SequentialCompactLatticeReader::ReadBlock delivers such blocks).
+  void AddBlock(std::vector<CompactLat>* block, bool keep_lattice) {
+    const size_t n0 = lats.size(), nb = block->size();
+    for (const CompactLat& l : *block) {
+      state_off.push_back(state_off.back() + l.nstates);
+      arc_off.push_back(arc_off.back() + (int64_t)l.src.size());
+    }
+    const size_t E = (size_t)arc_off.back(), S = (size_t)state_off.back();
+    src.resize(E), dst.resize(E), label.resize(E), dur.resize(E), graph.resize(E), acoustic.resize(E);
+    fin_graph.resize(S), fin_acoustic.resize(S), fin_dur.resize(S);
+    lats.resize(n0 + nb);
+    ParallelFor(nb, [&](size_t i) {
+      CompactLat& l = (*block)[i];
+      const size_t e = (size_t)arc_off[n0 + i], s = (size_t)state_off[n0 + i], na = l.src.size();
+      if (na) {
+        memcpy(&src[e], l.src.data(), 4 * na), memcpy(&dst[e], l.dst.data(), 4 * na);
+        memcpy(&label[e], l.label.data(), 4 * na), memcpy(&dur[e], l.dur.data(), 4 * na);
+        memcpy(&graph[e], l.graph.data(), 4 * na), memcpy(&acoustic[e], l.acoustic.data(), 4 * na);
+      }
+      if (l.nstates) {
+        memcpy(&fin_graph[s], l.fin_graph.data(), 4 * (size_t)l.nstates);
+        memcpy(&fin_acoustic[s], l.fin_acoustic.data(), 4 * (size_t)l.nstates);
+        memcpy(&fin_dur[s], l.fin_dur.data(), 4 * (size_t)l.nstates);
+      }
+      if (keep_lattice) {
+        lats[n0 + i] = std::move(l);
+      } else {
+        lats[n0 + i].key = l.key;
+        lats[n0 + i].nstates = l.nstates;
+      }
+    });
+    block->clear();
   }
   klu_lattices View() const {
     klu_lattices v;
@@ -266,12 +307,48 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */ || KLU_TOOL == 8 /* KLU_POSITION_POST */ || KLU_TOOL == 10 /* KLU_LENGTH_DIST */
   const std::vector<int32_t>&nf = r->i0, &frame = r->i1, &word = r->i2;
   const std::vector<float>& lp = r->f0;
-  for (int32_t l = 0; l < L; ++l) {
+  // [ext] PosteriorHolder: text "[ lab p lab p ] [ ... ] \n"; binary "\0B" +
+  // int32 #frames, per frame int32 n then n x (int32, float), every number behind its
+  // size byte.  Binary entries are laid out in memory, several lattices at a time on as
+  // many threads, and written with one call each.
+  if (bin && w.IsOpen()) {
+    std::vector<std::string> bufs((size_t)L);
+    ParallelFor((size_t)L, [&](size_t l) {
+      const size_t a = (size_t)off[l], e = (size_t)off[l + 1];
+      std::string& buf = bufs[l];
+      buf.resize(2 + 5 + 5 * (size_t)nf[l] + 10 * (e - a));
+      char* q = &buf[0];
+      auto put32 = [&q](const void* v) {
+        *q++ = 4;
+        memcpy(q, v, 4);
+        q += 4;
+      };
+      *q++ = '\0';
+      *q++ = 'B';
+      put32(&nf[l]);
+      size_t i = a;
+      for (int32_t k = 0; k < nf[l]; ++k) {
+        size_t j = i;
+        while (j < e && frame[j] == k) ++j;
+        const int32_t n = (int32_t)(j - i);
+        put32(&n);
+        for (; i < j; ++i) {
+          put32(&word[i]);
+          put32(&lp[i]);
+        }
+      }
+      buf.resize((size_t)(q - &buf[0]));  // rows outside 0..nf-1 (there are none) would have been skipped
+    });
+    for (int32_t l = 0; l < L; ++l) {
+      std::ostream& os = w.Begin(b->lats[l].key);
+      os.write(bufs[l].data(), (std::streamsize)bufs[l].size());
+      w.End();
+    }
+  }
+  for (int32_t l = 0; l < L && !(bin && w.IsOpen()); ++l) {
     std::ostream& os = w.Begin(b->lats[l].key);
     size_t i = (size_t)off[l];
     const size_t e = (size_t)off[l + 1];
-    // [ext] PosteriorHolder: text "[ lab p lab p ] [ ... ] \n"; binary "\0B" +
-    // int32 #frames, per frame int32 n then n x (int32, float)
     if (bin) {
       os.put('\0');
       os.put('B');
@@ -370,28 +447,116 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
   KIO_VLOG(1, "Batch of " << L << " lattices (" << b->arcs() << " arcs): done in " << r->sec << " seconds.");
 }
 
-// A wave = up to one batch per GPU, computed concurrently (one host thread + one
-// CUDA stream per GPU, no shared mutable state between contexts), then written in
-// input order.
-void ProcessWave(ToolState* st, std::vector<Batch>* wave) {
-  const size_t nb = wave->size();
-  if (nb == 0) return;
-  std::vector<Results> res(nb);
-  if (nb == 1) {
-    ComputeBatch(st->ctxs[0], &st->opts, &(*wave)[0], &res[0]);
-  } else {
-    std::vector<std::thread> th;
-    for (size_t i = 0; i < nb; ++i)
-      th.emplace_back(ComputeBatch, st->ctxs[i], &st->opts, &(*wave)[i], &res[i]);
-    for (auto& t : th) t.join();
+// Reading, GPU work and writing overlap: the main thread parses lattices into batches,
+// one worker thread per context (KLU_DEVICES; a GPU may be listed more than once) packs,
+// runs and fetches them, and a writer thread emits the results strictly in input order
+// (the TaskSequencer contract, P9).  At most contexts + 2 batches exist at a time.
+class Pipeline {
+ public:
+  explicit Pipeline(ToolState* st) : st_(st) {
+    for (klu_ctx* ctx : st->ctxs) workers_.emplace_back(&Pipeline::Work, this, ctx);
+    writer_ = std::thread(&Pipeline::Write, this);
   }
-  for (size_t i = 0; i < nb; ++i) EmitBatch(st, &(*wave)[i], &res[i]);
-  wave->clear();
-}
+  ~Pipeline() { Shutdown(); }
+
+  // Hands a batch over; blocks while the pipeline is full.  False once a stage has failed.
+  bool Submit(Batch&& b) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return abort_ || jobs_.size() < st_->ctxs.size() + 2; });
+    if (abort_) return false;
+    jobs_.emplace_back(new Job());
+    jobs_.back()->b = std::move(b);
+    cv_.notify_all();
+    return true;
+  }
+
+  // Waits for everything submitted to be written; rethrows the first failure of any stage.
+  void Finish() {
+    Shutdown();
+    if (failure_) std::rethrow_exception(failure_);
+  }
+
+ private:
+  struct Job {
+    Batch b;
+    Results r;
+    bool done = false;
+  };
+
+  void Shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      closing_ = true;
+      cv_.notify_all();
+    }
+    for (auto& t : workers_)
+      if (t.joinable()) t.join();
+    if (writer_.joinable()) writer_.join();
+  }
+
+  void Fail() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!failure_) failure_ = std::current_exception();
+    abort_ = true;
+    cv_.notify_all();
+  }
+
+  void Work(klu_ctx* ctx) {
+    for (;;) {
+      Job* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return abort_ || claimed_ < jobs_.size() || closing_; });
+        if (abort_ || claimed_ >= jobs_.size()) return;  // closing and nothing left to claim
+        job = jobs_[claimed_++].get();
+      }
+      ComputeBatch(ctx, &st_->opts, &job->b, &job->r);  // failures travel in r.error to the writer
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        job->done = true;
+        cv_.notify_all();
+      }
+    }
+  }
+
+  void Write() {
+    try {
+      for (;;) {
+        std::unique_ptr<Job> job;
+        {
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&] { return abort_ || (!jobs_.empty() && jobs_.front()->done) || (closing_ && jobs_.empty()); });
+          if (abort_ || jobs_.empty()) return;
+          job = std::move(jobs_.front());
+          jobs_.pop_front();
+          --claimed_;
+          cv_.notify_all();
+        }
+        EmitBatch(st_, &job->b, &job->r);
+      }
+    } catch (...) {
+      Fail();
+    }
+  }
+
+  ToolState* st_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::unique_ptr<Job>> jobs_;  // input order; the front is the next one to write
+  size_t claimed_ = 0;                     // jobs_[0 .. claimed_) have been taken by a worker
+  bool closing_ = false, abort_ = false;
+  std::exception_ptr failure_;
+  std::vector<std::thread> workers_;
+  std::thread writer_;
+};
 
 }  // namespace
 
 int main(int argc, char* argv[]) {
+  // the parser threads allocate and free MB-sized arrays all the time: keep those in the
+  // heap (no mmap / munmap and fresh page faults per array)
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
 #if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
   const int kErrorCode = 1;  // kwsbin2/lattice-char-index-position.cc:405-408
 #else
@@ -623,17 +788,28 @@ int main(int argc, char* argv[]) {
     const std::string lattice_rspecifier = po.GetArg(kLatArg);
     TableWriter writer(po.GetOptArg(kLatArg + 1));
     st.writer = &writer;
-    std::vector<Batch> wave(1);
     const bool keep = KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */;
-    for (SequentialCompactLatticeReader reader(lattice_rspecifier, keep); !reader.Done(); reader.Next()) {
-      wave.back().Add(std::move(reader.Value()), keep);
-      if (wave.back().arcs() >= batch_arcs) {
-        if (wave.size() == st.ctxs.size()) ProcessWave(&st, &wave);
-        wave.emplace_back();
+    {
+      Pipeline pipe(&st);
+      Batch batch;
+      bool ok = true;
+      SequentialCompactLatticeReader reader(lattice_rspecifier, keep);
+      std::vector<CompactLat> block;
+      while (ok && !reader.Done()) {
+        if (reader.ReadBlock(batch_arcs - batch.arcs(), &block)) {  // in-memory archive: parsed in parallel
+          batch.AddBlock(&block, keep);
+        } else {
+          batch.Add(std::move(reader.Value()), keep);
+          reader.Next();
+        }
+        if (batch.arcs() >= batch_arcs) {
+          ok = pipe.Submit(std::move(batch));
+          batch = Batch();
+        }
       }
+      if (ok && !batch.lats.empty()) pipe.Submit(std::move(batch));
+      pipe.Finish();
     }
-    if (wave.back().lats.empty()) wave.pop_back();
-    ProcessWave(&st, &wave);
     if (writer.IsOpen()) writer.Close();
 #if KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     KIO_LOG("Overall cost per frame is " << (st.total_cost / st.total_frames) << " over " << st.total_frames
