@@ -47,6 +47,8 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     if r.returncode != 0:
         sys.stderr.write(r.stderr.decode()[-2000:])
         sys.exit(1)
+    if os.environ.get("KLU_TRACE"):
+        sys.stderr.write("\n".join(l for l in r.stderr.decode().splitlines() if "time:" in l) + "\n")
     print(json.dumps({"tool": args.tool, "shape": args.shape, "lattices": args.lattices, "arcs": arcs,
                       "ark_bytes": os.path.getsize(ark), "out_bytes": os.path.getsize(os.path.join(d, "out.ark")),
                       "seconds": dt, "arcs_per_s": arcs / dt, "ark_write_seconds": t_gen,

@@ -138,6 +138,7 @@ struct ToolState {
   double total_cost = 0.0;       // best-path2
   int64_t total_frames = 0;
   size_t num_lattices = 0;
+  double sec_read = 0.0, sec_wait = 0.0, sec_gpu = 0.0, sec_emit = 0.0;  // KLU_TRACE summary
 };
 
 [[maybe_unused]] void WriteTupleSep(std::ostream& os, bool binary, size_t i, size_t n) {
@@ -532,7 +533,10 @@ class Pipeline {
           --claimed_;
           cv_.notify_all();
         }
+        const auto t0 = std::chrono::steady_clock::now();
+        st_->sec_gpu += job->r.sec;
         EmitBatch(st_, &job->b, &job->r);
+        st_->sec_emit += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       }
     } catch (...) {
       Fail();
@@ -793,6 +797,7 @@ int main(int argc, char* argv[]) {
       Pipeline pipe(&st);
       Batch batch;
       bool ok = true;
+      auto t_read = std::chrono::steady_clock::now();
       SequentialCompactLatticeReader reader(lattice_rspecifier, keep);
       std::vector<CompactLat> block;
       while (ok && !reader.Done()) {
@@ -803,14 +808,22 @@ int main(int argc, char* argv[]) {
           reader.Next();
         }
         if (batch.arcs() >= batch_arcs) {
+          const auto t1 = std::chrono::steady_clock::now();
+          st.sec_read += std::chrono::duration<double>(t1 - t_read).count();
           ok = pipe.Submit(std::move(batch));
           batch = Batch();
+          t_read = std::chrono::steady_clock::now();
+          st.sec_wait += std::chrono::duration<double>(t_read - t1).count();
         }
       }
+      st.sec_read += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_read).count();
       if (ok && !batch.lats.empty()) pipe.Submit(std::move(batch));
       pipe.Finish();
     }
     if (writer.IsOpen()) writer.Close();
+    if (getenv("KLU_TRACE"))
+      KIO_LOG("time: reading " << st.sec_read << " s, waiting for the pipeline " << st.sec_wait << " s, GPU calls " << st.sec_gpu
+                             << " s, writing " << st.sec_emit << " s");
 #if KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     KIO_LOG("Overall cost per frame is " << (st.total_cost / st.total_frames) << " over " << st.total_frames
                                          << " frames.");
