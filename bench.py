@@ -451,6 +451,10 @@ def main():
             "clocks": sampler.summary()}))
     if eng.h:
         eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
