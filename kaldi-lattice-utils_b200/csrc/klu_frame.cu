@@ -931,20 +931,6 @@ int build_frame_groups(klu_ctx* c) {
       k_fg_heads<false><<<hgrid, 256, 0, c->stream>>>(a);
     }
     if ((rc = check_launch("k_fg_heads"))) break;
-    if (getenv("KLU_DEBUG_WINDOWS") && a.num_items > 0) {
-      std::vector<int32_t> lo(a.num_items), hi(a.num_items);
-      cudaMemcpyAsync(lo.data(), a.run_lo, 4 * (size_t)a.num_items, cudaMemcpyDeviceToHost, c->stream);
-      cudaMemcpyAsync(hi.data(), a.run_hi, 4 * (size_t)a.num_items, cudaMemcpyDeviceToHost, c->stream);
-      cudaStreamSynchronize(c->stream);
-      long long sum = 0, mx = 0, big = 0;
-      for (int i = 0; i < a.num_items; ++i) {
-        const long long w = hi[i] >= lo[i] ? (long long)hi[i] - lo[i] + 1 : 0;
-        sum += w;
-        mx = std::max(mx, w);
-        big += w > 5120;
-      }
-      fprintf(stderr, "frame windows: items %d mean %.1f max %lld over-cap %lld\n", a.num_items, (double)sum / a.num_items, mx, big);
-    }
     {
       KLU_LAUNCH(c, "k_fg_scan");
       k_fg_scan<<<L, 256, 0, c->stream>>>(a);
