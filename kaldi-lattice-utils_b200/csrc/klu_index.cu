@@ -371,6 +371,45 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* cnt, int l0
   if (tid == 0) off[L] = carry_s;
 }
 
+// The order sort runs on the high bits of its 64-bit keys only (half the radix passes).
+// Elements whose keys agree in those bits (log-posteriors equal to ~1e-6 relative:
+// a handful per lattice) are left in input order by the stable sort; here every such
+// run is put in full-key order by a stable insertion sort, one thread per run.
+struct OrderFixArgs {
+  const int64_t* seg_base;
+  const int32_t* seg_cnt;
+  const unsigned char* where;
+  unsigned long long *key_a, *key_b;
+  unsigned int *val_a, *val_b;
+  int lo_bit;
+};
+
+__global__ void __launch_bounds__(256) k_order_fixup(OrderFixArgs a) {
+  const int l = blockIdx.y;
+  const int n = a.seg_cnt[l];
+  const int64_t base = a.seg_base[l];
+  unsigned long long* K = (a.where[l] ? a.key_b : a.key_a) + base;
+  unsigned int* V = (a.where[l] ? a.val_b : a.val_a) + base;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long t = K[i] >> a.lo_bit;
+    if ((i > 0 && (K[i - 1] >> a.lo_bit) == t) || (K[i + 1] >> a.lo_bit) != t) continue;  // not the head of a run
+    int j = i + 1;
+    while (j < n && (K[j] >> a.lo_bit) == t) {  // insert element j into the ordered [i, j)
+      const unsigned long long k = K[j];
+      const unsigned int v = V[j];
+      int q = j;
+      while (q > i && K[q - 1] > k) {
+        K[q] = K[q - 1];
+        V[q] = V[q - 1];
+        --q;
+      }
+      K[q] = k;
+      V[q] = v;
+      ++j;
+    }
+  }
+}
+
 struct GatherArgs {
   BatchView b;
   int tool;
@@ -846,13 +885,29 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     s2.key_b = c->d_scratch[S_KEYA].as<unsigned long long>();
     s2.val_b = c->d_scratch[S_IDXA].as<unsigned int>();
     s2.where = c->d_scratch[S_WHERE].as<unsigned char>() + L + l0;
-    s2.lo_bit = 0;
+    // f64 order keys: sort on the high half, settle the few near-ties afterwards
+    const bool half_keys = !(tool == KLU_FRAME_POST || tool == KLU_POSITION_POST);
+    s2.lo_bit = half_keys ? 32 : 0;
     s2.hi_bit = 64;
     {
       KLU_LAUNCH(c, "k_seg_radix_sort");
       k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s2);
     }
     KLU_TRY(check_launch("k_seg_radix_sort(order)"));
+    if (half_keys) {
+      OrderFixArgs f;
+      f.seg_base = s2.seg_base;
+      f.seg_cnt = s2.seg_cnt;
+      f.where = s2.where;
+      f.key_a = s2.key_a, f.key_b = s2.key_b;
+      f.val_a = s2.val_a, f.val_b = s2.val_b;
+      f.lo_bit = s2.lo_bit;
+      {
+        KLU_LAUNCH(c, "k_order_fixup");
+        k_order_fixup<<<dim3(tiles, nl), 256, 0, c->stream>>>(f);
+      }
+      KLU_TRY(check_launch("k_order_fixup"));
+    }
     {
       KLU_LAUNCH(c, "k_scan_counts");
       k_scan_counts<<<1, 1024, 0, c->stream>>>(r.rcnt, l0, l1, c->d_res[5].as<int64_t>());

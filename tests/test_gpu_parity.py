@@ -347,6 +347,28 @@ def test_frame_post_ties_and_near_ties(klu, ora, engine):
             assert a[1] > b[1] or (a[1] == b[1] and a[0] < b[0])
 
 
+def test_index_order_with_ties_and_near_ties(klu, ora, engine):
+    """The index tools sort by (double logp desc, key asc).  The order sort looks at the
+    high half of the key only and settles what agrees there afterwards: exact ties
+    must come out in key order, near-ties (1e-9 .. 1e-13 apart) in value order."""
+    arcs = []
+    for w in range(30):
+        arcs.append((0, 1, 100 + w, 1.0, 0.5, 1))                          # 30-way exact tie
+    for w in range(30):
+        arcs.append((0, 1, 200 + w, 2.0, 0.5 + 2.0 ** -20 * (29 - w), 1))  # float weights one ulp-ish apart
+    for w in range(30):
+        arcs.append((0, 2, 300 + w, 1.5, 0.25, 2))
+    arcs.append((1, 3, 7, 0.5, 0.5, 2))
+    arcs.append((2, 3, 8, 0.5, 0.5, 1))
+    lat = klu.make_lattice("order", 4, arcs, {3: (0.0, 0.0)})
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    for name, ncol in (("segment", 3), ("position", 2), ("utterance", 1)):
+        got, want = getattr(engine, name)()[0], getattr(ora, name)(lat)
+        assert [r[:ncol] for r in got] == [r[:ncol] for r in want], name
+        for a, b in zip(got[:-1], got[1:]):  # the comparator on OUR doubles
+            assert a[-1] > b[-1] or (a[-1] == b[-1] and a[:ncol] < b[:ncol]), (name, a, b)
+
+
 def test_unreachable_and_dead_end_states(klu, ora, engine):
     # state 2 cannot be reached from the start (and has no arcs: CompactLatticeStateTimes
     # asserts otherwise), state 3 cannot reach a final state
