@@ -234,6 +234,26 @@ struct ReduceArgs {
 // One CTA per lattice: fold each run of equal keys with LogAdd (in sorted =
 // emission order), subtract the lattice total, compact, and write the sort key of
 // the output ordering.
+// Streaming log-sum-exp over the values of one key run: a running maximum m and the sum s
+// of exp(v - m), rescaled when the maximum moves -- one cheap exp per term where a chain
+// of Kaldi LogAdd calls costs an exp and a log1p each.  The callers keep LogAdd itself for
+// runs of one or two terms (bit-identical to the reference there); longer runs agree with
+// the reference's chain to ~1e-15.
+struct RunSum {
+  double m, s;
+  __device__ RunSum() : m(neg_inf()), s(0.0) {}
+  __device__ void add(double v) {
+    if (v == neg_inf()) return;
+    if (v <= m) {
+      s += fast_exp(v - m);
+    } else {
+      s = (m == neg_inf() ? 0.0 : s * fast_exp(m - v)) + 1.0;
+      m = v;
+    }
+  }
+  __device__ double value() const { return m == neg_inf() ? neg_inf() : m + fast_log(s); }
+};
+
 __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
@@ -288,7 +308,14 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       const int slot = add + x - 1;
       double sum = val[idx[i]];
       int q = i + 1;
-      for (; q < n && key[q] == k; ++q) sum = log_add(sum, val[idx[q]]);
+      if (q + 1 < n && key[q + 1] == k) {  // three or more terms
+        RunSum rs;
+        rs.add(sum);
+        for (; q < n && key[q] == k; ++q) rs.add(val[idx[q]]);
+        sum = rs.value();
+      } else {
+        for (; q < n && key[q] == k; ++q) sum = log_add(sum, val[idx[q]]);
+      }
       const double post = fmin(0.0, sum - a.beta[a.b.s_off[l]]);
       double ls;  // LogSub(0, post) [ext]
       if (post >= 0.0) ls = neg_inf();
@@ -308,10 +335,14 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       double sum = val[j];
       double bestv = sum;
       unsigned int besta = aux[j];
+      const bool longrun = i + 2 < n && key[i + 2] == k;  // three or more terms
+      RunSum rs;
+      if (longrun) rs.add(sum);
       for (int q = i + 1; q < n && key[q] == k; ++q) {
         j = idx[q];
         const double v = val[j];
-        sum = log_add(sum, v);
+        if (longrun) rs.add(v);
+        else sum = log_add(sum, v);
         if (a.tool == KLU_POSITION) {
           // strict '>' in reference iteration order (input state, arc order):
           // kwsbin2/lattice-word-index-position.cc:178
@@ -322,6 +353,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
           }
         }
       }
+      if (longrun) sum = rs.value();
       double logp = sum - total;
       a.rkey[base + slot] = k;
       a.rval[base + slot] = logp;
@@ -628,7 +660,19 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   if (tool == KLU_FWD_BWD || L == 0) return 0;
 
   // ---- chunk plan: contiguous lattice ranges with bounded scratch ----
-  int64_t kEntryBudget = (int64_t)1 << 28;  // entries per chunk (~92 B of scratch each)
+  // Entries per chunk (~92 B of scratch each).  The kernels downstream work one CTA or warp per
+  // lattice, so a chunk should hold as many lattices as memory allows: half of what is free
+  // (counting the scratch this context already holds), between 2^28 and 2^30 entries.
+  int64_t kEntryBudget = (int64_t)1 << 28;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      size_t held = 0;
+      for (const DevBuf& b : c->d_scratch) held += b.cap;
+      const int64_t fit = (int64_t)((free_b + held) / 2 / 92);
+      kEntryBudget = std::min<int64_t>((int64_t)1 << 30, std::max<int64_t>(kEntryBudget, fit));
+    }
+  }
   if (const char* env = getenv("KLU_ENTRY_BUDGET")) kEntryBudget = std::max<long long>(1, atoll(env));  // tests
   const int64_t kBandBudget = (int64_t)1 << 30;   // (state,len) cells per chunk (8 B each)
   std::vector<int64_t> ent_base(L + 1, 0);        // chunk-local first entry slot of each lattice
