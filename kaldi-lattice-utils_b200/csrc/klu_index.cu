@@ -257,6 +257,12 @@ struct RunSum {
 __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
+  // the tile's keys, values and arc ranks, staged by all threads at once: the run heads
+  // below then walk their runs in shared memory instead of a chain of dependent global
+  // gathers (key -> index -> value); only the part of a run past the tile reads global
+  __shared__ unsigned long long s_key[256];
+  __shared__ double s_val[256];
+  __shared__ unsigned int s_aux[256];
   const int l = a.l0 + blockIdx.x;
   const int n = a.ent_cnt[l];
   const int64_t base = a.ent_base[l];
@@ -276,7 +282,15 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
     if (i < n) {
       k = key[i];
       head = k != a.drop_key && (i == 0 || key[i - 1] != k);
+      const unsigned int j0 = idx[i];
+      s_key[tid] = k;
+      s_val[tid] = val[j0];
+      s_aux[tid] = aux[j0];
     }
+    const int tile_end = min(n, tile + 256);
+    auto key_at = [&](int q) { return q < tile_end ? s_key[q - tile] : key[q]; };
+    auto val_at = [&](int q) { return q < tile_end ? s_val[q - tile] : val[idx[q]]; };
+    auto aux_at = [&](int q) { return q < tile_end ? s_aux[q - tile] : aux[idx[q]]; };
     int x = head ? 1 : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -306,15 +320,15 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       // latbin/lattice-best-path2.cc:122-147,175: posterior of (label, position),
       // clamped to <= 0, turned into the float cost 1 - P of every arc carrying it
       const int slot = add + x - 1;
-      double sum = val[idx[i]];
+      double sum = s_val[tid];
       int q = i + 1;
-      if (q + 1 < n && key[q + 1] == k) {  // three or more terms
+      if (q + 1 < n && key_at(q + 1) == k) {  // three or more terms
         RunSum rs;
         rs.add(sum);
-        for (; q < n && key[q] == k; ++q) rs.add(val[idx[q]]);
+        for (; q < n && key_at(q) == k; ++q) rs.add(val_at(q));
         sum = rs.value();
       } else {
-        for (; q < n && key[q] == k; ++q) sum = log_add(sum, val[idx[q]]);
+        for (; q < n && key_at(q) == k; ++q) sum = log_add(sum, val_at(q));
       }
       const double post = fmin(0.0, sum - a.beta[a.b.s_off[l]]);
       double ls;  // LogSub(0, post) [ext]
@@ -331,22 +345,20 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       a.raux[base + slot] = 0;
     } else if (head) {
       const int slot = add + x - 1;
-      unsigned int j = idx[i];
-      double sum = val[j];
+      double sum = s_val[tid];
       double bestv = sum;
-      unsigned int besta = aux[j];
-      const bool longrun = i + 2 < n && key[i + 2] == k;  // three or more terms
+      unsigned int besta = s_aux[tid];
+      const bool longrun = i + 2 < n && key_at(i + 2) == k;  // three or more terms
       RunSum rs;
       if (longrun) rs.add(sum);
-      for (int q = i + 1; q < n && key[q] == k; ++q) {
-        j = idx[q];
-        const double v = val[j];
+      for (int q = i + 1; q < n && key_at(q) == k; ++q) {
+        const double v = val_at(q);
         if (longrun) rs.add(v);
         else sum = log_add(sum, v);
         if (a.tool == KLU_POSITION) {
           // strict '>' in reference iteration order (input state, arc order):
           // kwsbin2/lattice-word-index-position.cc:178
-          const unsigned int ar = aux[j];
+          const unsigned int ar = aux_at(q);
           if (v > bestv || (v == bestv && a.b.out_orig[e0 + ar] < a.b.out_orig[e0 + besta])) {
             bestv = v;
             besta = ar;
