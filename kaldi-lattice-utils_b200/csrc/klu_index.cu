@@ -229,11 +229,21 @@ struct ReduceArgs {
   int l0;
   const double* beta;  // best-path2 normalises by bw[start]
   double* val_rw;      // best-path2: per-entry cost written back over the values
+  int32_t* tile_heads;  // per 256-entry tile: key-run heads in it, then (k_reduce_offsets) heads before it
 };
 
-// One CTA per lattice: fold each run of equal keys with LogAdd (in sorted =
-// emission order), subtract the lattice total, compact, and write the sort key of
-// the output ordering.
+// slot of tile t of chunk-local lattice ll in tile_heads (entry bases are not tile aligned:
+// one spare slot per lattice keeps the ranges apart)
+__device__ __forceinline__ int64_t tile_slot(const ReduceArgs& a, int l, int t) {
+  return (a.ent_base[l] >> 8) + (l - a.l0) + t;
+}
+
+// Fold each run of equal keys with LogAdd (in sorted = emission order), subtract the
+// lattice total, compact, and write the sort key of the output ordering.  Tiles of 256
+// entries are independent CTAs (grid: tiles x lattices): k_reduce_count counts the run
+// heads of every tile, k_reduce_offsets turns the counts of a lattice into output offsets
+// (and the lattice's number of unique keys), k_reduce does the folding -- the head of a
+// run owns it to its end, also past the end of its tile.
 // Streaming log-sum-exp over the values of one key run: a running maximum m and the sum s
 // of exp(v - m), rescaled when the maximum moves -- one cheap exp per term where a chain
 // of Kaldi LogAdd calls costs an exp and a log1p each.  The callers keep LogAdd itself for
@@ -254,16 +264,63 @@ struct RunSum {
   __device__ double value() const { return m == neg_inf() ? neg_inf() : m + fast_log(s); }
 };
 
-__global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
+__global__ void __launch_bounds__(256) k_reduce_count(ReduceArgs a) {
+  const int l = a.l0 + blockIdx.y;
+  const int n = a.ent_cnt[l];
+  const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + a.ent_base[l];
+  for (int tile = blockIdx.x * 256; tile < n; tile += gridDim.x * 256) {
+    const int i = tile + threadIdx.x;
+    bool head = false;
+    if (i < n) {
+      const unsigned long long k = key[i];
+      head = k != a.drop_key && (i == 0 || key[i - 1] != k);
+    }
+    const int cnt = __syncthreads_count(head);
+    if (threadIdx.x == 0) a.tile_heads[tile_slot(a, l, tile >> 8)] = cnt;
+  }
+}
+
+// One CTA per lattice: exclusive prefix of its tile counts, in place; rcnt = their sum.
+__global__ void __launch_bounds__(256) k_reduce_offsets(ReduceArgs a) {
   __shared__ int warp_sum[8];
   __shared__ int carry_s;
+  const int l = a.l0 + blockIdx.x;
+  const int n = a.ent_cnt[l];
+  const int ntiles = (n + 255) >> 8;
+  int32_t* cnt = a.tile_heads + tile_slot(a, l, 0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < ntiles; t0 += 256) {
+    const int t = t0 + tid;
+    const int v = t < ntiles ? cnt[t] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    int add = carry_s;
+    for (int w = 0; w < warp; ++w) add += warp_sum[w];
+    if (t < ntiles) cnt[t] = add + x - v;
+    __syncthreads();
+    if (tid == 255) carry_s = add + x;
+    __syncthreads();
+  }
+  if (tid == 0) a.rcnt[l] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
+  __shared__ int warp_sum[8];
   // the tile's keys, values and arc ranks, staged by all threads at once: the run heads
   // below then walk their runs in shared memory instead of a chain of dependent global
   // gathers (key -> index -> value); only the part of a run past the tile reads global
   __shared__ unsigned long long s_key[256];
   __shared__ double s_val[256];
   __shared__ unsigned int s_aux[256];
-  const int l = a.l0 + blockIdx.x;
+  const int l = a.l0 + blockIdx.y;
   const int n = a.ent_cnt[l];
   const int64_t base = a.ent_base[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + base;
@@ -273,9 +330,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   const double total = a.total[l];
   const int e0 = a.b.e_off[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int tile = 0; tile < n; tile += 256) {
+  for (int tile = blockIdx.x * 256; tile < n; tile += gridDim.x * 256) {
     const int i = tile + tid;
     unsigned long long k = a.drop_key;
     bool head = false;
@@ -299,7 +354,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
     }
     if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    int add = carry_s;
+    int add = a.tile_heads[tile_slot(a, l, tile >> 8)];  // heads of this lattice before the tile
     for (int w = 0; w < warp; ++w) add += warp_sum[w];
     if (head && a.tool == KLU_UTTERANCE) {
       // run of arcs carrying word k: record where it starts, how long it is and
@@ -379,11 +434,8 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
       }
       a.idx2[base + slot] = (unsigned int)slot;
     }
-    __syncthreads();
-    if (tid == 255) carry_s = add + x;
-    __syncthreads();
+    __syncthreads();  // the staging arrays are rewritten by the next tile
   }
-  if (tid == 0) a.rcnt[l] = carry_s;
 }
 
 // res_off[l] = sum_{l' < l} rcnt[l'] (single block, L is small next to the arcs)
@@ -878,8 +930,24 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     r.beta = a.beta;
     r.val_rw = a.val;
     {
+      int64_t max_cap = 1;
+      for (int32_t l = l0; l < l1; ++l) max_cap = std::max<int64_t>(max_cap, ent_base[l + 1 < l1 ? l + 1 : l] - ent_base[l]);
+      max_cap = std::max<int64_t>(max_cap, chunk_cap - ent_base[l1 - 1]);
+      const int rtiles = (int)std::min<int64_t>((max_cap + 255) / 256, 8192);
+      KLU_TRY(c->d_tile_heads.reserve(4 * (size_t)((chunk_cap >> 8) + nl + 2)));
+      r.tile_heads = c->d_tile_heads.as<int32_t>();
+      {
+        KLU_LAUNCH(c, "k_reduce_count");
+        k_reduce_count<<<dim3(rtiles, nl), 256, 0, c->stream>>>(r);
+      }
+      KLU_TRY(check_launch("k_reduce_count"));
+      {
+        KLU_LAUNCH(c, "k_reduce_offsets");
+        k_reduce_offsets<<<nl, 256, 0, c->stream>>>(r);
+      }
+      KLU_TRY(check_launch("k_reduce_offsets"));
       KLU_LAUNCH(c, "k_reduce");
-      k_reduce<<<nl, 256, 0, c->stream>>>(r);
+      k_reduce<<<dim3(rtiles, nl), 256, 0, c->stream>>>(r);
     }
     KLU_TRY(check_launch("k_reduce"));
     if (tool == KLU_BEST_PATH2) {
