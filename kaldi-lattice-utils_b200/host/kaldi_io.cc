@@ -929,10 +929,6 @@ template <typename T>
 void WriteRaw(std::ostream& os, T v) {
   os.write(reinterpret_cast<const char*>(&v), sizeof(T));
 }
-void WriteFstString(std::ostream& os, const std::string& s) {
-  WriteRaw<int32_t>(os, (int32_t)s.size());
-  os.write(s.data(), (std::streamsize)s.size());
-}
 }  // namespace
 
 void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat) {
@@ -958,36 +954,51 @@ void WriteCompactLattice(std::ostream& os, bool binary, const CompactLat& lat) {
     os << '\n';
     return;
   }
-  os.put('\0');  // Kaldi's binary-mode marker (CompactLatticeHolder::Write -> InitKaldiOutputStream) [ext]
-  os.put('B');
-  WriteRaw<int32_t>(os, 2125659606);
-  WriteFstString(os, "vector");
-  WriteFstString(os, "compactlattice44");
-  WriteRaw<int32_t>(os, 2);                  // file version
-  WriteRaw<int32_t>(os, 0);                  // flags: no symbol tables
-  WriteRaw<uint64_t>(os, 0x3ULL);            // kExpanded | kMutable, everything else unknown
-  WriteRaw<int64_t>(os, lat.nstates ? 0 : -1);
-  WriteRaw<int64_t>(os, lat.nstates);
-  WriteRaw<int64_t>(os, 0);                  // arc count: left at zero by OpenFst's VectorFst writer
+  // The entry is laid out in memory and written with one call ("\0B" = Kaldi's binary-mode
+  // marker, CompactLatticeHolder::Write -> InitKaldiOutputStream [ext]; then OpenFst's
+  // FstHeader and VectorFst body).
+  size_t bytes = 2 + 4 + (4 + 6) + (4 + 16) + 4 + 4 + 8 + 3 * 8 + (size_t)lat.nstates * 20 + na * 24;
+  for (int32_t s = 0; s < lat.nstates; ++s) bytes += 4 * lat.fin_tids[s].size();
+  for (size_t e = 0; e < na; ++e) bytes += 4 * lat.tids[e].size();
+  std::string buf(bytes, '\0');
+  char* q = &buf[0];
+  auto put = [&q](const void* v, size_t n) {
+    memcpy(q, v, n);
+    q += n;
+  };
+  auto put32 = [&put](int32_t v) { put(&v, 4); };
+  auto put64 = [&put](int64_t v) { put(&v, 8); };
+  auto putf = [&put](float v) { put(&v, 4); };
+  put("\0B", 2);
+  put32(2125659606);
+  put32(6), put("vector", 6);
+  put32(16), put("compactlattice44", 16);
+  put32(2);                      // file version
+  put32(0);                      // flags: no symbol tables
+  put64(0x3LL);                  // kExpanded | kMutable, everything else unknown
+  put64(lat.nstates ? 0 : -1);   // start state
+  put64(lat.nstates);
+  put64(0);                      // arc count: left at zero by OpenFst's VectorFst writer
   size_t e = 0;
   for (int32_t s = 0; s < lat.nstates; ++s) {
-    WriteRaw<float>(os, lat.fin_graph[s]);
-    WriteRaw<float>(os, lat.fin_acoustic[s]);
-    WriteRaw<int32_t>(os, (int32_t)lat.fin_tids[s].size());
-    for (int32_t t : lat.fin_tids[s]) WriteRaw<int32_t>(os, t);
+    putf(lat.fin_graph[s]);
+    putf(lat.fin_acoustic[s]);
+    put32((int32_t)lat.fin_tids[s].size());
+    put(lat.fin_tids[s].data(), 4 * lat.fin_tids[s].size());
     size_t e1 = e;
     while (e1 < na && lat.src[e1] == s) ++e1;
-    WriteRaw<int64_t>(os, (int64_t)(e1 - e));
+    put64((int64_t)(e1 - e));
     for (; e < e1; ++e) {
-      WriteRaw<int32_t>(os, lat.label[e]);
-      WriteRaw<int32_t>(os, lat.label[e]);
-      WriteRaw<float>(os, lat.graph[e]);
-      WriteRaw<float>(os, lat.acoustic[e]);
-      WriteRaw<int32_t>(os, (int32_t)lat.tids[e].size());
-      for (int32_t t : lat.tids[e]) WriteRaw<int32_t>(os, t);
-      WriteRaw<int32_t>(os, lat.dst[e]);
+      put32(lat.label[e]);
+      put32(lat.label[e]);
+      putf(lat.graph[e]);
+      putf(lat.acoustic[e]);
+      put32((int32_t)lat.tids[e].size());
+      put(lat.tids[e].data(), 4 * lat.tids[e].size());
+      put32(lat.dst[e]);
     }
   }
+  os.write(buf.data(), (std::streamsize)(q - buf.data()));
 }
 
 // ------------------------------------------------------------------- tables ---
