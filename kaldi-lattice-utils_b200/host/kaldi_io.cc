@@ -378,10 +378,10 @@ namespace {
 struct RawArc {
   int32_t src, dst, ilabel, olabel;
   float g, a;
-  std::vector<int32_t> tids;
+  TidString tids;
 };
 
-void ParseWeight(const std::string& tok, bool compact, float* g, float* a, std::vector<int32_t>* tids) {
+void ParseWeight(const std::string& tok, bool compact, float* g, float* a, TidString* tids) {
   // "g,a" or "g,a,t1_t2_..."; empty fields mean 0
   *g = 0.0f;
   *a = 0.0f;
@@ -422,7 +422,7 @@ void ParseWeight(const std::string& tok, bool compact, float* g, float* a, std::
 
 struct RawLat {
   std::vector<RawArc> arcs;  // any order
-  std::map<int32_t, std::tuple<float, float, std::vector<int32_t> > > finals;
+  std::map<int32_t, std::tuple<float, float, TidString> > finals;
   int32_t nstates = 0;
   int32_t start = -1;
   bool compact = true;
@@ -468,7 +468,7 @@ void FactorLattice(RawLat* lat) {
     a.src = newid[a.src];
     a.dst = newid[a.dst];
   }
-  std::map<int32_t, std::tuple<float, float, std::vector<int32_t> > > fin;
+  std::map<int32_t, std::tuple<float, float, TidString> > fin;
   for (auto& kv : lat->finals) fin[newid[kv.first]] = kv.second;
   lat->finals.swap(fin);
   lat->arcs.swap(out);
@@ -488,7 +488,7 @@ void Finish(RawLat* raw, CompactLat* lat) {
       a.src = sw(a.src);
       a.dst = sw(a.dst);
     }
-    std::map<int32_t, std::tuple<float, float, std::vector<int32_t> > > fin;
+    std::map<int32_t, std::tuple<float, float, TidString> > fin;
     for (auto& kv : raw->finals) fin[sw(kv.first)] = kv.second;
     raw->finals.swap(fin);
   }
@@ -516,7 +516,7 @@ void Finish(RawLat* raw, CompactLat* lat) {
   lat->fin_graph.assign(n, inf);
   lat->fin_acoustic.assign(n, inf);
   lat->fin_dur.assign(n, 0);
-  lat->fin_tids.assign(n, std::vector<int32_t>());
+  lat->fin_tids.assign(n, TidString());
   for (auto& kv : raw->finals) {
     lat->fin_graph[kv.first] = std::get<0>(kv.second);
     lat->fin_acoustic[kv.first] = std::get<1>(kv.second);
@@ -543,7 +543,7 @@ void ReadText(std::istream& is, CompactLat* lat) {
     if (tok.size() <= 2) {  // final state
       const int32_t s = atoi(tok[0].c_str());
       float g = 0, w = 0;
-      std::vector<int32_t> tids;
+      TidString tids;
       if (tok.size() == 2) ParseWeight(tok[1], true, &g, &w, &tids);
       raw.finals[s] = std::make_tuple(g, w, tids);
       maxs = std::max(maxs, s);
@@ -571,7 +571,7 @@ void ReadText(std::istream& is, CompactLat* lat) {
       arc.ilabel = atoi(tok[2].c_str());
       arc.olabel = atoi(tok[3].c_str());
       arc.g = arc.a = 0.0f;
-      std::vector<int32_t> dummy;
+      TidString dummy;
       if (tok.size() == 5) ParseWeight(tok[4], false, &arc.g, &arc.a, &dummy);
     }
     if (raw.start < 0) raw.start = arc.src;
@@ -656,7 +656,7 @@ bool ReadBinaryCompactMem(MemBuf* mb, int64_t nstates, int64_t narcs, bool keep_
   lat->fin_graph.assign(n, inf);
   lat->fin_acoustic.assign(n, inf);
   lat->fin_dur.assign(n, 0);
-  if (keep_tids) lat->fin_tids.assign(n, std::vector<int32_t>());
+  if (keep_tids) lat->fin_tids.assign(n, TidString());
   lat->src.resize(na_total);
   lat->dst.resize(na_total);
   lat->label.resize(na_total);
@@ -734,7 +734,7 @@ void ReadBinaryCompactFast(std::istream& is, int64_t nstates, int64_t narcs_hint
   lat->fin_graph.assign(n, inf);
   lat->fin_acoustic.assign(n, inf);
   lat->fin_dur.assign(n, 0);
-  if (keep_tids) lat->fin_tids.assign(n, std::vector<int32_t>());
+  if (keep_tids) lat->fin_tids.assign(n, TidString());
   if (narcs_hint > 0 && narcs_hint < ((int64_t)1 << 31)) {
     const size_t r = (size_t)narcs_hint;
     lat->src.reserve(r);
@@ -808,7 +808,7 @@ void ReadBinary(std::istream& is, CompactLat* lat, bool keep_tids) {
   else KIO_ERR("Unsupported arc type " << arctype << " (expected compactlattice44 or lattice4)");
   raw.nstates = (int32_t)nstates;
   raw.start = (int32_t)start;
-  auto read_weight = [&](float* g, float* a, std::vector<int32_t>* tids) {
+  auto read_weight = [&](float* g, float* a, TidString* tids) {
     *g = ReadRaw<float>(is);
     *a = ReadRaw<float>(is);
     tids->clear();
@@ -820,7 +820,7 @@ void ReadBinary(std::istream& is, CompactLat* lat, bool keep_tids) {
   };
   for (int64_t s = 0; s < nstates; ++s) {
     float g, a;
-    std::vector<int32_t> tids;
+    TidString tids;
     read_weight(&g, &a, &tids);
     if (!(std::isinf(g) && std::isinf(a))) raw.finals[(int32_t)s] = std::make_tuple(g, a, tids);
     const int64_t na = ReadRaw<int64_t>(is);
@@ -918,7 +918,7 @@ void TopSortIfNeeded(CompactLat* lat) {
 }
 
 namespace {
-void WriteTextWeight(std::ostream& os, float g, float a, const std::vector<int32_t>& tids) {
+void WriteTextWeight(std::ostream& os, float g, float a, const TidString& tids) {
   WriteKaldiFloat(os, g);
   os << ",";
   WriteKaldiFloat(os, a);

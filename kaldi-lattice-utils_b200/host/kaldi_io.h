@@ -15,6 +15,7 @@
 #define KLU_KALDI_IO_H_
 
 #include <stdint.h>
+#include <string.h>
 #include <stdio.h>
 
 #include <cmath>
@@ -95,16 +96,112 @@ class ParseOptions {
 bool SplitStringToIntegers(const std::string& full, const char* delim, bool omit_empty, std::vector<int32_t>* out);
 
 // ------------------------------------------------------------------ lattice ---
+// A transition-id string (the "string" half of a CompactLatticeWeight): one per arc and
+// per final state, almost always a handful of ids.  Up to six live inside the object; a
+// std::vector here meant one heap allocation per arc when lattices are read to be written
+// back (four times the parse time of everything else together).
+class TidString {
+ public:
+  TidString() {}
+  TidString(const TidString& o) { CopyFrom(o); }
+  TidString(TidString&& o) noexcept { MoveFrom(&o); }
+  TidString(const std::vector<int32_t>& v) { Assign(v.data(), v.size()); }
+  TidString& operator=(const TidString& o) {
+    if (this != &o) {
+      Release();
+      CopyFrom(o);
+    }
+    return *this;
+  }
+  TidString& operator=(TidString&& o) noexcept {
+    if (this != &o) {
+      Release();
+      MoveFrom(&o);
+    }
+    return *this;
+  }
+  ~TidString() { Release(); }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  int32_t* data() { return cap_ > kInline ? heap_ : inl_; }
+  const int32_t* data() const { return cap_ > kInline ? heap_ : inl_; }
+  int32_t& operator[](size_t i) { return data()[i]; }
+  int32_t operator[](size_t i) const { return data()[i]; }
+  const int32_t* begin() const { return data(); }
+  const int32_t* end() const { return data() + n_; }
+  void clear() { n_ = 0; }
+  void resize(size_t n) {
+    Reserve(n);
+    if (n > n_) memset(data() + n_, 0, 4 * (n - n_));
+    n_ = (uint32_t)n;
+  }
+  void assign(size_t n, int32_t v) {
+    Reserve(n);
+    n_ = (uint32_t)n;
+    for (size_t i = 0; i < n; ++i) data()[i] = v;
+  }
+  void push_back(int32_t v) {
+    if (n_ == cap_) Reserve(2 * (size_t)cap_);
+    data()[n_++] = v;
+  }
+  void swap(TidString& o) {
+    TidString t(std::move(o));
+    o = std::move(*this);
+    *this = std::move(t);
+  }
+  bool operator==(const TidString& o) const { return n_ == o.n_ && memcmp(data(), o.data(), 4 * (size_t)n_) == 0; }
+
+ private:
+  static constexpr uint32_t kInline = 6;
+  void Reserve(size_t n) {
+    if (n <= cap_) return;
+    int32_t* nb = new int32_t[n];
+    memcpy(nb, data(), 4 * (size_t)n_);
+    if (cap_ > kInline) delete[] heap_;
+    heap_ = nb;
+    cap_ = (uint32_t)n;
+  }
+  void Release() {
+    if (cap_ > kInline) delete[] heap_;
+    cap_ = kInline;
+    n_ = 0;
+  }
+  void Assign(const int32_t* p, size_t n) {
+    Reserve(n);
+    if (n) memcpy(data(), p, 4 * n);
+    n_ = (uint32_t)n;
+  }
+  void CopyFrom(const TidString& o) { Assign(o.data(), o.n_); }
+  void MoveFrom(TidString* o) {
+    if (o->cap_ > kInline) {
+      heap_ = o->heap_;
+      cap_ = o->cap_;
+      n_ = o->n_;
+      o->cap_ = kInline;
+      o->n_ = 0;
+    } else {
+      memcpy(inl_, o->inl_, sizeof(inl_));
+      n_ = o->n_;
+      o->n_ = 0;
+    }
+  }
+  uint32_t n_ = 0, cap_ = kInline;
+  union {
+    int32_t inl_[kInline];
+    int32_t* heap_;
+  };
+};
+
 struct CompactLat {
   std::string key;
   int32_t nstates = 0;
   // arcs grouped by ascending src (stored order inside a state)
   std::vector<int32_t> src, dst, label, dur;
   std::vector<float> graph, acoustic;
-  std::vector<std::vector<int32_t> > tids;  // transition-id strings (kept for lattice output)
+  std::vector<TidString> tids;  // transition-id strings (kept for lattice output)
   std::vector<float> fin_graph, fin_acoustic;  // +inf = not final
   std::vector<int32_t> fin_dur;
-  std::vector<std::vector<int32_t> > fin_tids;
+  std::vector<TidString> fin_tids;
 };
 
 // Reads one table entry body (after "key ") from `is`: text or binary.

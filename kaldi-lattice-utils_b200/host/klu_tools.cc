@@ -413,7 +413,7 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
     out.fin_graph.assign(nstates, inf);
     out.fin_acoustic.assign(nstates, inf);
     out.fin_dur.assign(nstates, 0);
-    out.fin_tids.assign(nstates, std::vector<int32_t>());
+    out.fin_tids.assign(nstates, TidString());
     for (int32_t s = 0; s < in.nstates; ++s) {
       const int32_t m = smap[s0 + s];
       if (m < 0) continue;
