@@ -48,6 +48,18 @@ def test_invalid_option_is_an_error():
     assert r.returncode in (255, 1) and b"Invalid option" in r.stderr
 
 
+def test_tools_fail_loudly_without_a_gpu():
+    """No CPU fallback in the product path: on a box without a usable CUDA device the tools
+    stop with the reference's error exit code and say why."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = run("lattice-word-index-position", "ark:" + os.path.join(GOLD, "lattice.ark.txt"), "ark,t:-")
+    assert r.returncode == 255 and b"GPU engine" in r.stderr and r.stdout == b""
+    r = run("lattice-char-index-position", "1", "ark:" + os.path.join(GOLD, "lattice.char.ark.txt"), "ark,t:-")
+    assert r.returncode == 1 and b"GPU engine" in r.stderr and r.stdout == b""
+
+
 # ------------------------------------------------------------------ GPU ---------
 WORD = "ark:" + os.path.join(GOLD, "lattice.ark.txt")
 CHAR = "ark:" + os.path.join(GOLD, "lattice.char.ark.txt")
