@@ -97,6 +97,33 @@ def test_oracle_vs_bruteforce(klu, ora, seed):
         assert max(abs(got[k] - bf[k]) for k in got) < 1e-4
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_position_post_and_length_dist_vs_bruteforce(klu, ora, seed):
+    """The SURVEY 8f tools have no golden in the reference: their restatements are checked
+    against the all-paths enumeration.  Per (position, word) the posterior is the position
+    tool's; the mass of transcripts with at least p words is the sum over the words at
+    position p, and P(length = n) is the difference of two consecutive such masses."""
+    import math
+    batch = klu.synth_batch("tiny", 3, seed=300 + seed)
+    for lat in batch.lattices():
+        bp = ora.brute(ora.BRUTE_POSITION, lat)
+        pp = ora.position_post(lat)
+        got = {(w, k + 1): v for k, row in enumerate(pp) for w, v in row}
+        assert set(got) == {(w, p) for w, p, _ in bp}
+        # float32 rows, costs added in float (latbin/lattice-to-word-position-post.cc:104)
+        assert max(abs(got[(w, p)] - bp[(w, p, 0)]) for w, p, _ in bp) < 1e-4
+        for row in pp:  # each position's rows ordered by posterior
+            assert all(a[1] >= b[1] for a, b in zip(row[:-1], row[1:]))
+        at_least = {}
+        for (w, p, _), v in bp.items():
+            at_least[p] = at_least.get(p, 0.0) + math.exp(v)
+        ld = dict(ora.length_dist(lat))
+        for n, lp in ld.items():
+            want = (at_least.get(n, 0.0) if n > 0 else 1.0) - at_least.get(n + 1, 0.0)
+            assert abs(math.exp(lp) - want) < 1e-5, (n, lp, want)
+        assert abs(sum(math.exp(v) for v in ld.values()) - 1.0) < 1e-5
+
+
 def test_oracle_flags_consistency(klu, ora):
     # --acoustic-scale / --graph-scale / --insertion-penalty: equal to running the
     # default tool on a lattice whose float weights were transformed the way
