@@ -14,6 +14,12 @@ using namespace kio;
 
 int main(int argc, char** argv) {
   try {
+    if (argc == 2 && strcmp(argv[1], "--format-selftest") == 0) {  // tests/test_io.py
+      const std::string diff = FormatSelfTest(2000000);
+      if (!diff.empty()) KIO_ERR("text formatting differs: " << diff);
+      KIO_LOG("Text formatting identical to iostream / printf on 6000000 values.");
+      return 0;
+    }
     bool sequential = false;
     int a = 1;
     if (a < argc && strcmp(argv[a], "--sequential") == 0) {

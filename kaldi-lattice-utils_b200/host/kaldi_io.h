@@ -322,6 +322,7 @@ class TableWriter {  // archive writer: "key " + payload
 
 // Kaldi basic types
 void WriteKaldiFloat(std::ostream& os, double v);          // text: precision-7 general format
+std::string FormatSelfTest(size_t n);  // text formatters vs iostream / printf; "" = identical
 void WriteBasicInt32(std::ostream& os, bool binary, int32_t v);
 void WriteBasicFloat(std::ostream& os, bool binary, float v);
 void WriteBasicDouble(std::ostream& os, bool binary, double v);

@@ -142,7 +142,7 @@ struct ToolState {
 };
 
 [[maybe_unused]] void WriteTupleSep(std::ostream& os, bool binary, size_t i, size_t n) {
-  if (!binary && i + 1 < n) os << "; ";
+  if (!binary && i + 1 < n) os.rdbuf()->sputn("; ", 2);
 }
 
 // Everything klu_fetch_* returns for one batch (which fields are used depends on the tool).

@@ -111,3 +111,11 @@ def test_truncated_archive_is_an_error(tmp_path, mode):
     open(cut, "wb").write(d[:len(d) - 1000])
     r = copy(*mode, "ark:" + cut, "ark:" + str(tmp_path / "out.ark"))
     assert r.returncode == 1 and b"ERROR" in r.stderr
+
+
+def test_text_field_formatting_matches_iostream_and_printf():
+    """Text tables are formatted with std::to_chars; the binary checks itself against
+    `os << int` / printf("%.7g") on six million values (every exponent, subnormals,
+    infinities, NaN, typical log-posteriors)."""
+    r = subprocess.run([COPY, "--format-selftest"], capture_output=True)
+    assert r.returncode == 0 and b"identical" in r.stderr, r.stderr.decode()
