@@ -309,6 +309,10 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   KLU_CUDA(cudaSetDevice(c->device));
   c->loaded = false;
   c->last_tool = -1;
+  if (lats->num_lattices > 65535) {  // lattices are indexed with gridDim.y
+    set_error("klu_load: more than 65535 lattices in one batch; split it");
+    return 1;
+  }
   c->h_frame_res_off.assign(1, 0);
   c->fr_items = 0;
   klu_lattices with_src;

@@ -1236,7 +1236,7 @@ bool ScanEntry(MemBuf* mb, EntrySpan* sp) {
 }
 }  // namespace
 
-bool SequentialCompactLatticeReader::ReadBlock(int64_t max_arcs, std::vector<CompactLat>* out) {
+bool SequentialCompactLatticeReader::ReadBlock(int64_t max_arcs, std::vector<CompactLat>* out, size_t max_lattices) {
   out->clear();
   if (done_ || spec_.is_scp) return false;
   MemBuf* mb = dynamic_cast<MemBuf*>(in_->Stream().rdbuf());
@@ -1277,9 +1277,11 @@ bool SequentialCompactLatticeReader::ReadBlock(int64_t max_arcs, std::vector<Com
   };
   std::vector<std::thread> helpers;
   for (int t = 1, n = IoThreads(); t < n; ++t) helpers.emplace_back(parse);
-  while (arcs < max_arcs) {
+  size_t found = 1;  // the current entry
+  while (arcs < max_arcs && found < max_lattices) {
     EntrySpan sp;
     if (!ScanEntry(mb, &sp)) break;
+    ++found;
     arcs += sp.narcs;
     {
       std::lock_guard<std::mutex> lk(mu);

@@ -289,10 +289,10 @@ class SequentialCompactLatticeReader {
   // Block mode, for archives held in memory (memory-mapped files, collected pipes): moves
   // the current entry and the following ones into `out` until they hold `max_arcs` arcs
   // (the entry that crosses the mark included, as a sequential reader filling a batch
-  // would), and leaves the reader on the entry after them.  The binary entries are located
+  // would) or number `max_lattices`, and leaves the reader on the entry after them.  The binary entries are located
   // by walking their length fields and parsed on several threads.  False, with nothing
   // consumed, when the archive is not a memory block (or Done()).
-  bool ReadBlock(int64_t max_arcs, std::vector<CompactLat>* out);
+  bool ReadBlock(int64_t max_arcs, std::vector<CompactLat>* out, size_t max_lattices = (size_t)-1);
 
  private:
   void ReadOne();

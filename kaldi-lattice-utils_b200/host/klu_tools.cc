@@ -50,6 +50,9 @@ namespace {
     if ((call) != 0) KIO_ERR("GPU engine: " << klu_last_error()); \
   } while (0)
 
+// A device batch holds at most this many lattices (the kernels index lattices with gridDim.y).
+constexpr size_t kMaxBatchLattices = 65535;
+
 struct Batch {
   std::vector<CompactLat> lats;
   std::vector<int64_t> state_off{0}, arc_off{0};
@@ -801,13 +804,13 @@ int main(int argc, char* argv[]) {
       SequentialCompactLatticeReader reader(lattice_rspecifier, keep);
       std::vector<CompactLat> block;
       while (ok && !reader.Done()) {
-        if (reader.ReadBlock(batch_arcs - batch.arcs(), &block)) {  // in-memory archive: parsed in parallel
-          batch.AddBlock(&block, keep);
+        if (reader.ReadBlock(batch_arcs - batch.arcs(), &block, kMaxBatchLattices - batch.lats.size())) {
+          batch.AddBlock(&block, keep);  // in-memory archive: parsed in parallel
         } else {
           batch.Add(std::move(reader.Value()), keep);
           reader.Next();
         }
-        if (batch.arcs() >= batch_arcs) {
+        if (batch.arcs() >= batch_arcs || batch.lats.size() >= kMaxBatchLattices) {
           const auto t1 = std::chrono::steady_clock::now();
           st.sec_read += std::chrono::duration<double>(t1 - t_read).count();
           ok = pipe.Submit(std::move(batch));
