@@ -63,7 +63,7 @@ enum klu_tool {
 /* A batch of lattices as concatenated SoA arrays.  state_off/arc_off have
  * num_lattices+1 entries; arc_src/arc_dst are lattice-LOCAL state ids. */
 typedef struct klu_lattices {
-  int32_t num_lattices;  /* at most 65535 per batch (klu_load refuses more: split the batch) */
+  int32_t num_lattices;
   const int64_t* state_off;
   const int64_t* arc_off;
   const int32_t* arc_src;

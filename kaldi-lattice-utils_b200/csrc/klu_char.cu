@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(128) k_char_fwd(CharArgs a) {
 // of -cost + beta[y])  (what RmEpsilon folds into the final weight, fstext-utils2.h:558-585)
 __global__ void __launch_bounds__(256) k_char_exit(CharArgs a) {
   const BatchView& b = a.b;
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = b.s_off[l], ns = b.s_off[l + 1] - s0;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns * a.NG; t += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < ns * a.NG; t += gridDim.y * blockDim.x) {
     const int s = s0 + t / a.NG, g = t % a.NG;
     double e = neg_inf();
     {
@@ -303,9 +303,9 @@ __device__ __forceinline__ unsigned long long frame_tag(const CharArgs& a, int x
 // depth 0: candidates per out-order arc = cells of the source whose group differs
 __global__ void __launch_bounds__(256) k_char_count0(CharArgs a, Frontier f) {
   const BatchView& b = a.b;
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int e0 = b.e_off[l], e1 = b.e_off[l + 1];
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
     const int4 r = b.out_rec[e];
     const int u = b.out_src[e];
     const int g = group_of(a, r.w);
@@ -322,10 +322,10 @@ __global__ void __launch_bounds__(256) k_char_count0(CharArgs a, Frontier f) {
 
 __global__ void __launch_bounds__(256) k_char_emit0(CharArgs a, Frontier f) {
   const BatchView& b = a.b;
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int e0 = b.e_off[l], e1 = b.e_off[l + 1];
   const int64_t base = f.cbase[l];
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
     if (f.cand_cnt[e] == 0) continue;
     const int4 r = b.out_rec[e];
     const int u = b.out_src[e];
@@ -361,10 +361,10 @@ __global__ void __launch_bounds__(256) k_char_emit0(CharArgs a, Frontier f) {
 // node scores of the current depth: the first item of every node folds the node's
 // items (they are sorted by state) with their exit weights
 __global__ void __launch_bounds__(256) k_char_accum(CharArgs a, Frontier f) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = f.icnt[l];
   const int64_t base = f.ibase[l];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const int node = f.it_node[base + i];
     if (i > 0 && f.it_node[base + i - 1] == node) continue;
     const int g = f.nd_grp[node];
@@ -393,10 +393,10 @@ __global__ void __launch_bounds__(256) k_char_accum(CharArgs a, Frontier f) {
 // expansion: candidates per item = same-group out arcs of its state
 __global__ void __launch_bounds__(256) k_char_count(CharArgs a, Frontier f) {
   const BatchView& b = a.b;
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = f.icnt[l];
   const int64_t base = f.ibase[l];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const int x = f.it_state[base + i];
     const int g = f.nd_grp[f.it_node[base + i]];
     int c = 0;
@@ -410,10 +410,10 @@ __global__ void __launch_bounds__(256) k_char_count(CharArgs a, Frontier f) {
 
 __global__ void __launch_bounds__(256) k_char_expand(CharArgs a, Frontier f) {
   const BatchView& b = a.b;
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = f.icnt[l];
   const int64_t base = f.ibase[l], cb = f.cbase[l];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     if (f.cand_cnt[base + i] == 0) continue;
     const int x = f.it_state[base + i];
     const int node = f.it_node[base + i];
@@ -445,11 +445,11 @@ __global__ void __launch_bounds__(256) k_char_expand(CharArgs a, Frontier f) {
 // segment mode, between the two stable sorts: candidates are ordered by destination
 // state; give them their main key (always in buffer A) for the second sort
 __global__ void __launch_bounds__(256) k_char_rekey(Frontier f, unsigned long long* key_a, unsigned int* val_a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = f.ccnt[l];
   const int64_t cb = f.cbase[l];
   const unsigned int* val = (f.where[l] ? f.val_b : f.val_a) + cb;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const unsigned int j = val[i];
     key_a[cb + i] = f.c_main[cb + j];
     val_a[cb + i] = j;
@@ -603,11 +603,11 @@ __global__ void __launch_bounds__(256) k_char_rowfill(RowArgs a) {
 
 // second sort key: descending log-probability
 __global__ void __launch_bounds__(256) k_char_rowkey(RowArgs a, int L) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = a.row_cnt[l];
   const int64_t base = a.row_base[l];
   const unsigned int* val = (a.where[l] ? a.val_b : a.val_a) + base;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const unsigned int node = val[i];
     const double logp = a.nd_total[node] - a.beta[a.s_off[l]];
     a.key[base + i] = ~ord_f64(logp + 0.0);
@@ -616,11 +616,11 @@ __global__ void __launch_bounds__(256) k_char_rowkey(RowArgs a, int L) {
 }
 
 __global__ void __launch_bounds__(256) k_char_select(RowArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = min(a.row_cnt[l], a.nbest);
   const int64_t base = a.row_base[l], ob = a.out_base[l];
   const unsigned int* val = (a.where[l] ? a.val_b : a.val_a) + base;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const int node = (int)val[i];
     a.o_node[ob + i] = node;
     a.o_pos[ob + i] = a.nd_cnt[node];
@@ -813,7 +813,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   KLU_TRY(check_launch("k_char_fwd"));
   {
     KLU_LAUNCH(c, "k_char_exit");
-    k_char_exit<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a);
+    k_char_exit<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_char_exit"));
 
@@ -863,7 +863,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
       f.cand_loc = cand_loc.as<int32_t>();
       {
         KLU_LAUNCH(c, "k_char_count0");
-        k_char_count0<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a, f);
+        k_char_count0<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, f);
       }
       KLU_TRY(check_launch("k_char_count0"));
       SegRange rg = {a.b.e_off, nullptr, nullptr};
@@ -875,12 +875,12 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
       f.cand_loc = cand_loc.as<int32_t>();
       {
         KLU_LAUNCH(c, "k_char_accum");
-        k_char_accum<<<dim3(64, L), 256, 0, c->stream>>>(a, f);
+        k_char_accum<<<dim3(L, 64), 256, 0, c->stream>>>(a, f);
       }
       KLU_TRY(check_launch("k_char_accum"));
       {
         KLU_LAUNCH(c, "k_char_count");
-        k_char_count<<<dim3(64, L), 256, 0, c->stream>>>(a, f);
+        k_char_count<<<dim3(L, 64), 256, 0, c->stream>>>(a, f);
       }
       KLU_TRY(check_launch("k_char_count"));
       SegRange rg = {nullptr, f.ibase, f.icnt};
@@ -942,10 +942,10 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
     f.node_pool_base = pool;
     if (depth == 0) {
       KLU_LAUNCH(c, "k_char_emit0");
-      k_char_emit0<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a, f);
+      k_char_emit0<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, f);
     } else {
       KLU_LAUNCH(c, "k_char_expand");
-      k_char_expand<<<dim3(64, L), 256, 0, c->stream>>>(a, f);
+      k_char_expand<<<dim3(L, 64), 256, 0, c->stream>>>(a, f);
     }
     KLU_TRY(check_launch("k_char_expand"));
     SegSortArgs ss;
@@ -973,7 +973,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
       for (int32_t l = 0; l < L; ++l) max_c = std::max<int64_t>(max_c, h_cnt[l]);
       {
         KLU_LAUNCH(c, "k_char_rekey");
-        k_char_rekey<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_c + 255) / 256, 64)), L), 256, 0,
+        k_char_rekey<<<dim3(L, (unsigned)std::max<int64_t>(1, std::min<int64_t>((max_c + 255) / 256, 64))), 256, 0,
                        c->stream>>>(f, ss.key_a, ss.val_a);
       }
       KLU_TRY(check_launch("k_char_rekey"));
@@ -1115,7 +1115,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   r.val = v2a.as<unsigned int>();
   {
     KLU_LAUNCH(c, "k_char_rowkey");
-    k_char_rowkey<<<dim3(row_tiles, L), 256, 0, c->stream>>>(r, L);
+    k_char_rowkey<<<dim3(L, row_tiles), 256, 0, c->stream>>>(r, L);
   }
   KLU_TRY(check_launch("k_char_rowkey"));
   ss.key_a = k2a.as<unsigned long long>();
@@ -1150,7 +1150,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   r.o_logp = c->d_res[4].as<double>();
   {
     KLU_LAUNCH(c, "k_char_select");
-    k_char_select<<<dim3(std::max(1, std::min((o->nbest + 255) / 256, 64)), L), 256, 0, c->stream>>>(r);
+    k_char_select<<<dim3(L, std::max(1, std::min((o->nbest + 255) / 256, 64))), 256, 0, c->stream>>>(r);
   }
   KLU_TRY(check_launch("k_char_select"));
   std::vector<int32_t> h_len(nsel);

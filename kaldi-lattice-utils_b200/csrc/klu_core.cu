@@ -261,9 +261,19 @@ int klu_create(int device, klu_ctx** out) {
   klu_ctx* c = new klu_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  KLU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  KLU_CUDA(cudaEventCreate(&c->ev0));
-  KLU_CUDA(cudaEventCreate(&c->ev1));
+  auto init = [&]() -> int {
+    KLU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    KLU_CUDA(cudaEventCreate(&c->ev0));
+    KLU_CUDA(cudaEventCreate(&c->ev1));
+    return 0;
+  };
+  if (init() != 0) {  // nothing of a half-made context is left behind
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 1;
+  }
   *out = c;
   return 0;
 }
@@ -309,10 +319,15 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   KLU_CUDA(cudaSetDevice(c->device));
   c->loaded = false;
   c->last_tool = -1;
-  if (lats->num_lattices > 65535) {  // lattices are indexed with gridDim.y
-    set_error("klu_load: more than 65535 lattices in one batch; split it");
+  if (lats->num_lattices < 0) {
+    set_error("klu_load: negative lattice count");
     return 1;
   }
+  for (int32_t l = 0; l < lats->num_lattices; ++l)  // negative sizes must not reach the kernels
+    if (lats->state_off[l + 1] < lats->state_off[l] || lats->arc_off[l + 1] < lats->arc_off[l]) {
+      set_error("klu_load: lattice " + std::to_string(l) + ": state_off / arc_off must be non-decreasing");
+      return 1;
+    }
   c->h_frame_res_off.assign(1, 0);
   c->fr_items = 0;
   klu_lattices with_src;

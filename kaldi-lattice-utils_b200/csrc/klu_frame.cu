@@ -77,12 +77,12 @@ __device__ __forceinline__ double arc_value(const FrameArgs& a, int j) {  // j: 
   return __dadd_rn(__dadd_rn(a.alpha[t.x], a.beta[t.y]), -rec_cost(r, a.cp));
 }
 
-// grid (tiles, L): the posterior of every word arc, once (cross-check path KLU_FRAME_UNFUSED)
+// grid (L, tiles): the posterior of every word arc, once (cross-check path KLU_FRAME_UNFUSED)
 __global__ void __launch_bounds__(256) k_arc_post(FrameArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const double total = a.total[l];
-  for (int j = e0 + blockIdx.x * blockDim.x + threadIdx.x; j < e1; j += gridDim.x * blockDim.x)
+  for (int j = e0 + blockIdx.y * blockDim.x + threadIdx.x; j < e1; j += gridDim.y * blockDim.x)
     a.parc[j] = __ldg(a.tlabel + j) != 0 ? fast_exp(arc_value(a, j) - total) : 0.0;
 }
 
@@ -544,22 +544,22 @@ struct GroupArgs {
   int32_t* tlabel;
 };
 
-// grid (tiles, L): sort input for the time order: key = start frame, val = out-order arc (lattice-local)
+// grid (L, tiles): sort input for the time order: key = start frame, val = out-order arc (lattice-local)
 __global__ void __launch_bounds__(256) k_fg_time_keys(GroupArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
     a.key[e] = (unsigned long long)max(a.b.time[a.b.out_src[e]], 0);
     a.val[e] = (unsigned int)(e - e0);
   }
 }
 
-// grid (tiles, L): the time-ordered arc copy and the inverse permutation
+// grid (L, tiles): the time-ordered arc copy and the inverse permutation
 __global__ void __launch_bounds__(256) k_fg_time_copy(GroupArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const unsigned int* val = (a.where[l] ? a.val_b : a.val_a) + e0;
-  for (int j = e0 + blockIdx.x * blockDim.x + threadIdx.x; j < e1; j += gridDim.x * blockDim.x) {
+  for (int j = e0 + blockIdx.y * blockDim.x + threadIdx.x; j < e1; j += gridDim.y * blockDim.x) {
     const int e = e0 + (int)val[j - e0];
     const int4 r = a.b.out_rec[e];
     a.tarc[j] = make_int4(a.b.out_src[e], r.x, r.y, r.z);
@@ -869,7 +869,7 @@ int build_frame_groups(klu_ctx* c) {
       if ((rc = small_h2d(c, seg.as<char>() + 8 * (size_t)(L + 1), arc_cnt.data(), 4 * (size_t)L))) break;
       {
         KLU_LAUNCH(c, "k_fg_time_keys");
-        k_fg_time_keys<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
+        k_fg_time_keys<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a);
       }
       rc = check_launch("k_fg_time_keys");
       if (!rc) {
@@ -891,7 +891,7 @@ int build_frame_groups(klu_ctx* c) {
       }
       if (!rc) {
         KLU_LAUNCH(c, "k_fg_time_copy");
-        k_fg_time_copy<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
+        k_fg_time_copy<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a);
         rc = check_launch("k_fg_time_copy");
       }
       cudaStreamSynchronize(c->stream);  // arc_base / arc_cnt go out of scope
@@ -1014,7 +1014,7 @@ int run_frame_post(klu_ctx* c, const klu_opts* o) {
       for (int32_t l = 0; l < L; ++l) max_arcs = std::max(max_arcs, c->h_e_off[l + 1] - c->h_e_off[l]);
       const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
       KLU_LAUNCH(c, "k_arc_post");
-      k_arc_post<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
+      k_arc_post<<<dim3(L, tiles), 256, 0, c->stream>>>(a);
     }
     KLU_TRY(check_launch("k_arc_post"));
     {

@@ -59,12 +59,12 @@ struct GP {
 
 __device__ __forceinline__ int ld_cg_i32(const int32_t* p) { return __ldcg(p); }
 
-// grid (tiles, L): first arc of every state + layout validation
+// grid (L, tiles): first arc of every state + layout validation
 __global__ void __launch_bounds__(256) k_gp_first_arc(GP a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
   for (int s = t; s < ns; s += stride) {
     int lo = e0, hi = e1;  // first arc with src >= s
     while (lo < hi) {
@@ -85,13 +85,13 @@ __global__ void __launch_bounds__(256) k_gp_first_arc(GP a) {
   if (bad) atomicMax(&a.meta[l * M_STRIDE + M_ERR], bad);
 }
 
-// grid (tiles, L): source state of every arc from the per-state first-arc offsets (input
+// grid (L, tiles): source state of every arc from the per-state first-arc offsets (input
 // without arc_src)
 __global__ void __launch_bounds__(256) k_gp_expand_src(GP a, int32_t* src_out) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const int e_end = a.e_off[l + 1];
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+  for (int s = blockIdx.y * blockDim.x + threadIdx.x; s < ns; s += gridDim.y * blockDim.x) {
     const int f0 = a.first_arc[s0 + s];
     const int f1 = s + 1 < ns ? a.first_arc[s0 + s + 1] : e_end;
     for (int e = f0; e < f1; ++e) src_out[e] = s;
@@ -184,9 +184,9 @@ __global__ void __launch_bounds__(128) k_gp_levels(GP a, int* counter) {
 
 // sort keys of the states: (level, input id) -> stable sort on level
 __global__ void __launch_bounds__(256) k_gp_state_keys(GP a, unsigned long long* key, unsigned int* val) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+  for (int s = blockIdx.y * blockDim.x + threadIdx.x; s < ns; s += gridDim.y * blockDim.x) {
     key[s0 + s] = (unsigned long long)(unsigned int)a.level[s0 + s];
     val[s0 + s] = (unsigned int)s;
   }
@@ -196,13 +196,13 @@ __global__ void __launch_bounds__(256) k_gp_state_keys(GP a, unsigned long long*
 __global__ void __launch_bounds__(256) k_gp_state_perm(GP a, const unsigned long long* key_a,
                                                         const unsigned long long* key_b, const unsigned int* val_a,
                                                         const unsigned int* val_b, const unsigned char* where) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const unsigned long long* key = (where[l] ? key_b : key_a) + s0;
   const unsigned int* val = (where[l] ? val_b : val_a) + s0;
   int32_t* lv = a.lvl_start + a.lvl_off[l];
   const int nl = a.lvl_off[l + 1] - a.lvl_off[l] - 1;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < ns; n += gridDim.x * blockDim.x) {
+  for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < ns; n += gridDim.y * blockDim.x) {
     const int old = (int)val[n];
     const int lev = (int)key[n];
     const int go = s0 + old, gn = s0 + n;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_gp_state_perm(GP a, const unsigned long
     if (n == 0 || (int)key[n - 1] != lev) lv[lev] = gn;
     if (n == ns - 1) lv[nl] = s0 + ns;
   }
-  if (ns == 0 && blockIdx.x == 0 && threadIdx.x == 0) lv[0] = s0;
+  if (ns == 0 && blockIdx.y == 0 && threadIdx.x == 0) lv[0] = s0;
 }
 
 // One CTA per lattice: exclusive scan of per-state int32 counts.  MODE 0: out32 =
@@ -289,21 +289,21 @@ __global__ void __launch_bounds__(1024) k_gp_scan_tot(long long* tot, int L) {
 // lattice-local int64 offsets -> global: off[i] += base[l]; also the closing entry
 __global__ void __launch_bounds__(256) k_gp_add_base(int64_t* off, const int32_t* seg_off, const long long* base,
                                                      int L, int64_t* closing) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int i0 = seg_off[l], n = seg_off[l + 1] - i0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) off[i0 + i] += base[l];
-  if (l == L - 1 && blockIdx.x == 0 && threadIdx.x == 0) *closing = base[L];
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) off[i0 + i] += base[l];
+  if (l == L - 1 && blockIdx.y == 0 && threadIdx.x == 0) *closing = base[L];
 }
 
-// grid (tiles, L): arcs to source order + per-lattice capacities of the expansions
+// grid (L, tiles): arcs to source order + per-lattice capacities of the expansions
 __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* key, unsigned int* val) {
   __shared__ long long red[2][8];
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l];
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
   const int T = a.meta[l * M_STRIDE + M_FRAMES];
   long long cf = 0, cp = 0;
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
     const int go = s0 + a.src[e], gd = s0 + a.dst[e];
     const int n = a.old2new[go], d = a.old2new[gd];
     const int p = a.out_off[n] + (e - a.first_arc[go]);
@@ -342,16 +342,16 @@ __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* ke
   }
 }
 
-// grid (tiles, L): destination-ordered records from the sorted (dst, out position) pairs
+// grid (L, tiles): destination-ordered records from the sorted (dst, out position) pairs
 __global__ void __launch_bounds__(256) k_gp_in_build(GP a, const unsigned long long* key_a,
                                                      const unsigned long long* key_b, const unsigned int* val_a,
                                                      const unsigned int* val_b, const unsigned char* where) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const int e0 = a.e_off[l], na = a.e_off[l + 1] - e0;
   const unsigned long long* key = (where[l] ? key_b : key_a) + e0;
   const unsigned int* val = (where[l] ? val_b : val_a) + e0;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
   for (int q = t; q < na; q += stride) {
     const int p = e0 + (int)val[q];
     const int4 r = a.out_rec[p];
@@ -375,24 +375,24 @@ __global__ void __launch_bounds__(256) k_gp_in_build(GP a, const unsigned long l
 
 // band widths per packed state (for the band offset scan)
 __global__ void __launch_bounds__(256) k_gp_band_counts2(GP a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < ns; n += gridDim.x * blockDim.x) {
+  for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < ns; n += gridDim.y * blockDim.x) {
     const int go = s0 + a.orig[s0 + n];
     const int hi = a.bhi[go];
     a.counts[s0 + n] = hi >= 0 ? hi - a.blo[go] + 1 : 0;
   }
 }
 
-// grid (tiles, L): frame histogram (phase 0) / fill (phase 1) of the frame -> arc CSR
+// grid (L, tiles): frame histogram (phase 0) / fill (phase 1) of the frame -> arc CSR
 template <int PHASE>
 __global__ void __launch_bounds__(256) k_gp_frames(GP a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
   const int T = a.fr_base[l + 1] - a.fr_base[l] - 1;
   int32_t* cnt = a.fr_cnt + a.fr_base[l];
   const int64_t* fo = a.fr_off + a.fr_base[l];
-  for (int p = e0 + blockIdx.x * blockDim.x + threadIdx.x; p < e1; p += gridDim.x * blockDim.x) {
+  for (int p = e0 + blockIdx.y * blockDim.x + threadIdx.x; p < e1; p += gridDim.y * blockDim.x) {
     const int4 r = a.out_rec[p];
     if (r.w == 0) continue;
     const int fa = max(a.ptime[a.out_src[p]], 0), fb = min(a.ptime[r.x], T);
@@ -571,13 +571,13 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
     KLU_TRY(check_launch("k_gp_lat_scan(src)"));
     {
       KLU_LAUNCH(c, "k_gp_expand_src");
-      k_gp_expand_src<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a, sc[R_SRC].as<int32_t>());
+      k_gp_expand_src<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a, sc[R_SRC].as<int32_t>());
     }
     KLU_TRY(check_launch("k_gp_expand_src"));
   }
   {
     KLU_LAUNCH(c, "k_gp_first_arc");
-    k_gp_first_arc<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
+    k_gp_first_arc<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_gp_first_arc"));
   {
@@ -660,7 +660,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   unsigned int* val_b = sc[R_VALB].as<unsigned int>();
   {
     KLU_LAUNCH(c, "k_gp_state_keys");
-    k_gp_state_keys<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a, key_a, val_a);
+    k_gp_state_keys<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a, key_a, val_a);
   }
   KLU_TRY(check_launch("k_gp_state_keys"));
   SegSortArgs ss;
@@ -680,7 +680,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_seg_radix_sort(states)"));
   {
     KLU_LAUNCH(c, "k_gp_state_perm");
-    k_gp_state_perm<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a, key_a, key_b, val_a, val_b, where);
+    k_gp_state_perm<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a, key_a, key_b, val_a, val_b, where);
   }
   KLU_TRY(check_launch("k_gp_state_perm"));
   // out_off = e_off[l] + scan(out-degree in packed order)
@@ -692,7 +692,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   // ---- arcs: source order by block move, destination order by stable sort ----
   {
     KLU_LAUNCH(c, "k_gp_scatter");
-    k_gp_scatter<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a, key_a, val_a);
+    k_gp_scatter<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, key_a, val_a);
   }
   KLU_TRY(check_launch("k_gp_scatter"));
   ss.seg_base = seg64 + L + 1;
@@ -704,13 +704,13 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_seg_radix_sort(arcs)"));
   {
     KLU_LAUNCH(c, "k_gp_in_build");
-    k_gp_in_build<<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a, key_a, key_b, val_a, val_b, where);
+    k_gp_in_build<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, key_a, key_b, val_a, val_b, where);
   }
   KLU_TRY(check_launch("k_gp_in_build"));
   // ---- band offsets: per-lattice scan + lattice bases ----
   {
     KLU_LAUNCH(c, "k_gp_band_counts");
-    k_gp_band_counts2<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a);
+    k_gp_band_counts2<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_gp_band_counts"));
   {
@@ -725,7 +725,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_gp_scan_tot(band)"));
   {
     KLU_LAUNCH(c, "k_gp_add_base");
-    k_gp_add_base<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a.band_off, a.s_off, a.lat_tot, L, a.band_off + S);
+    k_gp_add_base<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a.band_off, a.s_off, a.lat_tot, L, a.band_off + S);
   }
   KLU_TRY(check_launch("k_gp_add_base(band)"));
   // ---- host round trip 2: band bases and expansion capacities ----
@@ -752,7 +752,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(small_h2d(c, a.lat_tot, fa_base.data(), 8 * (size_t)(L + 1)));
   {
     KLU_LAUNCH(c, "k_gp_frames");
-    k_gp_frames<0><<<dim3(arc_tiles, L), 256, 0, c->stream>>>(a);
+    k_gp_frames<0><<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_gp_frames(count)"));
   {
@@ -763,7 +763,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   KLU_TRY(check_launch("k_gp_lat_scan(frames)"));
   {
     KLU_LAUNCH(c, "k_gp_add_base");
-    k_gp_add_base<<<dim3(st_tiles, L), 256, 0, c->stream>>>(a.fr_off, a.fr_base, a.lat_tot, L,
+    k_gp_add_base<<<dim3(L, st_tiles), 256, 0, c->stream>>>(a.fr_off, a.fr_base, a.lat_tot, L,
                                                             a.fr_off + c->h_fr_base[L]);
   }
   KLU_TRY(check_launch("k_gp_add_base(frames)"));

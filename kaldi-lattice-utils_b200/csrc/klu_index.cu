@@ -133,12 +133,12 @@ __device__ __forceinline__ bool emit_arc_pruned(const IndexArgs& a, int l, int s
   return fb > __dadd_rn(a.best[l], a.beam);
 }
 
-// grid (tiles, lattices): one thread per out-order arc.
+// grid (lattices, tiles): one thread per out-order arc.
 __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
-  const int l = a.l0 + blockIdx.y;
+  const int l = a.l0 + blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int64_t base = a.ent_base[l];
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
     const int4 r = a.b.out_rec[e];
     const int s = a.b.out_src[e];
     const int off = a.arc_ent_off[e];
@@ -265,10 +265,10 @@ struct RunSum {
 };
 
 __global__ void __launch_bounds__(256) k_reduce_count(ReduceArgs a) {
-  const int l = a.l0 + blockIdx.y;
+  const int l = a.l0 + blockIdx.x;
   const int n = a.ent_cnt[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + a.ent_base[l];
-  for (int tile = blockIdx.x * 256; tile < n; tile += gridDim.x * 256) {
+  for (int tile = blockIdx.y * 256; tile < n; tile += gridDim.y * 256) {
     const int i = tile + threadIdx.x;
     bool head = false;
     if (i < n) {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   __shared__ unsigned long long s_key[256];
   __shared__ double s_val[256];
   __shared__ unsigned int s_aux[256];
-  const int l = a.l0 + blockIdx.y;
+  const int l = a.l0 + blockIdx.x;
   const int n = a.ent_cnt[l];
   const int64_t base = a.ent_base[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + base;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   const double total = a.total[l];
   const int e0 = a.b.e_off[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int tile = blockIdx.x * 256; tile < n; tile += gridDim.x * 256) {
+  for (int tile = blockIdx.y * 256; tile < n; tile += gridDim.y * 256) {
     const int i = tile + tid;
     unsigned long long k = a.drop_key;
     bool head = false;
@@ -481,12 +481,12 @@ struct OrderFixArgs {
 };
 
 __global__ void __launch_bounds__(256) k_order_fixup(OrderFixArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int n = a.seg_cnt[l];
   const int64_t base = a.seg_base[l];
   unsigned long long* K = (a.where[l] ? a.key_b : a.key_a) + base;
   unsigned int* V = (a.where[l] ? a.val_b : a.val_a) + base;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.y * blockDim.x) {
     const unsigned long long t = K[i] >> a.lo_bit;
     if ((i > 0 && (K[i - 1] >> a.lo_bit) == t) || (K[i + 1] >> a.lo_bit) != t) continue;  // not the head of a run
     int j = i + 1;
@@ -525,13 +525,13 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
-  const int l = a.l0 + blockIdx.y;
+  const int l = a.l0 + blockIdx.x;
   const int n = a.rcnt[l];
   const int64_t base = a.ent_base[l];
   const int64_t out = a.res_off[l];
   const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + base;
   const int e0 = a.b.e_off[l];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const unsigned int j = idx[i];
     const unsigned long long k = a.rkey[base + j];
     const double logp = a.rval[base + j];
@@ -882,7 +882,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
     {
       KLU_LAUNCH(c, "k_emit");
-      k_emit<<<dim3(tiles, nl), 256, 0, c->stream>>>(a);
+      k_emit<<<dim3(nl, tiles), 256, 0, c->stream>>>(a);
     }
     KLU_TRY(check_launch("k_emit"));
 
@@ -938,7 +938,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       r.tile_heads = c->d_tile_heads.as<int32_t>();
       {
         KLU_LAUNCH(c, "k_reduce_count");
-        k_reduce_count<<<dim3(rtiles, nl), 256, 0, c->stream>>>(r);
+        k_reduce_count<<<dim3(nl, rtiles), 256, 0, c->stream>>>(r);
       }
       KLU_TRY(check_launch("k_reduce_count"));
       {
@@ -947,7 +947,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       }
       KLU_TRY(check_launch("k_reduce_offsets"));
       KLU_LAUNCH(c, "k_reduce");
-      k_reduce<<<dim3(rtiles, nl), 256, 0, c->stream>>>(r);
+      k_reduce<<<dim3(nl, rtiles), 256, 0, c->stream>>>(r);
     }
     KLU_TRY(check_launch("k_reduce"));
     if (tool == KLU_BEST_PATH2) {
@@ -1028,7 +1028,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       f.lo_bit = s2.lo_bit;
       {
         KLU_LAUNCH(c, "k_order_fixup");
-        k_order_fixup<<<dim3(tiles, nl), 256, 0, c->stream>>>(f);
+        k_order_fixup<<<dim3(nl, tiles), 256, 0, c->stream>>>(f);
       }
       KLU_TRY(check_launch("k_order_fixup"));
     }
@@ -1071,7 +1071,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     g.vf = c->d_res[4].as<float>();
     {
       KLU_LAUNCH(c, "k_gather");
-      k_gather<<<dim3(tiles, nl), 256, 0, c->stream>>>(g);
+      k_gather<<<dim3(nl, tiles), 256, 0, c->stream>>>(g);
     }
     KLU_TRY(check_launch("k_gather"));
   }

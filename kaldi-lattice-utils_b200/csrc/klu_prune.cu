@@ -163,12 +163,12 @@ __global__ void __launch_bounds__(256) k_prune_search(PruneArgs a) {
 
 // keep flags in the caller's index space
 __global__ void __launch_bounds__(256) k_prune_mark(PruneArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.b.s_off[l], s1 = a.b.s_off[l + 1];
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const bool all = a.iters[l] == 0;
   const double cut = a.cutoff[l];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
   for (int e = e0 + t; e < e1; e += stride) a.arc_keep[e0 + a.b.out_orig[e]] = (all || !(a.fb[e] > cut)) ? 1 : 0;
   for (int s = s0 + t; s < s1; s += stride) a.state_keep[s0 + a.b.orig[s]] = (all || !(a.smin[s] > cut)) ? 1 : 0;
 }
@@ -224,13 +224,13 @@ __device__ __forceinline__ void out_weights(float g, float w, int label, const P
 }
 
 __global__ void __launch_bounds__(256) k_prune_emit(PruneArgs a) {
-  const int l = blockIdx.y;
+  const int l = blockIdx.x;
   const int s0 = a.b.s_off[l], s1 = a.b.s_off[l + 1];
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int64_t out = a.res_off[l];
   const bool all = a.iters[l] == 0;
   const double cut = a.cutoff[l];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
   for (int e = e0 + t; e < e1; e += stride) {
     const int o = a.b.out_orig[e];
     const int pos = a.arc_keep[e0 + o];
@@ -370,7 +370,7 @@ int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o) {
   const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
   {
     KLU_LAUNCH(c, "k_prune_mark");
-    k_prune_mark<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
+    k_prune_mark<<<dim3(L, tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_prune_mark"));
   {
@@ -385,7 +385,7 @@ int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o) {
   KLU_TRY(check_launch("k_scan_counts"));
   {
     KLU_LAUNCH(c, "k_prune_emit");
-    k_prune_emit<<<dim3(tiles, L), 256, 0, c->stream>>>(a);
+    k_prune_emit<<<dim3(L, tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_prune_emit"));
   // a lattice whose loop cannot terminate is an error (the reference hangs on it)

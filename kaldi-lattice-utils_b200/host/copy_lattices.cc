@@ -2,7 +2,10 @@
 // compact lattices) through this package's table I/O layer -- text <-> binary conversion,
 // and a GPU-free way to exercise the readers and writers.
 //
-//   klu-copy-lattices [--sequential] <lattice-rspecifier> <lattice-wspecifier>
+//   klu-copy-lattices [--sequential] [--no-tids] <lattice-rspecifier> <lattice-wspecifier>
+//
+// --no-tids reads the way every tool but lattice-prune-dyn-beam does (transition-id strings
+// dropped, only their lengths kept) and writes each string back as that many ids "1".
 //
 // Archives held in memory are read in blocks parsed on several threads
 // (SequentialCompactLatticeReader::ReadBlock); --sequential forces one entry at a time.
@@ -26,14 +29,25 @@ int main(int argc, char** argv) {
       sequential = true;
       ++a;
     }
+    bool keep_tids = true;
+    if (a < argc && strcmp(argv[a], "--no-tids") == 0) {
+      keep_tids = false;
+      ++a;
+    }
     if (argc - a != 2) {
-      std::cerr << "Usage: klu-copy-lattices [--sequential] <lattice-rspecifier> <lattice-wspecifier>\n";
+      std::cerr << "Usage: klu-copy-lattices [--sequential] [--no-tids] <lattice-rspecifier> <lattice-wspecifier>\n";
       return 1;
     }
-    SequentialCompactLatticeReader reader(argv[a]);
+    SequentialCompactLatticeReader reader(argv[a], keep_tids);
     TableWriter writer(argv[a + 1]);
     size_t n = 0;
-    auto put = [&](const CompactLat& lat) {
+    auto put = [&](CompactLat& lat) {
+      if (!keep_tids) {
+        lat.tids.assign(lat.src.size(), TidString());
+        lat.fin_tids.assign((size_t)lat.nstates, TidString());
+        for (size_t e = 0; e < lat.src.size(); ++e) lat.tids[e].assign((size_t)lat.dur[e], 1);
+        for (int32_t s = 0; s < lat.nstates; ++s) lat.fin_tids[s].assign((size_t)lat.fin_dur[s], 1);
+      }
       std::ostream& os = writer.Begin(lat.key);
       WriteCompactLattice(os, writer.binary(), lat);
       writer.End();
@@ -42,7 +56,7 @@ int main(int argc, char** argv) {
     std::vector<CompactLat> block;
     while (!reader.Done()) {
       if (!sequential && reader.ReadBlock((int64_t)4 << 20, &block)) {
-        for (const CompactLat& lat : block) put(lat);
+        for (CompactLat& lat : block) put(lat);
       } else {
         put(reader.Value());
         reader.Next();

@@ -381,15 +381,11 @@ Input::Input(const std::string& name_in) {
   if (name == "-" || name.empty()) {
     is_ = &std::cin;
   } else if (name.back() == '|') {
-    pipe_ = popen(name.substr(0, name.size() - 1).c_str(), "r");
+    pipe_cmd_ = name.substr(0, name.size() - 1);
+    pipe_ = popen(pipe_cmd_.c_str(), "r");
     if (!pipe_) KIO_ERR("Failed opening pipe for reading, command is: " << name);
-    char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof(buf), pipe_)) > 0) buffer_.append(buf, n);
-    pclose(pipe_);
-    pipe_ = nullptr;
-    membuf_.reset(new MemBuf(buffer_.data(), buffer_.size()));
-    owned_.reset(new std::istream(membuf_.get()));
+    pipe_sb_.reset(new StdioBuf(pipe_, false));  // streamed: block mode is off for pipes
+    owned_.reset(new std::istream(pipe_sb_.get()));
     is_ = owned_.get();
   } else {
     // "path:offset" (scp entries)
@@ -432,19 +428,88 @@ Input::Input(const std::string& name_in) {
   }
 }
 
+void Input::Close() {
+  if (!pipe_) return;
+  FILE* f = pipe_;
+  pipe_ = nullptr;
+  const int status = pclose(f);
+  if (status != 0) KIO_ERR("Pipe " << pipe_cmd_ << "| had nonzero return status " << status);
+}
+
 Input::~Input() {
+  if (pipe_) pclose(pipe_);
+  pipe_ = nullptr;
   owned_.reset();
   membuf_.reset();
   if (map_) munmap(map_, map_len_);
 }
 
-Output::Output(const std::string& name) {
+StdioBuf::StdioBuf(FILE* f, bool writing) : f_(f), writing_(writing), buf_(1 << 20) {
+  if (writing_) setp(buf_.data(), buf_.data() + buf_.size());
+  else setg(buf_.data(), buf_.data(), buf_.data());
+}
+
+StdioBuf::int_type StdioBuf::underflow() {
+  if (writing_) return traits_type::eof();
+  if (gptr() < egptr()) return traits_type::to_int_type(*gptr());
+  const size_t n = fread(buf_.data(), 1, buf_.size(), f_);
+  if (n == 0) return traits_type::eof();
+  setg(buf_.data(), buf_.data(), buf_.data() + n);
+  return traits_type::to_int_type(*gptr());
+}
+
+bool StdioBuf::FlushOut() {
+  const size_t n = (size_t)(pptr() - pbase());
+  if (n && fwrite(pbase(), 1, n, f_) != n) failed_ = true;
+  setp(buf_.data(), buf_.data() + buf_.size());
+  return !failed_;
+}
+
+StdioBuf::int_type StdioBuf::overflow(int_type c) {
+  if (!writing_ || !FlushOut()) return traits_type::eof();
+  if (!traits_type::eq_int_type(c, traits_type::eof())) {
+    *pptr() = traits_type::to_char_type(c);
+    pbump(1);
+  }
+  return traits_type::not_eof(c);
+}
+
+std::streamsize StdioBuf::xsputn(const char* s, std::streamsize n) {
+  if (!writing_) return 0;
+  if (n <= epptr() - pptr()) {
+    memcpy(pptr(), s, (size_t)n);
+    pbump((int)n);
+    return n;
+  }
+  if (!FlushOut()) return 0;
+  if ((size_t)n >= buf_.size()) {  // large blocks go straight through
+    if (fwrite(s, 1, (size_t)n, f_) != (size_t)n) {
+      failed_ = true;
+      return 0;
+    }
+    return n;
+  }
+  memcpy(pptr(), s, (size_t)n);
+  pbump((int)n);
+  return n;
+}
+
+int StdioBuf::sync() {
+  if (!writing_) return 0;
+  if (!FlushOut()) return -1;
+  if (fflush(f_) != 0) failed_ = true;
+  return failed_ ? -1 : 0;
+}
+
+Output::Output(const std::string& name) : name_(name) {
   if (name == "-" || name.empty()) {
     os_ = &std::cout;
   } else if (name[0] == '|') {
     pipe_ = popen(name.substr(1).c_str(), "w");
     if (!pipe_) KIO_ERR("Failed opening pipe for writing, command is: " << name);
-    os_ = &pipe_buf_;
+    pipe_sb_.reset(new StdioBuf(pipe_, true));  // streamed to the command as it is produced
+    owned_.reset(new std::ostream(pipe_sb_.get()));
+    os_ = owned_.get();
   } else {
     auto* f = new std::ofstream(name, std::ios::out | std::ios::binary);
     owned_.reset(f);
@@ -453,18 +518,29 @@ Output::Output(const std::string& name) {
   }
 }
 
+bool Output::Good() { return os_ && os_->good() && !(pipe_sb_ && pipe_sb_->failed()); }
+
 void Output::Close() {
+  if (closed_) return;
+  closed_ = true;
+  if (os_) os_->flush();
+  bool ok = Good();
+  int status = 0;
   if (pipe_) {
-    const std::string s = pipe_buf_.str();
-    fwrite(s.data(), 1, s.size(), pipe_);
-    pclose(pipe_);
+    FILE* f = pipe_;
     pipe_ = nullptr;
-  } else if (os_) {
-    os_->flush();
+    status = pclose(f);
   }
+  if (!ok) KIO_ERR("Error writing to " << (name_.empty() ? std::string("standard output") : name_));
+  if (status != 0) KIO_ERR("Pipe " << name_ << " had nonzero return status " << status);
 }
 
-Output::~Output() { Close(); }
+Output::~Output() {
+  try {
+    Close();
+  } catch (const std::exception&) {  // a destructor cannot raise; explicit Close() calls do
+  }
+}
 
 // ---------------------------------------------------------------- lattices ---
 namespace {
@@ -636,6 +712,7 @@ void ReadText(std::istream& is, CompactLat* lat) {
     while (ls >> t) tok.push_back(t);
     if (tok.size() <= 2) {  // final state
       const int32_t s = atoi(tok[0].c_str());
+      if (s < 0) KIO_ERR("Lattice " << lat->key << ": negative state id in line: " << line);
       float g = 0, w = 0;
       TidString tids;
       if (tok.size() == 2) ParseWeight(tok[1], true, &g, &w, &tids);
@@ -647,6 +724,7 @@ void ReadText(std::istream& is, CompactLat* lat) {
     RawArc arc;
     arc.src = atoi(tok[0].c_str());
     arc.dst = atoi(tok[1].c_str());
+    if (arc.src < 0 || arc.dst < 0) KIO_ERR("Lattice " << lat->key << ": negative state id in line: " << line);
     bool is_compact;
     if (tok.size() == 3) is_compact = true;
     else if (tok.size() == 5) is_compact = false;
@@ -900,6 +978,8 @@ void ReadBinary(std::istream& is, CompactLat* lat, bool keep_tids) {
   if (arctype == "compactlattice44") raw.compact = true;
   else if (arctype == "lattice4") raw.compact = false;
   else KIO_ERR("Unsupported arc type " << arctype << " (expected compactlattice44 or lattice4)");
+  if (nstates < 0 || nstates >= ((int64_t)1 << 31) || start < -1 || start >= std::max<int64_t>(nstates, 1))
+    KIO_ERR("Corrupt FST header of lattice " << lat->key << " (states " << nstates << ", start " << start << ")");
   raw.nstates = (int32_t)nstates;
   raw.start = (int32_t)start;
   auto read_weight = [&](float* g, float* a, TidString* tids) {
@@ -925,6 +1005,8 @@ void ReadBinary(std::istream& is, CompactLat* lat, bool keep_tids) {
       arc.olabel = ReadRaw<int32_t>(is);
       read_weight(&arc.g, &arc.a, &arc.tids);
       arc.dst = ReadRaw<int32_t>(is);
+      if (arc.dst < 0 || arc.dst >= nstates)
+        KIO_ERR("Lattice " << lat->key << ": arc refers to state " << arc.dst << " outside [0, " << nstates << ")");
       raw.arcs.push_back(arc);
     }
   }
@@ -946,8 +1028,25 @@ void ReadCompactLattice(std::istream& is, CompactLat* lat, bool keep_tids) {
   else KIO_ERR("Reading compact lattice " << lat->key << ": does not appear to be an FST");
 }
 
+// State ids straight from a file index vectors below (and in every tool): refuse anything
+// outside [0, nstates) here, with the reference's error path, before they are used.
+void ValidateStateIds(const CompactLat& lat) {
+  const int32_t n = lat.nstates;
+  const size_t na = lat.src.size();
+  for (size_t i = 0; i < na; ++i) {
+    const int32_t u = lat.src[i], v = lat.dst[i];
+    if (u < 0 || u >= n || v < 0 || v >= n)
+      KIO_ERR("Lattice " << lat.key << ": arc " << i << " refers to state " << (u < 0 || u >= n ? u : v)
+                         << " outside [0, " << n << ")");
+  }
+}
+
 void TopSortIfNeeded(CompactLat* lat) {
+  ValidateStateIds(*lat);
   const size_t na = lat->src.size();
+  // transition-id strings are only there when the lattice is read to be written back
+  const bool have_tids = lat->tids.size() == na && na > 0;
+  const bool have_fin_tids = lat->fin_tids.size() == (size_t)lat->nstates && lat->nstates > 0;
   bool sorted = true;
   for (size_t i = 0; i < na && sorted; ++i) sorted = lat->src[i] < lat->dst[i];
   if (sorted) return;
@@ -996,17 +1095,17 @@ void TopSortIfNeeded(CompactLat* lat) {
     out.dur.push_back(lat->dur[p]);
     out.graph.push_back(lat->graph[p]);
     out.acoustic.push_back(lat->acoustic[p]);
-    out.tids.push_back(lat->tids[p]);
+    if (have_tids) out.tids.push_back(lat->tids[p]);
   }
   out.fin_graph.resize(n);
   out.fin_acoustic.resize(n);
   out.fin_dur.resize(n);
-  out.fin_tids.resize(n);
+  if (have_fin_tids) out.fin_tids.resize(n);
   for (int32_t s = 0; s < n; ++s) {
     out.fin_graph[order[s]] = lat->fin_graph[s];
     out.fin_acoustic[order[s]] = lat->fin_acoustic[s];
     out.fin_dur[order[s]] = lat->fin_dur[s];
-    out.fin_tids[order[s]] = lat->fin_tids[s];
+    if (have_fin_tids) out.fin_tids[order[s]] = lat->fin_tids[s];
   }
   *lat = out;
 }
@@ -1119,9 +1218,11 @@ void SequentialCompactLatticeReader::ReadOne() {
       std::string path = line.substr(line.find_first_not_of(" \t", sp));
       scp_item_.reset(new Input(path));
       ReadCompactLattice(scp_item_->Stream(), &cur_, keep_tids_);
+      scp_item_->Close();  // "cmd|" entries: a failing command is an error
       return;
     }
     done_ = true;
+    in_->Close();
     return;
   }
   // archive: skip whitespace, read the key token, one space, then the object
@@ -1129,6 +1230,7 @@ void SequentialCompactLatticeReader::ReadOne() {
   while ((c = is.peek()) != EOF && isspace(c)) is.get();
   if (c == EOF) {
     done_ = true;
+    in_->Close();  // pipe rspecifiers: a failing producer command is an error, not an empty table
     return;
   }
   std::string key;
@@ -1302,6 +1404,11 @@ bool SequentialCompactLatticeReader::ReadBlock(int64_t max_arcs, std::vector<Com
   for (CompactLat& l : lats) out->push_back(std::move(l));
   ReadOne();  // the entry after the block (or the end of the archive)
   return true;
+}
+
+void TableWriter::End() {
+  if (spec_.ark == "-") out_->Stream().flush();
+  if (!out_->Good()) KIO_ERR("Write failure to " << (spec_.ark.empty() ? std::string("table") : spec_.ark));
 }
 
 TableWriter::TableWriter(const std::string& wspecifier) {

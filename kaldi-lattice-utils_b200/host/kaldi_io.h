@@ -244,11 +244,35 @@ class MemBuf : public std::streambuf {
   pos_type seekpos(pos_type pos, std::ios_base::openmode m) override { return seekoff(off_type(pos), std::ios_base::beg, m); }
 };
 
+// Stream buffer over a stdio FILE (the two ends of popen): pipes are streamed through a
+// 1 MB buffer, never collected in memory.  A failed fwrite is remembered (failed()).
+class StdioBuf : public std::streambuf {
+ public:
+  StdioBuf(FILE* f, bool writing);
+  ~StdioBuf() override { sync(); }
+  bool failed() const { return failed_; }
+
+ protected:
+  int_type underflow() override;
+  int_type overflow(int_type c) override;
+  std::streamsize xsputn(const char* s, std::streamsize n) override;
+  int sync() override;
+
+ private:
+  bool FlushOut();
+  FILE* f_;
+  bool writing_, failed_ = false;
+  std::vector<char> buf_;
+};
+
 class Input {  // file, stdin or pipe opened for reading (binary-safe)
  public:
   explicit Input(const std::string& name);
   ~Input();
   std::istream& Stream() { return *is_; }
+  // Ends a pipe and raises a KaldiError when its command failed (Kaldi does the same when
+  // it closes a pipe input); no-op for files.  The destructor closes quietly.
+  void Close();
 
  private:
   std::string filebuf_;  // stream buffer of a file input (declared first: destroyed after owned_)
@@ -258,7 +282,8 @@ class Input {  // file, stdin or pipe opened for reading (binary-safe)
   std::unique_ptr<std::istream> owned_;
   std::istream* is_ = nullptr;
   FILE* pipe_ = nullptr;
-  std::string buffer_;
+  std::string pipe_cmd_;
+  std::unique_ptr<StdioBuf> pipe_sb_;
 };
 
 class Output {
@@ -266,13 +291,19 @@ class Output {
   explicit Output(const std::string& name);
   ~Output();
   std::ostream& Stream() { return *os_; }
+  // Flushes; raises a KaldiError when a write failed (full disk, closed pipe) or the
+  // consumer command of a pipe exited non-zero.  The destructor closes quietly.
   void Close();
+  // True while every write so far has reached the stream.
+  bool Good();
 
  private:
   std::unique_ptr<std::ostream> owned_;
   std::ostream* os_ = nullptr;
   FILE* pipe_ = nullptr;
-  std::ostringstream pipe_buf_;
+  std::string name_;
+  std::unique_ptr<StdioBuf> pipe_sb_;
+  bool closed_ = false;
 };
 
 // fn(i) for every i in [0, n) on up to `threads` threads (0 = $KLU_IO_THREADS, else the
@@ -309,9 +340,9 @@ class TableWriter {  // archive writer: "key " + payload
   explicit TableWriter(const std::string& wspecifier);
   bool binary() const { return !spec_.text; }
   std::ostream& Begin(const std::string& key);  // writes the key, returns the stream
-  void End() {
-    if (spec_.ark == "-" ) out_->Stream().flush();
-  }
+  // End of one entry; a failed write raises here (the reference's TableWriter::Write
+  // returns os.good() and Kaldi raises on false).
+  void End();
   void Close() { out_->Close(); }
   bool IsOpen() const { return out_ != nullptr; }
 

@@ -50,8 +50,9 @@ namespace {
     if ((call) != 0) KIO_ERR("GPU engine: " << klu_last_error()); \
   } while (0)
 
-// A device batch holds at most this many lattices (the kernels index lattices with gridDim.y).
-constexpr size_t kMaxBatchLattices = 65535;
+// The tools close a batch at this many lattices whatever their size (archives of tiny lattices:
+// bounds the per-lattice host metadata of a batch); the library itself has no such limit.
+constexpr size_t kMaxBatchLattices = (size_t)1 << 20;
 
 struct Batch {
   std::vector<CompactLat> lats;

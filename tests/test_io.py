@@ -119,3 +119,158 @@ def test_text_field_formatting_matches_iostream_and_printf():
     infinities, NaN, typical log-posteriors)."""
     r = subprocess.run([COPY, "--format-selftest"], capture_output=True)
     assert r.returncode == 0 and b"identical" in r.stderr, r.stderr.decode()
+
+
+# ---- lattices that are not topologically sorted, and corrupt state ids -----------------
+def _parse_binary_lattice(d):
+    """(key, states) of a one-entry binary CompactLattice archive; states = list of
+    (final (g, a, tids) or None, [(label, g, a, tids, dst)])."""
+    key, rest = d.split(b" ", 1)
+    assert rest[:2] == b"\0B"
+    p = 2 + 4
+    for _ in range(2):
+        n = struct.unpack_from("<i", rest, p)[0]
+        p += 4 + n
+    p += 4 + 4 + 8
+    start, nstates, _ = struct.unpack_from("<qqq", rest, p)
+    p += 24
+    assert start == 0
+    states = []
+    for _ in range(nstates):
+        g, a, sz = struct.unpack_from("<ffi", rest, p)
+        p += 12
+        tids = struct.unpack_from("<%di" % sz, rest, p)
+        p += 4 * sz
+        na = struct.unpack_from("<q", rest, p)[0]
+        p += 8
+        arcs = []
+        for _ in range(na):
+            il, ol, ag, aa, asz = struct.unpack_from("<iiffi", rest, p)
+            p += 20
+            at = struct.unpack_from("<%di" % asz, rest, p)
+            p += 4 * asz
+            dst = struct.unpack_from("<i", rest, p)[0]
+            p += 4
+            arcs.append((ol, ag, aa, at, dst))
+        states.append(((g, a, tids) if g != float("inf") else None, arcs))
+    assert p == len(rest)
+    return key, states
+
+
+def _write_binary_lattice(key, states):
+    out = key + b" \0B" + struct.pack("<i", FST_MAGIC)
+    for name in (b"vector", b"compactlattice44"):
+        out += struct.pack("<i", len(name)) + name
+    out += struct.pack("<iiQqqq", 2, 0, 0, 0, len(states), 0)
+    inf = float("inf")
+    for fin, arcs in states:
+        g, a, tids = fin if fin else (inf, inf, ())
+        out += struct.pack("<ffi", g, a, len(tids)) + struct.pack("<%di" % len(tids), *tids)
+        out += struct.pack("<q", len(arcs))
+        for ol, ag, aa, at, dst in arcs:
+            out += struct.pack("<iiffi", ol, ol, ag, aa, len(at)) + struct.pack("<%di" % len(at), *at)
+            out += struct.pack("<i", dst)
+    return out
+
+
+def _permuted(states, perm):
+    """State i becomes perm[i] (perm[0] == 0: the start stays 0)."""
+    out = [None] * len(states)
+    for i, (fin, arcs) in enumerate(states):
+        out[perm[i]] = (fin, [(ol, g, a, t, perm[d]) for ol, g, a, t, d in arcs])
+    return out
+
+
+def _strip_tids(text):
+    rows = []
+    for line in text.decode().splitlines():
+        f = line.split()
+        if f and "," in f[-1]:
+            w = f[-1].split(",")
+            f[-1] = "%s,%s,%d" % (w[0], w[1], len([x for x in w[2].split("_") if x]) if len(w) > 2 else 0)
+        rows.append(" ".join(f))
+    return rows
+
+
+@pytest.mark.parametrize("mode", [[], ["--sequential"]])
+@pytest.mark.parametrize("tids", [[], ["--no-tids"]])
+def test_unsorted_binary_lattice_is_topsorted_on_read(tmp_path, mode, tids):
+    """A binary CompactLattice whose state ids are not in topological order goes through
+    TopSortCompactLatticeIfNeeded [ext] on read -- with and without the transition-id strings
+    (every tool but lattice-prune-dyn-beam reads without them)."""
+    b, u, t1, t2 = (str(tmp_path / x) for x in ("a.bin", "u.bin", "a.txt", "u.txt"))
+    assert copy("ark:" + WORD, "ark:" + b).returncode == 0
+    key, states = _parse_binary_lattice(open(b, "rb").read())
+    n = len(states)
+    perm = [0] + list(range(n - 1, 0, -1))  # reverse everything but the start
+    open(u, "wb").write(_write_binary_lattice(key, _permuted(states, perm)) * 3)
+    r = copy(*mode, *tids, "ark:" + u, "ark,t:" + t2)
+    assert r.returncode == 0, r.stderr.decode()
+    assert copy("ark:" + b, "ark,t:" + t1).returncode == 0
+    want = _strip_tids(open(t1, "rb").read())
+    got = _strip_tids(open(t2, "rb").read())
+    # the README lattice has one topological order up to the two parallel branches; the sorted
+    # copy must describe the same arcs (src < dst everywhere) with the same weights and durations
+    assert len(got) == 3 * len(want)
+    one = got[:len(want)]
+    assert one[0] == want[0] == "lat1"
+    arcs = [r.split() for r in one[1:] if len(r.split()) == 4]
+    assert all(int(a[0]) < int(a[1]) for a in arcs)
+    assert sorted((a[2], a[3]) for a in arcs) == sorted(
+        (a[2], a[3]) for a in (r.split() for r in want[1:]) if len(a) == 4)
+
+
+@pytest.mark.parametrize("bad_dst", [-1, 10 ** 6])
+@pytest.mark.parametrize("tids", [[], ["--no-tids"]])
+def test_out_of_range_state_ids_are_an_error(tmp_path, bad_dst, tids):
+    b, u = str(tmp_path / "a.bin"), str(tmp_path / "u.bin")
+    assert copy("ark:" + WORD, "ark:" + b).returncode == 0
+    key, states = _parse_binary_lattice(open(b, "rb").read())
+    fin, arcs = states[2]
+    states[2] = (fin, [arcs[0][:4] + (bad_dst,)] + arcs[1:])
+    open(u, "wb").write(_write_binary_lattice(key, states))
+    for mode in ([], ["--sequential"]):
+        r = copy(*mode, *tids, "ark:" + u, "ark,t:" + str(tmp_path / "o.txt"))
+        assert r.returncode == 1 and b"ERROR" in r.stderr and b"outside" in r.stderr
+
+
+def test_negative_state_id_in_text_is_an_error(tmp_path):
+    t = str(tmp_path / "neg.txt")
+    open(t, "w").write("bad\n0 1 5 1.0,2.0,3_4\n1 -2 6 1.0,2.0,7\n1\n\n")
+    r = copy("ark:" + t, "ark,t:" + str(tmp_path / "o.txt"))
+    assert r.returncode == 1 and b"negative state id" in r.stderr
+
+
+# ---- pipes are streamed and their exit status counts; write failures are errors ----------
+def test_failing_input_pipe_is_an_error(tmp_path):
+    o = str(tmp_path / "o.txt")
+    r = copy("ark:cat /nonexistent/file 2>/dev/null |", "ark,t:" + o)
+    assert r.returncode == 1 and b"nonzero return status" in r.stderr
+    # output produced, then a failure: still an error (a truncated table must not pass)
+    r = copy("ark:cat %s; exit 3 |" % WORD, "ark,t:" + o)
+    assert r.returncode == 1 and b"nonzero return status" in r.stderr
+
+
+def test_failing_output_pipe_is_an_error(tmp_path):
+    r = copy("ark:" + WORD, "ark,t:| cat > /dev/null; exit 3")
+    assert r.returncode == 1 and b"nonzero return status" in r.stderr
+    ok = str(tmp_path / "ok.txt")
+    r = copy("ark:" + WORD, "ark,t:| cat > " + ok)
+    assert r.returncode == 0 and open(ok).read().startswith("lat1")
+
+
+def test_write_failure_is_an_error():
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    r = copy("ark:" + WORD, "ark,t:/dev/full")
+    assert r.returncode == 1 and b"ERROR" in r.stderr
+
+
+def test_large_pipe_is_streamed(tmp_path):
+    """Pipe input and output go through a fixed-size buffer (no whole-archive copy in RAM):
+    the copy of a pipe equals the copy of the file."""
+    ark, a, b = (str(tmp_path / x) for x in ("in.ark", "a.ark", "b.ark"))
+    synth_ark(ark, 60)
+    assert copy("ark:cat %s |" % ark, "ark:| cat > " + a).returncode == 0
+    assert copy("ark:" + ark, "ark:" + b).returncode == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
