@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <functional>
 #include <map>
 #include <queue>
 #include <set>
@@ -1405,9 +1406,231 @@ void BruteForce(const Lat& lat, int32 mode, Result* r) {
   r->ds0 = total;
 }
 
+
+// ---------------------------------------------------------------------------
+// Brute-force pins for the tools the reference has no golden for (V1-V4): every
+// complete path of a (tiny) lattice is listed with its weight and label sequence,
+// and the tool's definition is applied to that list -- no sweeps, no unfolding.
+struct ListedPath {
+  std::vector<int32> arcs;    // orig indices of the arcs, in path order
+  std::vector<int32> states;  // states visited (arcs.size() + 1)
+  std::vector<int32> labels;  // non-epsilon labels
+  double cost;                // sum of arc costs in path order + final cost
+};
+
+void ListPaths(const Lat& lat, std::vector<ListedPath>* out) {
+  out->clear();
+  if (lat.Empty()) return;
+  ListedPath cur;
+  cur.states.push_back(0);
+  std::vector<double> cost(1, 0.0);
+  std::function<void(int32)> rec = [&](int32 s) {
+    if (lat.IsFinal(s)) {
+      ListedPath p = cur;
+      p.cost = cost.back() + Cost(lat.fg[s], lat.fa[s]);
+      out->push_back(p);
+    }
+    for (const auto& arc : lat.out[s]) {
+      cur.arcs.push_back(arc.orig);
+      cur.states.push_back(arc.next);
+      if (arc.label != 0) cur.labels.push_back(arc.label);
+      cost.push_back(cost.back() + Cost(arc.g, arc.a));
+      rec(arc.next);
+      cost.pop_back();
+      if (arc.label != 0) cur.labels.pop_back();
+      cur.states.pop_back();
+      cur.arcs.pop_back();
+    }
+  };
+  rec(0);
+}
+
+// latbin/lattice-best-path2.cc:78-211 by its definition: pad every label sequence with
+// kNoLabel (-1) to the longest one (fstext/fstext-utils2.h:218-271), P(v at position k) =
+// mass of the paths carrying v at k, a path costs sum_k (1 - P(v_k at k)), the answer is the
+// cheapest label sequence.  Rows: i0 = its labels; ds0 = its cost; ds1 = distance to the
+// cheapest DIFFERENT label sequence (+inf if there is none): the tests only insist on the
+// labels when that margin is well above float noise.
+void BruteBestPath2(Lat lat, const Opts& o, Result* r) {
+  Prologue(&lat, o, false);
+  std::vector<ListedPath> paths;
+  ListPaths(lat, &paths);
+  if (paths.empty()) { r->ds0 = kInf; r->ds1 = kInf; return; }
+  size_t maxlen = 0;
+  double total = kLogZeroDouble;
+  for (const auto& p : paths) {
+    maxlen = std::max(maxlen, p.labels.size());
+    total = LogAdd(total, -p.cost);
+  }
+  std::map<std::pair<int32, int32>, double> post;  // (label, 1-based position) -> probability
+  for (const auto& p : paths) {
+    const double pr = std::exp(-p.cost - total);
+    for (size_t k = 0; k < maxlen; ++k) post[std::make_pair(k < p.labels.size() ? p.labels[k] : -1, (int32)k + 1)] += pr;
+  }
+  std::map<std::vector<int32>, double> seq_cost;
+  for (const auto& p : paths) {
+    if (seq_cost.count(p.labels)) continue;
+    double c = 0.0;
+    for (size_t k = 0; k < maxlen; ++k)
+      c += 1.0 - std::min(1.0, post[std::make_pair(k < p.labels.size() ? p.labels[k] : -1, (int32)k + 1)]);
+    seq_cost[p.labels] = c;
+  }
+  const std::vector<int32>* best = nullptr;
+  double best_c = kInf, second_c = kInf;
+  for (const auto& kv : seq_cost) {
+    if (kv.second < best_c) {
+      second_c = best_c;
+      best_c = kv.second;
+      best = &kv.first;
+    } else if (kv.second < second_c) {
+      second_c = kv.second;
+    }
+  }
+  r->i0 = *best;
+  r->ds0 = best_c;
+  r->ds1 = second_c - best_c;
+}
+
+// latbin/lattice-prune-dyn-beam.cc:27-90,148-207 by its definition: an arc (a final weight)
+// survives beam b iff it lies on a complete path of cost <= best + b; the lattice's own beam is
+// the largest such distance; the beam shrinks by --beam-ratio until the survivors fit
+// --max-arcs / --max-states (or it reaches --min-beam).  Rows as PruneDynBeam; d0[0] = distance
+// of the nearest arc/final to the last cutoff used (the tests only insist on the surviving set
+// when that is well above rounding noise: the reference adds the same costs in another order).
+void BrutePruneDynBeam(Lat lat, const Opts& o, Result* r) {
+  if (o.acoustic_scale != 1.0 || o.graph_scale != 1.0) ScaleLattice(&lat, o.graph_scale, o.acoustic_scale);
+  if (o.insertion_penalty != 0.0) AddWordInsPen(&lat, o.insertion_penalty);
+  std::vector<ListedPath> paths;
+  ListPaths(lat, &paths);
+  const int32 n = lat.NumStates();
+  const int64_t na = lat.NumArcs();
+  std::vector<double> arc_best(na, kInf), fin_best(n, kInf);
+  double best = kInf;
+  for (const auto& p : paths) {
+    best = std::min(best, p.cost);
+    for (int32 e : p.arcs) arc_best[e] = std::min(arc_best[e], p.cost);
+    fin_best[p.states.back()] = std::min(fin_best[p.states.back()], p.cost);
+  }
+  // ComputeLatticeBeam looks at every arc it can reach from the start with a finite forward
+  // cost, including arcs that lead nowhere (their fb cost is +inf): the tests feed trim lattices
+  double worst = best;
+  for (double c : arc_best) if (c < kInf) worst = std::max(worst, c);
+  for (double c : fin_best) if (c < kInf) worst = std::max(worst, c);
+  const double original_beam = paths.empty() ? 0.0 : worst - best;
+  double beam = original_beam;
+  std::vector<char> arc_on(na, 0), fin_on(n, 0), st_on(n, 0);
+  double cutoff = kInf, margin = kInf;
+  int64_t n_try = 0;
+  auto apply = [&](double cut) {
+    int32 arcs = 0, states = 0;
+    std::fill(st_on.begin(), st_on.end(), 0);
+    for (int32 s = 0; s < n; ++s) {
+      fin_on[s] = fin_best[s] <= cut;
+      if (fin_on[s]) st_on[s] = 1;
+      for (const auto& arc : lat.out[s]) {
+        arc_on[arc.orig] = arc_best[arc.orig] <= cut;
+        if (arc_on[arc.orig]) {
+          ++arcs;
+          st_on[s] = st_on[arc.next] = 1;
+        }
+      }
+    }
+    for (int32 s = 0; s < n; ++s) states += st_on[s];
+    return std::make_pair(arcs, states);
+  };
+  std::pair<int32, int32> cnt = apply(kInf);
+  // (before the first PruneLattice call the reference counts the arcs and states of the input
+  // as it is, trim or not)
+  cnt.first = (int32)na;
+  cnt.second = n;
+  const float beam_ratio = o.beam_ratio, min_beam = o.min_beam;
+  while (beam > min_beam && (cnt.first > o.max_arcs || cnt.second > o.max_states)) {
+    ++n_try;
+    beam = beam_ratio * beam;
+    cutoff = best + (float)beam;
+    cnt = apply(cutoff);
+    if (n_try > 100000) { r->error = "prune loop does not terminate"; return; }
+  }
+  if (n_try == 0) apply(kInf);
+  for (double c : arc_best) if (c < kInf) margin = std::min(margin, std::fabs(c - cutoff));
+  for (double c : fin_best) if (c < kInf) margin = std::min(margin, std::fabs(c - cutoff));
+  std::vector<int32> newid(n, -1);
+  int32 m = 0;
+  if (n_try == 0) {
+    for (int32 s = 0; s < n; ++s) newid[s] = m++;  // untouched
+  } else {
+    for (int32 s = 0; s < n; ++s) if (st_on[s]) newid[s] = m++;
+  }
+  // weights in the original scale after the float round trip (:188-192)
+  const double ig = 1.0 / o.graph_scale, ia = 1.0 / o.acoustic_scale;
+  const bool scaled = o.acoustic_scale != 1.0 || o.graph_scale != 1.0;
+  auto back = [&](float g, float a, bool word, float* go, float* ao) {
+    if (scaled) {  // LatticeScale(1 / graph_scale, 1 / acoustic_scale): double products, float storage
+      g = (float)(ig * g);
+      a = (float)(ia * a);
+    }
+    if (word && o.insertion_penalty != 0.0) g = g + (-o.insertion_penalty);
+    *go = g;
+    *ao = a;
+  };
+  for (int32 s = 0; s < n; ++s)
+    for (const auto& arc : lat.out[s]) {
+      if (n_try > 0 && !arc_on[arc.orig]) continue;
+      float g, a;
+      back(arc.g, arc.a, arc.label != 0, &g, &a);
+      r->i0.push_back(arc.orig);
+      r->i1.push_back(newid[s]);
+      r->i2.push_back(newid[arc.next]);
+      r->i3.push_back(arc.label);
+      r->f0.push_back(g);
+      r->f1.push_back(a);
+    }
+  for (int32 s = 0; s < n; ++s) {
+    if (!lat.IsFinal(s) || (n_try > 0 && !fin_on[s])) continue;
+    float g, a;
+    back(lat.fg[s], lat.fa[s], false, &g, &a);
+    r->i0.push_back(-1);
+    r->i1.push_back(newid[s]);
+    r->i2.push_back(lat.fdur[s]);
+    r->i3.push_back(0);
+    r->f0.push_back(g);
+    r->f1.push_back(a);
+  }
+  r->s0 = m;
+  r->s1 = n_try;
+  r->ds0 = original_beam;
+  r->ds1 = beam;
+  r->d0.push_back(margin);
+}
+
+// [ext] fst::TopSort as TopSortCompactLatticeIfNeeded calls it: depth-first visit from the
+// start state, then from every state not yet seen in id order, arcs in stored order; a state
+// is numbered by the reverse of the order in which the visit leaves it.  Rows: i0[old] = new id.
+// The lattice may be numbered in any way (that is the point); a cycle is an error.
+void OpenFstTopOrder(const Lat& lat, Result* r) {
+  const int32 n = lat.NumStates();
+  std::vector<int32> colour(n, 0), left;
+  bool cyclic = false;
+  std::function<void(int32)> visit = [&](int32 s) {
+    colour[s] = 1;
+    for (const auto& arc : lat.out[s]) {
+      if (colour[arc.next] == 1) cyclic = true;
+      else if (colour[arc.next] == 0) visit(arc.next);
+    }
+    colour[s] = 2;
+    left.push_back(s);
+  };
+  if (n > 0) visit(0);
+  for (int32 s = 0; s < n; ++s)
+    if (colour[s] == 0) visit(s);
+  if (cyclic) { r->error = "cyclic lattice"; return; }
+  r->i0.assign(n, -1);
+  for (int32 k = 0; k < n; ++k) r->i0[left[n - 1 - k]] = k;
+}
+
 Lat BuildLat(int32 nstates, int32 narcs, const int32* src, const int32* dst, const int32* label,
              const int32* dur, const float* g, const float* a, const float* fin_g, const float* fin_a,
-             const int32* fin_dur, std::string* err) {
+             const int32* fin_dur, std::string* err, bool any_order = false) {
   Lat lat;
   lat.out.resize(nstates);
   lat.fg.assign(fin_g, fin_g + nstates);
@@ -1416,7 +1639,12 @@ Lat BuildLat(int32 nstates, int32 narcs, const int32* src, const int32* dst, con
   else lat.fdur.assign(nstates, 0);
   int32 prev = 0;
   for (int32 e = 0; e < narcs; ++e) {
-    if (src[e] < prev || src[e] >= nstates || dst[e] <= src[e] || dst[e] >= nstates) {
+    if (any_order) {
+      if (src[e] < 0 || src[e] >= nstates || dst[e] < 0 || dst[e] >= nstates) {
+        *err = "state id out of range";
+        return Lat();
+      }
+    } else if (src[e] < prev || src[e] >= nstates || dst[e] <= src[e] || dst[e] >= nstates) {
       *err = "arcs must be grouped by ascending src and topologically sorted (src < dst)";
       return Lat();
     }
@@ -1454,7 +1682,8 @@ typedef struct ora_opts {
 
 enum { ORA_SEGMENT = 0, ORA_POSITION = 1, ORA_UTTERANCE = 2, ORA_FRAME_POST = 3, ORA_PRUNE_DYN_BEAM = 4,
        ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_CHAR_SEGMENT = 9, ORA_LENGTH_DIST = 14, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
-       ORA_BRUTE_FRAME = 12, ORA_BRUTE_UTTERANCE = 13 };
+       ORA_BRUTE_FRAME = 12, ORA_BRUTE_UTTERANCE = 13, ORA_TOP_ORDER = 15, ORA_BRUTE_BEST_PATH2 = 16,
+       ORA_BRUTE_PRUNE = 17, ORA_FWD_BWD = 18 };
 
 static Opts ConvertOpts(const ora_opts* o) {
   Opts r;
@@ -1478,9 +1707,21 @@ static Opts ConvertOpts(const ora_opts* o) {
 
 static void RunTool(int tool, const ora_lat* l, const Opts& o, Result* r) {
   Lat lat = BuildLat(l->nstates, l->narcs, l->src, l->dst, l->label, l->dur, l->graph, l->acoustic,
-                     l->fin_graph, l->fin_acoustic, l->fin_dur, &r->error);
+                     l->fin_graph, l->fin_acoustic, l->fin_dur, &r->error, tool == ORA_TOP_ORDER);
   if (!r->error.empty()) return;
   switch (tool) {
+    case ORA_TOP_ORDER: OpenFstTopOrder(lat, r); break;
+    case ORA_FWD_BWD: {  // the alpha / beta vectors themselves (d0 = alphas, then betas)
+      Lat l2 = lat;
+      Prologue(&l2, o, false);
+      std::vector<double> al, be;
+      if (!l2.Empty()) r->ds0 = AlphasAndBetas(l2, &al, &be);
+      r->d0 = al;
+      r->d0.insert(r->d0.end(), be.begin(), be.end());
+      break;
+    }
+    case ORA_BRUTE_BEST_PATH2: BruteBestPath2(lat, o, r); break;
+    case ORA_BRUTE_PRUNE: BrutePruneDynBeam(lat, o, r); break;
     case ORA_SEGMENT: WordIndexSegment(lat, o, r); break;
     case ORA_POSITION: WordIndexPosition(lat, o, r); break;
     case ORA_UTTERANCE: WordIndexUtterance(lat, o, r); break;

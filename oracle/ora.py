@@ -17,7 +17,9 @@ SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSIT
 POSITION_POST = 8
 CHAR_SEGMENT = 9
 LENGTH_DIST = 14
+FWD_BWD = 18
 BRUTE_SEGMENT, BRUTE_POSITION, BRUTE_FRAME, BRUTE_UTTERANCE = 10, 11, 12, 13
+TOP_ORDER, BRUTE_BEST_PATH2, BRUTE_PRUNE = 15, 16, 17
 
 INT_MAX = 2**31 - 1
 
@@ -221,6 +223,45 @@ def prune_dyn_beam(lat, **o):
         else:
             finals.append((int(r.i[1][k]), float(r.f[0][k]), float(r.f[1][k])))
     return dict(arcs=arcs, finals=finals, nstates=r.s0, iters=r.s1, beam0=r.ds0, beam=r.ds1)
+
+
+def _prune_rows(r):
+    arcs, finals = [], []
+    for k in range(len(r.i[0])):
+        if r.i[0][k] >= 0:
+            arcs.append((int(r.i[0][k]), int(r.i[1][k]), int(r.i[2][k]), int(r.i[3][k]), float(r.f[0][k]),
+                         float(r.f[1][k])))
+        else:
+            finals.append((int(r.i[1][k]), float(r.f[0][k]), float(r.f[1][k])))
+    return arcs, finals
+
+
+def brute_prune_dyn_beam(lat, **o):
+    """lattice-prune-dyn-beam from the list of all paths (tiny lattices): same fields as
+    prune_dyn_beam plus `margin`, the distance of the nearest arc to the last cutoff."""
+    r = run(BRUTE_PRUNE, lat, **o)
+    arcs, finals = _prune_rows(r)
+    return dict(arcs=arcs, finals=finals, nstates=r.s0, iters=r.s1, beam0=r.ds0, beam=r.ds1,
+                margin=float(r.d[0]) if len(r.d) else float("inf"))
+
+
+def brute_best_path2(lat, **o):
+    """lattice-best-path2 from the list of all paths: (labels, cost, margin to the next-best
+    different label sequence)."""
+    r = run(BRUTE_BEST_PATH2, lat, **o)
+    return r.i[0].tolist(), r.ds0, r.ds1
+
+
+def top_order(lat):
+    """[ext] fst::TopSort order of a lattice numbered in any way: new id of every old state."""
+    return run(TOP_ORDER, lat).i[0].tolist()
+
+
+def fwd_bwd(lat, **o):
+    """Per-state alpha, beta of ComputeLatticeAlphasAndBetas [ext] and its return value."""
+    r = run(FWD_BWD, lat, **o)
+    n = len(r.d) // 2
+    return r.d[:n].copy(), r.d[n:].copy(), r.ds0
 
 
 def char_position(lat, wspace, other_groups=(), **o):

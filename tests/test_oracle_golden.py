@@ -163,3 +163,74 @@ def test_oracle_prune_dyn_beam_noop_and_prune(klu, ora):
     # survivors keep their relative order
     idx = [a[0] for a in r2["arcs"]]
     assert idx == sorted(idx)
+
+
+# ---- independent pins for the V rows (no golden in the reference) ------------------------
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("flags", [dict(), dict(acoustic_scale=0.3, insertion_penalty=0.5), dict(graph_scale=2.0)])
+def test_oracle_best_path2_vs_all_paths(klu, ora, seed, flags):
+    """latbin/lattice-best-path2.cc:122-199 by its definition: pad all label sequences to the
+    longest one, posterior of (label, position) from the list of all paths, expected position
+    loss of every label sequence, arg-min.  The restatement (length unfolding + padding chain +
+    forward-backward + float shortest path) must pick the same sequence whenever the runner-up
+    is further away than float noise, and report the same cost."""
+    checked = 0
+    for lat in klu.synth_batch("tiny", 5, seed=700 + seed).lattices():
+        labels, cost, margin = ora.brute_best_path2(lat, **flags)
+        got_labels, got_cost = ora.best_path2(lat, **flags)
+        assert abs(got_cost - cost) <= 1e-5 * max(1.0, cost)
+        if margin > 1e-4:
+            assert got_labels == labels
+            checked += 1
+    assert checked >= 3
+
+
+def test_oracle_best_path2_vs_all_paths_padded_sequence(klu, ora):
+    # two label sequences of different length on a diamond: the shorter one is padded with kNoLabel
+    arcs = [(0, 1, 5, 1.0, 0.0, 1), (0, 2, 6, 0.25, 0.0, 1), (1, 3, 7, 0.5, 0.0, 1), (2, 3, 0, 0.5, 0.0, 1),
+            (3, 4, 8, 0.0, 0.0, 1)]
+    lat = klu.make_lattice("diamond", 5, arcs, {4: (0.0, 0.0)})
+    labels, cost, margin = ora.brute_best_path2(lat)
+    got_labels, got_cost = ora.best_path2(lat)
+    assert abs(got_cost - cost) < 1e-6
+    assert margin > 1e-3 and got_labels == labels == [6, 8]
+
+
+PRUNE_FLAGS = [dict(max_arcs=40, max_states=30), dict(max_arcs=15), dict(max_states=12, beam_ratio=0.5),
+               dict(acoustic_scale=0.1, graph_scale=0.7, insertion_penalty=0.5, max_arcs=60),
+               dict(max_arcs=1, min_beam=0.5), dict()]
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("flags", PRUNE_FLAGS)
+def test_oracle_prune_dyn_beam_vs_all_paths(klu, ora, seed, flags):
+    """latbin/lattice-prune-dyn-beam.cc:27-90,166-184 by its definition: an arc survives beam b
+    iff it lies on a path of cost <= best + b, the lattice's own beam is the largest such
+    distance, the beam shrinks by --beam-ratio until the limits hold.  Surviving arcs, their new
+    state ids and their output weights must be identical; the beams agree to rounding (the
+    sweeps add the same costs in another order)."""
+    import math
+    checked = 0
+    for lat in klu.synth_batch("tiny", 4, seed=800 + seed).lattices():
+        want = ora.brute_prune_dyn_beam(lat, **flags)
+        got = ora.prune_dyn_beam(lat, **flags)
+        assert got["iters"] == want["iters"]
+        assert math.isclose(got["beam0"], want["beam0"], rel_tol=1e-12, abs_tol=1e-12)
+        assert math.isclose(got["beam"], want["beam"], rel_tol=1e-12, abs_tol=1e-12)
+        if want["margin"] > 1e-9:
+            assert got["nstates"] == want["nstates"]
+            assert got["arcs"] == want["arcs"] and got["finals"] == want["finals"]
+            checked += 1
+    assert checked >= 3
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_top_order_properties(klu, ora, seed):
+    """[ext] fst::TopSort restated as a recursive depth-first visit: the order is a
+    topological one (a permutation with every arc going up)."""
+    from test_topsort import _random_dag
+    rng = np.random.RandomState(seed)
+    lat = _random_dag(klu, rng, 4 + 5 * seed)
+    order = ora.top_order(lat)
+    assert sorted(order) == list(range(lat.nstates))
+    assert all(order[s] < order[d] for s, d in zip(lat.src.tolist(), lat.dst.tolist()))

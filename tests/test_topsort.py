@@ -1,5 +1,6 @@
-"""klu_topsort (host side of the C ABI) against the Python restatement of
-TopSortCompactLatticeIfNeeded [ext] in kaldi-lattice-utils_b200/lattice.py."""
+"""klu_topsort (host side of the C ABI) against the oracle's restatement of
+TopSortCompactLatticeIfNeeded [ext] (oracle/klu_oracle.cc OpenFstTopOrder, a recursive depth-first
+visit) and against the Python twin in kaldi-lattice-utils_b200/lattice.py."""
 import ctypes as C
 
 import numpy as np
@@ -30,6 +31,34 @@ def _random_dag(klu, rng, n, shuffle=True):
     arcs = [(int(perm[s]), int(perm[d]), w, g, a, t) for (s, d, w, g, a, t) in arcs]
     arcs.sort(key=lambda x: x[0])  # grouped by source, as OpenFst stores them
     return klu.make_lattice("dag", n, arcs, {int(perm[n - 1]): (0.5, 0.25)})
+
+
+def _apply_order(klu, lat, order):
+    """The lattice renumbered by order[old] = new, arcs regrouped by new source (stable)."""
+    arcs = [(order[s], order[d], int(w), float(g), float(a), int(t)) for s, d, w, g, a, t in
+            zip(lat.src.tolist(), lat.dst.tolist(), lat.label.tolist(), lat.graph.tolist(), lat.acoustic.tolist(),
+                lat.dur.tolist())]
+    arcs.sort(key=lambda x: x[0])
+    finals = {order[s]: (float(lat.fin_graph[s]), float(lat.fin_acoustic[s])) for s in range(lat.nstates)
+              if not np.isinf(lat.fin_graph[s])}
+    return klu.make_lattice(lat.key, lat.nstates, arcs, finals)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_topsort_matches_oracle(klu, ora, seed):
+    """State ids after the sort decide what lattice-prune-dyn-beam writes: klu_topsort must
+    number the states exactly as the oracle's fst::TopSort restatement does."""
+    rng = np.random.RandomState(100 + seed)
+    lat = _random_dag(klu, rng, 3 + seed * 5)
+    want_order = ora.top_order(lat)
+    rc, got, order = _call(klu, lat)
+    assert rc == 0
+    assert order.tolist() == want_order
+    want = _apply_order(klu, lat, want_order)
+    for k in ("src", "dst", "label", "dur"):
+        assert np.array_equal(got[k], np.asarray(getattr(want, k))), k
+    for k in ("graph", "acoustic", "fin_graph", "fin_acoustic"):
+        assert np.array_equal(got[k], np.asarray(getattr(want, k), dtype=np.float32)), k
 
 
 @pytest.mark.parametrize("seed", range(6))

@@ -40,6 +40,40 @@ def assert_rows_match(got, want, nkey, tol=TOL, what=""):
             assert close(g[-1], w[-1], tol), what + ": order differs beyond tolerance at %d: %r vs %r" % (i, g, w)
 
 
+def assert_cols_match(gkeys, gexact, gval, wkeys, wexact, wval, tol=TOL, what="", ordered=True):
+    """assert_rows_match over numpy columns (for results with millions of rows): keys and
+    exact fields identical as a keyed map, values within tol, and -- when `ordered` -- values
+    non-increasing with the reference's order wherever it is decided by more than tol."""
+    import numpy as np
+    gkeys, wkeys = [np.asarray(k) for k in gkeys], [np.asarray(k) for k in wkeys]
+    gval, wval = np.asarray(gval, dtype=np.float64), np.asarray(wval, dtype=np.float64)
+    assert len(gval) == len(wval), what + ": %d rows, reference has %d" % (len(gval), len(wval))
+    go, wo = np.lexsort(gkeys[::-1]), np.lexsort(wkeys[::-1])
+    for g, w in zip(gkeys, wkeys):
+        assert np.array_equal(g[go], w[wo]), what + ": key sets differ"
+    if len(gval) > 1:
+        same = np.ones(len(gval) - 1, bool)
+        for g in gkeys:
+            same &= g[go][1:] == g[go][:-1]
+        assert not same.any(), what + ": duplicate keys in result"
+    for g, w in zip(gexact, wexact):
+        assert np.array_equal(np.asarray(g)[go], np.asarray(w)[wo]), what + ": exact fields differ"
+    gv, wv = gval[go], wval[wo]
+    inf = np.isinf(gv) | np.isinf(wv)
+    assert np.array_equal(gv[inf], wv[inf]), what + ": infinite values differ"
+    if (~inf).any():
+        d = np.abs(gv[~inf] - wv[~inf]).max()
+        assert d <= tol, what + ": values differ by %g" % d
+    if ordered and len(gval) > 1:
+        assert (np.diff(gval) <= 0).all(), what + ": not sorted"
+        moved = np.zeros(len(gval), bool)
+        for g, w in zip(gkeys, wkeys):
+            moved |= g != w
+        if moved.any():
+            ok = np.abs(gval[moved] - wval[moved]) <= tol
+            assert ok.all(), what + ": order differs beyond tolerance"
+
+
 def char_lattice(klu, rng, key, nwords=4, alphabet=5, punct=(), eps_prob=0.0):
     """Synthetic HTR-like character lattice: a time-layered DAG, one frame per arc,
     1-2 states per frame and 1-2 labels per state pair; label 1 is the whitespace
