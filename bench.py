@@ -1,23 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- lattice arcs/sec through the forward-backward + posterior-index
-hot path on B200 (metric of BASELINE.json), with roofline and CPU baseline.
+"""bench.py -- lattice arcs/sec through the forward-backward + posterior-index hot path on
+B200 (metric of BASELINE.json), with roofline, pack time, per-tool numbers and CPU baselines.
 
   python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
   python bench.py --impl reference --gpus N --steps K ...  (reference arm: the CPU
       restatement of the reference's algorithm -- oracle/ -- on all host threads;
       the reference itself needs Kaldi+OpenFst and cannot be built in this image)
 
-A "step" = one pass of the hot path over one batch: BASELINE.json configs[1]
-(10k synthetic lattices, ~2k states / ~50k arcs each, 50k vocabulary,
-lattice-to-word-frame-post with --acoustic-scale=0.1) PER GPU (weak scaling:
-lattices are independent, every rank owns its own shard, no collective on the
-data path).  `value` times {alpha sweep, beta sweep, arc-posterior emit, sort by
-key, segmented log-add, output ordering} with the packed batch resident in HBM;
-`e2e` times klu_load (host packer + H2D from pinned host arrays) + klu_run +
-klu_fetch_* (D2H of the whole index) through the C ABI.
+The headline line is BASELINE.json configs[1]: lattice-to-word-frame-post with
+--acoustic-scale=0.1 on 10k synthetic lattices PER GPU (~2k states / ~50k arcs each, 50k
+vocabulary; weak scaling: lattices are independent, every rank owns its own shard, no
+collective on the data path).
+
+  value            arcs/s of a "step" = {alpha sweep, beta sweep, per-frame group sums of the
+                   arc posteriors, per-frame ordering} with the packed batch AND its frame
+                   index resident in HBM.  The sort of the arc x frame instances by
+                   (frame, word) is NOT in this step: it depends on the lattice structure
+                   only and runs once per batch, in the device packer -- see pack_ms.
+  pack_ms          CUDA-event time of what the device does once per batch before the first
+                   step: the packer of klu_load (levels, CSR, bands) + the frame index.
+  value_incl_pack  arcs/s with pack_ms added to every step: the figure for a tool that
+                   loads a batch and runs it once (what the drop-in binaries do).
+  e2e              klu_load (H2D of the caller's pinned SoA arrays + packer) + klu_run +
+                   klu_fetch_* (D2H of the whole index) through the C ABI, wall clock.
+  tools            the other tools of BASELINE.json's configs, one entry each (N = 1 only):
+                   ms per step, arcs/s, pack_ms, their own byte model, a bounded CPU baseline.
+  --scaling strong one fixed batch partitioned by arc count over the ranks (shard.py).
 """
 import argparse
-import importlib.util
 import json
 import os
 import subprocess
@@ -32,32 +42,28 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 TOOLS = {"frame_post": 3, "segment": 0, "position": 1, "utterance": 2, "fwd_bwd": 7, "prune_dyn_beam": 4,
-         "best_path2": 5}
+         "best_path2": 5, "position_post": 8, "char_position": 6}
+METRIC = "lattice arcs/sec (fwd-bwd + word-position index)"  # BASELINE.json's metric name, kept verbatim
+METRIC_NOTE = ("`value` is measured on BASELINE.json configs[1] (lattice-to-word-frame-post, the configuration the "
+               "metric is quoted on); the word-position index tool itself (lattice-word-index-position) is "
+               "tools['position@c2']")
 # algorithmic HBM bytes: per arc / per state / per emitted entry
 ALGO = {
     # alpha sweep src+g+a (12) + beta sweep dst+g+a (12); alpha+beta written once (16/state)
     "k_log_sweeps": dict(arc=24.0, state=16.0, entry=0.0),
-    "k_log_sweeps(fwd)": dict(arc=12.0, state=8.0, entry=0.0),
-    # backward sweep + arc posteriors: record read (12 B of it algorithmic) + posterior written (8 B)
-    "k_log_sweeps(bwd+post)": dict(arc=20.0, state=16.0, entry=0.0),
-    "k_banded_alpha": dict(arc=12.0, state=0.0, entry=0.0, band=8.0),
+    "k_banded_alpha": dict(arc=0.0, state=0.0, entry=0.0, band=8.0, unfolded=12.0),
+    "k_pos_cells": dict(arc=0.0, state=0.0, entry=16.0, unfolded=20.0),
     "k_emit": dict(arc=20.0, state=0.0, entry=16.0),
     "k_seg_radix_sort": dict(arc=0.0, state=0.0, entry=16.0),
     "k_reduce": dict(arc=0.0, state=0.0, entry=16.0),
     "k_count_scan": dict(arc=8.0, state=0.0, entry=0.0),
     "k_gather": dict(arc=0.0, state=0.0, entry=16.0),
-    # arc posterior pre-pass: record (16) + source id (4) read, posterior (8) written
-    "k_arc_post": dict(arc=28.0, state=16.0, entry=0.0),
-    # frame-synchronous group-by + order: every arc x frame instance reads its arc id (4 B)
-    # and the arc's posterior (8 B); every (frame, word, logp) row is written once (12 B)
-    # group sums: every arc x frame instance reads its arc id (4 B) and the arc's posterior
-    # (8 B); per group 4 B offset read + 4 B log-posterior written
-    "k_group_post": dict(arc=0.0, state=0.0, entry=8.0, inst=12.0),
     # per-frame ordering: 4 B logp + 4 B word read, (word, logp) written in order (the frame column is static)
     "k_frame_order": dict(arc=0.0, state=0.0, entry=16.0),
     # fused window kernel: record + source id per arc (20 B), arc id per instance (4 B), offset read +
     # log-posterior written per group (8 B)
     "k_frame_groups": dict(arc=20.0, state=16.0, entry=8.0, inst=4.0),
+    "k_trop_sweeps": dict(arc=24.0, state=16.0, entry=0.0),
 }
 
 
@@ -126,11 +132,11 @@ class ClockSampler(threading.Thread):
 
 
 def dist_setup(n):
-    """Returns (rank, world, reduce_max, barrier)."""
+    """Returns (rank, world, reduce_max, barrier, gather_obj)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if world == 1:
-        return 0, 1, (lambda x: x), (lambda: None)
+        return 0, 1, (lambda x: x), (lambda: None), (lambda x: [x])
     import torch
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -146,39 +152,81 @@ def dist_setup(n):
         dist.barrier()
         torch.cuda.synchronize()
 
-    return rank, world, reduce_max, barrier
+    def gather_obj(x):
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
+    return rank, world, reduce_max, barrier, gather_obj
 
 
 def flags_for(tool):
     if tool == "prune_dyn_beam":  # BASELINE.json configs[2]
         return dict(max_arcs=20000, max_states=1500, beam_ratio=0.9)
+    if tool == "char_position":
+        return dict(nbest=100)
     return dict(acoustic_scale=0.1)
 
 
+def run_tool(eng, klu, tool, flags):
+    if tool == "char_position":
+        lg, inc, dele = klu.binding.char_groups([1], ())
+        o, keep = klu.binding.make_opts(label_group=lg, inc_groups=inc, del_groups=dele, **flags)
+        eng.run_opts(klu.CHAR_POSITION, o)
+    else:
+        eng.run(TOOLS[tool], **flags)
+
+
 def fetch_for(eng, klu, tool, out=None):
+    """(rows, bytes brought to the host) of the last run."""
     t = TOOLS[tool]
     if t == klu.FRAME_POST:
         r = eng.fetch_frame_post(out=out)
-        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
-    if t == klu.SEGMENT:
+    elif t == klu.SEGMENT:
         r = eng.fetch_segment()
-        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
-    if t == klu.POSITION:
+    elif t == klu.POSITION:
         r = eng.fetch_position()
-        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
-    if t == klu.UTTERANCE:
+    elif t == klu.POSITION_POST:
+        r = eng.fetch_position_post()
+    elif t == klu.UTTERANCE:
         r = eng.fetch_utterance()
-        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
-    if t == klu.FWD_BWD:
+    elif t == klu.FWD_BWD:
         r = eng.fetch_fwd_bwd()
         return 0, sum(int(x.nbytes) for x in r)
-    if t == klu.PRUNE_DYN_BEAM:
+    elif t == klu.PRUNE_DYN_BEAM:
         r = eng.fetch_prune()
-        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
-    if t == klu.BEST_PATH2:
+    elif t == klu.BEST_PATH2:
         r = eng.fetch_best_path2()
-        return int(r[0][-1]), sum(int(x.nbytes) for x in r)
-    raise ValueError(tool)
+    elif t == klu.CHAR_POSITION:
+        r = eng.fetch_char_position()
+    else:
+        raise ValueError(tool)
+    return int(r[0][-1]), sum(int(x.nbytes) for x in r)
+
+
+def time_steps(eng, klu, tool, flags, steps, warmup):
+    for _ in range(warmup):
+        run_tool(eng, klu, tool, flags)
+    eng.sync()
+    eng.timer_start()
+    for _ in range(steps):
+        run_tool(eng, klu, tool, flags)
+    return eng.timer_stop() / steps
+
+
+def kernel_profile(eng, klu, tool, flags, runs=2):
+    eng.profile(True)
+    for _ in range(runs):
+        run_tool(eng, klu, tool, flags)
+    prof = eng.profile_json()
+    eng.profile(False)
+    return {k: {"launches_per_step": v["launches"] / runs, "ms_per_step": v["ms"] / runs} for k, v in prof.items()}
+
+
+def oracle_tool(ora, tool):
+    return {"frame_post": ora.FRAME_POST, "segment": ora.SEGMENT, "position": ora.POSITION,
+            "utterance": ora.UTTERANCE, "best_path2": ora.BEST_PATH2, "prune_dyn_beam": ora.PRUNE_DYN_BEAM,
+            "position_post": ora.POSITION_POST}[tool]
 
 
 def run_reference(args, rank, world):
@@ -192,8 +240,7 @@ def run_reference(args, rank, world):
     n = args.ref_lattices
     batch = klu.synth_batch(args.shape, n, seed=args.seed)
     lats = batch.lattices()
-    tool = {"frame_post": ora.FRAME_POST, "segment": ora.SEGMENT, "position": ora.POSITION,
-            "utterance": ora.UTTERANCE}[args.tool]
+    tool = oracle_tool(ora, args.tool)
     for _ in range(min(args.warmup, 1)):
         ora.run_batch(tool, lats[:cores], cores, **flags_for(args.tool))
     times = []
@@ -205,7 +252,7 @@ def run_reference(args, rank, world):
     v = batch.num_arcs / sec
     sample = "%d lattices of the workload (%d arcs) per step, %d host threads" % (n, batch.num_arcs, cores)
     print(json.dumps({
-        "impl": "reference", "metric": "lattice arcs/sec (fwd-bwd + word-position index)", "value": v,
+        "impl": "reference", "metric": METRIC, "value": v,
         "unit": "arcs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, args.lattices),
@@ -224,6 +271,156 @@ def workload_config(args, nlat):
             "parallelism": "independent lattice shards per GPU, no collective"}
 
 
+# ------------------------------------------------------------------ per-tool section ---
+def model_bytes(tool, st, entries, unfolded):
+    """Algorithmic HBM bytes of one step."""
+    arcs, states = st["arcs"], st["states"]
+    if tool in ("segment", "utterance"):
+        # alpha 12 + beta 12 + emit read 20 + emit write 16 + reduce read 16 per arc; 28 per state
+        return 76.0 * arcs + 28.0 * states, "76 B/arc + 28 B/state"
+    if tool in ("position", "best_path2", "position_post"):
+        # fwd-bwd (24 B/arc + 16 B/state) + per arc of the length-unfolded lattice (E x I_L): banded
+        # sweep 12, emit read 20 + write 16, reduce read 16; 8 B per (state, length) cell written
+        return (24.0 * arcs + 16.0 * states + 64.0 * unfolded + 8.0 * st["band"],
+                "24 B/arc + 16 B/state + 64 B/unfolded arc + 8 B/(state,len) cell")
+    if tool == "prune_dyn_beam":
+        return 37.0 * arcs + 16.0 * states, "37 B/arc + 16 B/state"
+    if tool == "fwd_bwd":
+        return 24.0 * arcs + 16.0 * states, "24 B/arc + 16 B/state"
+    return None, None
+
+
+def unfolded_arcs(batch):
+    """Arcs of the length-unfolded lattice, sum over arcs of the source state's number of
+    distinct label counts (E x I_L of SURVEY.md 8d): a forward DP over (min, max) label
+    counts per state, exact when every count in between is reachable (true of the shapes here)."""
+    total = 0
+    for l in range(len(batch)):
+        s0, s1 = int(batch.state_off[l]), int(batch.state_off[l + 1])
+        e0, e1 = int(batch.arc_off[l]), int(batch.arc_off[l + 1])
+        n = s1 - s0
+        src, dst, nz = batch.src[e0:e1], batch.dst[e0:e1], (batch.label[e0:e1] != 0).astype(np.int64)
+        lo = np.full(n, 1 << 40, np.int64)
+        hi = np.full(n, -1, np.int64)
+        if n:
+            lo[0] = hi[0] = 0
+        first = np.searchsorted(src, np.arange(n + 1))
+        for s in range(n):
+            a, b = first[s], first[s + 1]
+            if b > a and hi[s] >= 0:
+                np.minimum.at(lo, dst[a:b], lo[s] + nz[a:b])
+                np.maximum.at(hi, dst[a:b], hi[s] + nz[a:b])
+        w = np.where(hi >= 0, hi - lo + 1, 0)
+        total += int(w[src][batch.label[e0:e1] != 0].sum())
+    return total
+
+
+def cpu_sample(klu, ora, tool, batch, n, flags, cores, **extra):
+    sub = batch.slice(0, min(n, len(batch)))
+    t0 = time.perf_counter()
+    ora.run_batch(oracle_tool(ora, tool), sub.lattices(), cores, **flags, **extra)
+    dt = time.perf_counter() - t0
+    return sub, dt
+
+
+def bench_tools(klu, local, args, peak):
+    """Device-resident numbers of the other tools named by BASELINE.json's configs, each with
+    its pack time, byte model and a bounded CPU baseline (oracle port on all host threads)."""
+    from oracle import ora
+    ora.build()
+    cores = os.cpu_count() or 1
+    out = {}
+    specs = [("segment@c2", "segment", "c2", args.tools_scale * 3000, 256),
+             ("position@c2", "position", "c2", args.tools_scale * 256, cores),
+             ("utterance@c4", "utterance", "c4", args.tools_scale * 32, cores),
+             ("prune_dyn_beam->best_path2@c2", "prune_dyn_beam", "c2", args.tools_scale * 1024, 2 * cores),
+             ("char_position@c5", "char_position", "c5", args.tools_scale * 512, 2 * cores)]
+    for name, tool, shape, nlat, ncpu in specs:
+        nlat = int(max(1, nlat))
+        eng = klu.Engine(local)
+        try:
+            t0 = time.perf_counter()
+            batch = klu.synth_batch(shape, nlat, seed=args.seed)
+            flags = flags_for(tool)
+            eng.load(batch)
+            up_ms, pack_ms, _ = eng.load_times()
+            st = eng.stats()
+            ms = time_steps(eng, klu, tool, flags, args.tools_steps, 2)
+            entries, _ = fetch_for(eng, klu, tool)
+            kern = kernel_profile(eng, klu, tool, flags, 1)
+            entry = {"tool": tool, "shape": shape, "lattices": nlat, "arcs": st["arcs"], "states": st["states"],
+                     "flags": flags, "ms_per_step": ms, "arcs_per_s": st["arcs"] / (ms * 1e-3), "pack_ms": pack_ms,
+                     "arcs_per_s_incl_pack": st["arcs"] / ((ms + pack_ms) * 1e-3), "index_entries": entries,
+                     "kernels_ms": {k: round(v["ms_per_step"], 3) for k, v in kern.items()}}
+            unf = unfolded_arcs(batch.slice(0, min(8, nlat))) * (st["arcs"] / max(1, batch.slice(0, min(8, nlat)).num_arcs)) \
+                if tool == "position" else 0
+            if tool == "position":
+                entry["unfolded_arcs"] = unf
+            mb, mdesc = model_bytes(tool, st, entries, unf)
+            if mb:
+                entry["model"] = mdesc
+                entry["model_bytes_per_step"] = mb
+                entry["hbm_frac"] = mb / (ms * 1e-3) / 1e9 / peak
+            # ---- second stage of configs[2]: lattice-best-path2 on the pruned lattices
+            if tool == "prune_dyn_beam":
+                pruned = eng.pruned_batch()
+                eng.load(pruned)
+                _, pack2, _ = eng.load_times()
+                f2 = dict()
+                ms2 = time_steps(eng, klu, "best_path2", f2, args.tools_steps, 2)
+                st2 = eng.stats()
+                entry.update({"ms_prune": ms, "ms_best_path2": ms2, "pruned_arcs": st2["arcs"], "ms_per_step": ms + ms2,
+                              "pack_ms": pack_ms + pack2, "arcs_per_s": st["arcs"] / ((ms + ms2) * 1e-3),
+                              "arcs_per_s_incl_pack": st["arcs"] / ((ms + ms2 + pack_ms + pack2) * 1e-3)})
+                entry.pop("hbm_frac", None)
+            # ---- CPU baseline: bounded sample on all host threads
+            if not args.no_cpu_baseline:
+                if tool == "utterance":
+                    # the reference composes the lattice with a query automaton per word (~40k words x
+                    # 500k arcs per c4 lattice: tens of minutes per lattice): a sample of words through
+                    # --include-words, scaled to all words
+                    lat0 = batch[0]
+                    words = np.unique(lat0.label[lat0.label != 0])
+                    pick = np.random.RandomState(1).choice(words, min(48, len(words)), replace=False).tolist()
+                    sub, dt = cpu_sample(klu, ora, tool, batch, ncpu, flags, cores, include_words=pick)
+                    done = sum(int(np.isin(np.unique(l.label), pick).sum()) for l in sub.lattices())
+                    allw = sum(int(np.unique(l.label[l.label != 0]).size) for l in sub.lattices())
+                    dt_full = dt * allw / max(1, done)
+                    entry["cpu_baseline"] = {"value": sub.num_arcs / dt_full, "unit": "arcs/s", "cores": cores, "kind": "port",
+                                             "sample": "first %d lattices, %d of their %d (lattice, word) queries run "
+                                                       "(--include-words) in %.1f s on %d threads, scaled to all words"
+                                                       % (len(sub), done, allw, dt, cores), "extrapolated": True}
+                elif tool == "prune_dyn_beam":
+                    sub, dt = cpu_sample(klu, ora, tool, batch, ncpu, flags, cores)
+                    sub2 = pruned.slice(0, len(sub))
+                    t0b = time.perf_counter()
+                    ora.run_batch(ora.BEST_PATH2, sub2.lattices(), cores)
+                    dt2 = time.perf_counter() - t0b
+                    entry["cpu_baseline"] = {"value": sub.num_arcs / (dt + dt2), "unit": "arcs/s", "cores": cores,
+                                             "kind": "port", "sample": "first %d lattices: prune %.1f s + best-path2 on "
+                                             "the pruned lattices %.1f s, %d threads" % (len(sub), dt, dt2, cores)}
+                elif tool == "char_position":
+                    sub = batch.slice(0, min(ncpu, nlat))
+                    lg = {0: 0, 1: 1}
+                    t0b = time.perf_counter()
+                    ora.run_batch(ora.CHAR_POSITION, sub.lattices(), cores, label_group=lg, inc_groups=[ora.INT_MAX],
+                                  del_groups=[1], **flags)
+                    dt = time.perf_counter() - t0b
+                    entry["cpu_baseline"] = {"value": sub.num_arcs / dt, "unit": "arcs/s", "cores": cores, "kind": "port",
+                                             "sample": "first %d lattices, %.1f s on %d threads" % (len(sub), dt, cores)}
+                else:
+                    sub, dt = cpu_sample(klu, ora, tool, batch, ncpu, flags, cores)
+                    entry["cpu_baseline"] = {"value": sub.num_arcs / dt, "unit": "arcs/s", "cores": cores, "kind": "port",
+                                             "sample": "first %d lattices, %.1f s on %d threads" % (len(sub), dt, cores)}
+            entry["wall_s"] = round(time.perf_counter() - t0, 1)
+            out[name] = entry
+        except Exception as ex:  # one tool failing must not lose the headline line
+            out[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        finally:
+            eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,13 +429,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tool", default="frame_post", choices=sorted(TOOLS))
     ap.add_argument("--shape", default="c2")
-    ap.add_argument("--lattices", type=int, default=10000, help="lattices per GPU")
+    ap.add_argument("--lattices", type=int, default=10000, help="lattices per GPU (weak) / in total (strong)")
     ap.add_argument("--ref-lattices", type=int, default=2500, help="bounded CPU sample (lattices) per step")
     ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-slices", type=int, default=8, help="slices of the pipelined end-to-end run (1 = off)")
     ap.add_argument("--e2e-contexts", type=int, default=3, help="contexts (host threads) of the pipelined run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tools", action="store_true", help="skip the per-tool section")
+    ap.add_argument("--tools-steps", type=int, default=3)
+    ap.add_argument("--tools-scale", type=float, default=1.0, help="scales the per-tool lattice counts")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -247,15 +448,14 @@ def main():
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
 
-    rank, world, reduce_max, barrier = dist_setup(args.gpus)
+    rank, world, reduce_max, barrier, gather_obj = dist_setup(args.gpus)
     klu = load_package()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     eng = klu.Engine(local)
     tool = TOOLS[args.tool]
     flags = flags_for(args.tool)
-    nlat = args.lattices
 
-    # ---- synthetic shard of this rank, generated straight into pinned host memory
+    # ---- this rank's lattices, generated straight into pinned host memory
     keep = []
 
     def alloc(nbytes):
@@ -264,18 +464,51 @@ def main():
         return buf
 
     t0 = time.perf_counter()
-    batch = klu.synth_batch(args.shape, nlat, seed=args.seed, first_id=rank * nlat, alloc=alloc)
+    strong = None
+    if args.scaling == "strong" and world > 1:
+        # ONE batch of --lattices lattices for the whole job, cut by total arc count with the
+        # product's partitioner (shard.partition_by_arcs: greedy longest-first); every rank
+        # generates only its own lattices (the generator is deterministic in (seed, id))
+        so = np.zeros(args.lattices + 1, np.int64)
+        ao = np.zeros(args.lattices + 1, np.int64)
+        cfg = klu.lattice.SynthCfg(**klu.lattice.SHAPES[args.shape])
+        import ctypes as C
+        klu.lattice.hostlib().klu_synth_sizes(C.byref(cfg), args.seed, 0, args.lattices, so.ctypes.data,
+                                              ao.ctypes.data, min(os.cpu_count() or 1, 64))
+        counts = np.diff(ao)
+        shards = klu.partition_by_arcs(counts, world)
+        mine = shards[rank]
+        parts = [klu.synth_batch(args.shape, 1, seed=args.seed, first_id=i, nthreads=1) for i in mine]
+        per = [int(counts[s].sum()) for s in shards]
+        strong = {"total_lattices": args.lattices, "total_arcs": int(counts.sum()), "arcs_per_shard": per,
+                  "imbalance_max_over_mean": max(per) / (sum(per) / len(per)), "partitioner": "shard.partition_by_arcs"}
+        cat = klu.LatticeBatch.from_lattices([p[0] for p in parts])
+
+        def pin(x):  # the shard's arrays in pinned host memory, like the generated ones
+            buf = np.frombuffer(alloc(max(x.nbytes, 1)), dtype=x.dtype, count=x.size)
+            buf[:] = x
+            return buf
+
+        batch = klu.LatticeBatch(cat.keys, cat.state_off, cat.arc_off, *[pin(getattr(cat, f)) for f in (
+            "src", "dst", "label", "dur", "graph", "acoustic", "fin_graph", "fin_acoustic", "fin_dur")])
+        nlat = len(batch)
+    else:
+        nlat = args.lattices
+        batch = klu.synth_batch(args.shape, nlat, seed=args.seed, first_id=rank * nlat, alloc=alloc)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng.load(batch)
     t_load = time.perf_counter() - t0
     st = eng.stats()
     arcs, states = st["arcs"], st["states"]
+    total_arcs = sum(gather_obj(arcs))
 
     # ---- device-resident timing (value) ----
     for _ in range(max(args.warmup, 3)):
-        eng.run(tool, **flags)
+        run_tool(eng, klu, args.tool, flags)
     eng.sync()
+    up_ms, pack_ms, frame_ms = eng.load_times()  # the frame index is built by the first frame-post run
+    pack_total = pack_ms + frame_ms
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
@@ -283,53 +516,55 @@ def main():
     eng.sync()
     eng.timer_start()
     for _ in range(args.steps):
-        eng.run(tool, **flags)
+        run_tool(eng, klu, args.tool, flags)
     ms = eng.timer_stop()
     barrier()
     sampler.stop_flag = True
     launches = eng.launch_count() - launches0
     ms = reduce_max(ms)
     ms_per_step = ms / args.steps
+    pack_total = reduce_max(pack_total)
     entries, _ = fetch_for(eng, klu, args.tool)
-    value = world * arcs / (ms_per_step * 1e-3)
+    value = total_arcs / (ms_per_step * 1e-3)
 
     # ---- per-kernel profile (CUDA events on the launching stream) ----
-    eng.profile(True)
-    for _ in range(2):
-        eng.run(tool, **flags)
-    prof = eng.profile_json()
-    eng.profile(False)
-    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    dom = max(prof, key=lambda k: prof[k]["ms"])
+    prof = kernel_profile(eng, klu, args.tool, flags, 2)
+    tot_ms = sum(v["ms_per_step"] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k]["ms_per_step"])
     peak, peak_src = peaks()
     band = st["band"]
+    unf = unfolded_arcs(batch.slice(0, min(8, nlat))) * (arcs / max(1, batch.slice(0, min(8, nlat)).num_arcs)) \
+        if args.tool in ("position", "best_path2", "position_post") else 0
 
     def algo_bytes(name):
         a = ALGO.get(name, dict(arc=0, state=0, entry=0))
         return (a["arc"] * arcs + a["state"] * states + a["entry"] * entries + a.get("band", 0) * band +
-                a.get("inst", 0) * st.get("frame_instances", 0))
+                a.get("inst", 0) * st.get("frame_instances", 0) + a.get("unfolded", 0) * unf)
 
     kern = {}
     for k, v in prof.items():
-        per_launch_ms = v["ms"] / v["launches"]
+        per_launch_ms = v["ms_per_step"] / max(v["launches_per_step"], 1e-9)
         ab = algo_bytes(k)
-        kern[k] = {"launches_per_step": v["launches"] / 2, "ms_per_launch": per_launch_ms,
-                   "share": v["ms"] / tot_ms,
-                   "algo_GBps": ab / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
-    dom_ms = prof[dom]["ms"] / prof[dom]["launches"]
-    achieved = algo_bytes(dom) / (dom_ms * 1e-3) / 1e9
-    # whole-pipeline algorithmic model of SURVEY.md 8d: 76 B/arc + 28 B/state
+        kern[k] = {"launches_per_step": v["launches_per_step"], "ms_per_launch": per_launch_ms,
+                   "share": v["ms_per_step"] / tot_ms,
+                   "algo_GBps": ab / (v["ms_per_step"] * 1e-3) / 1e9 if v["ms_per_step"] > 0 else None}
+    dom_ms = prof[dom]["ms_per_step"] / max(prof[dom]["launches_per_step"], 1e-9)
+    achieved = algo_bytes(dom) / max(prof[dom]["launches_per_step"], 1e-9) / (dom_ms * 1e-3) / 1e9
+    # whole-pipeline algorithmic model of SURVEY.md 8d: 76 B/arc + 28 B/state (the segment / position tools'
+    # emit + reduce-by-key pipeline; quoted for the frame-post step only as a common yardstick)
     pipe_bytes = 76.0 * arcs + 28.0 * states
-    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    traffic, traffic_note = None, None  # DRAM bytes per launch of the dominant kernel (ncu --set full)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if dom in tj:
             traffic = tj[dom]["dram_bytes_per_arc"] * arcs
+            traffic_note = tj[dom].get("note")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes(dom),
+                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes(dom) / max(prof[dom]["launches_per_step"], 1e-9),
                 "pipeline_frac_76B_per_arc": pipe_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                "pipeline_frac_76B_per_arc_incl_pack": pipe_bytes / ((ms_per_step + pack_total) * 1e-3) / 1e9 / peak,
                 "kernels": kern}
 
     # ---- end to end through the C ABI: host arrays -> index on the host ----
@@ -352,13 +587,13 @@ def main():
     if args.tool == "frame_post":  # results land in pinned host buffers
         out = (eng.pinned_array(np.int32, entries), eng.pinned_array(np.int32, entries),
                eng.pinned_array(np.float32, entries))
-    e2e_ms, parts = [], []
-    for i in range(args.e2e_steps + 1):
+    e2e_ms, parts, packs = [], [], []
+    for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
         eng.load(batch, state_num_arcs=narcs)
         t1 = time.perf_counter()
-        eng.run(tool, **flags)
+        run_tool(eng, klu, args.tool, flags)
         eng.sync()
         t2 = time.perf_counter()
         _, d2h = fetch_for(eng, klu, args.tool, out)
@@ -367,7 +602,10 @@ def main():
         if i > 0:
             e2e_ms.append(1e3 * dt)
             parts.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t0 + dt - t2)))
+            packs.append(eng.load_times())
     single_step = reduce_max(sum(e2e_ms) / len(e2e_ms)) if e2e_ms else None
+    if packs:  # pack time of a load with nothing else queued on the GPU (the e2e loads)
+        pack_total = reduce_max(float(np.mean([p[1] + p[2] for p in packs])))
     pipe_step = None
     if args.e2e_steps > 0 and args.e2e_slices > 1 and args.tool == "frame_post":
         eng.close()  # its device memory goes to the pipeline contexts
@@ -411,11 +649,14 @@ def main():
         for e in engines:
             e.close()
     e2e_step = pipe_step if pipe_step else single_step
-    e2e = {"value": world * arcs / (e2e_step * 1e-3) if e2e_step else None, "unit": "arcs/s",
+    e2e = {"value": total_arcs / (e2e_step * 1e-3) if e2e_step else None, "unit": "arcs/s",
            "ms_per_step": e2e_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "h2d_GBps_per_rank": h2d / (e2e_step * 1e-3) / 1e9 if e2e_step else None,
            "single_call_ms_per_step": single_step,
            "single_call_ms_load_run_fetch": [round(float(np.mean([p[k] for p in parts])), 2) for k in range(3)]
            if parts else None,
+           "single_call_ms_upload_pack_frameindex": [round(float(np.mean([p[k] for p in packs])), 2) for k in range(3)]
+           if packs else None,
            "pipeline": {"slices": args.e2e_slices, "contexts": args.e2e_contexts} if pipe_step else None,
            "note": "klu_load (H2D of the caller's pinned SoA arrays + device packer) + klu_run + klu_fetch "
                    "(D2H of the full index into pinned buffers), wall clock, max over ranks; value = the "
@@ -423,32 +664,48 @@ def main():
 
     # ---- CPU baseline (rank 0, bounded sample of the same workload) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.tool in ("frame_post", "segment", "position",
-                                                                                "utterance"):
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.tool in (
+            "frame_post", "segment", "position", "utterance", "best_path2", "position_post"):
         from oracle import ora
         ora.build()
         cores = os.cpu_count() or 1
         n = min(4 * args.ref_lattices, nlat)  # ~10-30 s of CPU work at full size
+        if args.tool in ("position", "best_path2", "position_post"):
+            n = min(n, 2 * cores)
+        elif args.tool == "utterance":
+            n = min(n, cores)
         sub = batch.slice(0, n)
-        otool = {"frame_post": ora.FRAME_POST, "segment": ora.SEGMENT, "position": ora.POSITION,
-                 "utterance": ora.UTTERANCE}[args.tool]
         t0 = time.perf_counter()
-        ora.run_batch(otool, sub.lattices(), cores, **flags)
+        ora.run_batch(oracle_tool(ora, args.tool), sub.lattices(), cores, **flags)
         dt = time.perf_counter() - t0
         cpu = {"value": sub.num_arcs / dt, "unit": "arcs/s", "cores": cores, "kind": "port",
                "sample": "first %d lattices of the workload (%d arcs), one oracle run on %d host threads, %.1f s"
                          % (n, sub.num_arcs, cores, dt)}
 
+    tools = None
+    if rank == 0 and world == 1 and not args.no_tools and args.tool == "frame_post":
+        if eng.h:
+            eng.close()
+        del batch, keep
+        tools = bench_tools(klu, local, args, peak)
+
     if rank == 0:
         print(json.dumps({
-            "metric": "lattice arcs/sec (fwd-bwd + word-position index)", "value": value, "unit": "arcs/s",
+            "metric": METRIC, "metric_note": METRIC_NOTE, "value": value, "unit": "arcs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, nlat),
             "batch": {"lattices": st["lattices"], "states": states, "arcs": arcs, "levels": st["levels"],
-                      "index_entries": entries, "gen_s": t_gen, "load_s": t_load},
+                      "index_entries": entries, "gen_s": t_gen, "load_s": t_load, "total_arcs_all_ranks": total_arcs},
+            "pack_ms": pack_total,
+            "value_incl_pack": total_arcs / ((ms_per_step + pack_total) * 1e-3),
+            "pack_note": "device time, once per batch, of the packer in klu_load plus the frame index "
+                         "(the (frame, word) sort) built by the first frame-post run; `value` leaves it out, "
+                         "`value_incl_pack` adds it to every step",
+            "strong_scaling": strong,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": sampler.summary()}))
+            "tools": tools, "clocks": sampler.summary()}))
     if eng.h:
         eng.close()
     if world > 1:

@@ -19,6 +19,7 @@
  *   KLU_POSITION_POST  latbin/lattice-to-word-position-post.cc:70-141
  *   KLU_CHAR_SEGMENT   kwsbin2/lattice-char-index-segment.cc:93-223
  *   KLU_LENGTH_DIST    latbin/lattice-to-transcript-length-dist.cc:64-125
+ *   KLU_PRUNE_ARCS     latbin/lattice-prune-arcs.cc:34-84,136-165
  *
  * Plain pointers and sizes only; all pointers are HOST pointers.  Every function
  * returns 0 on success; on failure klu_last_error() (thread-local) explains.
@@ -57,7 +58,8 @@ enum klu_tool {
   KLU_FWD_BWD = 7, /* alpha/beta only (ComputeLatticeAlphasAndBetas [ext]) */
   KLU_POSITION_POST = 8,
   KLU_CHAR_SEGMENT = 9,
-  KLU_LENGTH_DIST = 10
+  KLU_LENGTH_DIST = 10,
+  KLU_PRUNE_ARCS = 11
 };
 
 /* A batch of lattices as concatenated SoA arrays.  state_off/arc_off have
@@ -160,7 +162,8 @@ int klu_fetch_length_dist(klu_ctx* ctx, int32_t* length, float* logp);
 /* best-path2: entries are the transcript labels; cost[num_lattices] (float path
  * cost, latbin/lattice-best-path2.cc:192), num_frames[num_lattices]. */
 int klu_fetch_best_path2(klu_ctx* ctx, int32_t* label, float* cost, int32_t* num_frames);
-/* prune-dyn-beam: entries are surviving arcs: index of the arc in the caller's
+/* prune-dyn-beam and prune-arcs (for the latter beams[2*l] = beam - total, [2*l+1] = rank of
+ * the first arc put back; a state's arcs come in the order AddArc left them): entries are surviving arcs: index of the arc in the caller's
  * arrays (lattice-local), its new src/dst state ids and its output weights
  * (original scale after the float round trip, :188-192).  state_map has one
  * entry per input state (concatenated like fin_graph): new id or -1; fin_* are
@@ -189,6 +192,11 @@ int klu_launch_count(klu_ctx* ctx, int64_t* n);
  * {"kernel": {"launches": n, "ms": total}, ...} into buf. */
 int klu_profile_enable(klu_ctx* ctx, int on);
 int klu_profile_json(klu_ctx* ctx, char* buf, size_t cap);
+/* Device-side cost of the last klu_load, for honest throughput figures: upload_ms = wall
+ * clock of the host-to-device copies of the caller's arrays; pack_ms = CUDA-event time of
+ * the device packer (levels, CSR, bands); frame_index_ms = CUDA-event time of the frame index
+ * that the first KLU_FRAME_POST run on the batch builds (0 until then). */
+int klu_load_times(klu_ctx* ctx, float* upload_ms, float* pack_ms, float* frame_index_ms);
 /* Totals of the loaded batch: {lattices, states, arcs, levels, entries of last run}. */
 int klu_batch_stats(klu_ctx* ctx, int64_t stats[8]);
 /* Writes `bytes` of device memory to evict L2 between timed iterations. */

@@ -12,13 +12,13 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST, CHAR_SEGMENT, LENGTH_DIST = range(11)
+SEGMENT, POSITION, UTTERANCE, FRAME_POST, PRUNE_DYN_BEAM, BEST_PATH2, CHAR_POSITION, FWD_BWD, POSITION_POST, CHAR_SEGMENT, LENGTH_DIST, PRUNE_ARCS = range(12)
 TOOL_NAMES = {SEGMENT: "lattice-word-index-segment", POSITION: "lattice-word-index-position",
               UTTERANCE: "lattice-word-index-utterance", FRAME_POST: "lattice-to-word-frame-post",
               PRUNE_DYN_BEAM: "lattice-prune-dyn-beam", BEST_PATH2: "lattice-best-path2",
               CHAR_POSITION: "lattice-char-index-position", FWD_BWD: "fwd-bwd",
               POSITION_POST: "lattice-to-word-position-post", CHAR_SEGMENT: "lattice-char-index-segment",
-              LENGTH_DIST: "lattice-to-transcript-length-dist"}
+              LENGTH_DIST: "lattice-to-transcript-length-dist", PRUNE_ARCS: "lattice-prune-arcs"}
 INT_MAX = 2**31 - 1
 
 # every symbol include/klu.h declares (checked by tests/test_capi_symbols.py)
@@ -27,7 +27,7 @@ SYMBOLS = ["klu_last_error", "klu_version", "klu_opts_default", "klu_device_coun
            "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_position_post", "klu_fetch_length_dist",
            "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position", "klu_fetch_char_segment",
            "klu_fetch_fwd_bwd", "klu_timer_start", "klu_timer_stop", "klu_launch_count", "klu_profile_enable",
-           "klu_profile_json", "klu_batch_stats", "klu_flush_l2"]
+           "klu_profile_json", "klu_batch_stats", "klu_flush_l2", "klu_load_times"]
 
 
 class KluLattices(C.Structure):
@@ -324,8 +324,19 @@ class Engine:
         off, lab, cost, nf = self.fetch_best_path2()
         return [(lab[a:b].tolist(), float(cost[l])) for l, (a, b) in enumerate(zip(off[:-1], off[1:]))]
 
+    def prune_arcs(self, **o):
+        """lattice-prune-arcs: like prune_dyn_beam(); `first_kept` / `cutoff` instead of the beams."""
+        self.run(PRUNE_ARCS, **o)
+        res = self._pruned_lattices()
+        for r in res:
+            r["cutoff"], r["first_kept"] = r.pop("beam0"), int(r.pop("beam"))
+        return res
+
     def prune_dyn_beam(self, **o):
         self.run(PRUNE_DYN_BEAM, **o)
+        return self._pruned_lattices()
+
+    def _pruned_lattices(self):
         off, ai, ns, nd, g, a, smap, fg, fa, beams = self.fetch_prune()
         b = self.batch
         res = []
@@ -340,6 +351,24 @@ class Engine:
             res.append(dict(arcs=arcs, finals=finals, nstates=int((m >= 0).sum()), beam0=float(beams[2 * l]),
                             beam=float(beams[2 * l + 1])))
         return res
+
+    def pruned_batch(self):
+        """The lattices lattice-prune-dyn-beam would write, as a LatticeBatch (numpy only): the
+        input of the second stage of BASELINE.json configs[2] (prune piped into best-path2)."""
+        from .lattice import LatticeBatch
+        off, ai, ns, nd, g, a, smap, fg, fa, beams = self.fetch_prune()
+        b = self.batch
+        L = len(b)
+        keep = smap >= 0
+        lat_of_state = np.repeat(np.arange(L), np.diff(b.state_off))
+        so = np.zeros(L + 1, np.int64)
+        np.cumsum(np.bincount(lat_of_state[keep], minlength=L), out=so[1:])
+        lat_of_arc = np.repeat(np.arange(L), np.diff(off))
+        orig = b.arc_off[lat_of_arc] + ai
+        return LatticeBatch(list(b.keys), so, off.astype(np.int64), np.ascontiguousarray(ns), np.ascontiguousarray(nd),
+                            np.ascontiguousarray(b.label[orig]), np.ascontiguousarray(b.dur[orig]),
+                            np.ascontiguousarray(g), np.ascontiguousarray(a), np.ascontiguousarray(fg[keep]),
+                            np.ascontiguousarray(fa[keep]), np.ascontiguousarray(b.fin_dur[keep]))
 
     def char_position(self, wspace, other_groups=(), **o):
         lg, inc, dele = char_groups(wspace, other_groups)
@@ -400,6 +429,12 @@ class Engine:
         _chk(self.L.klu_batch_stats(self.h, s))
         return dict(lattices=s[0], states=s[1], arcs=s[2], levels=s[3], entries=s[4], band=s[5], frame_instances=s[6],
                     max_time=s[7])
+
+    def load_times(self):
+        """(upload ms, device packer ms, frame index ms) of the last load (klu_load_times)."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _chk(self.L.klu_load_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def flush_l2(self):
         _chk(self.L.klu_flush_l2(self.h))

@@ -31,8 +31,7 @@ struct BpArgs {
   long long band_base;
   const double* alpha2;
   const double* beta;
-  const int64_t* ent_base;
-  const int32_t* arc_ent_off;
+  const long long* arc_cellbase;
   const double* ecost;
   float* d2;       // chunk-local cells
   int32_t* par;    // chunk-local cells: in-order arc (global index) or -1
@@ -79,7 +78,6 @@ __global__ void __launch_bounds__(128) k_bp_viterbi(BpArgs a) {
     if (s_begin == s_end) continue;
     const int* lv = b.lvl_start + b.lvl_off[l];
     const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
-    const int64_t ebase = a.ent_base[l];
     for (int s = lv[0] + lane; s < lv[1]; s += 32)
       if (s == s_begin) {
         d2[b.band_off[s]] = 0.0f;
@@ -120,7 +118,7 @@ __global__ void __launch_bounds__(128) k_bp_viterbi(BpArgs a) {
           if (!(du < inf)) continue;
           const int eo = b.in2out[e];
           float w = 0.0f;
-          if (nz) w = (float)a.ecost[ebase + a.arc_ent_off[eo] + (plen - plo)];
+          if (nz) w = (float)a.ecost[a.arc_cellbase[eo] + plen];
           Cand cnd;
           cnd.v = __fadd_rn(du, w);
           cnd.k1 = ((unsigned long long)(unsigned int)plen << 32) | (unsigned int)b.orig[r.x];
@@ -348,8 +346,7 @@ int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch)
   a.band_base = ch.band_base;
   a.alpha2 = ch.alpha2;
   a.beta = c->d_beta.as<double>();
-  a.ent_base = ch.ent_base;
-  a.arc_ent_off = ch.arc_ent_off;
+  a.arc_cellbase = ch.arc_cellbase;
   a.ecost = ch.ecost;
   a.d2 = c->d_vfwd.as<float>();
   a.par = c->d_vbwd.as<int32_t>();

@@ -126,6 +126,9 @@ struct klu_ctx {
   };
   std::vector<StagedRead> stage_reads;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;  // around the device packer
+  float load_upload_ms = 0.f, load_pack_ms = 0.f, lazy_pack_ms = 0.f;  // klu_load_times
+  bool frame_ready = false;  // frame index of the loaded batch built (klu_frame.cu; on first use)
   int num_sms = 148;
   int64_t launches = 0;
   bool profile = false;
@@ -196,26 +199,29 @@ int check_launch(const char* what);
 int pack_and_upload(klu_ctx* c, const klu_lattices* lats);       // host packer (KLU_HOST_PACKER=1)
 // klu_gpack.cu
 int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* lats);   // device packer (default)
+int ensure_frame_index(klu_ctx* c);  // frame -> arc offsets + (frame, word) groups, on first use
 // klu_sweep.cu
 int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam);
 int run_tropical_sweeps(klu_ctx* c, const CostParams& cp);
 int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam, int l0, int l1);
 // klu_index.cu
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o);
+// klu_position.cu: lattice-word-index-position, lattice-to-word-position-post, lattice-best-path2
+int run_position_tool(klu_ctx* c, int tool, const klu_opts* o);
 // klu_frame.cu
 int build_frame_groups(klu_ctx* c);  // pack time: (frame, word)-sorted instances, head bits, output offsets
 int run_frame_post(klu_ctx* c, const klu_opts* o);
 // klu_prune.cu
 int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o);
+int run_prune_arcs(klu_ctx* c, const klu_opts* o);  // lattice-prune-arcs
 // klu_bestpath.cu: decode stage of lattice-best-path2 for lattices [l0, l1); the
 // (label, position) posteriors were already turned into per-entry float costs.
 struct BestPathChunk {
   int l0, l1;
-  long long band_base;          // first band cell of the chunk
-  const double* alpha2;         // chunk-local banded alpha
-  const int64_t* ent_base;      // [L] chunk-local first entry slot per lattice
-  const int32_t* arc_ent_off;   // [E] lattice-local first entry of each out-order arc
-  const double* ecost;          // per entry: (double)(float) cost of its (label, position)
+  long long band_base;            // first band cell of the chunk
+  const double* alpha2;           // chunk-local banded alpha
+  const long long* arc_cellbase;  // [E] per out-order arc: its (label, position) cell = arc_cellbase[e] + position
+  const double* ecost;            // per (label, position) cell: (double)(float) cost 1 - P
   bool first_chunk;
 };
 int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch);

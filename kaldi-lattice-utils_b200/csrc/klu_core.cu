@@ -265,11 +265,15 @@ int klu_create(int device, klu_ctx** out) {
     KLU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KLU_CUDA(cudaEventCreate(&c->ev0));
     KLU_CUDA(cudaEventCreate(&c->ev1));
+    KLU_CUDA(cudaEventCreate(&c->ev_p0));
+    KLU_CUDA(cudaEventCreate(&c->ev_p1));
     return 0;
   };
   if (init() != 0) {  // nothing of a half-made context is left behind
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_p0) cudaEventDestroy(c->ev_p0);
+    if (c->ev_p1) cudaEventDestroy(c->ev_p1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 1;
@@ -298,6 +302,8 @@ int klu_destroy(klu_ctx* c) {
   }
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_p0);
+  cudaEventDestroy(c->ev_p1);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -361,8 +367,14 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
       lats = &with_src;
     }
   }
-  if (getenv("KLU_HOST_PACKER")) KLU_TRY(pack_and_upload(c, lats));
-  else KLU_TRY(pack_and_upload_gpu(c, lats));
+  c->load_upload_ms = c->load_pack_ms = c->lazy_pack_ms = 0.f;
+  c->frame_ready = false;
+  if (getenv("KLU_HOST_PACKER")) {
+    KLU_TRY(pack_and_upload(c, lats));  // builds the frame index as it goes
+    c->frame_ready = true;
+  } else {
+    KLU_TRY(pack_and_upload_gpu(c, lats));
+  }
   c->loaded = true;
   klu_trace(c, "load: done");
   return 0;
@@ -389,15 +401,24 @@ int klu_run(klu_ctx* c, int tool, const klu_opts* opts) {
       rc = getenv("KLU_GENERIC_FRAME_POST") ? run_index_tool(c, tool, opts) : run_frame_post(c, opts);
       break;
     case KLU_SEGMENT:
-    case KLU_POSITION:
     case KLU_FWD_BWD:
     case KLU_UTTERANCE:
-    case KLU_BEST_PATH2:
-    case KLU_POSITION_POST:
       rc = run_index_tool(c, tool, opts);
+      break;
+    case KLU_POSITION:
+    case KLU_POSITION_POST:
+      // (word, position) cells; KLU_GENERIC_POSITION=1 selects the generic emit/sort/reduce
+      // pipeline over one entry per (arc, length) instead (kept as a cross-check)
+      rc = getenv("KLU_GENERIC_POSITION") ? run_index_tool(c, tool, opts) : run_position_tool(c, tool, opts);
+      break;
+    case KLU_BEST_PATH2:
+      rc = run_position_tool(c, tool, opts);
       break;
     case KLU_PRUNE_DYN_BEAM:
       rc = run_prune_dyn_beam(c, opts);
+      break;
+    case KLU_PRUNE_ARCS:
+      rc = run_prune_arcs(c, opts);
       break;
     case KLU_CHAR_POSITION:
       rc = run_char_position(c, opts);
@@ -476,6 +497,13 @@ int klu_profile_json(klu_ctx* c, char* buf, size_t cap) {
     return 1;
   }
   memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+
+int klu_load_times(klu_ctx* c, float* upload_ms, float* pack_ms, float* frame_index_ms) {
+  if (upload_ms) *upload_ms = c->load_upload_ms;
+  if (pack_ms) *pack_ms = c->load_pack_ms;
+  if (frame_index_ms) *frame_index_ms = c->lazy_pack_ms;
   return 0;
 }
 

@@ -967,6 +967,7 @@ int build_frame_groups(klu_ctx* c) {
 
 int run_frame_post(klu_ctx* c, const klu_opts* o) {
   const int32_t L = c->L;
+  KLU_TRY(ensure_frame_index(c));
   for (int32_t l = 0; l < L; ++l)
     if (!c->h_times_ok[l]) {
       set_error("lattice " + std::to_string(l) + ": inconsistent state times (lattice is not aligned)");

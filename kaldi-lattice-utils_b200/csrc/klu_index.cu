@@ -950,20 +950,6 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       k_reduce<<<dim3(nl, rtiles), 256, 0, c->stream>>>(r);
     }
     KLU_TRY(check_launch("k_reduce"));
-    if (tool == KLU_BEST_PATH2) {
-      BestPathChunk ch;
-      ch.l0 = l0;
-      ch.l1 = l1;
-      ch.band_base = a.band_base;
-      ch.alpha2 = a.alpha2;
-      ch.ent_base = a.ent_base;
-      ch.arc_ent_off = a.arc_ent_off;
-      ch.ecost = a.val;
-      ch.first_chunk = k == 0;
-      KLU_TRY(best_path2_decode(c, cp, ch));
-      continue;
-    }
-
     if (tool == KLU_UTTERANCE) {
       UttArgs u;
       u.b = a.b;

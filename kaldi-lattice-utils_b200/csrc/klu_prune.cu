@@ -18,7 +18,10 @@
 
 #include <algorithm>
 
+#include <string.h>
+
 #include "klu_common.cuh"
+#include "klu_sort.cuh"
 
 namespace klu {
 
@@ -285,7 +288,304 @@ __global__ void __launch_bounds__(1024) k_scan_counts32(const int32_t* cnt, int 
   if (tid == 0) off[L] = carry_s;
 }
 
+// ----------------------------------------------------------- lattice-prune-arcs ---
+// latbin/lattice-prune-arcs.cc:34-84.  As written there: arcs sorted by
+// ascending cost-through = cost_arc - alpha[s] - beta[next] (most probable first), their mass
+// accumulated in that order until -log(mass) < beam - total, and the arcs FROM that one on put
+// back with AddArc (so a state's arcs come back in sorted order); Connect [ext] trims the rest.
+// The source's std::sort compares the cost alone, so arcs of EQUAL cost have no defined order
+// there; here they keep the lattice's own arc order (a stable sort -- one of its valid outcomes).
+struct PruneArcsArgs {
+  const double* alpha;
+  const double* beta;
+  const double* total;
+  double beam;
+  const int64_t* seg_base;  // [L] = e_off
+  const int32_t* seg_cnt;   // [L]
+  unsigned long long *key_a, *key_b;
+  unsigned int *idx_a, *idx_b;
+  const unsigned char* where;
+  int* first_kept;      // [L] rank of the first arc put back (== arcs: nothing is)
+  int* rank;            // [E] by (e_off + original arc index): position in the sorted order
+  unsigned char* reach; // [S] packed states: bit 0 accessible, bit 1 co-accessible over the kept arcs
+};
+
+// grid (lattices, tiles): sort key of every arc, laid out in the caller's arc order (the
+// stable sort then breaks ties by that order)
+__global__ void __launch_bounds__(256) k_pa_keys(PruneArgs a, PruneArcsArgs p) {
+  const int l = blockIdx.x;
+  const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
+  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
+    const int4 r = a.b.out_rec[e];
+    const int s = a.b.out_src[e];
+    const int o = a.b.out_orig[e];
+    // cost_arc + alphas[s] + betas[nextstate] with both vectors negated, :52-53
+    const double ct = __dadd_rn(__dadd_rn(rec_cost(r, a.cp), -p.alpha[s]), -p.beta[r.x]);
+    p.key_a[e0 + o] = ord_f64(ct);
+    p.idx_a[e0 + o] = (unsigned int)o;
+  }
+}
+
+// one thread per lattice: the accumulation loop of :62-69 in sorted order, to the cut
+__global__ void __launch_bounds__(128) k_pa_cut(PruneArgs a, PruneArcsArgs p, double* beams) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= a.b.L) return;
+  const int n = p.seg_cnt[l];
+  const unsigned long long* key = (p.where[l] ? p.key_b : p.key_a) + p.seg_base[l];
+  const double cutoff = a.b.s_off[l] == a.b.s_off[l + 1] ? 0.0 : __dadd_rn(p.beam, -p.total[l]);
+  double cost_acc = pos_inf();
+  int i = 0;
+  for (; i < n; ++i) {
+    const unsigned long long k = key[i];
+    const unsigned long long bits = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;  // ord_f64 inverted
+    const double ct = __longlong_as_double((long long)bits);
+    cost_acc = -log_add(-cost_acc, -ct);
+    if (cost_acc < cutoff) break;
+  }
+  p.first_kept[l] = i;
+  beams[2 * l] = cutoff;
+  beams[2 * l + 1] = (double)i;
+}
+
+// grid (lattices, tiles): rank of every arc in the sorted order, by original arc index
+__global__ void __launch_bounds__(256) k_pa_rank(PruneArgs a, PruneArcsArgs p) {
+  const int l = blockIdx.x;
+  const int n = p.seg_cnt[l];
+  const int e0 = a.b.e_off[l];
+  const unsigned int* idx = (p.where[l] ? p.idx_b : p.idx_a) + p.seg_base[l];
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < n; q += gridDim.y * blockDim.x) p.rank[e0 + (int)idx[q]] = q;
+}
+
+// One warp per lattice: fst::Connect over the arcs put back -- accessible from the start
+// (forward over the levels), co-accessible to a final state (backward) -- then the keep flags
+// in the caller's index space.
+__global__ void __launch_bounds__(128) k_pa_connect(PruneArgs a, PruneArcsArgs p) {
+  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (l >= a.b.L) return;
+  const BatchView& b = a.b;
+  const int s0 = b.s_off[l], s1 = b.s_off[l + 1];
+  const int e0 = b.e_off[l], e1 = b.e_off[l + 1];
+  if (s0 == s1) return;
+  const int first = p.first_kept[l];
+  const bool none = first >= e1 - e0;  // nothing put back: DeleteStates(), :71-73
+  const int* lv = b.lvl_start + b.lvl_off[l];
+  const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
+  for (int s = s0 + lane; s < s1; s += 32) p.reach[s] = (!none && s == s0) ? 1 : 0;
+  __syncwarp();
+  for (int j = 1; j < nl && !none; ++j) {
+    for (int s = lv[j] + lane; s < lv[j + 1]; s += 32) {
+      unsigned char r = 0;
+      for (int e = b.in_off[s]; e < b.in_off[s + 1] && !r; ++e) {
+        const int src = b.in_rec[e].x;
+        if (p.rank[e0 + b.out_orig[b.in2out[e]]] >= first && (p.reach[src] & 1)) r = 1;
+      }
+      p.reach[s] = r;
+    }
+    __syncwarp();
+  }
+  for (int j = nl - 1; j >= 0 && !none; --j) {
+    for (int s = lv[j] + lane; s < lv[j + 1]; s += 32) {
+      const float fg = b.fin_g[s], fa = b.fin_a[s];
+      unsigned char r = !(isinf(fg) && isinf(fa)) ? 2 : 0;
+      for (int e = b.out_off[s]; e < b.out_off[s + 1] && !r; ++e)
+        if (p.rank[e0 + b.out_orig[e]] >= first && (p.reach[b.out_rec[e].x] & 2)) r = 2;
+      p.reach[s] |= r;
+    }
+    __syncwarp();
+  }
+  const bool start_ok = !none && p.reach[s0] == 3;  // Connect deletes everything when the start is not kept
+  for (int s = s0 + lane; s < s1; s += 32) a.state_keep[s0 + b.orig[s]] = (start_ok && p.reach[s] == 3) ? 1 : 0;
+  __syncwarp();
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int o = b.out_orig[e];
+    const bool keep = start_ok && p.rank[e0 + o] >= first && p.reach[b.out_src[e]] == 3 && p.reach[b.out_rec[e].x] == 3;
+    a.arc_keep[e0 + o] = keep ? 1 : 0;
+  }
+}
+
+// grid (lattices, tiles): the lattice that is written.  arc_keep / state_keep hold exclusive ranks
+// in the caller's order (k_prune_scan); a state's arcs come out in sorted (cost) order, as AddArc
+// appended them.
+__global__ void __launch_bounds__(256) k_pa_emit(PruneArgs a, PruneArcsArgs p) {
+  const int l = blockIdx.x;
+  const BatchView& b = a.b;
+  const int s0 = b.s_off[l], s1 = b.s_off[l + 1];
+  const int e0 = b.e_off[l], e1 = b.e_off[l + 1];
+  const int64_t out = a.res_off[l];
+  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+  for (int e = e0 + t; e < e1; e += stride) {
+    const int o = b.out_orig[e];
+    if (a.arc_keep[e0 + o] < 0) continue;
+    const int s = b.out_src[e];
+    const int mine = p.rank[e0 + o];
+    int base = 0x7fffffff, before = 0;
+    for (int q = b.out_off[s]; q < b.out_off[s + 1]; ++q) {  // the state's kept arcs (a contiguous run of ranks)
+      const int oq = b.out_orig[q];
+      const int kq = a.arc_keep[e0 + oq];
+      if (kq < 0) continue;
+      base = min(base, kq);
+      before += p.rank[e0 + oq] < mine ? 1 : 0;
+    }
+    const int pos = base + before;
+    const int4 r = b.out_rec[e];
+    a.o_arc[out + pos] = o;
+    a.o_src[out + pos] = a.state_keep[s0 + b.orig[s]];
+    a.o_dst[out + pos] = a.state_keep[s0 + b.orig[r.x]];
+    float g, w;
+    out_weights(__int_as_float(r.y), __int_as_float(r.z), r.w, a, &g, &w);
+    a.o_g[out + pos] = g;
+    a.o_a[out + pos] = w;
+  }
+  for (int s = s0 + t; s < s1; s += stride) {
+    const int os = s0 + b.orig[s];
+    a.o_smap[os] = a.state_keep[os];
+    float g = b.fin_g[s], w = b.fin_a[s];
+    const bool keep_final = !(isinf(g) && isinf(w)) && a.state_keep[os] >= 0;
+    if (keep_final) out_weights(g, w, 0, a, &g, &w);
+    a.o_fg[os] = keep_final ? g : INFINITY;
+    a.o_fa[os] = keep_final ? w : INFINITY;
+  }
+}
+
 }  // namespace
+
+int run_prune_arcs(klu_ctx* c, const klu_opts* o) {
+  if (!(o->beam > 0.0f)) {
+    set_error("--beam_ratio must be in the open range (0.0, inf).");  // latbin/lattice-prune-arcs.cc:131-133 (sic)
+    return 1;
+  }
+  const int32_t L = c->L;
+  c->h_res_off.assign(L + 1, 0);
+  c->last_entries = 0;
+  CostParams cp = make_cost_params(o, false);
+  KLU_TRY(run_log_sweeps(c, cp, false, 0.f));
+  if (L == 0) return 0;
+  const int64_t S = std::max<int64_t>(c->S, 1), E = std::max<int64_t>(c->E, 1);
+  enum { P_KEYA = 0, P_KEYB, P_IDXA, P_BEAMS, P_IDXB, P_SEG, P_RANK, P_AKEEP, P_SKEEP, P_ACNT, P_SCNT, P_REACH };
+  DevBuf* sc = c->d_scratch;
+  KLU_TRY(sc[P_KEYA].reserve(8 * E));
+  KLU_TRY(sc[P_KEYB].reserve(8 * E));
+  KLU_TRY(sc[P_IDXA].reserve(4 * E));
+  KLU_TRY(sc[P_IDXB].reserve(4 * E));
+  KLU_TRY(sc[P_BEAMS].reserve(16 * (size_t)L));  // slot 3: klu_fetch_prune reads the beams there
+  KLU_TRY(sc[P_SEG].reserve(8 * (size_t)(L + 1) + 4 * (size_t)L + 4 * (size_t)L + (size_t)L + 64));
+  KLU_TRY(sc[P_RANK].reserve(4 * E));
+  KLU_TRY(sc[P_AKEEP].reserve(4 * E));
+  KLU_TRY(sc[P_SKEEP].reserve(4 * S));
+  KLU_TRY(sc[P_ACNT].reserve(4 * (size_t)L));
+  KLU_TRY(sc[P_SCNT].reserve(4 * (size_t)L));
+  KLU_TRY(sc[P_REACH].reserve((size_t)S));
+  KLU_TRY(c->d_res[5].reserve(8 * (size_t)(L + 1)));
+  for (int i = 0; i < 4; ++i) KLU_TRY(c->d_res[i].reserve(4 * E));
+  KLU_TRY(c->d_res[4].reserve(8 * E));
+  KLU_TRY(c->d_res[6].reserve(8 * S));
+  KLU_TRY(c->d_res[7].reserve(8 * S));
+  int64_t* d_seg_base = sc[P_SEG].as<int64_t>();
+  int32_t* d_seg_cnt = reinterpret_cast<int32_t*>(d_seg_base + L + 1);
+  int* d_first = d_seg_cnt + L;
+  unsigned char* d_where = reinterpret_cast<unsigned char*>(d_first + L);
+  std::vector<int32_t> seg_cnt(L);
+  int64_t max_arcs = 0;
+  for (int32_t l = 0; l < L; ++l) {
+    seg_cnt[l] = (int32_t)(c->h_e_off[l + 1] - c->h_e_off[l]);
+    max_arcs = std::max<int64_t>(max_arcs, seg_cnt[l]);
+  }
+  KLU_CUDA(cudaMemcpyAsync(d_seg_base, c->h_e_off.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
+  KLU_CUDA(cudaMemcpyAsync(d_seg_cnt, seg_cnt.data(), 4 * (size_t)L, cudaMemcpyHostToDevice, c->stream));
+  PruneArgs a;
+  memset(&a, 0, sizeof(a));
+  a.b = c->view();
+  a.cp = cp;
+  a.arc_keep = sc[P_AKEEP].as<int>();
+  a.state_keep = sc[P_SKEEP].as<int>();
+  a.arc_cnt = sc[P_ACNT].as<int>();
+  a.state_cnt = sc[P_SCNT].as<int>();
+  a.res_off = c->d_res[5].as<int64_t>();
+  a.o_arc = c->d_res[0].as<int32_t>();
+  a.o_src = c->d_res[1].as<int32_t>();
+  a.o_dst = c->d_res[2].as<int32_t>();
+  a.o_g = c->d_res[3].as<float>();
+  a.o_a = c->d_res[4].as<float>();
+  a.o_smap = c->d_res[6].as<int32_t>();
+  a.o_fg = c->d_res[7].as<float>();
+  a.o_fa = c->d_res[7].as<float>() + S;
+  a.inv_gs = 1.0 / (double)o->graph_scale;
+  a.inv_as = 1.0 / (double)o->acoustic_scale;
+  PruneArcsArgs p;
+  p.alpha = c->d_alpha.as<double>();
+  p.beta = c->d_beta.as<double>();
+  p.total = c->d_total.as<double>();
+  p.beam = (double)o->beam;
+  p.seg_base = d_seg_base;
+  p.seg_cnt = d_seg_cnt;
+  p.key_a = sc[P_KEYA].as<unsigned long long>();
+  p.key_b = sc[P_KEYB].as<unsigned long long>();
+  p.idx_a = sc[P_IDXA].as<unsigned int>();
+  p.idx_b = sc[P_IDXB].as<unsigned int>();
+  p.where = d_where;
+  p.first_kept = d_first;
+  p.rank = sc[P_RANK].as<int>();
+  p.reach = sc[P_REACH].as<unsigned char>();
+  const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
+  {
+    KLU_LAUNCH(c, "k_pa_keys");
+    k_pa_keys<<<dim3(L, tiles), 256, 0, c->stream>>>(a, p);
+  }
+  KLU_TRY(check_launch("k_pa_keys"));
+  SegSortArgs ss;
+  ss.seg_base = d_seg_base;
+  ss.seg_cnt = d_seg_cnt;
+  ss.key_a = p.key_a;
+  ss.val_a = p.idx_a;
+  ss.key_b = p.key_b;
+  ss.val_b = p.idx_b;
+  ss.where = d_where;
+  ss.lo_bit = 32;  // high half of the f64 keys first, runs that agree there settled afterwards
+  ss.hi_bit = 64;
+  {
+    KLU_LAUNCH(c, "k_seg_radix_sort");
+    k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+  }
+  KLU_TRY(check_launch("k_seg_radix_sort(arc costs)"));
+  {
+    KLU_LAUNCH(c, "k_order_fixup");
+    k_seg_order_fixup<<<dim3(L, tiles), 256, 0, c->stream>>>(ss, 0);
+  }
+  KLU_TRY(check_launch("k_order_fixup"));
+  {
+    KLU_LAUNCH(c, "k_pa_cut");
+    k_pa_cut<<<(L + 127) / 128, 128, 0, c->stream>>>(a, p, sc[P_BEAMS].as<double>());
+  }
+  KLU_TRY(check_launch("k_pa_cut"));
+  {
+    KLU_LAUNCH(c, "k_pa_rank");
+    k_pa_rank<<<dim3(L, tiles), 256, 0, c->stream>>>(a, p);
+  }
+  KLU_TRY(check_launch("k_pa_rank"));
+  {
+    KLU_LAUNCH(c, "k_pa_connect");
+    k_pa_connect<<<(int)(((int64_t)L * 32 + 127) / 128), 128, 0, c->stream>>>(a, p);
+  }
+  KLU_TRY(check_launch("k_pa_connect"));
+  {
+    KLU_LAUNCH(c, "k_prune_scan");
+    k_prune_scan<<<L, 256, 0, c->stream>>>(a);
+  }
+  KLU_TRY(check_launch("k_prune_scan"));
+  {
+    KLU_LAUNCH(c, "k_scan_counts");
+    k_scan_counts32<<<1, 1024, 0, c->stream>>>(a.arc_cnt, L, c->d_res[5].as<int64_t>());
+  }
+  KLU_TRY(check_launch("k_scan_counts"));
+  {
+    KLU_LAUNCH(c, "k_pa_emit");
+    k_pa_emit<<<dim3(L, tiles), 256, 0, c->stream>>>(a, p);
+  }
+  KLU_TRY(check_launch("k_pa_emit"));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));  // seg_cnt is a stack object
+  c->last_entries = -1;
+  return 0;
+}
 
 int run_prune_dyn_beam(klu_ctx* c, const klu_opts* o) {
   if (!(o->beam_ratio > 0.0f && o->beam_ratio < 1.0f)) {
@@ -409,8 +709,8 @@ using namespace klu;
 extern "C" int klu_fetch_prune(klu_ctx* c, int32_t* arc_index, int32_t* new_src, int32_t* new_dst, float* graph,
                                float* acoustic, int32_t* state_map, float* fin_graph, float* fin_acoustic,
                                double* beams) {
-  if (c->last_tool != KLU_PRUNE_DYN_BEAM) {
-    set_error("klu_fetch_prune: last run was not KLU_PRUNE_DYN_BEAM");
+  if (c->last_tool != KLU_PRUNE_DYN_BEAM && c->last_tool != KLU_PRUNE_ARCS) {
+    set_error("klu_fetch_prune: last run was not KLU_PRUNE_DYN_BEAM / KLU_PRUNE_ARCS");
     return 1;
   }
   KLU_CUDA(cudaSetDevice(c->device));

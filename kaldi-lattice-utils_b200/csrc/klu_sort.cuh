@@ -143,6 +143,36 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort(SegSortA
   }
   if (tid == 0) a.where[seg] = (unsigned char)(executed & 1);
 }
+
+// After a sort that looked at the bits >= a.lo_bit only: every run of elements whose keys agree
+// there is put in full-key order by a stable insertion sort, one thread per run (the runs are
+// log-posteriors equal to ~1e-6 relative: a handful per segment).  Grid (segments, tiles);
+// where[] as k_seg_radix_sort left it; seg0 = first segment of this launch.
+static __global__ void __launch_bounds__(256) k_seg_order_fixup(SegSortArgs a, int seg0) {
+  const int seg = seg0 + blockIdx.x;
+  const int n = a.seg_cnt[seg];
+  const int64_t base = a.seg_base[seg];
+  unsigned long long* K = (a.where[seg] ? a.key_b : a.key_a) + base;
+  unsigned int* V = (a.where[seg] ? a.val_b : a.val_a) + base;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.y * blockDim.x) {
+    const unsigned long long t = K[i] >> a.lo_bit;
+    if ((i > 0 && (K[i - 1] >> a.lo_bit) == t) || (K[i + 1] >> a.lo_bit) != t) continue;  // not the head of a run
+    int j = i + 1;
+    while (j < n && (K[j] >> a.lo_bit) == t) {  // insert element j into the ordered [i, j)
+      const unsigned long long k = K[j];
+      const unsigned int v = V[j];
+      int q = j;
+      while (q > i && K[q - 1] > k) {
+        K[q] = K[q - 1];
+        V[q] = V[q - 1];
+        --q;
+      }
+      K[q] = k;
+      V[q] = v;
+      ++j;
+    }
+  }
+}
 #endif
 
 }  // namespace klu

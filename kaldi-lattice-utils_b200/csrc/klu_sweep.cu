@@ -431,83 +431,148 @@ __global__ void __launch_bounds__(128) k_trop_sweeps(SweepArgs a, double* vfwd, 
 
 // ------------------------------------------------------------- banded log ---
 // alpha2[band_off[s] + (len - band_lo[s])] = log-sum of all paths start -> s that
-// carry exactly `len` non-epsilon labels.  A group owns one (state, len) cell.
-template <int G, bool BEAM>
-__global__ void __launch_bounds__(128) k_banded_alpha(SweepArgs a, double* alpha2_chunk, int l0, int l1,
-                                                      long long band_base) {
+// carry exactly `len` non-epsilon labels: the forward scores of the lattice that
+// DisambiguateStateInputSequenceLength (fstext/fstext-utils2.h:109-215) unfolds,
+// without unfolding it.
+//
+// One CTA owns one lattice (work queue).  A level's cells -- (state, len) pairs, a
+// contiguous run of the band array -- are spread over the threads with consecutive
+// threads on consecutive lengths, so the predecessor's scores are read as contiguous
+// runs.  Per level (cut into pieces of <= kBandStates states / kBandArcs arcs) the
+// incoming arcs are staged once in shared memory as {cost, where the source's band
+// starts relative to the length axis, its valid length range}: a cell's inner loop is
+// two shared-memory reads, a range test and one coalesced global read per arc.
+// Sums of one or two terms are Kaldi's LogAdd exactly; longer ones a streaming
+// log-sum-exp (one exp per term).
+constexpr int kBandThreads = 256;
+constexpr int kBandArcs = 768;
+constexpr int kBandStates = 128;
+
+struct LogSumRun {  // streaming log-sum-exp that remembers its first two terms
+  double m, s, x1, x2;
+  int n;
+  __device__ LogSumRun() : m(neg_inf()), s(0.0), x1(neg_inf()), x2(neg_inf()), n(0) {}
+  __device__ __forceinline__ void add(double v) {
+    if (v == neg_inf()) return;
+    if (n == 0) x1 = v;
+    else if (n == 1) x2 = v;
+    ++n;
+    if (v <= m) {
+      s += fast_exp(v - m);
+    } else {
+      s = (m == neg_inf() ? 0.0 : s * fast_exp(m - v)) + 1.0;
+      m = v;
+    }
+  }
+  __device__ __forceinline__ double value() const {
+    if (n == 0) return neg_inf();
+    if (n == 1) return x1;
+    if (n == 2) return log_add(x1, x2);
+    return m + fast_log(s);
+  }
+};
+
+template <bool BEAM>
+__global__ void __launch_bounds__(kBandThreads) k_banded_alpha(SweepArgs a, double* alpha2_chunk, int l0, int l1,
+                                                                long long band_base) {
+  __shared__ double sa_cost[kBandArcs];
+  __shared__ long long sa_base[kBandArcs];
+  __shared__ int2 sa_range[kBandArcs];
+  __shared__ int ss_arc[kBandStates + 1];
+  __shared__ long long ss_cell[kBandStates + 1];
+  __shared__ int ss_lo[kBandStates];
+  __shared__ int s_item, s_take;
   double* alpha2 = alpha2_chunk - band_base;  // indexed with global band offsets
-  const int lane = threadIdx.x & 31;
   const BatchView& b = a.b;
-  constexpr int SPW = 32 / G;
-  const int grp = lane / G, sl = lane % G;
+  const int tid = threadIdx.x;
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(a.counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= l1 - l0) break;
-    const int l = l0 + item;
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    if (s_item >= l1 - l0) break;
+    const int l = l0 + s_item;
     const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
     if (s_begin == s_end) continue;
     const int* lv = b.lvl_start + b.lvl_off[l];
     const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
-    for (int s = lv[0] + lane; s < lv[1]; s += 32)
-      if (s == s_begin) alpha2[b.band_off[s]] = 0.0;  // other level-0 states are unreachable (width 0)
-    __syncwarp();
+    // level 0: the start state has the single cell (len 0) = 0; other sources are unreachable (width 0)
+    for (int s = lv[0] + tid; s < lv[1]; s += kBandThreads)
+      if (s == s_begin && b.band_off[s + 1] > b.band_off[s]) alpha2[b.band_off[s]] = 0.0;
     for (int j = 1; j < nl; ++j) {
-      const int a0 = lv[j], a1 = lv[j + 1];
-      const long long c0 = b.band_off[a0], c1 = b.band_off[a1];  // cells of this level
-      for (long long base = c0; base < c1; base += SPW) {
-        const long long cell = base + grp;
-        const bool act = cell < c1;
-        int s = a0;
-        if (act) {  // binary search: last state with band_off[s] <= cell
-          int lo = a0, hi = a1 - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (b.band_off[mid] <= cell) lo = mid;
-            else hi = mid - 1;
-          }
-          s = lo;
+      const int a1 = lv[j + 1];
+      int s0 = lv[j];
+      while (s0 < a1) {
+        __syncthreads();  // the previous piece's cells are written, its staging arrays free
+        // ---- the piece: states [s0, s0 + take), as many as fit the staging arrays (>= 1)
+        const int nst = min(a1 - s0, kBandStates);
+        for (int k = tid; k <= nst; k += kBandThreads) {
+          ss_arc[k] = b.in_off[s0 + k];
+          ss_cell[k] = b.band_off[s0 + k];
+          if (k < nst) ss_lo[k] = b.band_lo[s0 + k];
         }
-        const int len = act ? b.band_lo[s] + (int)(cell - b.band_off[s]) : 0;
-        const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
-        double m = neg_inf();
-        int arg = -1;
-        for (int e = e0 + sl; e < e1; e += G) {
-          const int4 r = __ldg(b.in_rec + e);
-          const int plen = len - (r.w != 0 ? 1 : 0);
-          const int plo = b.band_lo[r.x];
-          const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
-          if (plo < 0 || plen < plo || plen >= plo + pw) continue;
-          const double cost = rec_cost(r, a.cp);
-          if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
-          const double x = alpha2[b.band_off[r.x] + plen - plo] - cost;
-          if (x > m) {
-            m = x;
-            arg = e;
-          }
-        }
-        const double lm = m;
-        m = group_max<G>(m);
-        if (!elect_max_lane<G>(lm, m, lane)) arg = -1;
-        double sum = 0.0;
-        if (m > neg_inf()) {
-          for (int e = e0 + sl; e < e1; e += G) {
-            if (e == arg) continue;
-            const int4 r = __ldg(b.in_rec + e);
-            const int plen = len - (r.w != 0 ? 1 : 0);
+        if (tid == 0) s_take = 1;
+        __syncthreads();
+        const int e_base = ss_arc[0];
+        for (int k = tid + 1; k <= nst; k += kBandThreads)
+          if (ss_arc[k] - e_base <= kBandArcs) atomicMax(&s_take, k);
+        __syncthreads();
+        const int take = s_take;
+        const int narcs = ss_arc[take] - e_base;
+        const bool staged = narcs <= kBandArcs;  // else: one state with more arcs than fit (take == 1)
+        if (staged) {
+          for (int i = tid; i < narcs; i += kBandThreads) {
+            const int4 r = __ldg(b.in_rec + e_base + i);
             const int plo = b.band_lo[r.x];
             const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
-            if (plo < 0 || plen < plo || plen >= plo + pw) continue;
-            const double cost = rec_cost(r, a.cp);
-            if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
-            sum += exp(alpha2[b.band_off[r.x] + plen - plo] - cost - m);
+            const int nz = r.w != 0 ? 1 : 0;
+            bool dead = plo < 0 || pw <= 0;
+            if (BEAM && !dead) {
+              int lo = 0, hi = take - 1;  // the arc's destination: last k with ss_arc[k] <= e
+              while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (ss_arc[mid] - e_base <= i) lo = mid;
+                else hi = mid - 1;
+              }
+              dead = arc_pruned(a, l, r.x, s0 + lo, r);
+            }
+            sa_cost[i] = rec_cost(r, a.cp);
+            sa_base[i] = b.band_off[r.x] - plo - nz;           // cell of (source, len - nz) = base + len
+            sa_range[i] = dead ? make_int2(0, 0) : make_int2(plo + nz, plo + pw + nz);  // valid len: [x, y)
           }
         }
-        sum = group_sum<G>(sum);
-        if (act && sl == 0) alpha2[cell] = (m > neg_inf()) ? m + log1p(sum) : neg_inf();
+        __syncthreads();
+        const long long c0 = ss_cell[0], c1 = ss_cell[take];
+        for (long long cell = c0 + tid; cell < c1; cell += kBandThreads) {
+          int lo = 0, hi = take - 1;  // last k with ss_cell[k] <= cell
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (ss_cell[mid] <= cell) lo = mid;
+            else hi = mid - 1;
+          }
+          const int len = ss_lo[lo] + (int)(cell - ss_cell[lo]);
+          LogSumRun acc;
+          if (staged) {
+            const int i1 = ss_arc[lo + 1] - e_base;
+            for (int i = ss_arc[lo] - e_base; i < i1; ++i) {
+              const int2 rg = sa_range[i];
+              if (len >= rg.x && len < rg.y) acc.add(alpha2[sa_base[i] + len] - sa_cost[i]);
+            }
+          } else {
+            const int s = s0 + lo;
+            for (int e = b.in_off[s]; e < b.in_off[s + 1]; ++e) {
+              const int4 r = __ldg(b.in_rec + e);
+              const int plen = len - (r.w != 0 ? 1 : 0);
+              const int plo = b.band_lo[r.x];
+              const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
+              if (plo < 0 || plen < plo || plen >= plo + pw) continue;
+              if (BEAM && arc_pruned(a, l, r.x, s, r)) continue;
+              acc.add(alpha2[b.band_off[r.x] + plen - plo] - rec_cost(r, a.cp));
+            }
+          }
+          alpha2[cell] = acc.value();
+        }
+        s0 += take;
       }
-      __syncwarp();
     }
   }
 }
@@ -606,12 +671,11 @@ int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam
   if (l1 <= l0) return 0;
   KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
   SweepArgs a = make_args(c, cp, use_beam, beam);
-  const int G = pick_group(c->avg_deg);
-  const int grid = sweep_grid(c, l1 - l0);
+  const int grid = std::max(1, std::min(l1 - l0, c->num_sms * 8));  // one CTA per lattice in flight
   {
     KLU_LAUNCH(c, "k_banded_alpha");
-    KLU_DISPATCH_G(G, if (use_beam) k_banded_alpha<kG, true><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>(), l0, l1, band_base);
-                   else k_banded_alpha<kG, false><<<grid, 128, 0, c->stream>>>(a, c->d_alpha2.as<double>(), l0, l1, band_base));
+    if (use_beam) k_banded_alpha<true><<<grid, kBandThreads, 0, c->stream>>>(a, c->d_alpha2.as<double>(), l0, l1, band_base);
+    else k_banded_alpha<false><<<grid, kBandThreads, 0, c->stream>>>(a, c->d_alpha2.as<double>(), l0, l1, band_base);
   }
   return check_launch("k_banded_alpha");
 }

@@ -206,7 +206,7 @@ void ComputeBatch(klu_ctx* ctx, const klu_opts* opts, const Batch* b, Results* r
 #elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     r->i0.resize(n), r->i1.resize(L), r->f0.resize(L);
     KLU_CHECK(klu_fetch_best_path2(ctx, r->i0.data(), r->f0.data(), r->i1.data()));
-#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */ || KLU_TOOL == 11 /* KLU_PRUNE_ARCS */
     const size_t S = (size_t)b->state_off.back();
     r->i0.resize(n), r->i1.resize(n), r->i2.resize(n), r->smap.resize(S);
     r->f0.resize(n), r->f1.resize(n), r->f2.resize(S), r->f3.resize(S), r->beams.resize(2 * (size_t)L);
@@ -401,7 +401,7 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
     st->total_frames += nf[l];
     KIO_LOG("For utterance " << b->lats[l].key << ", best cost is " << cost[l] << " over " << nf[l] << " frames.");
   }
-#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
+#elif KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */ || KLU_TOOL == 11 /* KLU_PRUNE_ARCS */
   const std::vector<int32_t>&ai = r->i0, &ns = r->i1, &nd = r->i2, &smap = r->smap;
   const std::vector<float>&g = r->f0, &a = r->f1, &fg = r->f2, &fa = r->f3;
   const std::vector<double>& beams = r->beams;
@@ -438,6 +438,12 @@ void EmitBatch(ToolState* st, Batch* b, Results* r) {
     WriteCompactLattice(os, bin, out);
     w.End();
     const int64_t oa = (int64_t)in.src.size(), na = off[l + 1] - off[l];
+#if KLU_TOOL == 11 /* KLU_PRUNE_ARCS */
+    (void)beams;
+    KIO_LOG("Lattice " << in.key << " pruned #states from " << in.nstates << " to " << nstates << " and #arcs from "
+                       << oa << " to " << na);  // latbin/lattice-prune-arcs.cc:161-164
+    continue;
+#endif
     if (in.nstates == nstates && oa == na) {
       KIO_LOG("Lattice " << in.key << " was not pruned (beam = " << beams[2 * l] << ", # states = " << in.nstates
                          << ", # arcs = " << oa << ")");
@@ -633,6 +639,10 @@ int main(int argc, char* argv[]) {
     const char* usage =
         "Iteratively reduce the beam of the lattice until a maximum number of arcs and states is achieved.\n\n"
         "Usage: lattice-prune-dyn-beam [options] lat-rspecifier lat-wspecifier\n";
+#elif KLU_TOOL == 11 /* KLU_PRUNE_ARCS */
+    const char* usage =
+        "Iteratively reduce the beam of the lattice until a maximum number of arcs and states is achieved.\n\n"
+        "Usage: lattice-prune-arcs [options] lat-rspecifier lat-wspecifier\n";  // (the reference's own text)
 #elif KLU_TOOL == 5 /* KLU_BEST_PATH2 */
     const char* usage =
         "Generate especial 1-best path through lattices, which minimizes the expected number of position-wise "
@@ -669,6 +679,9 @@ int main(int argc, char* argv[]) {
                 "Specific labels to group as words. Groups are separated with a semicolon, labels within a group "
                 "with spaces.");
 #endif
+#if KLU_TOOL == 11 /* KLU_PRUNE_ARCS */
+    po.Register("beam", &beam, "");  // latbin/lattice-prune-arcs.cc:117
+#endif
 #if KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */
     po.Register("beam-ratio", &st.opts.beam_ratio, "Reduce the maximum beam by this ratio at each iteration.");
     po.Register("min-beam", &st.opts.min_beam, "Minimum beam threshold");
@@ -703,6 +716,13 @@ int main(int argc, char* argv[]) {
     const int kLatArg = 1;
     if (st.opts.beam_ratio <= 0.0 || st.opts.beam_ratio >= 1.0)
       KIO_ERR("--beam_ratio must be in the open range (0.0, 1.0).");
+#elif KLU_TOOL == 11 /* KLU_PRUNE_ARCS */
+    if (po.NumArgs() < 2) {
+      po.PrintUsage();
+      exit(1);
+    }
+    const int kLatArg = 1;
+    if (beam <= 0.0) KIO_ERR("--beam_ratio must be in the open range (0.0, inf).");  // :131-133 (sic)
 #else
     if (po.NumArgs() != 2) {
       po.PrintUsage();
@@ -796,7 +816,7 @@ int main(int argc, char* argv[]) {
     const std::string lattice_rspecifier = po.GetArg(kLatArg);
     TableWriter writer(po.GetOptArg(kLatArg + 1));
     st.writer = &writer;
-    const bool keep = KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */;
+    const bool keep = KLU_TOOL == 4 /* KLU_PRUNE_DYN_BEAM */ || KLU_TOOL == 11 /* KLU_PRUNE_ARCS */;
     {
       Pipeline pipe(&st);
       Batch batch;

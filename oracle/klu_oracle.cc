@@ -1603,6 +1603,186 @@ void BrutePruneDynBeam(Lat lat, const Opts& o, Result* r) {
   r->d0.push_back(margin);
 }
 
+
+// latbin/lattice-prune-arcs.cc:34-84 PruneLatticeArcs + main :136-165.  As written there:
+// arcs are sorted by ASCENDING cost-through (cost_arc - alpha[s] - beta[next], i.e. most
+// probable first; the comment in the source says the opposite), their mass is accumulated in
+// that order until -log(mass) drops below beam - total, and the arcs FROM that one on are put
+// back (the ones before it -- the most probable -- are gone); Connect [ext] trims the rest.
+// The source sorts with std::sort on the cost alone, so the order of arcs with EQUAL cost is
+// unspecified there; here (and in the CUDA path) ties keep the lattice's own arc order (state
+// by state, arcs in stored order) -- a stable sort, one of std::sort's valid outcomes.
+// Rows as PruneDynBeam; s1 = index of the first arc put back; ds0 = beam - total.
+void PruneArcs(Lat lat, const Opts& o, Result* r) {
+  if (o.acoustic_scale != 1.0 || o.graph_scale != 1.0) ScaleLattice(&lat, o.graph_scale, o.acoustic_scale);
+  if (o.insertion_penalty != 0.0) AddWordInsPen(&lat, o.insertion_penalty);
+  const double beam = (double)o.beam;
+  int64_t first_kept = 0;
+  double cost_cutoff = 0.0;
+  if (!lat.Empty()) {
+    std::vector<double> alphas, betas;
+    const double total = AlphasAndBetas(lat, &alphas, &betas);
+    cost_cutoff = beam - total;
+    for (size_t i = 0; i < alphas.size(); ++i) {
+      alphas[i] = -alphas[i];
+      betas[i] = -betas[i];
+    }
+    struct Item { double cost; int32 s; Arc arc; };
+    std::vector<Item> arcs;
+    for (int32 s = 0; s < lat.NumStates(); ++s) {
+      for (const auto& arc : lat.out[s]) {
+        const double cost_arc = Cost(arc.g, arc.a);
+        const double cost_through = cost_arc + alphas[s] + betas[arc.next];
+        arcs.push_back(Item{cost_through, s, arc});
+      }
+      lat.out[s].clear();
+    }
+    std::stable_sort(arcs.begin(), arcs.end(), [](const Item& a, const Item& b) { return a.cost < b.cost; });
+    size_t i = 0;
+    double cost_acc = kInf;
+    for (; i < arcs.size(); ++i) {
+      cost_acc = -LogAdd(-cost_acc, -arcs[i].cost);
+      if (cost_acc < cost_cutoff) break;
+    }
+    first_kept = (int64_t)i;
+    if (i == arcs.size()) lat = Lat();  // DeleteStates()
+    // AddArc appends: the arcs of a state come back in sorted (cost) order, not in their old order
+    for (; i < arcs.size(); ++i) lat.out[arcs[i].s].push_back(arcs[i].arc);
+    std::vector<int32> o2n;
+    Connect(&lat, &o2n);
+  }
+  if (o.acoustic_scale != 1.0 || o.graph_scale != 1.0) {
+    const double ig = 1.0 / o.graph_scale, ia = 1.0 / o.acoustic_scale;
+    for (int32 s = 0; s < lat.NumStates(); ++s) {
+      for (auto& arc : lat.out[s]) {
+        const float g = (float)(ig * arc.g + 0.0 * arc.a);
+        const float a = (float)(0.0 * arc.g + ia * arc.a);
+        arc.g = g;
+        arc.a = a;
+      }
+      if (lat.IsFinal(s)) {
+        const float g = (float)(ig * lat.fg[s] + 0.0 * lat.fa[s]);
+        const float a = (float)(0.0 * lat.fg[s] + ia * lat.fa[s]);
+        lat.fg[s] = g;
+        lat.fa[s] = a;
+      }
+    }
+  }
+  if (o.insertion_penalty != 0.0) AddWordInsPen(&lat, -o.insertion_penalty);
+  for (int32 s = 0; s < lat.NumStates(); ++s)
+    for (const auto& arc : lat.out[s]) {
+      r->i0.push_back(arc.orig);
+      r->i1.push_back(s);
+      r->i2.push_back(arc.next);
+      r->i3.push_back(arc.label);
+      r->f0.push_back(arc.g);
+      r->f1.push_back(arc.a);
+    }
+  for (int32 s = 0; s < lat.NumStates(); ++s)
+    if (lat.IsFinal(s)) {
+      r->i0.push_back(-1);
+      r->i1.push_back(s);
+      r->i2.push_back(lat.fdur[s]);
+      r->i3.push_back(0);
+      r->f0.push_back(lat.fg[s]);
+      r->f1.push_back(lat.fa[s]);
+    }
+  r->s0 = lat.NumStates();
+  r->s1 = first_kept;
+  r->ds0 = cost_cutoff;
+}
+
+// lattice-prune-arcs from the list of all paths: an arc's cost-through is -log of the mass of
+// the paths through it; sort, accumulate, cut, keep the tail, keep what still lies on a path
+// made of kept arcs only.  d0[0] = distance of the accumulated cost to the cutoff at the cut
+// (and one arc before it): the tests only insist on the surviving set when that is well above
+// rounding noise.
+void BrutePruneArcs(Lat lat, const Opts& o, Result* r) {
+  if (o.acoustic_scale != 1.0 || o.graph_scale != 1.0) ScaleLattice(&lat, o.graph_scale, o.acoustic_scale);
+  if (o.insertion_penalty != 0.0) AddWordInsPen(&lat, o.insertion_penalty);
+  std::vector<ListedPath> paths;
+  ListPaths(lat, &paths);
+  const int64_t na = lat.NumArcs();
+  const int32 n = lat.NumStates();
+  std::vector<double> mass(na, kLogZeroDouble);
+  double total = kLogZeroDouble;
+  for (const auto& p : paths) {
+    total = LogAdd(total, -p.cost);
+    for (int32 e : p.arcs) mass[e] = LogAdd(mass[e], -p.cost);
+  }
+  std::vector<int32> order(na);
+  for (int64_t e = 0; e < na; ++e) order[e] = (int32)e;
+  std::stable_sort(order.begin(), order.end(), [&](int32 x, int32 y) { return -mass[x] < -mass[y]; });
+  const double cutoff = (double)o.beam - total;
+  double acc = kLogZeroDouble, margin = kInf;
+  int64_t i = 0;
+  for (; i < na; ++i) {
+    acc = LogAdd(acc, mass[order[i]]);
+    margin = std::min(margin, std::fabs(-acc - cutoff));
+    if (-acc < cutoff) break;
+  }
+  std::vector<char> on(na, 0);
+  for (int64_t k = i; k < na; ++k) on[order[k]] = 1;
+  // what survives Connect: arcs / states on a complete path of kept arcs
+  std::vector<char> arc_live(na, 0), st_live(n, 0);
+  if (i < na)
+    for (const auto& p : paths) {
+      bool ok = true;
+      for (int32 e : p.arcs) ok = ok && on[e];
+      if (!ok) continue;
+      for (int32 e : p.arcs) arc_live[e] = 1;
+      for (int32 s : p.states) st_live[s] = 1;
+    }
+  std::vector<int32> newid(n, -1);
+  int32 m = 0;
+  for (int32 s = 0; s < n; ++s) if (st_live[s]) newid[s] = m++;
+  if (n > 0 && !st_live[0]) { m = 0; std::fill(newid.begin(), newid.end(), -1); }
+  const double ig = 1.0 / o.graph_scale, ia = 1.0 / o.acoustic_scale;
+  const bool scaled = o.acoustic_scale != 1.0 || o.graph_scale != 1.0;
+  auto back = [&](float g, float a, bool word, float* go, float* ao) {
+    if (scaled) {
+      g = (float)(ig * g);
+      a = (float)(ia * a);
+    }
+    if (word && o.insertion_penalty != 0.0) g = g + (-o.insertion_penalty);
+    *go = g;
+    *ao = a;
+  };
+  // arcs of a state come back in sorted order (AddArc appends)
+  std::vector<int32> rank(na);
+  for (int64_t k = 0; k < na; ++k) rank[order[k]] = (int32)k;
+  for (int32 s = 0; s < n && m > 0; ++s) {
+    std::vector<const Arc*> out;
+    for (const auto& arc : lat.out[s]) if (arc_live[arc.orig]) out.push_back(&arc);
+    std::sort(out.begin(), out.end(), [&](const Arc* x, const Arc* y) { return rank[x->orig] < rank[y->orig]; });
+    for (const Arc* arc : out) {
+      float g, a;
+      back(arc->g, arc->a, arc->label != 0, &g, &a);
+      r->i0.push_back(arc->orig);
+      r->i1.push_back(newid[s]);
+      r->i2.push_back(newid[arc->next]);
+      r->i3.push_back(arc->label);
+      r->f0.push_back(g);
+      r->f1.push_back(a);
+    }
+  }
+  for (int32 s = 0; s < n && m > 0; ++s) {
+    if (!lat.IsFinal(s) || !st_live[s]) continue;
+    float g, a;
+    back(lat.fg[s], lat.fa[s], false, &g, &a);
+    r->i0.push_back(-1);
+    r->i1.push_back(newid[s]);
+    r->i2.push_back(lat.fdur[s]);
+    r->i3.push_back(0);
+    r->f0.push_back(g);
+    r->f1.push_back(a);
+  }
+  r->s0 = m;
+  r->s1 = i;
+  r->ds0 = cutoff;
+  r->d0.push_back(margin);
+}
+
 // [ext] fst::TopSort as TopSortCompactLatticeIfNeeded calls it: depth-first visit from the
 // start state, then from every state not yet seen in id order, arcs in stored order; a state
 // is numbered by the reverse of the order in which the visit leaves it.  Rows: i0[old] = new id.
@@ -1683,7 +1863,8 @@ typedef struct ora_opts {
 enum { ORA_SEGMENT = 0, ORA_POSITION = 1, ORA_UTTERANCE = 2, ORA_FRAME_POST = 3, ORA_PRUNE_DYN_BEAM = 4,
        ORA_BEST_PATH2 = 5, ORA_CHAR_POSITION = 6, ORA_POSITION_POST = 8, ORA_CHAR_SEGMENT = 9, ORA_LENGTH_DIST = 14, ORA_BRUTE_SEGMENT = 10, ORA_BRUTE_POSITION = 11,
        ORA_BRUTE_FRAME = 12, ORA_BRUTE_UTTERANCE = 13, ORA_TOP_ORDER = 15, ORA_BRUTE_BEST_PATH2 = 16,
-       ORA_BRUTE_PRUNE = 17, ORA_FWD_BWD = 18 };
+       ORA_BRUTE_PRUNE = 17, ORA_FWD_BWD = 18, ORA_PRUNE_ARCS = 19,
+       ORA_BRUTE_PRUNE_ARCS = 20 };
 
 static Opts ConvertOpts(const ora_opts* o) {
   Opts r;
@@ -1722,6 +1903,8 @@ static void RunTool(int tool, const ora_lat* l, const Opts& o, Result* r) {
     }
     case ORA_BRUTE_BEST_PATH2: BruteBestPath2(lat, o, r); break;
     case ORA_BRUTE_PRUNE: BrutePruneDynBeam(lat, o, r); break;
+    case ORA_PRUNE_ARCS: PruneArcs(lat, o, r); break;
+    case ORA_BRUTE_PRUNE_ARCS: BrutePruneArcs(lat, o, r); break;
     case ORA_SEGMENT: WordIndexSegment(lat, o, r); break;
     case ORA_POSITION: WordIndexPosition(lat, o, r); break;
     case ORA_UTTERANCE: WordIndexUtterance(lat, o, r); break;

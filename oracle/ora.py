@@ -18,6 +18,7 @@ POSITION_POST = 8
 CHAR_SEGMENT = 9
 LENGTH_DIST = 14
 FWD_BWD = 18
+PRUNE_ARCS, BRUTE_PRUNE_ARCS = 19, 20
 BRUTE_SEGMENT, BRUTE_POSITION, BRUTE_FRAME, BRUTE_UTTERANCE = 10, 11, 12, 13
 TOP_ORDER, BRUTE_BEST_PATH2, BRUTE_PRUNE = 15, 16, 17
 
@@ -242,6 +243,21 @@ def brute_prune_dyn_beam(lat, **o):
     r = run(BRUTE_PRUNE, lat, **o)
     arcs, finals = _prune_rows(r)
     return dict(arcs=arcs, finals=finals, nstates=r.s0, iters=r.s1, beam0=r.ds0, beam=r.ds1,
+                margin=float(r.d[0]) if len(r.d) else float("inf"))
+
+
+def prune_arcs(lat, **o):
+    """latbin/lattice-prune-arcs: the lattice it writes (arcs of a state in the order AddArc left
+    them), `first_kept` = index of the first arc put back, `cutoff` = beam - total."""
+    r = run(PRUNE_ARCS, lat, **o)
+    arcs, finals = _prune_rows(r)
+    return dict(arcs=arcs, finals=finals, nstates=r.s0, first_kept=r.s1, cutoff=r.ds0)
+
+
+def brute_prune_arcs(lat, **o):
+    r = run(BRUTE_PRUNE_ARCS, lat, **o)
+    arcs, finals = _prune_rows(r)
+    return dict(arcs=arcs, finals=finals, nstates=r.s0, first_kept=r.s1, cutoff=r.ds0,
                 margin=float(r.d[0]) if len(r.d) else float("inf"))
 
 

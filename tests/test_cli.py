@@ -13,7 +13,7 @@ BIN = os.path.join(ROOT, "kaldi-lattice-utils_b200", "bin")
 TOOLS = ["lattice-word-index-segment", "lattice-word-index-position", "lattice-word-index-utterance",
          "lattice-to-word-frame-post", "lattice-prune-dyn-beam", "lattice-best-path2", "lattice-char-index-position",
          "lattice-to-word-position-post", "lattice-char-index-segment",
-         "lattice-to-transcript-length-dist"]
+         "lattice-to-transcript-length-dist", "lattice-prune-arcs"]
 
 
 def run(tool, *args, env=None, stdin=None):
@@ -191,3 +191,18 @@ def test_error_path_exit_code(tmp_path):
     bad.write_text("cyc\n0 1 1 0,0,1\n1 0 2 0,0,1\n1\n\n")
     r = run("lattice-word-index-segment", "ark:" + str(bad), "ark,t:-")
     assert r.returncode == 255 and b"cyclic" in r.stderr           # main() returns -1
+
+
+@pytest.mark.gpu
+def test_prune_arcs_lattice_roundtrip(tmp_path):
+    # default --beam=inf: everything is put back (the lattice comes out unchanged up to the order
+    # of a state's arcs); a tiny beam drops the most probable arcs, as the reference's code does
+    r = run("lattice-prune-arcs", WORD, "ark,t:-")
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"pruned #states from 10 to 10 and #arcs from 10 to 10" in r.stderr
+    assert r.stdout.decode().split("\n")[0].strip() == "lat1"
+    r = run("lattice-prune-arcs", "--beam=0.5", WORD, "ark,t:-")
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"#arcs from 10 to" in r.stderr
+    r = run("lattice-prune-arcs", "--beam=-1", WORD, "ark,t:-")
+    assert r.returncode == 255 and b"must be in the open range" in r.stderr

@@ -383,3 +383,47 @@ def test_unreachable_and_dead_end_states(klu, ora, engine):
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert_rows_match(g, w, 1, what="holes frame-post")
+
+
+# ---- (word, position) cells vs the generic one-entry-per-(arc, length) pipeline -----------
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+def test_position_cells_equal_generic_pipeline(klu, engine, monkeypatch, shape, n, seed):
+    batch = klu.synth_batch(shape, n, seed=seed + 400)
+    engine.load(batch)
+    flags = dict(acoustic_scale=0.3, beam=7.0)
+    new = dict(pos=engine.position(**flags), pp=engine.position_post(acoustic_scale=0.3))
+    monkeypatch.setenv("KLU_GENERIC_POSITION", "1")
+    old = dict(pos=engine.position(**flags), pp=engine.position_post(acoustic_scale=0.3))
+    for a, b in zip(new["pos"], old["pos"]):
+        assert_rows_match(a, b, 2, tol=1e-9, what="cells vs generic")
+    for a, b in zip(new["pp"], old["pp"]):
+        assert len(a) == len(b)
+        for fa, fb in zip(a, b):
+            assert_rows_match(fa, fb, 1, tol=1e-6, what="cells vs generic, position-post")
+
+
+# ---- lattice-prune-arcs ------------------------------------------------
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", [dict(), dict(beam=0.05), dict(beam=0.5), dict(beam=3.0),
+                                   dict(beam=0.2, acoustic_scale=0.1, graph_scale=0.7, insertion_penalty=0.5)])
+def test_prune_arcs_parity(klu, ora, engine, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 610)
+    lats = batch.lattices() + [klu.make_lattice("empty", 0, [], {}), klu.make_lattice("single", 1, [], {0: (0.5, 0.25)})]
+    engine.load(klu.LatticeBatch.from_lattices(lats))
+    got = engine.prune_arcs(**flags)
+    for l, lat in enumerate(lats):
+        want = ora.prune_arcs(lat, **flags)
+        assert got[l]["first_kept"] == want["first_kept"], "lattice %d" % l
+        assert got[l]["nstates"] == want["nstates"]
+        assert got[l]["arcs"] == want["arcs"]        # surviving arcs in the order AddArc left them, float weights bit-exact
+        assert got[l]["finals"] == want["finals"]
+
+
+def test_prune_arcs_ties_keep_arc_order(klu, ora, engine):
+    # arcs of exactly equal cost-through: the sort is stable (documented tie rule)
+    arcs = [(0, 1, 5 + k, 1.0, 0.5, 1) for k in range(6)] + [(1, 2, 7, 0.5, 0.5, 1), (1, 2, 8, 0.5, 0.5, 1)]
+    lat = klu.make_lattice("ties", 3, arcs, {2: (0.0, 0.0)})
+    engine.load(klu.LatticeBatch.from_lattices([lat]))
+    for beam in (0.1, 1.0, 2.5):
+        got, want = engine.prune_arcs(beam=beam)[0], ora.prune_arcs(lat, beam=beam)
+        assert got["arcs"] == want["arcs"] and got["first_kept"] == want["first_kept"]

@@ -151,11 +151,28 @@ def test_topsort_then_prune_matches_oracle(klu, ora, engine):
     """Lattices with shuffled state ids: klu_topsort numbers the states, lattice-prune-dyn-beam
     writes them; both must equal the oracle's fst::TopSort restatement followed by its
     PruneDynBeam (arcs, new state ids, weights bit-exact)."""
-    from test_topsort import _apply_order, _call, _random_dag
+    from test_topsort import _apply_order, _call
+
+    def connected_dag(n):
+        # every state reachable from the start and on a path to the final state (the reference's
+        # pruning loop does not terminate on anything else: infinite lattice beam)
+        arcs = []
+        for s in range(1, n):
+            for p in set([int(rng.randint(max(0, s - 3), s))] + [int(rng.randint(max(0, s - 6), s)) for _ in range(2)]):
+                arcs.append((p, s, int(rng.randint(0, 6)), float(rng.uniform(0, 3)), float(rng.uniform(0, 3)), s - p))
+        for s in range(n - 1):
+            if not any(a[0] == s for a in arcs):
+                arcs.append((s, s + 1, 1, 1.0, 1.0, 1))
+        perm = np.arange(n)
+        perm[1:] = rng.permutation(np.arange(1, n))
+        arcs = [(int(perm[u]), int(perm[v]), w, g, a, t) for (u, v, w, g, a, t) in arcs]
+        arcs.sort(key=lambda x: x[0])
+        return klu.make_lattice("dag", n, arcs, {int(perm[n - 1]): (0.5, 0.25)})
+
     rng = np.random.RandomState(77)
     sorted_lats, want = [], []
     for k in range(10):
-        lat = _random_dag(klu, rng, 20 + 5 * k)
+        lat = connected_dag(20 + 5 * k)
         rc, got, order = _call(klu, lat)
         assert rc == 0 and order.tolist() == ora.top_order(lat)
         s = _apply_order(klu, lat, order.tolist())

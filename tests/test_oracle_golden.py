@@ -234,3 +234,31 @@ def test_oracle_top_order_properties(klu, ora, seed):
     order = ora.top_order(lat)
     assert sorted(order) == list(range(lat.nstates))
     assert all(order[s] < order[d] for s, d in zip(lat.src.tolist(), lat.dst.tolist()))
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("flags", [dict(beam=0.05), dict(beam=0.5), dict(beam=3.0), dict(),
+                                   dict(beam=0.2, acoustic_scale=0.1, graph_scale=0.7, insertion_penalty=0.5)])
+def test_oracle_prune_arcs_vs_all_paths(klu, ora, seed, flags):
+    """latbin/lattice-prune-arcs.cc:34-84 by its definition (an arc's cost-through is -log of the
+    mass of the paths through it; ascending sort; accumulate; put back the arcs from the cut on;
+    keep what still lies on a path of kept arcs) against the restatement through alpha/beta."""
+    checked = 0
+    for lat in klu.synth_batch("tiny", 4, seed=900 + seed).lattices():
+        want = ora.brute_prune_arcs(lat, **flags)
+        got = ora.prune_arcs(lat, **flags)
+        assert abs(got["cutoff"] - want["cutoff"]) <= 1e-9 * max(1.0, abs(want["cutoff"])) or want["cutoff"] == got["cutoff"]
+        if want["margin"] > 1e-9:
+            assert got["first_kept"] == want["first_kept"] and got["nstates"] == want["nstates"]
+            assert got["arcs"] == want["arcs"] and got["finals"] == want["finals"]
+            checked += 1
+    assert checked >= 3
+
+
+def test_oracle_prune_arcs_default_beam_keeps_everything(klu, ora):
+    lat = klu.synth_batch("small", 1, seed=3)[0]
+    r = ora.prune_arcs(lat)
+    assert r["first_kept"] == 0 and r["nstates"] == lat.nstates and len(r["arcs"]) == lat.narcs
+    assert sorted(a[0] for a in r["arcs"]) == list(range(lat.narcs))
+    # a state's arcs come back in ascending cost-through order (AddArc appends), not in stored order
+    assert [a[0] for a in r["arcs"]] != list(range(lat.narcs))
