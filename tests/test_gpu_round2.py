@@ -208,13 +208,15 @@ def test_c3_prune_then_best_path2_through_the_binaries(klu, ora, tmp_path):
     prune = [os.path.join(BIN, "lattice-prune-dyn-beam"), "--max-arcs=20000", "--max-states=1500",
              "--beam-ratio=0.9", "ark:" + ark, "ark:-"]
     best = [os.path.join(BIN, "lattice-best-path2"), "ark:-", "ark,t:" + out]
-    p1 = subprocess.Popen(prune, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    p2 = subprocess.Popen(best, stdin=p1.stdout, stderr=subprocess.PIPE)
-    p1.stdout.close()
-    err2 = p2.communicate()[1]
-    err1 = p1.stderr.read()
-    assert p1.wait() == 0, err1.decode()[-2000:]
-    assert p2.returncode == 0, err2.decode()[-2000:]
+    # (the tools log one line per lattice: stderr goes to files, an unread pipe would fill up)
+    with open(str(tmp_path / "prune.err"), "wb") as e1, open(str(tmp_path / "best.err"), "wb") as e2:
+        p1 = subprocess.Popen(prune, stdout=subprocess.PIPE, stderr=e1)
+        p2 = subprocess.Popen(best, stdin=p1.stdout, stderr=e2)
+        p1.stdout.close()
+        p2.wait()
+        p1.wait()
+    assert p1.returncode == 0, open(str(tmp_path / "prune.err")).read()[-2000:]
+    assert p2.returncode == 0, open(str(tmp_path / "best.err")).read()[-2000:]
     lines = open(out).read().strip("\n").split("\n")
     assert [x.split()[0] for x in lines] == ["utt%07d" % i for i in range(n)]
     os.remove(ark)
