@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 TOOLS = {"frame_post": 3, "segment": 0, "position": 1, "utterance": 2, "fwd_bwd": 7, "prune_dyn_beam": 4,
-         "best_path2": 5, "position_post": 8, "char_position": 6}
+         "best_path2": 5, "position_post": 8, "char_position": 6, "prune_arcs": 11}
 METRIC = "lattice arcs/sec (fwd-bwd + word-position index)"  # BASELINE.json's metric name, kept verbatim
 METRIC_NOTE = ("`value` is measured on BASELINE.json configs[1] (lattice-to-word-frame-post, the configuration the "
                "metric is quoted on); the word-position index tool itself (lattice-word-index-position) is "
@@ -165,6 +165,8 @@ def flags_for(tool):
         return dict(max_arcs=20000, max_states=1500, beam_ratio=0.9)
     if tool == "char_position":
         return dict(nbest=100)
+    if tool == "prune_arcs":
+        return dict(acoustic_scale=0.1, beam=0.5)
     return dict(acoustic_scale=0.1)
 
 
@@ -193,7 +195,7 @@ def fetch_for(eng, klu, tool, out=None):
     elif t == klu.FWD_BWD:
         r = eng.fetch_fwd_bwd()
         return 0, sum(int(x.nbytes) for x in r)
-    elif t == klu.PRUNE_DYN_BEAM:
+    elif t in (klu.PRUNE_DYN_BEAM, klu.PRUNE_ARCS):
         r = eng.fetch_prune()
     elif t == klu.BEST_PATH2:
         r = eng.fetch_best_path2()
@@ -343,6 +345,7 @@ def bench_tools(klu, local, args, peak):
             batch = klu.synth_batch(shape, nlat, seed=args.seed)
             flags = flags_for(tool)
             eng.load(batch)
+            eng.load(batch)  # the second load's times: no first-use cudaMalloc inside the events
             up_ms, pack_ms, _ = eng.load_times()
             st = eng.stats()
             ms = time_steps(eng, klu, tool, flags, args.tools_steps, 2)
@@ -364,6 +367,7 @@ def bench_tools(klu, local, args, peak):
             # ---- second stage of configs[2]: lattice-best-path2 on the pruned lattices
             if tool == "prune_dyn_beam":
                 pruned = eng.pruned_batch()
+                eng.load(pruned)
                 eng.load(pruned)
                 _, pack2, _ = eng.load_times()
                 f2 = dict()

@@ -58,89 +58,141 @@ __device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) {
   return a.k2 < b.k2;
 }
 
-// (state, len) min-plus sweep; a group of G lanes owns one cell.
-template <int G>
-__global__ void __launch_bounds__(128) k_bp_viterbi(BpArgs a) {
-  const int lane = threadIdx.x & 31;
+// (state, len) min-plus sweep.  One CTA owns one lattice (work queue); a level's cells are
+// spread over the threads with consecutive threads on consecutive lengths, and the level's
+// incoming arcs are staged once per piece in shared memory (where the source's band starts
+// on the length axis, its valid range, where the arc's (label, position) costs start, the
+// two tie-break keys), exactly as k_banded_alpha does for the log semiring: the cost and the
+// predecessor's distance are then contiguous reads along the length axis.
+constexpr int kBpThreads = 256;
+constexpr int kBpArcs = 512;
+constexpr int kBpStates = 128;
+
+__global__ void __launch_bounds__(kBpThreads) k_bp_viterbi(BpArgs a) {
+  __shared__ long long sv_base[kBpArcs];   // d2 index of (source, len - nz) = base + len
+  __shared__ long long sv_cost[kBpArcs];   // cost index of (arc, len - nz) = cost + len; LLONG_MIN: epsilon arc
+  __shared__ unsigned long long sv_k2[kBpArcs];  // (label, input arc index)
+  __shared__ int2 sv_range[kBpArcs];       // valid len: [x, y)
+  __shared__ int2 sv_src[kBpArcs];         // (input id of the source, nz)
+  __shared__ int ss_arc[kBpStates + 1];
+  __shared__ long long ss_cell[kBpStates + 1];
+  __shared__ int ss_lo[kBpStates];
+  __shared__ int s_item, s_take;
   const BatchView& b = a.b;
-  constexpr int SPW = 32 / G;
-  const int grp = lane / G, sl = lane % G;
   float* d2 = a.d2 - a.band_base;
   int32_t* par = a.par - a.band_base;
   const float inf = __int_as_float(0x7f800000);
+  const long long kEps = (long long)0x8000000000000000LL;
+  const int tid = threadIdx.x;
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(a.counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= a.l1 - a.l0) break;
-    const int l = a.l0 + item;
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    if (s_item >= a.l1 - a.l0) break;
+    const int l = a.l0 + s_item;
     const int s_begin = b.s_off[l], s_end = b.s_off[l + 1];
     if (s_begin == s_end) continue;
     const int* lv = b.lvl_start + b.lvl_off[l];
     const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
-    for (int s = lv[0] + lane; s < lv[1]; s += 32)
-      if (s == s_begin) {
+    for (int s = lv[0] + tid; s < lv[1]; s += kBpThreads)
+      if (s == s_begin && b.band_off[s + 1] > b.band_off[s]) {
         d2[b.band_off[s]] = 0.0f;
         par[b.band_off[s]] = -1;
       }
-    __syncwarp();
     for (int j = 1; j < nl; ++j) {
-      const int a0 = lv[j], a1 = lv[j + 1];
-      const long long c0 = b.band_off[a0], c1 = b.band_off[a1];
-      for (long long base = c0; base < c1; base += SPW) {
-        const long long cell = base + grp;
-        const bool act = cell < c1;
-        int s = a0;
-        if (act) {
-          int lo = a0, hi = a1 - 1;
+      const int a1 = lv[j + 1];
+      int s0 = lv[j];
+      while (s0 < a1) {
+        __syncthreads();
+        const int nst = min(a1 - s0, kBpStates);
+        for (int k = tid; k <= nst; k += kBpThreads) {
+          ss_arc[k] = b.in_off[s0 + k];
+          ss_cell[k] = b.band_off[s0 + k];
+          if (k < nst) ss_lo[k] = b.band_lo[s0 + k];
+        }
+        if (tid == 0) s_take = 1;
+        __syncthreads();
+        const int e_base = ss_arc[0];
+        for (int k = tid + 1; k <= nst; k += kBpThreads)
+          if (ss_arc[k] - e_base <= kBpArcs) atomicMax(&s_take, k);
+        __syncthreads();
+        const int take = s_take;
+        const int narcs = ss_arc[take] - e_base;
+        const bool staged = narcs <= kBpArcs;  // else: one state with more arcs than fit (take == 1)
+        if (staged) {
+          for (int i = tid; i < narcs; i += kBpThreads) {
+            const int4 r = __ldg(b.in_rec + e_base + i);
+            const int plo = b.band_lo[r.x];
+            const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
+            const int nz = r.w != 0 ? 1 : 0;
+            const int eo = b.in2out[e_base + i];
+            sv_base[i] = b.band_off[r.x] - plo - nz;
+            sv_range[i] = (plo < 0 || pw <= 0) ? make_int2(0, 0) : make_int2(plo + nz, plo + pw + nz);
+            sv_cost[i] = nz ? a.arc_cellbase[eo] - nz : kEps;
+            sv_src[i] = make_int2(b.orig[r.x], nz);
+            sv_k2[i] = ((unsigned long long)(unsigned int)r.w << 32) | (unsigned int)b.out_orig[eo];
+          }
+        }
+        __syncthreads();
+        const long long c0 = ss_cell[0], c1 = ss_cell[take];
+        for (long long cell = c0 + tid; cell < c1; cell += kBpThreads) {
+          int lo = 0, hi = take - 1;  // last k with ss_cell[k] <= cell
           while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (b.band_off[mid] <= cell) lo = mid;
+            if (ss_cell[mid] <= cell) lo = mid;
             else hi = mid - 1;
           }
-          s = lo;
-        }
-        const int len = act ? b.band_lo[s] + (int)(cell - b.band_off[s]) : 0;
-        const int e0 = act ? b.in_off[s] : 0, e1 = act ? b.in_off[s + 1] : 0;
-        Cand best;
-        best.v = inf;
-        best.k1 = ~0ULL;
-        best.k2 = ~0ULL;
-        best.e = -1;
-        for (int e = e0 + sl; e < e1; e += G) {
-          const int4 r = __ldg(b.in_rec + e);
-          const int nz = r.w != 0 ? 1 : 0;
-          const int plen = len - nz;
-          const int plo = b.band_lo[r.x];
-          const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
-          if (plo < 0 || plen < plo || plen >= plo + pw) continue;
-          const float du = d2[b.band_off[r.x] + plen - plo];
-          if (!(du < inf)) continue;
-          const int eo = b.in2out[e];
-          float w = 0.0f;
-          if (nz) w = (float)a.ecost[a.arc_cellbase[eo] + plen];
-          Cand cnd;
-          cnd.v = __fadd_rn(du, w);
-          cnd.k1 = ((unsigned long long)(unsigned int)plen << 32) | (unsigned int)b.orig[r.x];
-          cnd.k2 = ((unsigned long long)(unsigned int)r.w << 32) | (unsigned int)b.out_orig[eo];
-          cnd.e = e;
-          if (cand_less(cnd, best)) best = cnd;
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-          Cand ot;
-          ot.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-          ot.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o);
-          ot.k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
-          ot.e = __shfl_xor_sync(0xffffffffu, best.e, o);
-          if (cand_less(ot, best)) best = ot;
-        }
-        if (act && sl == 0) {
+          const int len = ss_lo[lo] + (int)(cell - ss_cell[lo]);
+          Cand best;
+          best.v = inf;
+          best.k1 = ~0ULL;
+          best.k2 = ~0ULL;
+          best.e = -1;
+          if (staged) {
+            const int i1 = ss_arc[lo + 1] - e_base;
+#pragma unroll 2
+            for (int i = ss_arc[lo] - e_base; i < i1; ++i) {
+              const int2 rg = sv_range[i];
+              if (len < rg.x || len >= rg.y) continue;
+              const float du = d2[sv_base[i] + len];
+              if (!(du < inf)) continue;
+              const long long cb = sv_cost[i];
+              const float w = cb == kEps ? 0.0f : (float)a.ecost[cb + len];
+              const int2 sn = sv_src[i];
+              Cand cnd;
+              cnd.v = __fadd_rn(du, w);
+              cnd.k1 = ((unsigned long long)(unsigned int)(len - sn.y) << 32) | (unsigned int)sn.x;
+              cnd.k2 = sv_k2[i];
+              cnd.e = e_base + i;
+              if (cand_less(cnd, best)) best = cnd;
+            }
+          } else {
+            const int s = s0 + lo;
+            for (int e = b.in_off[s]; e < b.in_off[s + 1]; ++e) {
+              const int4 r = __ldg(b.in_rec + e);
+              const int nz = r.w != 0 ? 1 : 0;
+              const int plen = len - nz;
+              const int plo = b.band_lo[r.x];
+              const int pw = (int)(b.band_off[r.x + 1] - b.band_off[r.x]);
+              if (plo < 0 || plen < plo || plen >= plo + pw) continue;
+              const float du = d2[b.band_off[r.x] + plen - plo];
+              if (!(du < inf)) continue;
+              const int eo = b.in2out[e];
+              float w = 0.0f;
+              if (nz) w = (float)a.ecost[a.arc_cellbase[eo] + plen];
+              Cand cnd;
+              cnd.v = __fadd_rn(du, w);
+              cnd.k1 = ((unsigned long long)(unsigned int)plen << 32) | (unsigned int)b.orig[r.x];
+              cnd.k2 = ((unsigned long long)(unsigned int)r.w << 32) | (unsigned int)b.out_orig[eo];
+              cnd.e = e;
+              if (cand_less(cnd, best)) best = cnd;
+            }
+          }
           d2[cell] = best.v;
           par[cell] = best.e;
         }
+        s0 += take;
       }
-      __syncwarp();
     }
   }
 }
@@ -367,11 +419,10 @@ int best_path2_decode(klu_ctx* c, const CostParams& cp, const BestPathChunk& ch)
     k_bp_pad<<<(nl * 32 + 127) / 128, 128, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_bp_pad"));
-  const int G = pick_group(c->avg_deg);
   {
     KLU_LAUNCH(c, "k_bp_viterbi");
-    const int grid = std::max(1, std::min((nl + 3) / 4, c->num_sms * 16));
-    KLU_DISPATCH_G(G, k_bp_viterbi<kG><<<grid, 128, 0, c->stream>>>(a));
+    const int grid = std::max(1, std::min(nl, c->num_sms * 8));  // one CTA per lattice in flight
+    k_bp_viterbi<<<grid, kBpThreads, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_bp_viterbi"));
   {

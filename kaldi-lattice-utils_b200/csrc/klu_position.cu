@@ -42,6 +42,15 @@ struct __align__(16) ArcRec {
   int lo, hi;      // positions the source's band holds: [lo, hi)
 };
 
+// One (word, position) cell as the ordering / gather stages read it: one 32-byte sector.
+struct __align__(16) CellRec {
+  double val;               // log-posterior
+  unsigned long long key;   // (word, position) packed; position-post: (position + 1, word)
+  int t0, t1;               // position index: segment of the best single arc
+  unsigned int exists;      // some arc reaches the cell
+  unsigned int pad;
+};
+
 struct PosArgs {
   BatchView b;
   CostParams cp;
@@ -76,12 +85,12 @@ struct PosArgs {
   const int64_t* cell_base;  // [L] chunk-local first cell of each lattice
   int e_chunk0;              // first arc of the chunk
   ArcRec* rec;               // [chunk arcs] in sorted order
-  double* cval;
-  unsigned int* caux;
-  unsigned long long* ckey;
+  CellRec* cell;   // position / position-post
+  double* ccost;   // best-path2: float cost 1 - P of the cell, as a double
   int32_t* ctile;  // per 256-cell tile: existing cells in it, then (prefix) existing cells before it
   int32_t* rcnt;   // [L] existing cells = output rows
-  unsigned long long* key2;
+  unsigned long long* key2;  // order keys: 64-bit (position-post) ...
+  unsigned int* key32;       // ... or the high half of the f64 key only (position)
   unsigned int* idx2;
   long long* arc_cellbase;  // [E] best-path2: cell of (arc, position) = arc_cellbase[e] + position
 };
@@ -323,19 +332,25 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
       const int pos = a.g_plo[e0 + g] + (int)(cell - celloff[g]);
       const int q0 = a.g_start[e0 + g], q1 = q0 + a.g_len[e0 + g];
       const bool plain = a.tool != KLU_POSITION;
-      double m = neg_inf(), s = 0.0, x1 = neg_inf(), x2 = neg_inf();
-      int nterm = 0;
-      double bestv = neg_inf();
-      int besta = -1;
+      // fw[(len, s)] + arc_lkh + bw[next] (position tool, :162-163); fw[u] + bw[v] - cost
+      // (best-path2 :134, position-post :111-113); -inf when the arc's source does not hold `pos`
+      auto fw = [&](const ArcRec& rc) -> double {  // -inf: (length, state) is not a state of the unfolded lattice
+        return (pos >= rc.lo && pos < rc.hi) ? a.alpha2[rc.base + pos] : neg_inf();
+      };
+      auto term = [&](const ArcRec& rc, double al) -> double {
+        return plain ? __dadd_rn(__dadd_rn(al, rc.beta), rc.tail) : __dadd_rn(__dadd_rn(al, rc.tail), rc.beta);
+      };
+      // Pass 1 (no loop-carried chain beyond a compare): maximum, number of finite terms, the
+      // first two of them, the best single arc.
+      double m = neg_inf(), x1 = neg_inf(), x2 = neg_inf(), bestv = neg_inf();
+      int nterm = 0, besta = -1;
+#pragma unroll 2
       for (int q = q0; q < q1; ++q) {
         const ArcRec rc = rec[q];
-        if (pos < rc.lo || pos >= rc.hi) continue;
-        const double al = a.alpha2[rc.base + pos];
-        if (!(al > neg_inf())) continue;  // (length, state) is not a state of the unfolded lattice
+        const double al = fw(rc);
+        const double v = term(rc, al);
+        if (!(al > neg_inf())) continue;
         exists = true;
-        // fw[(len, s)] + arc_lkh + bw[next] (position tool, :162-163); fw[u] + bw[v] - cost
-        // (best-path2 :134, position-post :111-113)
-        const double v = plain ? __dadd_rn(__dadd_rn(al, rc.beta), rc.tail) : __dadd_rn(__dadd_rn(al, rc.tail), rc.beta);
         if (besta < 0) {
           bestv = v;
           besta = q;
@@ -354,15 +369,28 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
         if (nterm == 0) x1 = v;
         else if (nterm == 1) x2 = v;
         ++nterm;
-        if (v <= m) {
-          s += fast_exp(v - m);
-        } else {
-          s = (m == neg_inf() ? 0.0 : s * fast_exp(m - v)) + 1.0;
-          m = v;
-        }
+        m = fmax(m, v);
       }
       if (exists) {
-        double sum = nterm == 0 ? neg_inf() : nterm == 1 ? x1 : nterm == 2 ? log_add(x1, x2) : m + fast_log(s);
+        double sum;
+        if (nterm >= 3) {
+          // Pass 2: exp terms into two accumulators (exp(-inf) = 0 for the arcs that do not reach)
+          double s0 = 0.0, s1 = 0.0;
+          int q = q0;
+          for (; q + 1 < q1; q += 2) {
+            const ArcRec ra = rec[q], rb = rec[q + 1];
+            const double va = term(ra, fw(ra)), vb = term(rb, fw(rb));
+            s0 += fast_exp(va - m);
+            s1 += fast_exp(vb - m);
+          }
+          if (q < q1) {
+            const ArcRec ra = rec[q];
+            s0 += fast_exp(term(ra, fw(ra)) - m);
+          }
+          sum = m + fast_log(s0 + s1);
+        } else {
+          sum = nterm == 0 ? neg_inf() : nterm == 1 ? x1 : log_add(x1, x2);  // Kaldi's LogAdd exactly
+        }
         const unsigned int word = (unsigned int)a.g_word[e0 + g];
         if (a.tool == KLU_BEST_PATH2) {
           // latbin/lattice-best-path2.cc:145-147,175: posterior clamped to <= 0, float cost 1 - P
@@ -373,16 +401,34 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
             ls = log(1.0 - exp(post));
             if (ls != ls) ls = neg_inf();
           }
-          a.cval[cbase + cell] = (double)(float)exp(ls);
+          a.ccost[cbase + cell] = (double)(float)exp(ls);
         } else {
-          a.cval[cbase + cell] = sum - norm;
-          a.caux[cbase + cell] = (unsigned int)besta;
-          a.ckey[cbase + cell] = a.tool == KLU_POSITION_POST
-                                     ? (((unsigned long long)(pos + 1) << a.bits_label) | word)
-                                     : (((unsigned long long)word << a.bits_len) | (unsigned long long)pos);
+          CellRec cr;
+          cr.val = sum - norm;
+          cr.exists = 1u;
+          cr.pad = 0u;
+          if (a.tool == KLU_POSITION_POST) {
+            cr.key = ((unsigned long long)(pos + 1) << a.bits_label) | word;
+            cr.t0 = cr.t1 = 0;
+          } else {
+            const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + a.seg_base[l];
+            const int e = e0 + (int)idx[besta];
+            cr.key = ((unsigned long long)word << a.bits_len) | (unsigned long long)pos;
+            cr.t0 = a.b.time[a.b.out_src[e]];
+            cr.t1 = a.b.time[a.b.out_rec[e].x];
+          }
+          a.cell[cbase + cell] = cr;
         }
       }
-      if (!exists && a.tool != KLU_BEST_PATH2) a.caux[cbase + cell] = 0xffffffffu;
+      if (!exists && a.tool != KLU_BEST_PATH2) {
+        CellRec cr;
+        cr.val = 0.0;
+        cr.key = 0ULL;
+        cr.t0 = cr.t1 = 0;
+        cr.exists = 0u;
+        cr.pad = 0u;
+        a.cell[cbase + cell] = cr;
+      }
     }
     if (a.tool != KLU_BEST_PATH2) {
       const int cnt = __syncthreads_count(exists);
@@ -400,7 +446,10 @@ __global__ void __launch_bounds__(256) k_pos_compact(PosArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (long long tile = (long long)blockIdx.y * 256; tile < ncells; tile += (long long)gridDim.y * 256) {
     const long long cell = tile + tid;
-    const bool exists = cell < ncells && a.caux[cbase + cell] != 0xffffffffu;
+    CellRec cr;
+    cr.exists = 0u;
+    if (cell < ncells) cr = a.cell[cbase + cell];
+    const bool exists = cr.exists != 0u;
     int x = exists ? 1 : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -413,15 +462,13 @@ __global__ void __launch_bounds__(256) k_pos_compact(PosArgs a) {
     for (int w = 0; w < warp; ++w) add += warp_sum[w];
     if (exists) {
       const int slot = add + x - 1;
-      const double logp = a.cval[cbase + cell] + 0.0;  // -0.0 and +0.0 compare equal in the reference's sort
-      unsigned long long k2;
+      const double logp = cr.val + 0.0;  // -0.0 and +0.0 compare equal in the reference's sort
       if (a.tool == KLU_POSITION_POST) {
         const float f = (float)logp + 0.0f;
-        k2 = ((a.ckey[cbase + cell] >> a.bits_label) << 32) | (unsigned long long)(~ord_f32(f));
+        a.key2[cbase + slot] = ((cr.key >> a.bits_label) << 32) | (unsigned long long)(~ord_f32(f));
       } else {
-        k2 = ~ord_f64(logp);
+        a.key32[cbase + slot] = (unsigned int)((~ord_f64(logp)) >> 32);
       }
-      a.key2[cbase + slot] = k2;
       a.idx2[cbase + slot] = (unsigned int)cell;
     }
     __syncthreads();
@@ -456,37 +503,39 @@ __global__ void __launch_bounds__(1024) k_pos_scan_counts(const int32_t* cnt, in
   if (tid == 0) off[L] = carry_s;
 }
 
-// The order sort runs on the high half of the f64 keys; runs that agree there are settled
-// by a stable insertion sort on the full key, one thread per run (see klu_index.cu).
+// The order sort of the position index runs on the high half of the f64 keys only (32-bit
+// keys: a third less traffic per pass); runs that agree there (log-posteriors equal to ~1e-6
+// relative: a handful per lattice) are settled here by a stable insertion sort on the full
+// key, read back from the cell values, one thread per run.
 struct PosFixArgs {
   const int64_t* seg_base;
   const int32_t* seg_cnt;
   const unsigned char* where;
-  unsigned long long *key_a, *key_b;
+  unsigned int *key_a, *key_b;
   unsigned int *val_a, *val_b;
-  int lo_bit, l0;
+  const CellRec* cell;
+  int l0;
 };
 
 __global__ void __launch_bounds__(256) k_pos_order_fixup(PosFixArgs a) {
   const int l = a.l0 + blockIdx.x;
   const int n = a.seg_cnt[l];
   const int64_t base = a.seg_base[l];
-  unsigned long long* K = (a.where[blockIdx.x] ? a.key_b : a.key_a) + base;
+  const unsigned int* K = (a.where[blockIdx.x] ? a.key_b : a.key_a) + base;
   unsigned int* V = (a.where[blockIdx.x] ? a.val_b : a.val_a) + base;
+  const CellRec* cv = a.cell + base;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.y * blockDim.x) {
-    const unsigned long long t = K[i] >> a.lo_bit;
-    if ((i > 0 && (K[i - 1] >> a.lo_bit) == t) || (K[i + 1] >> a.lo_bit) != t) continue;  // not the head of a run
+    const unsigned int t = K[i];
+    if ((i > 0 && K[i - 1] == t) || K[i + 1] != t) continue;  // not the head of a run
     int j = i + 1;
-    while (j < n && (K[j] >> a.lo_bit) == t) {
-      const unsigned long long k = K[j];
+    while (j < n && K[j] == t) {  // insert element j into the ordered [i, j)
       const unsigned int v = V[j];
+      const unsigned long long k = ~ord_f64(cv[v].val + 0.0);
       int q = j;
-      while (q > i && K[q - 1] > k) {
-        K[q] = K[q - 1];
+      while (q > i && (~ord_f64(cv[V[q - 1]].val + 0.0)) > k) {
         V[q] = V[q - 1];
         --q;
       }
-      K[q] = k;
       V[q] = v;
       ++j;
     }
@@ -510,26 +559,21 @@ __global__ void __launch_bounds__(256) k_pos_gather(PosGatherArgs g) {
   const int n = a.rcnt[l];
   const int64_t cbase = a.cell_base[l];
   const int64_t out = g.res_off[l];
-  const int e0 = a.b.e_off[l];
   const unsigned int* ord = (g.where2[blockIdx.x] ? g.idx2_b : g.idx2_a) + cbase;
-  const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + a.seg_base[l];
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
-    const unsigned int cell = ord[i];
-    const unsigned long long k = a.ckey[cbase + cell];
-    const double logp = a.cval[cbase + cell];
+    const CellRec cr = a.cell[cbase + ord[i]];  // the one scattered read of a row
     if (a.tool == KLU_POSITION) {
       const unsigned long long lm = (1ULL << a.bits_len) - 1ULL;
-      const int e = e0 + (int)idx[a.caux[cbase + cell]];
-      g.c0[out + i] = (int32_t)(k >> a.bits_len);
-      g.c1[out + i] = (int32_t)(k & lm) + 1;  // 1-based position, :107
-      g.c2[out + i] = a.b.time[a.b.out_src[e]];
-      g.c3[out + i] = a.b.time[a.b.out_rec[e].x];
-      g.v[out + i] = logp;
+      g.c0[out + i] = (int32_t)(cr.key >> a.bits_len);
+      g.c1[out + i] = (int32_t)(cr.key & lm) + 1;  // 1-based position, :107
+      g.c2[out + i] = cr.t0;
+      g.c3[out + i] = cr.t1;
+      g.v[out + i] = cr.val;
     } else {  // position-post: (0-based position index, word, float)
       const unsigned long long lm = (1ULL << a.bits_label) - 1ULL;
-      g.c0[out + i] = (int32_t)(k >> a.bits_label) - 1;
-      g.c1[out + i] = (int32_t)(k & lm);
-      g.vf[out + i] = (float)logp;
+      g.c0[out + i] = (int32_t)(cr.key >> a.bits_label) - 1;
+      g.c1[out + i] = (int32_t)(cr.key & lm);
+      g.vf[out + i] = (float)cr.val;
     }
   }
 }
@@ -703,13 +747,13 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
       set_error("lattice " + std::to_string(l) + ": more than 2^31 (word, position) cells");
       return 1;
     }
-  // ---- chunk plan: contiguous lattice ranges whose cells (44 B each) and bands (8 B per cell) fit
+  // ---- chunk plan: contiguous lattice ranges whose cells (56 B each) and bands (8 B per cell) fit
   int64_t cell_budget = (int64_t)1 << 28;
   {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
       size_t held = sc[P_REC].cap + sc[P_CELL].cap + sc[P_ORDER].cap + sc[P_CTILES].cap;
-      const int64_t fit = (int64_t)((free_b + held) / 3 / 44);
+      const int64_t fit = (int64_t)((free_b + held) / 3 / 56);
       cell_budget = std::min<int64_t>((int64_t)1 << 31, std::max<int64_t>((int64_t)1 << 24, fit));
     }
   }
@@ -741,21 +785,23 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
   KLU_CUDA(cudaMemcpyAsync(d_cell_base, cell_base.data(), 8 * (size_t)(L + 1), cudaMemcpyHostToDevice, c->stream));
   KLU_TRY(sc[P_REC].reserve(sizeof(ArcRec) * (size_t)max_chunk_arcs));
   const bool bp2 = tool == KLU_BEST_PATH2;
-  KLU_TRY(sc[P_CELL].reserve((bp2 ? 8 : 20) * (size_t)N + 64));
+  KLU_TRY(sc[P_CELL].reserve((bp2 ? 8 : sizeof(CellRec)) * (size_t)N + 64));
   if (!bp2) {
     KLU_TRY(sc[P_ORDER].reserve(24 * (size_t)N + 64));
     KLU_TRY(sc[P_CTILES].reserve(4 * (((size_t)N >> 8) + (size_t)L + 2)));
   }
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // cell_base is a stack object
   a.rec = sc[P_REC].as<ArcRec>();
-  a.cval = sc[P_CELL].as<double>();
-  a.ckey = reinterpret_cast<unsigned long long*>(a.cval + N);
-  a.caux = reinterpret_cast<unsigned int*>(a.ckey + N);
+  a.cell = sc[P_CELL].as<CellRec>();
+  a.ccost = sc[P_CELL].as<double>();
   unsigned long long* key2_a = sc[P_ORDER].as<unsigned long long>();
   unsigned long long* key2_b = key2_a + N;
   unsigned int* idx2_a = reinterpret_cast<unsigned int*>(key2_b + N);
   unsigned int* idx2_b = idx2_a + N;
+  unsigned int* key32_a = reinterpret_cast<unsigned int*>(key2_a);  // the position index sorts 32-bit keys
+  unsigned int* key32_b = reinterpret_cast<unsigned int*>(key2_b);
   a.key2 = key2_a;
+  a.key32 = key32_a;
   a.idx2 = idx2_a;
   a.ctile = sc[P_CTILES].as<int32_t>();
   a.arc_cellbase = bp2 ? d_arc_cellbase : nullptr;
@@ -812,7 +858,7 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
       ch.band_base = a.band_base;
       ch.alpha2 = a.alpha2;
       ch.arc_cellbase = d_arc_cellbase;
-      ch.ecost = a.cval;
+      ch.ecost = a.ccost;
       ch.first_chunk = k == 0;
       KLU_TRY(best_path2_decode(c, cp, ch));
       continue;
@@ -827,36 +873,52 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
       k_pos_compact<<<dim3(nl, ctiles), 256, 0, c->stream>>>(a);
     }
     KLU_TRY(check_launch("k_pos_compact"));
-    SegSortArgs s2;
-    s2.seg_base = d_cell_base + l0;
-    s2.seg_cnt = a.rcnt + l0;
-    s2.key_a = key2_a;
-    s2.val_a = idx2_a;
-    s2.key_b = key2_b;
-    s2.val_b = idx2_b;
-    s2.where = d_where + L;  // chunk-local flags
-    const bool half_keys = tool == KLU_POSITION;  // f64 order keys: high half first, near-ties settled after
-    s2.lo_bit = half_keys ? 32 : 0;
-    s2.hi_bit = 64;
-    {
-      KLU_LAUNCH(c, "k_seg_radix_sort");
-      k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s2);
-    }
-    KLU_TRY(check_launch("k_seg_radix_sort(order)"));
-    if (half_keys) {
+    unsigned char* where2 = d_where + L;  // chunk-local flags
+    if (tool == KLU_POSITION) {
+      SegSortArgs32 s2;
+      s2.seg_base = d_cell_base + l0;
+      s2.seg_cnt = a.rcnt + l0;
+      s2.key_a = key32_a;
+      s2.val_a = idx2_a;
+      s2.key_b = key32_b;
+      s2.val_b = idx2_b;
+      s2.where = where2;
+      s2.lo_bit = 0;
+      s2.hi_bit = 32;
+      {
+        KLU_LAUNCH(c, "k_seg_radix_sort");
+        k_seg_radix_sort32<<<nl, kSortThreads, 0, c->stream>>>(s2);
+      }
+      KLU_TRY(check_launch("k_seg_radix_sort(order)"));
       PosFixArgs f;
       f.seg_base = d_cell_base;
       f.seg_cnt = a.rcnt;
-      f.where = s2.where;
-      f.key_a = key2_a, f.key_b = key2_b;
+      f.where = where2;
+      f.key_a = key32_a, f.key_b = key32_b;
       f.val_a = idx2_a, f.val_b = idx2_b;
-      f.lo_bit = 32;
+      f.cell = a.cell;
       f.l0 = l0;
       {
         KLU_LAUNCH(c, "k_order_fixup");
         k_pos_order_fixup<<<dim3(nl, ctiles), 256, 0, c->stream>>>(f);
       }
       KLU_TRY(check_launch("k_order_fixup"));
+    } else {
+      SegSortArgs s2;
+      s2.seg_base = d_cell_base + l0;
+      s2.seg_cnt = a.rcnt + l0;
+      s2.key_a = key2_a;
+      s2.val_a = idx2_a;
+      s2.key_b = key2_b;
+      s2.val_b = idx2_b;
+      s2.where = where2;
+      s2.lo_bit = 0;
+      s2.hi_bit = 64;
+      {
+        KLU_LAUNCH(c, "k_seg_radix_sort");
+        k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s2);
+      }
+      KLU_TRY(check_launch("k_seg_radix_sort(order)"));
     }
     {
       KLU_LAUNCH(c, "k_scan_counts");
@@ -874,7 +936,7 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
     PosGatherArgs g;
     g.p = a;
     g.res_off = c->d_res[5].as<int64_t>();
-    g.where2 = s2.where;
+    g.where2 = where2;
     g.idx2_a = idx2_a;
     g.idx2_b = idx2_b;
     g.c0 = c->d_res[0].as<int32_t>();

@@ -552,11 +552,42 @@ __global__ void __launch_bounds__(kBandThreads) k_banded_alpha(SweepArgs a, doub
           const int len = ss_lo[lo] + (int)(cell - ss_cell[lo]);
           LogSumRun acc;
           if (staged) {
-            const int i1 = ss_arc[lo + 1] - e_base;
-            for (int i = ss_arc[lo] - e_base; i < i1; ++i) {
+            // Two passes over the state's staged arcs, both free of loop-carried chains longer than
+            // one instruction: the maximum (independent loads), then the exp terms into two
+            // accumulators.  A serial running log-sum-exp here made a level cost its arcs x
+            // (load latency + exp latency) per thread.
+            const int i0 = ss_arc[lo] - e_base, i1 = ss_arc[lo + 1] - e_base;
+            double m = neg_inf();
+            int nterm = 0;
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) {
               const int2 rg = sa_range[i];
-              if (len >= rg.x && len < rg.y) acc.add(alpha2[sa_base[i] + len] - sa_cost[i]);
+              const double x = (len >= rg.x && len < rg.y) ? alpha2[sa_base[i] + len] - sa_cost[i] : neg_inf();
+              nterm += x > neg_inf() ? 1 : 0;
+              m = fmax(m, x);
             }
+            if (nterm >= 3) {
+              double sum0 = 0.0, sum1 = 0.0;
+              int i = i0;
+              for (; i + 1 < i1; i += 2) {
+                const int2 ra = sa_range[i], rb = sa_range[i + 1];
+                const double xa = (len >= ra.x && len < ra.y) ? alpha2[sa_base[i] + len] - sa_cost[i] : neg_inf();
+                const double xb = (len >= rb.x && len < rb.y) ? alpha2[sa_base[i + 1] + len] - sa_cost[i + 1] : neg_inf();
+                sum0 += fast_exp(xa - m);  // exp(-inf) = 0 for the arcs that do not reach this length
+                sum1 += fast_exp(xb - m);
+              }
+              if (i < i1) {
+                const int2 ra = sa_range[i];
+                if (len >= ra.x && len < ra.y) sum0 += fast_exp(alpha2[sa_base[i] + len] - sa_cost[i] - m);
+              }
+              alpha2[cell] = m + fast_log(sum0 + sum1);
+              continue;
+            }
+            if (nterm > 0)  // one or two terms: Kaldi's LogAdd exactly
+              for (int i = i0; i < i1; ++i) {
+                const int2 rg = sa_range[i];
+                if (len >= rg.x && len < rg.y) acc.add(alpha2[sa_base[i] + len] - sa_cost[i]);
+              }
           } else {
             const int s = s0 + lo;
             for (int e = b.in_off[s]; e < b.in_off[s + 1]; ++e) {
