@@ -593,6 +593,7 @@ struct UttArgs {
   const double* best;
   double beam;
   int* counter;
+  const int64_t* res_off;  // [L+1] words (output rows) of the lattices before each one
 };
 
 __device__ __forceinline__ bool utt_arc_pruned(const UttArgs& a, int l, int src, int dst, const int4& r) {
@@ -604,28 +605,41 @@ __device__ __forceinline__ bool utt_arc_pruned(const UttArgs& a, int l, int src,
 
 template <int G>
 __global__ void __launch_bounds__(256) k_utt_tasks(UttArgs a) {
-  __shared__ int lat_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int SPW = 32 / G;
   const int grp = lane / G, sl = lane % G;
   double* anw = a.scratch + ((size_t)blockIdx.x * 8 + warp) * (size_t)a.max_states;
   const BatchView& b = a.b;
+  // Work items are (lattice, word) pairs, numbered through the prefix of the lattices' word
+  // counts (res_off) and handed out four at a time to the WARPS of the whole grid: a batch of a
+  // few deep lattices (tens of thousands of words each) fills the machine like one of many
+  // shallow ones does.
+  const long long t_begin = a.res_off[a.l0], t_end = a.res_off[a.l0 + a.nl];
+  int l = a.l0;
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) lat_s = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const int item = lat_s;
-    if (item >= a.nl) break;
-    const int l = a.l0 + item;
-    const int n = a.rcnt[l];
-    if (n == 0) continue;
-    const int64_t base = a.ent_base[l];
-    const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + base;
-    const unsigned int* aux = a.aux + base;
-    const int e0 = b.e_off[l], s0 = b.s_off[l];
-    const int* lv = b.lvl_start + b.lvl_off[l];
-    const double total = a.beta[s0];  // bw_lkh[clat->Start()], :123
-    for (int slot = warp; slot < n; slot += 8) {
+    unsigned int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(reinterpret_cast<unsigned int*>(a.counter), 4u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const long long tc = t_begin + (long long)chunk;
+    if (tc >= t_end) break;
+    {  // lattice of the chunk's first item: last l with res_off[l] <= tc
+      int lo = a.l0, hi = a.l0 + a.nl - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.res_off[mid] <= tc) lo = mid;
+        else hi = mid - 1;
+      }
+      l = lo;
+    }
+    for (long long t = tc; t < min(tc + 4, t_end); ++t) {
+      while (a.res_off[l + 1] <= t) ++l;
+      const int slot = (int)(t - a.res_off[l]);
+      const int64_t base = a.ent_base[l];
+      const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + base;
+      const unsigned int* aux = a.aux + base;
+      const int e0 = b.e_off[l], s0 = b.s_off[l];
+      const int* lv = b.lvl_start + b.lvl_off[l];
+      const double total = a.beta[s0];  // bw_lkh[clat->Start()], :123
       const int w = (int)a.rkey[base + slot];
       const int start = (int)a.raux[base + slot];
       const int len = (int)a.idx2[base + slot];
@@ -975,7 +989,13 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       u.vbwd = a.vbwd;
       u.best = a.best;
       u.beam = a.beam;
-      const int grid = std::max(1, std::min(nl, c->num_sms * 4));
+      {
+        KLU_LAUNCH(c, "k_scan_counts");
+        k_scan_counts<<<1, 1024, 0, c->stream>>>(r.rcnt, l0, l1, c->d_res[5].as<int64_t>());
+      }
+      KLU_TRY(check_launch("k_scan_counts"));
+      u.res_off = c->d_res[5].as<int64_t>();
+      const int grid = std::max(1, c->num_sms * 4);
       KLU_TRY(c->d_alpha2.reserve(sizeof(double) * (size_t)grid * 8 * (size_t)u.max_states));
       u.scratch = c->d_alpha2.as<double>();
       KLU_CUDA(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
