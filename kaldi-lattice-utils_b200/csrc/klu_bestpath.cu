@@ -64,7 +64,7 @@ __device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) {
 // on the length axis, its valid range, where the arc's (label, position) costs start, the
 // two tie-break keys), exactly as k_banded_alpha does for the log semiring: the cost and the
 // predecessor's distance are then contiguous reads along the length axis.
-constexpr int kBpThreads = 256;
+constexpr int kBpThreads = 512;
 constexpr int kBpArcs = 512;
 constexpr int kBpStates = 128;
 

@@ -88,6 +88,7 @@ struct PosArgs {
   CellRec* cell;   // position / position-post
   double* ccost;   // best-path2: float cost 1 - P of the cell, as a double
   int32_t* ctile;  // per 256-cell tile: existing cells in it, then (prefix) existing cells before it
+  int32_t* tile_group;  // per 256-cell tile: group of its first cell (k_pos_tile_groups)
   int32_t* rcnt;   // [L] existing cells = output rows
   unsigned long long* key2;  // order keys: 64-bit (position-post) ...
   unsigned int* key32;       // ... or the high half of the f64 key only (position)
@@ -298,6 +299,25 @@ __global__ void __launch_bounds__(256) k_pos_arcrec(PosArgs a) {
   }
 }
 
+// grid (chunk lattices, tiles): group of the first cell of every 256-cell tile (one bisection per tile)
+__global__ void __launch_bounds__(256) k_pos_tile_groups(PosArgs a) {
+  const int l = a.l0 + blockIdx.x;
+  const long long ncells = a.lat_cells[l];
+  const int ng = a.ngroups[l];
+  const int32_t* celloff = a.g_celloff + a.b.e_off[l];
+  const long long ntiles = (ncells + 255) >> 8;
+  for (long long t = (long long)blockIdx.y * blockDim.x + threadIdx.x; t < ntiles; t += (long long)gridDim.y * blockDim.x) {
+    const long long first = t << 8;
+    int lo = 0, hi = ng - 1;  // last group with celloff <= first
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((long long)celloff[mid] <= first) lo = mid;
+      else hi = mid - 1;
+    }
+    a.tile_group[tile_slot(a.cell_base, l, a.l0, (int)t)] = lo;
+  }
+}
+
 // grid (chunk lattices, tiles of 256 cells): one thread per (word, position) cell
 __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
   const int l = a.l0 + blockIdx.x;
@@ -308,24 +328,9 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
   const ArcRec* rec = a.rec + (e0 - a.e_chunk0);
   const int64_t cbase = a.cell_base[l];
   const double norm = a.tool == KLU_BEST_PATH2 ? a.beta[a.b.s_off[l]] : a.total[l];
-  const int lane = threadIdx.x & 31;
   for (long long tile = (long long)blockIdx.y * 256; tile < ncells; tile += (long long)gridDim.y * 256) {
     const long long cell = tile + threadIdx.x;
-    // the warp's first cell finds its group by bisection, the lanes walk on from there
-    int g = 0;
-    {
-      const long long first = tile + (threadIdx.x & ~31);
-      if (lane == 0 && first < ncells) {
-        int lo = 0, hi = ng - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if ((long long)celloff[mid] <= first) lo = mid;
-          else hi = mid - 1;
-        }
-        g = lo;
-      }
-      g = __shfl_sync(0xffffffffu, g, 0);
-    }
+    int g = a.tile_group[tile_slot(a.cell_base, l, a.l0, (int)(tile >> 8))];  // the lanes walk on from the tile's first group
     bool exists = false;
     if (cell < ncells) {
       while (g + 1 < ng && (long long)celloff[g + 1] <= cell) ++g;
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
       };
       // Pass 1 (no loop-carried chain beyond a compare): maximum, number of finite terms, the
       // first two of them, the best single arc.
-      double m = neg_inf(), x1 = neg_inf(), x2 = neg_inf(), bestv = neg_inf();
+      double bestv = neg_inf();  // the best single term: also the maximum the sum is taken around
       int nterm = 0, besta = -1;
 #pragma unroll 2
       for (int q = q0; q < q1; ++q) {
@@ -350,27 +355,19 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
         const double al = fw(rc);
         const double v = term(rc, al);
         if (!(al > neg_inf())) continue;
-        exists = true;
-        if (besta < 0) {
-          bestv = v;
-          besta = q;
-        } else if (a.tool == KLU_POSITION) {
+        nterm += v > neg_inf() ? 1 : 0;
+        if (besta < 0 || v > bestv) {
           // strict '>' in the reference's iteration order (input state, arc order):
           // kwsbin2/lattice-word-index-position.cc:178
-          if (v > bestv) {
-            bestv = v;
-            besta = q;
-          } else if (v == bestv) {
-            const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + a.seg_base[l];
-            if (a.b.out_orig[e0 + (int)idx[q]] < a.b.out_orig[e0 + (int)idx[besta]]) besta = q;
-          }
+          bestv = v;
+          besta = q;
+        } else if (a.tool == KLU_POSITION && v == bestv) {
+          const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + a.seg_base[l];
+          if (a.b.out_orig[e0 + (int)idx[q]] < a.b.out_orig[e0 + (int)idx[besta]]) besta = q;
         }
-        if (v == neg_inf()) continue;
-        if (nterm == 0) x1 = v;
-        else if (nterm == 1) x2 = v;
-        ++nterm;
-        m = fmax(m, v);
       }
+      exists = besta >= 0;
+      const double m = bestv;
       if (exists) {
         double sum;
         if (nterm >= 3) {
@@ -388,8 +385,12 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
             s0 += fast_exp(term(ra, fw(ra)) - m);
           }
           sum = m + fast_log(s0 + s1);
-        } else {
-          sum = nterm == 0 ? neg_inf() : nterm == 1 ? x1 : log_add(x1, x2);  // Kaldi's LogAdd exactly
+        } else {  // one or two terms: Kaldi's LogAdd exactly
+          sum = neg_inf();
+          for (int q = q0; q < q1; ++q) {
+            const ArcRec rc = rec[q];
+            sum = log_add(sum, term(rc, fw(rc)));
+          }
         }
         const unsigned int word = (unsigned int)a.g_word[e0 + g];
         if (a.tool == KLU_BEST_PATH2) {
@@ -788,8 +789,8 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
   KLU_TRY(sc[P_CELL].reserve((bp2 ? 8 : sizeof(CellRec)) * (size_t)N + 64));
   if (!bp2) {
     KLU_TRY(sc[P_ORDER].reserve(24 * (size_t)N + 64));
-    KLU_TRY(sc[P_CTILES].reserve(4 * (((size_t)N >> 8) + (size_t)L + 2)));
   }
+  KLU_TRY(sc[P_CTILES].reserve(8 * (((size_t)N >> 8) + (size_t)L + 2)));
   KLU_CUDA(cudaStreamSynchronize(c->stream));  // cell_base is a stack object
   a.rec = sc[P_REC].as<ArcRec>();
   a.cell = sc[P_CELL].as<CellRec>();
@@ -804,6 +805,7 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
   a.key32 = key32_a;
   a.idx2 = idx2_a;
   a.ctile = sc[P_CTILES].as<int32_t>();
+  a.tile_group = a.ctile + (((size_t)N >> 8) + (size_t)L + 2);
   a.arc_cellbase = bp2 ? d_arc_cellbase : nullptr;
 
   int64_t res_cap = 0, res_used = 0;
@@ -846,6 +848,12 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
       k_pos_arcrec<<<dim3(nl, tiles), 256, 0, c->stream>>>(a);
     }
     KLU_TRY(check_launch("k_pos_arcrec"));
+    {
+      KLU_LAUNCH(c, "k_pos_tile_groups");
+      k_pos_tile_groups<<<dim3(nl, (unsigned)std::max<int64_t>(1, std::min<int64_t>(((chunk_max_cells >> 8) + 256) / 256, 64))), 256, 0,
+                          c->stream>>>(a);
+    }
+    KLU_TRY(check_launch("k_pos_tile_groups"));
     {
       KLU_LAUNCH(c, "k_pos_cells");
       k_pos_cells<<<dim3(nl, ctiles), 256, 0, c->stream>>>(a);

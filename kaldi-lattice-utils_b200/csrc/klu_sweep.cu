@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(128) k_trop_sweeps(SweepArgs a, double* vfwd, 
 // two shared-memory reads, a range test and one coalesced global read per arc.
 // Sums of one or two terms are Kaldi's LogAdd exactly; longer ones a streaming
 // log-sum-exp (one exp per term).
-constexpr int kBandThreads = 256;
+constexpr int kBandThreads = 512;
 constexpr int kBandArcs = 768;
 constexpr int kBandStates = 128;
 
