@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define KLU_VERSION 1
+#define KLU_VERSION 2
 
 typedef struct klu_ctx klu_ctx; /* one per GPU; owns a stream and all device buffers */
 
@@ -82,6 +82,12 @@ typedef struct klu_lattices {
    * source state in state order (how OpenFst stores them), which saves a sixth of the
    * host-to-device traffic. */
   const int32_t* state_num_arcs;
+  /* Optional compact forms; each replaces its 32-bit array (which may then be NULL) and cuts the
+   * host-to-device traffic: durations that all fit a byte, and destinations as dst - src when
+   * every difference fits 16 bits (a topologically sorted lattice has dst > src).  20 -> 15 bytes
+   * per arc together with state_num_arcs. */
+  const uint8_t* arc_dur_u8;
+  const uint16_t* arc_dst_delta_u16;
 } klu_lattices;
 
 /* Command-line flags of the tools.  klu_opts_default() fills the

@@ -34,7 +34,8 @@ class KluLattices(C.Structure):
     _fields_ = [("num_lattices", C.c_int32), ("state_off", C.c_void_p), ("arc_off", C.c_void_p),
                 ("arc_src", C.c_void_p), ("arc_dst", C.c_void_p), ("arc_label", C.c_void_p), ("arc_dur", C.c_void_p),
                 ("arc_graph", C.c_void_p), ("arc_acoustic", C.c_void_p), ("fin_graph", C.c_void_p),
-                ("fin_acoustic", C.c_void_p), ("fin_dur", C.c_void_p), ("state_num_arcs", C.c_void_p)]
+                ("fin_acoustic", C.c_void_p), ("fin_dur", C.c_void_p), ("state_num_arcs", C.c_void_p),
+                ("arc_dur_u8", C.c_void_p), ("arc_dst_delta_u16", C.c_void_p)]
 
 
 class KluOpts(C.Structure):
@@ -102,6 +103,15 @@ def char_groups(wspace, other_groups=()):
     return label_group, inc, [1]
 
 
+def compact_arcs(batch):
+    """(dur_u8, dst_delta_u16) of a batch -- klu_lattices.arc_dur_u8 / arc_dst_delta_u16 -- or None
+    for a form that does not fit (a duration over 255, a destination more than 65535 states ahead)."""
+    dur8 = batch.dur.astype(np.uint8) if batch.dur.size == 0 or (batch.dur.min() >= 0 and batch.dur.max() < 256) else None
+    delta = batch.dst - batch.src
+    d16 = delta.astype(np.uint16) if delta.size == 0 or (delta.min() >= 0 and delta.max() < 65536) else None
+    return dur8, d16
+
+
 def make_opts(acoustic_scale=1.0, graph_scale=1.0, insertion_penalty=0.0, beam=float("inf"), include_words=(),
               exclude_words=(), beam_ratio=0.9, min_beam=1e-3, max_arcs=INT_MAX, max_states=INT_MAX, nbest=100,
               label_group=None, inc_groups=(), del_groups=()):
@@ -150,12 +160,15 @@ class Engine:
         return buf
 
     # -- data -----------------------------------------------------------------
-    def load(self, batch, state_num_arcs=None):
-        """state_num_arcs (optional, int32 per state): upload without the per-arc source array."""
+    def load(self, batch, state_num_arcs=None, dur_u8=None, dst_delta_u16=None):
+        """state_num_arcs (optional, int32 per state): upload without the per-arc source array;
+        dur_u8 / dst_delta_u16 (optional, see compact_arcs()): the compact forms of arc_dur / arc_dst."""
         kl = KluLattices(len(batch), _p(batch.state_off), _p(batch.arc_off),
-                         None if state_num_arcs is not None else _p(batch.src), _p(batch.dst),
-                         _p(batch.label), _p(batch.dur), _p(batch.graph), _p(batch.acoustic), _p(batch.fin_graph),
-                         _p(batch.fin_acoustic), _p(batch.fin_dur), _p(state_num_arcs))
+                         None if state_num_arcs is not None else _p(batch.src),
+                         None if dst_delta_u16 is not None else _p(batch.dst),
+                         _p(batch.label), None if dur_u8 is not None else _p(batch.dur), _p(batch.graph),
+                         _p(batch.acoustic), _p(batch.fin_graph),
+                         _p(batch.fin_acoustic), _p(batch.fin_dur), _p(state_num_arcs), _p(dur_u8), _p(dst_delta_u16))
         _chk(self.L.klu_load(self.h, C.byref(kl)))
         self.batch = batch
 

@@ -916,8 +916,12 @@ int run_log_sweeps(klu_ctx* c, const CostParams& cp, bool use_beam, float beam) 
   }
   const int units = 2 * ((c->L + 32 / G - 1) / (32 / G));
   const int grid = sweep_grid(c, units);
-  // KLU_SWEEP_V1=1: the cp.async version (kept as a cross-check); KLU_SWEEP_CPL: records per lane per batch
-  static const bool v1 = getenv("KLU_SWEEP_V1") != nullptr;
+  // KLU_SWEEP_V2=1: the bulk-copy (cp.async.bulk + mbarrier, next batch prefetched) variant.  Measured
+  // slower than the cp.async one on 10 k c2 lattices (8.5-8.9 ms against 6.3 ms, profiles/r2_sweeps_v2.md):
+  // a batch's records are <= 2 KB, the bulk copy's issue-to-arrival latency is longer than one batch's
+  // math, and two record buffers per tile cost residency.  Kept selectable as a cross-check.
+  // KLU_SWEEP_CPL / KLU_SWEEP_MB: its records per lane per batch / resident CTAs the registers are cut for.
+  static const bool v1 = getenv("KLU_SWEEP_V2") == nullptr;
   static const int cpl = getenv("KLU_SWEEP_CPL") ? atoi(getenv("KLU_SWEEP_CPL")) : 8;
   static const int mb = getenv("KLU_SWEEP_MB") ? atoi(getenv("KLU_SWEEP_MB")) : 7;
   {

@@ -286,6 +286,27 @@ def test_load_from_state_arc_counts(klu, engine, monkeypatch):
         engine.load(batch, state_num_arcs=bad)
 
 
+def test_load_from_compact_arc_arrays(klu, engine, monkeypatch):
+    """klu_lattices.arc_dur_u8 / arc_dst_delta_u16 (15 instead of 20 bytes per arc on the way up)."""
+    batch = klu.synth_batch("small", 7, seed=32)
+    engine.load(batch)
+    want = dict(seg=engine.segment(acoustic_scale=0.3), pos=engine.position(), fp=engine.frame_post())
+    dur8, d16 = klu.binding.compact_arcs(batch)
+    assert dur8 is not None and d16 is not None
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("KLU_HOST_PACKER", "1")
+        for kw in (dict(dur_u8=dur8), dict(dst_delta_u16=d16), dict(dur_u8=dur8, dst_delta_u16=d16),
+                   dict(dur_u8=dur8, dst_delta_u16=d16, state_num_arcs=batch.state_num_arcs())):
+            engine.load(batch, **kw)
+            got = dict(seg=engine.segment(acoustic_scale=0.3), pos=engine.position(), fp=engine.frame_post())
+            assert got == want
+    bad = d16.copy()
+    bad[3] = 0  # dst == src: not topologically sorted
+    with pytest.raises(klu.KluError):
+        engine.load(batch, dst_delta_u16=bad)
+
+
 # ---- device packer vs host packer ----------------------------------------------
 def test_gpu_packer_equals_host_packer(klu, engine, monkeypatch):
     lats = klu.synth_batch("small", 9, seed=2024).lattices()
