@@ -325,6 +325,33 @@ def cpu_sample(klu, ora, tool, batch, n, flags, cores, **extra):
     return sub, dt
 
 
+def char_tool_entry(args, shape, nlat, ncpu, cores, local):
+    last = None
+    for attempt in range(3):
+        cmd = [sys.executable, os.path.abspath(__file__), "--tool", "char_position", "--shape", shape, "--lattices",
+               str(nlat), "--steps", str(args.tools_steps), "--warmup", "3", "--e2e-steps", "0", "--no-tools",
+               "--ref-lattices", str(ncpu), "--seed", str(args.seed)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        env = dict(os.environ, LOCAL_RANK=str(local))
+        for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            line = [x for x in r.stdout.splitlines() if x.startswith("{")]
+            if r.returncode == 0 and line:
+                d = json.loads(line[-1])
+                return {"tool": "char_position", "shape": shape, "lattices": nlat, "arcs": d["batch"]["arcs"],
+                        "states": d["batch"]["states"], "flags": flags_for("char_position"), "ms_per_step": d["ms_per_step"],
+                        "arcs_per_s": d["value"], "pack_ms": d["pack_ms"], "arcs_per_s_incl_pack": d["value_incl_pack"],
+                        "index_entries": d["batch"]["index_entries"],
+                        "kernels_ms": {k: round(v["ms_per_launch"] * v["launches_per_step"], 3)
+                                       for k, v in d["roofline"]["kernels"].items()},
+                        "cpu_baseline": d["cpu_baseline"], "attempts": attempt + 1, "own_process": True}
+            last = (r.stderr or r.stdout).strip().splitlines()[-1:] or ["rc=%d" % r.returncode]
+        except Exception as ex:
+            last = ["%s: %s" % (type(ex).__name__, ex)]
+    return {"error": last[0] if last else "failed", "attempts": 3}
+
+
 def bench_tools(klu, local, args, peak):
     """Device-resident numbers of the other tools named by BASELINE.json's configs, each with
     its pack time, byte model and a bounded CPU baseline (oracle port on all host threads)."""
@@ -336,9 +363,16 @@ def bench_tools(klu, local, args, peak):
              ("position@c2", "position", "c2", args.tools_scale * 256, cores),
              ("utterance@c4", "utterance", "c4", args.tools_scale * 32, cores),
              ("prune_dyn_beam->best_path2@c2", "prune_dyn_beam", "c2", args.tools_scale * 1024, 2 * cores),
-             ("char_position@c5", "char_position", "c5", args.tools_scale * 512, 2 * cores)]
+             ("char_position@c5", "char_position", "c5", args.tools_scale * 128, 2 * cores)]
     for name, tool, shape, nlat, ncpu in specs:
         nlat = int(max(1, nlat))
+        if tool == "char_position":
+            # The character tool runs in a process of its own, up to three times: at batches of
+            # a few hundred c5 lattices it intermittently ends in an illegal memory access (also
+            # with round 1's library; DESIGN.md "known issues"), which would take this process's
+            # CUDA context with it.
+            out[name] = char_tool_entry(args, shape, nlat, ncpu, cores, local)
+            continue
         eng = klu.Engine(local)
         try:
             t0 = time.perf_counter()
@@ -403,15 +437,6 @@ def bench_tools(klu, local, args, peak):
                     entry["cpu_baseline"] = {"value": sub.num_arcs / (dt + dt2), "unit": "arcs/s", "cores": cores,
                                              "kind": "port", "sample": "first %d lattices: prune %.1f s + best-path2 on "
                                              "the pruned lattices %.1f s, %d threads" % (len(sub), dt, dt2, cores)}
-                elif tool == "char_position":
-                    sub = batch.slice(0, min(ncpu, nlat))
-                    lg = {0: 0, 1: 1}
-                    t0b = time.perf_counter()
-                    ora.run_batch(ora.CHAR_POSITION, sub.lattices(), cores, label_group=lg, inc_groups=[ora.INT_MAX],
-                                  del_groups=[1], **flags)
-                    dt = time.perf_counter() - t0b
-                    entry["cpu_baseline"] = {"value": sub.num_arcs / dt, "unit": "arcs/s", "cores": cores, "kind": "port",
-                                             "sample": "first %d lattices, %.1f s on %d threads" % (len(sub), dt, cores)}
                 else:
                     sub, dt = cpu_sample(klu, ora, tool, batch, ncpu, flags, cores)
                     entry["cpu_baseline"] = {"value": sub.num_arcs / dt, "unit": "arcs/s", "cores": cores, "kind": "port",
@@ -685,6 +710,17 @@ def main():
 
     # ---- CPU baseline (rank 0, bounded sample of the same workload) ----
     cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.tool == "char_position":
+        from oracle import ora
+        ora.build()
+        cores = os.cpu_count() or 1
+        sub = batch.slice(0, min(args.ref_lattices, nlat))
+        t0 = time.perf_counter()
+        ora.run_batch(ora.CHAR_POSITION, sub.lattices(), cores, label_group={0: 0, 1: 1}, inc_groups=[ora.INT_MAX],
+                      del_groups=[1], **flags)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sub.num_arcs / dt, "unit": "arcs/s", "cores": cores, "kind": "port",
+               "sample": "first %d lattices, %.1f s on %d threads" % (len(sub), dt, cores)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.tool in (
             "frame_post", "segment", "position", "utterance", "best_path2", "position_post"):
         from oracle import ora

@@ -526,6 +526,7 @@ struct GroupArgs {
   const unsigned long long *key_a, *key_b;
   const unsigned int *val_a, *val_b;
   const unsigned char* where;
+  int k32;                   // the (frame, word) keys fit 32 bits: the key buffers hold unsigned ints
   int32_t* frame_arc;
   int32_t* frame_cnt;        // per frame slot: groups in the frame
   const int32_t* item_base;
@@ -608,7 +609,9 @@ __global__ void __launch_bounds__(256) k_fg_emit(GroupArgs a) {
     if (cnt > 0) {
       const unsigned long long word = (unsigned long long)(unsigned int)b.out_rec[e].w;
       for (int q = 0; q < cnt; ++q) {
-        a.key[base + off + q] = ((unsigned long long)(first + q) << a.bits_label) | word;
+        const unsigned long long k = ((unsigned long long)(first + q) << a.bits_label) | word;
+        if (a.k32) reinterpret_cast<unsigned int*>(a.key)[base + off + q] = (unsigned int)k;
+        else a.key[base + off + q] = k;
         a.val[base + off + q] = (unsigned int)a.rank_of[e];
       }
     }
@@ -637,6 +640,7 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
     const int k0 = (item - a.item_base[l]) * kFramesPerItem;
     const int k1 = min(T, k0 + kFramesPerItem);
     const unsigned long long* key = a.where[l] ? a.key_b : a.key_a;
+    const unsigned int* key32 = reinterpret_cast<const unsigned int*>(key);
     const unsigned int* val = a.where[l] ? a.val_b : a.val_a;
     const unsigned long long label_mask = (1ULL << a.bits_label) - 1ULL;
     int wlo = 0x7fffffff, whi = -1;  // arc id window of the run
@@ -649,8 +653,8 @@ __global__ void __launch_bounds__(256) k_fg_heads(GroupArgs a) {
         unsigned long long kk = 0;
         bool head = false;
         if (i < f1) {
-          kk = key[i];
-          head = i == f0 || key[i - 1] != kk;
+          kk = a.k32 ? (unsigned long long)key32[i] : key[i];
+          head = i == f0 || (a.k32 ? (unsigned long long)key32[i - 1] : key[i - 1]) != kk;
         }
         const unsigned int hm = __ballot_sync(0xffffffffu, head);
         if (!WORDS) {
@@ -897,22 +901,36 @@ int build_frame_groups(klu_ctx* c) {
       cudaStreamSynchronize(c->stream);  // arc_base / arc_cnt go out of scope
       if (rc) break;
     }
+    a.k32 = bits_label + bits_time <= 32 ? 1 : 0;
     {
       KLU_LAUNCH(c, "k_fg_emit");
       k_fg_emit<<<L, 256, 0, c->stream>>>(a);
     }
     if ((rc = check_launch("k_fg_emit"))) break;
-    SegSortArgs ss;
-    ss.seg_base = d_inst_base;
-    ss.seg_cnt = d_inst_cnt;
-    ss.key_a = key_a.as<unsigned long long>();
-    ss.val_a = val_a.as<unsigned int>();
-    ss.key_b = key_b.as<unsigned long long>();
-    ss.val_b = val_b.as<unsigned int>();
-    ss.where = d_where;
-    ss.lo_bit = 0;
-    ss.hi_bit = bits_label + bits_time;
-    {
+    if (a.k32) {  // (frame, word) fits 32 bits: a third less traffic per pass
+      SegSortArgs32 ss;
+      ss.seg_base = d_inst_base;
+      ss.seg_cnt = d_inst_cnt;
+      ss.key_a = key_a.as<unsigned int>();
+      ss.val_a = val_a.as<unsigned int>();
+      ss.key_b = key_b.as<unsigned int>();
+      ss.val_b = val_b.as<unsigned int>();
+      ss.where = d_where;
+      ss.lo_bit = 0;
+      ss.hi_bit = bits_label + bits_time;
+      KLU_LAUNCH(c, "k_seg_radix_sort");
+      k_seg_radix_sort32<<<L, kSortThreads, 0, c->stream>>>(ss);
+    } else {
+      SegSortArgs ss;
+      ss.seg_base = d_inst_base;
+      ss.seg_cnt = d_inst_cnt;
+      ss.key_a = key_a.as<unsigned long long>();
+      ss.val_a = val_a.as<unsigned int>();
+      ss.key_b = key_b.as<unsigned long long>();
+      ss.val_b = val_b.as<unsigned int>();
+      ss.where = d_where;
+      ss.lo_bit = 0;
+      ss.hi_bit = bits_label + bits_time;
       KLU_LAUNCH(c, "k_seg_radix_sort");
       k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
     }
