@@ -154,6 +154,7 @@ struct klu_ctx {
   int32_t fr_items = 0;                      // frame-post work items (runs of frames)
   int32_t fr_max_window = 0;                 // largest arc window of a run of frames
   int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0, max_states = 0;
+  int32_t max_span = 0;  // longest arc in frames (time[dst] - time[src])
   double avg_deg = 0;
   int64_t band_total = 0;
 

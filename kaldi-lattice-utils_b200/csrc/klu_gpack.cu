@@ -313,8 +313,10 @@ __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* ke
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
   const int T = a.meta[l * M_STRIDE + M_FRAMES];
   long long cf = 0, cp = 0;
+  int span = 0;
   for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
     const int go = s0 + a.src[e], gd = s0 + a.dst[e];
+    span = max(span, a.dur[e]);
     const int n = a.old2new[go], d = a.old2new[gd];
     const int p = a.out_off[n] + (e - a.first_arc[go]);
     const int lab = a.label[e];
@@ -335,10 +337,12 @@ __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* ke
   for (int o = 16; o > 0; o >>= 1) {
     cf += __shfl_xor_sync(0xffffffffu, cf, o);
     cp += __shfl_xor_sync(0xffffffffu, cp, o);
+    span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
   }
   if (lane == 0) {
     red[0][warp] = cf;
     red[1][warp] = cp;
+    if (span > 0) atomicMax(&a.meta[a.L * M_STRIDE], span);  // spare meta row: longest arc of the batch
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -553,7 +557,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   c->h_fr_base.assign(L + 1, 0);
   c->h_new2old.clear();
   c->h_old2new.clear();
-  c->max_label = c->max_time = c->max_len = c->max_indeg = c->max_outdeg = c->max_states = 0;
+  c->max_label = c->max_time = c->max_len = c->max_indeg = c->max_outdeg = c->max_states = c->max_span = 0;
   c->avg_deg = S ? (double)E / (double)S : 0.0;
   c->band_total = 0;
   c->frame_entries = 0;
@@ -768,6 +772,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   std::vector<long long> h_tot(L + 1), h_cap(2 * (size_t)L);
   KLU_TRY(small_d2h(c, h_tot.data(), a.lat_tot, 8 * (size_t)(L + 1)));
   KLU_TRY(small_d2h(c, h_cap.data(), a.cap, 16 * (size_t)L));
+  KLU_TRY(small_d2h(c, &c->max_span, a.meta + (size_t)L * M_STRIDE, 4));
   KLU_TRY(small_sync(c));
   klu_trace(c, "load: bands known");
   for (int32_t l = 0; l <= L; ++l) c->h_band_off[l] = h_tot[l];

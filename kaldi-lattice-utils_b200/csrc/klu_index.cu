@@ -44,7 +44,7 @@ struct IndexArgs {
   const double* best;
   double beam;
   // key layout; drop_key = one bit above every valid key (pruned / unreachable)
-  int bits_label, bits_time, bits_len;
+  int bits_label, bits_time, bits_len, bits_span;
   unsigned long long drop_key;
   // entries
   const int64_t* ent_base;  // [L] first entry slot of each lattice
@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
       const bool dead = a.use_beam && emit_arc_pruned(a, l, s, r);
       // fw[s] + arc_lkh + bw[next], kwsbin2/lattice-word-index-segment.cc:160-162
       const double v = __dadd_rn(__dadd_rn(a.alpha[s], -rec_cost(r, a.cp)), a.beta[r.x]);
-      const unsigned long long t0 = (unsigned long long)a.b.time[s], t1 = (unsigned long long)a.b.time[r.x];
-      const unsigned long long k = ((((unsigned long long)r.w << a.bits_time) | t0) << a.bits_time) | t1;
+      // (word, t0, t1 - t0): the same order as (word, t0, t1) in fewer bits (arcs span a few frames)
+      const unsigned long long t0 = (unsigned long long)a.b.time[s], sp = (unsigned long long)(a.b.time[r.x] - a.b.time[s]);
+      const unsigned long long k = ((((unsigned long long)r.w << a.bits_time) | t0) << a.bits_span) | sp;
       a.key[base + off] = dead ? a.drop_key : k;
       a.val[base + off] = v;
       a.aux[base + off] = arc_local;
@@ -223,6 +224,7 @@ struct ReduceArgs {
   int32_t* rcnt;
   // second-sort inputs
   unsigned long long* key2;
+  unsigned int* key32;  // high half of the f64 order key (what the order sort looks at)
   unsigned int* idx2;
   int bits_label;
   unsigned long long drop_key;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
         const float f = (float)logp + 0.0f;
         a.key2[base + slot] = ((k >> a.bits_label) << 32) | (unsigned long long)(~ord_f32(f));
       } else {
-        a.key2[base + slot] = ~ord_f64(logp);
+        a.key32[base + slot] = (unsigned int)((~ord_f64(logp)) >> 32);
       }
       a.idx2[base + slot] = (unsigned int)slot;
     }
@@ -467,39 +469,39 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* cnt, int l0
   if (tid == 0) off[L] = carry_s;
 }
 
-// The order sort runs on the high bits of its 64-bit keys only (half the radix passes).
-// Elements whose keys agree in those bits (log-posteriors equal to ~1e-6 relative:
-// a handful per lattice) are left in input order by the stable sort; here every such
-// run is put in full-key order by a stable insertion sort, one thread per run.
+// The order sort looks at the high half of the f64 keys only (32-bit keys: half the radix
+// passes, a third less traffic per pass).  Elements whose keys agree there (log-posteriors
+// equal to ~1e-6 relative: a handful per lattice) are left in input order by the stable
+// sort; here every such run is put in full-key order -- the full key is read back from the
+// reduced values -- by a stable insertion sort, one thread per run.
 struct OrderFixArgs {
   const int64_t* seg_base;
   const int32_t* seg_cnt;
   const unsigned char* where;
-  unsigned long long *key_a, *key_b;
+  unsigned int *key_a, *key_b;
   unsigned int *val_a, *val_b;
-  int lo_bit;
+  const double* rval;
 };
 
 __global__ void __launch_bounds__(256) k_order_fixup(OrderFixArgs a) {
   const int l = blockIdx.x;
   const int n = a.seg_cnt[l];
   const int64_t base = a.seg_base[l];
-  unsigned long long* K = (a.where[l] ? a.key_b : a.key_a) + base;
+  const unsigned int* K = (a.where[l] ? a.key_b : a.key_a) + base;
   unsigned int* V = (a.where[l] ? a.val_b : a.val_a) + base;
+  const double* rv = a.rval + base;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.y * blockDim.x) {
-    const unsigned long long t = K[i] >> a.lo_bit;
-    if ((i > 0 && (K[i - 1] >> a.lo_bit) == t) || (K[i + 1] >> a.lo_bit) != t) continue;  // not the head of a run
+    const unsigned int t = K[i];
+    if ((i > 0 && K[i - 1] == t) || K[i + 1] != t) continue;  // not the head of a run
     int j = i + 1;
-    while (j < n && (K[j] >> a.lo_bit) == t) {  // insert element j into the ordered [i, j)
-      const unsigned long long k = K[j];
+    while (j < n && K[j] == t) {  // insert element j into the ordered [i, j)
       const unsigned int v = V[j];
+      const unsigned long long k = ~ord_f64(rv[v] + 0.0);
       int q = j;
-      while (q > i && K[q - 1] > k) {
-        K[q] = K[q - 1];
+      while (q > i && (~ord_f64(rv[V[q - 1]] + 0.0)) > k) {
         V[q] = V[q - 1];
         --q;
       }
-      K[q] = k;
       V[q] = v;
       ++j;
     }
@@ -517,7 +519,7 @@ struct GatherArgs {
   const unsigned long long* rkey;
   const double* rval;
   const unsigned int* raux;
-  int bits_label, bits_time, bits_len;
+  int bits_label, bits_time, bits_len, bits_span;
   int32_t *c0, *c1, *c2, *c3;
   double* v;
   float* vf;
@@ -539,10 +541,11 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
       a.c0[out + i] = (int32_t)k;
       a.v[out + i] = logp;
     } else if (a.tool == KLU_SEGMENT) {
-      const unsigned long long tm = (1ULL << a.bits_time) - 1ULL;
-      a.c0[out + i] = (int32_t)(k >> (2 * a.bits_time));
-      a.c1[out + i] = (int32_t)((k >> a.bits_time) & tm);
-      a.c2[out + i] = (int32_t)(k & tm);
+      const unsigned long long tm = (1ULL << a.bits_time) - 1ULL, sm = (1ULL << a.bits_span) - 1ULL;
+      const int32_t t0 = (int32_t)((k >> a.bits_span) & tm);
+      a.c0[out + i] = (int32_t)(k >> (a.bits_time + a.bits_span));
+      a.c1[out + i] = t0;
+      a.c2[out + i] = t0 + (int32_t)(k & sm);
       a.v[out + i] = logp;
     } else if (a.tool == KLU_POSITION) {
       const unsigned long long lm = (1ULL << a.bits_len) - 1ULL;
@@ -582,6 +585,7 @@ struct UttArgs {
   const unsigned int* raux;
   double* rval;
   unsigned long long* key2;
+  unsigned int* key32;
   unsigned int* idx2;
   const double* alpha;
   const double* beta;
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(256) k_utt_tasks(UttArgs a) {
       if (lane == 0) {
         const double logp = acc - total;
         a.rval[base + slot] = logp;
-        a.key2[base + slot] = ~ord_f64(logp + 0.0);
+        a.key32[base + slot] = (unsigned int)((~ord_f64(logp + 0.0)) >> 32);
         a.idx2[base + slot] = (unsigned int)slot;
       }
       __syncwarp();
@@ -800,7 +804,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   KLU_TRY(c->d_scratch[S_RCNT].reserve(sizeof(int32_t) * L));
   // reduced entries: key (8) + val (8) + aux (4) per slot
   KLU_TRY(c->d_scratch[S_R].reserve(20 * (size_t)N + 64));
-  KLU_TRY(c->d_res[6].reserve(sizeof(int64_t) * N));  // ordering-sort keys
+  KLU_TRY(c->d_res[6].reserve(12 * (size_t)N));  // ordering-sort keys: 64-bit (float tools) | 32-bit (f64 tools)
   KLU_TRY(c->d_res[7].reserve(sizeof(int32_t) * N));  // ordering-sort values
   KLU_TRY(c->d_res[5].reserve(sizeof(int64_t) * (L + 1)));
   KLU_CUDA(cudaMemcpyAsync(c->d_scratch[S_BASE].p, ent_base.data(), sizeof(int64_t) * (L + 1),
@@ -830,6 +834,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   a.bits_label = bits_for(c->max_label);
   a.bits_time = bits_for(c->max_time);
   a.bits_len = bits_for(c->max_len);
+  a.bits_span = bits_for(c->max_span);
   a.ent_base = c->d_scratch[S_BASE].as<int64_t>();
   a.arc_ent_off = c->d_scratch[S_ARCOFF].as<int32_t>();
   a.ent_cnt = c->d_scratch[S_CNT].as<int32_t>();
@@ -839,7 +844,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
   a.aux = c->d_scratch[S_AUX].as<unsigned int>();
   int key_bits = 0;
   if (tool == KLU_UTTERANCE) key_bits = a.bits_label;
-  else if (tool == KLU_SEGMENT) key_bits = a.bits_label + 2 * a.bits_time;
+  else if (tool == KLU_SEGMENT) key_bits = a.bits_label + a.bits_time + a.bits_span;
   else if (tool == KLU_POSITION || tool == KLU_BEST_PATH2 || tool == KLU_POSITION_POST)
     key_bits = a.bits_label + a.bits_len + (tool == KLU_POSITION_POST ? 1 : 0);  // positions run to max_len inclusive
   else key_bits = a.bits_time + a.bits_label;
@@ -938,6 +943,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     // the ordering sort's input pair is separate from the first sort's buffers
     // (the reduce reads those); its ping-pong partner is the then-free A side.
     r.key2 = c->d_res[6].as<unsigned long long>();
+    r.key32 = reinterpret_cast<unsigned int*>(r.key2 + N);
     r.idx2 = c->d_res[7].as<unsigned int>();
     r.bits_label = a.bits_label;
     r.drop_key = a.drop_key;
@@ -980,6 +986,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       u.raux = r.raux;
       u.rval = r.rval;
       u.key2 = r.key2;
+      u.key32 = r.key32;
       u.idx2 = r.idx2;
       u.alpha = a.alpha;
       u.beta = a.beta;
@@ -1007,36 +1014,56 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       }
       KLU_TRY(check_launch("k_utt_tasks"));
     }
-    SegSortArgs s2;
-    s2.seg_base = a.ent_base + l0;
-    s2.seg_cnt = r.rcnt + l0;
-    s2.key_a = r.key2;
-    s2.val_a = r.idx2;
-    s2.key_b = c->d_scratch[S_KEYA].as<unsigned long long>();
-    s2.val_b = c->d_scratch[S_IDXA].as<unsigned int>();
-    s2.where = c->d_scratch[S_WHERE].as<unsigned char>() + L + l0;
-    // f64 order keys: sort on the high half, settle the few near-ties afterwards
+    // f64 order keys (segment, utterance): 32-bit sort on the high half, near-ties settled afterwards;
+    // float tools (generic frame-post / position-post): (frame or position, float) in 64 bits
     const bool half_keys = !(tool == KLU_FRAME_POST || tool == KLU_POSITION_POST);
-    s2.lo_bit = half_keys ? 32 : 0;
-    s2.hi_bit = 64;
-    {
-      KLU_LAUNCH(c, "k_seg_radix_sort");
-      k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s2);
-    }
-    KLU_TRY(check_launch("k_seg_radix_sort(order)"));
+    unsigned char* where2 = c->d_scratch[S_WHERE].as<unsigned char>() + L + l0;
+    unsigned int* ord_a = r.idx2;
+    unsigned int* ord_b = c->d_scratch[S_IDXA].as<unsigned int>();
     if (half_keys) {
+      SegSortArgs32 s2;
+      s2.seg_base = a.ent_base + l0;
+      s2.seg_cnt = r.rcnt + l0;
+      s2.key_a = r.key32;
+      s2.val_a = ord_a;
+      s2.key_b = c->d_scratch[S_KEYA].as<unsigned int>();
+      s2.val_b = ord_b;
+      s2.where = where2;
+      s2.lo_bit = 0;
+      s2.hi_bit = 32;
+      {
+        KLU_LAUNCH(c, "k_seg_radix_sort");
+        k_seg_radix_sort32<<<nl, kSortThreads, 0, c->stream>>>(s2);
+      }
+      KLU_TRY(check_launch("k_seg_radix_sort(order)"));
       OrderFixArgs f;
       f.seg_base = s2.seg_base;
       f.seg_cnt = s2.seg_cnt;
       f.where = s2.where;
       f.key_a = s2.key_a, f.key_b = s2.key_b;
       f.val_a = s2.val_a, f.val_b = s2.val_b;
-      f.lo_bit = s2.lo_bit;
+      f.rval = r.rval + 0;
       {
         KLU_LAUNCH(c, "k_order_fixup");
         k_order_fixup<<<dim3(nl, tiles), 256, 0, c->stream>>>(f);
       }
       KLU_TRY(check_launch("k_order_fixup"));
+    } else {
+      SegSortArgs s2;
+      s2.seg_base = a.ent_base + l0;
+      s2.seg_cnt = r.rcnt + l0;
+      s2.key_a = r.key2;
+      s2.val_a = ord_a;
+      s2.key_b = c->d_scratch[S_KEYA].as<unsigned long long>();
+      s2.val_b = ord_b;
+      s2.where = where2;
+      s2.lo_bit = 0;
+      s2.hi_bit = 64;
+      {
+        KLU_LAUNCH(c, "k_seg_radix_sort");
+        k_seg_radix_sort<<<nl, kSortThreads, 0, c->stream>>>(s2);
+      }
+      KLU_TRY(check_launch("k_seg_radix_sort(order)"));
     }
     {
       KLU_LAUNCH(c, "k_scan_counts");
@@ -1061,14 +1088,15 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     g.rcnt = r.rcnt;
     g.res_off = c->d_res[5].as<int64_t>();
     g.where = c->d_scratch[S_WHERE].as<unsigned char>() + L;
-    g.idx_a = s2.val_a;
-    g.idx_b = s2.val_b;
+    g.idx_a = ord_a;
+    g.idx_b = ord_b;
     g.rkey = r.rkey;
     g.rval = r.rval;
     g.raux = r.raux;
     g.bits_label = a.bits_label;
     g.bits_time = a.bits_time;
     g.bits_len = a.bits_len;
+    g.bits_span = a.bits_span;
     g.c0 = c->d_res[0].as<int32_t>();
     g.c1 = c->d_res[1].as<int32_t>();
     g.c2 = c->d_res[2].as<int32_t>();

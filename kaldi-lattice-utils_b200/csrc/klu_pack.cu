@@ -40,7 +40,7 @@ struct LatInfo {
   int32_t nl = 0;
   int32_t num_frames = 0;
   uint8_t times_ok = 1;
-  int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0;
+  int32_t max_label = 0, max_time = 0, max_len = 0, max_indeg = 0, max_outdeg = 0, max_span = 0;
   int64_t cap_frame = 0, cap_pos = 0, band = 0;
   std::string err;
 };
@@ -203,6 +203,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
               hi[v] = std::max(hi[v], hi[u] + nz);
             }
             li.max_label = std::max(li.max_label, lab);
+            li.max_span = std::max(li.max_span, in->arc_dur[e0 + e]);
           }
           int32_t utt = -1;
           for (int32_t s = 0; s < ns; ++s) {
@@ -350,8 +351,9 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   c->h_cap_frame.resize(L);
   c->h_cap_pos.resize(L);
   c->h_maxlen.resize(L);
-  c->max_label = c->max_time = c->max_len = c->max_indeg = c->max_outdeg = c->max_states = 0;
+  c->max_label = c->max_time = c->max_len = c->max_indeg = c->max_outdeg = c->max_states = c->max_span = 0;
   for (int32_t l = 0; l < L; ++l) {
+    c->max_span = std::max(c->max_span, info[l].max_span);
     c->h_num_frames[l] = info[l].num_frames;
     c->h_times_ok[l] = info[l].times_ok;
     c->h_cap_frame[l] = info[l].cap_frame;
