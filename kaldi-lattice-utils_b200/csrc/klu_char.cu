@@ -818,22 +818,17 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   KLU_TRY(check_launch("k_char_exit"));
 
   // ---- frontier buffers (grown as needed) ----
-  DevBuf it_node, it_state, it_t0, it_wsum, it_wmax;       // current items
-  DevBuf n_node, n_state, n_t0, n_wsum, n_wmax;             // next items
-  DevBuf ckey_a, ckey_b, cval_a, cval_b, c_wsum, c_wmax, c_t0, c_state, c_main, cand_cnt, cand_loc, where;
-  DevBuf nd_parent, nd_chr, nd_cnt, nd_grp, nd_lat, nd_t0, nd_t1, nd_len, nd_total, nd_best;
-  DevBuf d_ibase, d_icnt, d_cbase, d_ccnt, d_ncnt;
-  std::vector<DevBuf*> all = {&it_node, &it_state, &it_t0, &it_wsum, &it_wmax, &n_node, &n_state, &n_t0, &n_wsum, &n_wmax,
-                              &ckey_a, &ckey_b, &cval_a, &cval_b, &c_wsum, &c_wmax, &c_t0, &c_state, &c_main, &cand_cnt,
-                              &cand_loc, &where,
-                              &nd_parent, &nd_chr, &nd_cnt, &nd_grp, &nd_lat, &nd_t0, &nd_t1, &nd_len, &nd_total, &nd_best,
-                              &d_ibase, &d_icnt, &d_cbase, &d_ccnt, &d_ncnt};
-  struct Releaser {
-    std::vector<DevBuf*>& v;
-    ~Releaser() {
-      for (DevBuf* b : v) b->release();
-    }
-  } releaser{all};
+  // The frontier, trie and row buffers live in the context (c->d_char) and are reused from run to
+  // run: allocating and freeing ~50 buffers per run cost more than the kernels on small batches.
+  int nbuf = 0;
+  auto buf = [&]() -> DevBuf& { return c->d_char[nbuf++]; };
+  DevBuf &it_node = buf(), &it_state = buf(), &it_t0 = buf(), &it_wsum = buf(), &it_wmax = buf();  // current items
+  DevBuf &n_node = buf(), &n_state = buf(), &n_t0 = buf(), &n_wsum = buf(), &n_wmax = buf();       // next items
+  DevBuf &ckey_a = buf(), &ckey_b = buf(), &cval_a = buf(), &cval_b = buf(), &c_wsum = buf(), &c_wmax = buf(),
+         &c_t0 = buf(), &c_state = buf(), &c_main = buf(), &cand_cnt = buf(), &cand_loc = buf(), &where = buf();
+  DevBuf &nd_parent = buf(), &nd_chr = buf(), &nd_cnt = buf(), &nd_grp = buf(), &nd_lat = buf(), &nd_t0 = buf(),
+         &nd_t1 = buf(), &nd_len = buf(), &nd_total = buf(), &nd_best = buf();
+  DevBuf &d_ibase = buf(), &d_icnt = buf(), &d_cbase = buf(), &d_ccnt = buf(), &d_ncnt = buf();
   KLU_TRY(d_ibase.reserve(8 * (size_t)(L + 1)));
   KLU_TRY(d_icnt.reserve(4 * (size_t)L));
   KLU_TRY(d_cbase.reserve(8 * (size_t)(L + 1)));
@@ -1021,9 +1016,8 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   }
   if (pool == 0) return 0;
   // ---- rows ----
-  DevBuf row_cnt, row_base, cursor, rkey_a, rkey_b, rval_a, rval_b, out_base, o_node, chr_off;
-  std::vector<DevBuf*> all2 = {&row_cnt, &row_base, &cursor, &rkey_a, &rkey_b, &rval_a, &rval_b, &out_base, &o_node, &chr_off};
-  Releaser releaser2{all2};
+  DevBuf &row_cnt = buf(), &row_base = buf(), &cursor = buf(), &rkey_a = buf(), &rkey_b = buf(), &rval_a = buf(),
+         &rval_b = buf(), &out_base = buf(), &o_node = buf(), &chr_off = buf();
   KLU_TRY(row_cnt.reserve(4 * (size_t)L));
   KLU_TRY(cursor.reserve(4 * (size_t)L));
   KLU_TRY(row_base.reserve(8 * (size_t)(L + 1)));
@@ -1103,9 +1097,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   r.where = ss.where;
   // the keyed copy goes to a fresh pair of buffers so that a lattice whose first sort
   // ended in either buffer is read consistently
-  DevBuf k2a, k2b, v2a, v2b, where2;
-  std::vector<DevBuf*> all3 = {&k2a, &k2b, &v2a, &v2b, &where2};
-  Releaser releaser3{all3};
+  DevBuf &k2a = buf(), &k2b = buf(), &v2a = buf(), &v2b = buf(), &where2 = buf();
   KLU_TRY(k2a.reserve(8 * (size_t)nrows));
   KLU_TRY(k2b.reserve(8 * (size_t)nrows));
   KLU_TRY(v2a.reserve(4 * (size_t)nrows));
@@ -1226,6 +1218,7 @@ int run_char_segment(klu_ctx* c, const klu_opts* o) { return run_char_index(c, o
 void char_release(klu_ctx* c) {
   delete static_cast<CharState*>(c->char_state);
   c->char_state = nullptr;
+  for (DevBuf& b : c->d_char) b.release();
 }
 
 }  // namespace klu
