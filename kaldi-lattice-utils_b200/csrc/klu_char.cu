@@ -882,6 +882,12 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
       KLU_TRY(scan(rg, f.cand_cnt, cand_loc.as<int32_t>(), d_cbase.as<int64_t>()));
     }
     const int64_t ncand = h_base[L];
+    if (getenv("KLU_CHAR_DEBUG")) {
+      long long mx = 0;
+      for (int32_t l = 0; l < L; ++l) mx = std::max(mx, h_tot[l]);
+      fprintf(stderr, "[klu char] depth %d: %lld candidates (largest lattice %lld), pool %lld, items %lld\n", depth,
+              (long long)ncand, mx, (long long)pool, (long long)items_total);
+    }
     if (ncand == 0) break;
     for (int32_t l = 0; l < L; ++l) {
       h_cnt[l] = (int32_t)h_tot[l];

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -52,7 +53,13 @@ namespace {
 
 // The tools close a batch at this many lattices whatever their size (archives of tiny lattices:
 // bounds the per-lattice host metadata of a batch); the library itself has no such limit.
+#if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
+// The character tools keep every same-group sub-path of a batch in device memory at once (a trie
+// whose frontier can grow by the branching factor per character): small batches bound that.
+constexpr size_t kMaxBatchLattices = 64;
+#else
 constexpr size_t kMaxBatchLattices = (size_t)1 << 20;
+#endif
 
 struct Batch {
   std::vector<CompactLat> lats;
@@ -115,8 +122,16 @@ struct Batch {
     });
     block->clear();
   }
+  // What goes over PCIe: per-state arc counts instead of per-arc sources (the arcs are grouped by
+  // source state, as OpenFst stores them), durations as bytes and destinations as 16-bit distances
+  // from the source when they all fit (klu_lattices.state_num_arcs / arc_dur_u8 /
+  // arc_dst_delta_u16): 15 instead of 24 bytes per arc.  Built once per batch on the I/O threads.
+  mutable std::vector<int32_t> num_arcs_;
+  mutable std::vector<uint8_t> dur8_;
+  mutable std::vector<uint16_t> delta16_;
   klu_lattices View() const {
     klu_lattices v;
+    memset(&v, 0, sizeof(v));
     v.num_lattices = (int32_t)lats.size();
     v.state_off = state_off.data();
     v.arc_off = arc_off.data();
@@ -129,7 +144,41 @@ struct Batch {
     v.fin_graph = fin_graph.data();
     v.fin_acoustic = fin_acoustic.data();
     v.fin_dur = fin_dur.data();
-    v.state_num_arcs = nullptr;
+    if (getenv("KLU_PLAIN_UPLOAD")) return v;
+    const size_t E = src.size(), S = fin_graph.size(), nl = lats.size();
+    num_arcs_.assign(S, 0);
+    dur8_.resize(E);
+    delta16_.resize(E);
+    std::atomic<int> dur_ok(1), delta_ok(1), grouped(1);
+    ParallelFor(nl, [&](size_t l) {
+      const size_t e0 = (size_t)arc_off[l], e1 = (size_t)arc_off[l + 1], s0 = (size_t)state_off[l];
+      const int32_t ns = (int32_t)(state_off[l + 1] - state_off[l]);
+      bool d_ok = true, t_ok = true, g_ok = true;
+      for (size_t e = e0; e < e1; ++e) {
+        const int32_t u = src[e], dd = dst[e] - u, du = dur[e];
+        if (u < 0 || u >= ns || (e > e0 && src[e - 1] > u)) { g_ok = false; break; }
+        ++num_arcs_[s0 + (size_t)u];
+        if (du < 0 || du > 255) d_ok = false;
+        if (dd < 0 || dd > 65535) t_ok = false;
+        dur8_[e] = (uint8_t)du;
+        delta16_[e] = (uint16_t)dd;
+      }
+      if (!d_ok) dur_ok = 0;
+      if (!t_ok) delta_ok = 0;
+      if (!g_ok) grouped = 0;
+    });
+    if (grouped) {  // (otherwise klu_load reports the layout error from the plain arrays)
+      v.arc_src = nullptr;
+      v.state_num_arcs = num_arcs_.data();
+      if (dur_ok) {
+        v.arc_dur = nullptr;
+        v.arc_dur_u8 = dur8_.data();
+      }
+      if (delta_ok) {
+        v.arc_dst = nullptr;
+        v.arc_dst_delta_u16 = delta16_.data();
+      }
+    }
     return v;
   }
 };
