@@ -129,6 +129,8 @@ struct klu_ctx {
   cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;  // around the device packer
   float load_upload_ms = 0.f, load_pack_ms = 0.f, lazy_pack_ms = 0.f;  // klu_load_times
   bool frame_ready = false;  // frame index of the loaded batch built (klu_frame.cu; on first use)
+  bool seg_ready = false;    // arcs bucketed by start frame (klu_segment.cu; on first use)
+  int32_t seg_max_bucket = 0, seg_slots = 0;
   int num_sms = 148;
   int64_t launches = 0;
   bool profile = false;
@@ -144,6 +146,7 @@ struct klu_ctx {
   std::vector<int32_t> h_new2old;            // per packed state: input local id
   std::vector<int32_t> h_old2new;            // per input state (global): packed global id
   std::vector<int32_t> h_num_frames;         // utterance length per lattice
+  std::vector<int32_t> h_maxtime;            // largest state time per lattice
   std::vector<uint8_t> h_times_ok;           // consistent state times per lattice
   std::vector<int64_t> h_cap_frame, h_cap_pos;  // per lattice entry upper bounds
   std::vector<int32_t> h_maxlen;             // max #non-eps labels on a path, per lattice
@@ -161,7 +164,7 @@ struct klu_ctx {
   // ---- device: packed batch ----
   klu::DevBuf d_s_off, d_e_off, d_lvl_off, d_lvl_start, d_in_rec, d_out_rec, d_in_off, d_out_off, d_out_src,
       d_in2out, d_old2new, d_out_orig, d_fin_g, d_fin_a, d_time, d_orig, d_level, d_band_lo, d_band_off, d_order, d_fr_base, d_fr_off, d_frame_arc,
-      d_fr_item, d_fr_gloc, d_fr_res_off, d_fr_gword, d_fr_gstart, d_fr_gframe, d_fr_run_lo, d_fr_run_hi, d_fr_tarc, d_fr_tlabel, d_fr_seg, d_tile_heads;
+      d_fr_item, d_fr_gloc, d_fr_res_off, d_fr_gword, d_fr_gstart, d_fr_gframe, d_fr_run_lo, d_fr_run_hi, d_fr_tarc, d_fr_tlabel, d_fr_seg, d_tile_heads, d_sg_meta, d_sg_boff, d_sg_perm;
   // ---- device: per-run state ----
   klu::DevBuf d_alpha, d_beta, d_total, d_totfwd, d_counter, d_filter;
   klu::DevBuf d_vfwd, d_vbwd, d_best;  // tropical sweeps
@@ -208,6 +211,8 @@ int run_tropical_sweeps(klu_ctx* c, const CostParams& cp);
 int run_banded_alpha(klu_ctx* c, const CostParams& cp, bool use_beam, float beam, int l0, int l1);
 // klu_index.cu
 int run_index_tool(klu_ctx* c, int tool, const klu_opts* o);
+// klu_segment.cu: lattice-word-index-segment by start-frame buckets; *done = false -> use run_index_tool
+int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done);
 // klu_position.cu: lattice-word-index-position, lattice-to-word-position-post, lattice-best-path2
 int run_position_tool(klu_ctx* c, int tool, const klu_opts* o);
 // klu_frame.cu
@@ -254,6 +259,22 @@ int upload_filter(klu_ctx* c, const klu_opts* o, int* mode_out, int* n_out);
 // Device helpers
 #ifdef __CUDACC__
 namespace klu {
+
+// Kernels launched on a (lattices, tiles) grid: CTAs are dispatched x-fastest, so with the lattice
+// in blockIdx.x the ~1000 CTAs in flight touch ~1000 different lattices and their gathers (alpha,
+// beta, entries by sorted index) miss L2.  lat_tile() re-reads the same grid tile-fastest: the
+// CTAs in flight then cover a few lattices whose arrays stay in L2 (k_gather: 4.4 -> 0.9 ms).
+struct LatTile {
+  int l, tile, tiles;
+};
+__device__ __forceinline__ LatTile lat_tile() {
+  const unsigned long long lin = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;
+  LatTile t;
+  t.tiles = (int)gridDim.y;
+  t.l = (int)(lin / gridDim.y);
+  t.tile = (int)(lin % gridDim.y);
+  return t;
+}
 
 __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
 __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }

@@ -549,6 +549,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   c->h_s_off.assign(in->state_off, in->state_off + L + 1);
   c->h_e_off.assign(in->arc_off, in->arc_off + L + 1);
   c->h_num_frames.assign(L, 0);
+  c->h_maxtime.assign(L, 0);
   c->h_times_ok.assign(L, 1);
   c->h_cap_frame.assign(L, 0);
   c->h_cap_pos.assign(L, 0);
@@ -646,6 +647,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
     lvl_off[l + 1] = lvl_off[l] + m[M_NL] + 1;
     c->h_fr_base[l + 1] = c->h_fr_base[l] + m[M_FRAMES] + 1;
     c->h_num_frames[l] = m[M_FRAMES];
+    c->h_maxtime[l] = m[M_MAXTIME];
     c->h_times_ok[l] = (uint8_t)m[M_TIMES_OK];
     c->h_maxlen[l] = m[M_MAXLEN];
     c->max_label = std::max(c->max_label, m[M_MAXLABEL]);

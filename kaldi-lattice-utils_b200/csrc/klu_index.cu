@@ -135,10 +135,11 @@ __device__ __forceinline__ bool emit_arc_pruned(const IndexArgs& a, int l, int s
 
 // grid (lattices, tiles): one thread per out-order arc.
 __global__ void __launch_bounds__(256) k_emit(IndexArgs a) {
-  const int l = a.l0 + blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = a.l0 + lt.l;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int64_t base = a.ent_base[l];
-  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
+  for (int e = e0 + lt.tile * blockDim.x + threadIdx.x; e < e1; e += lt.tiles * blockDim.x) {
     const int4 r = a.b.out_rec[e];
     const int s = a.b.out_src[e];
     const int off = a.arc_ent_off[e];
@@ -267,10 +268,11 @@ struct RunSum {
 };
 
 __global__ void __launch_bounds__(256) k_reduce_count(ReduceArgs a) {
-  const int l = a.l0 + blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = a.l0 + lt.l;
   const int n = a.ent_cnt[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + a.ent_base[l];
-  for (int tile = blockIdx.y * 256; tile < n; tile += gridDim.y * 256) {
+  for (int tile = lt.tile * 256; tile < n; tile += lt.tiles * 256) {
     const int i = tile + threadIdx.x;
     bool head = false;
     if (i < n) {
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(256) k_reduce_offsets(ReduceArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   __shared__ int warp_sum[8];
   // the tile's keys, values and arc ranks, staged by all threads at once: the run heads
   // below then walk their runs in shared memory instead of a chain of dependent global
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   __shared__ unsigned long long s_key[256];
   __shared__ double s_val[256];
   __shared__ unsigned int s_aux[256];
-  const int l = a.l0 + blockIdx.x;
+  const int l = a.l0 + lt.l;
   const int n = a.ent_cnt[l];
   const int64_t base = a.ent_base[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + base;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs a) {
   const double total = a.total[l];
   const int e0 = a.b.e_off[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int tile = blockIdx.y * 256; tile < n; tile += gridDim.y * 256) {
+  for (int tile = lt.tile * 256; tile < n; tile += lt.tiles * 256) {
     const int i = tile + tid;
     unsigned long long k = a.drop_key;
     bool head = false;
@@ -484,13 +487,14 @@ struct OrderFixArgs {
 };
 
 __global__ void __launch_bounds__(256) k_order_fixup(OrderFixArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = a.seg_cnt[l];
   const int64_t base = a.seg_base[l];
   const unsigned int* K = (a.where[l] ? a.key_b : a.key_a) + base;
   unsigned int* V = (a.where[l] ? a.val_b : a.val_a) + base;
   const double* rv = a.rval + base;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i + 1 < n; i += lt.tiles * blockDim.x) {
     const unsigned int t = K[i];
     if ((i > 0 && K[i - 1] == t) || K[i + 1] != t) continue;  // not the head of a run
     int j = i + 1;
@@ -527,13 +531,14 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
-  const int l = a.l0 + blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = a.l0 + lt.l;
   const int n = a.rcnt[l];
   const int64_t base = a.ent_base[l];
   const int64_t out = a.res_off[l];
   const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + base;
   const int e0 = a.b.e_off[l];
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     const unsigned int j = idx[i];
     const unsigned long long k = a.rkey[base + j];
     const double logp = a.rval[base + j];

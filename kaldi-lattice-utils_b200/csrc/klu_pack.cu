@@ -347,6 +347,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   c->h_s_off.assign(in->state_off, in->state_off + L + 1);
   c->h_e_off.assign(in->arc_off, in->arc_off + L + 1);
   c->h_num_frames.resize(L);
+  c->h_maxtime.resize(L);
   c->h_times_ok.resize(L);
   c->h_cap_frame.resize(L);
   c->h_cap_pos.resize(L);
@@ -355,6 +356,7 @@ int pack_and_upload(klu_ctx* c, const klu_lattices* in) {
   for (int32_t l = 0; l < L; ++l) {
     c->max_span = std::max(c->max_span, info[l].max_span);
     c->h_num_frames[l] = info[l].num_frames;
+    c->h_maxtime[l] = std::max(info[l].max_time, info[l].num_frames);
     c->h_times_ok[l] = info[l].times_ok;
     c->h_cap_frame[l] = info[l].cap_frame;
     c->h_cap_pos[l] = info[l].cap_pos;

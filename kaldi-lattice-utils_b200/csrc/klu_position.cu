@@ -273,13 +273,14 @@ __global__ void __launch_bounds__(256) k_pos_cell_offsets(PosArgs a) {
 
 // grid (chunk lattices, tiles): per sorted arc the record the cell loop reads
 __global__ void __launch_bounds__(256) k_pos_arcrec(PosArgs a) {
-  const int l = a.l0 + blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = a.l0 + lt.l;
   const int n = a.seg_cnt[l];
   const int e0 = a.b.e_off[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + a.seg_base[l];
   const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + a.seg_base[l];
   ArcRec* rec = a.rec + (e0 - a.e_chunk0);
-  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < n; q += gridDim.y * blockDim.x) {
+  for (int q = lt.tile * blockDim.x + threadIdx.x; q < n; q += lt.tiles * blockDim.x) {
     if (key[q] == a.drop_key) continue;
     const int e = e0 + (int)idx[q];
     const int4 r = a.b.out_rec[e];
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(256) k_pos_tile_groups(PosArgs a) {
 
 // grid (chunk lattices, tiles of 256 cells): one thread per (word, position) cell
 __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
-  const int l = a.l0 + blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = a.l0 + lt.l;
   const long long ncells = a.lat_cells[l];
   const int e0 = a.b.e_off[l];
   const int ng = a.ngroups[l];
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
   const ArcRec* rec = a.rec + (e0 - a.e_chunk0);
   const int64_t cbase = a.cell_base[l];
   const double norm = a.tool == KLU_BEST_PATH2 ? a.beta[a.b.s_off[l]] : a.total[l];
-  for (long long tile = (long long)blockIdx.y * 256; tile < ncells; tile += (long long)gridDim.y * 256) {
+  for (long long tile = (long long)lt.tile * 256; tile < ncells; tile += (long long)lt.tiles * 256) {
     const long long cell = tile + threadIdx.x;
     int g = a.tile_group[tile_slot(a.cell_base, l, a.l0, (int)(tile >> 8))];  // the lanes walk on from the tile's first group
     bool exists = false;
@@ -440,12 +442,13 @@ __global__ void __launch_bounds__(256) k_pos_cells(PosArgs a) {
 
 // grid (chunk lattices, tiles): existing cells -> (order key, cell) pairs, densely
 __global__ void __launch_bounds__(256) k_pos_compact(PosArgs a) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   __shared__ int warp_sum[8];
-  const int l = a.l0 + blockIdx.x;
+  const int l = a.l0 + lt.l;
   const long long ncells = a.lat_cells[l];
   const int64_t cbase = a.cell_base[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (long long tile = (long long)blockIdx.y * 256; tile < ncells; tile += (long long)gridDim.y * 256) {
+  for (long long tile = (long long)lt.tile * 256; tile < ncells; tile += (long long)lt.tiles * 256) {
     const long long cell = tile + tid;
     CellRec cr;
     cr.exists = 0u;
@@ -519,13 +522,14 @@ struct PosFixArgs {
 };
 
 __global__ void __launch_bounds__(256) k_pos_order_fixup(PosFixArgs a) {
-  const int l = a.l0 + blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = a.l0 + lt.l;
   const int n = a.seg_cnt[l];
   const int64_t base = a.seg_base[l];
-  const unsigned int* K = (a.where[blockIdx.x] ? a.key_b : a.key_a) + base;
-  unsigned int* V = (a.where[blockIdx.x] ? a.val_b : a.val_a) + base;
+  const unsigned int* K = (a.where[lt.l] ? a.key_b : a.key_a) + base;
+  unsigned int* V = (a.where[lt.l] ? a.val_b : a.val_a) + base;
   const CellRec* cv = a.cell + base;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i + 1 < n; i += lt.tiles * blockDim.x) {
     const unsigned int t = K[i];
     if ((i > 0 && K[i - 1] == t) || K[i + 1] != t) continue;  // not the head of a run
     int j = i + 1;
@@ -555,13 +559,14 @@ struct PosGatherArgs {
 
 // grid (chunk lattices, tiles): output row i of a lattice = its i-th cell in log-posterior order
 __global__ void __launch_bounds__(256) k_pos_gather(PosGatherArgs g) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   const PosArgs& a = g.p;
-  const int l = a.l0 + blockIdx.x;
+  const int l = a.l0 + lt.l;
   const int n = a.rcnt[l];
   const int64_t cbase = a.cell_base[l];
   const int64_t out = g.res_off[l];
-  const unsigned int* ord = (g.where2[blockIdx.x] ? g.idx2_b : g.idx2_a) + cbase;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  const unsigned int* ord = (g.where2[lt.l] ? g.idx2_b : g.idx2_a) + cbase;
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     const CellRec cr = a.cell[cbase + ord[i]];  // the one scattered read of a row
     if (a.tool == KLU_POSITION) {
       const unsigned long long lm = (1ULL << a.bits_len) - 1ULL;

@@ -166,12 +166,13 @@ __global__ void __launch_bounds__(256) k_prune_search(PruneArgs a) {
 
 // keep flags in the caller's index space
 __global__ void __launch_bounds__(256) k_prune_mark(PruneArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int s0 = a.b.s_off[l], s1 = a.b.s_off[l + 1];
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const bool all = a.iters[l] == 0;
   const double cut = a.cutoff[l];
-  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+  const int t = lt.tile * blockDim.x + threadIdx.x, stride = lt.tiles * blockDim.x;
   for (int e = e0 + t; e < e1; e += stride) a.arc_keep[e0 + a.b.out_orig[e]] = (all || !(a.fb[e] > cut)) ? 1 : 0;
   for (int s = s0 + t; s < s1; s += stride) a.state_keep[s0 + a.b.orig[s]] = (all || !(a.smin[s] > cut)) ? 1 : 0;
 }
@@ -227,13 +228,14 @@ __device__ __forceinline__ void out_weights(float g, float w, int label, const P
 }
 
 __global__ void __launch_bounds__(256) k_prune_emit(PruneArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int s0 = a.b.s_off[l], s1 = a.b.s_off[l + 1];
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const int64_t out = a.res_off[l];
   const bool all = a.iters[l] == 0;
   const double cut = a.cutoff[l];
-  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+  const int t = lt.tile * blockDim.x + threadIdx.x, stride = lt.tiles * blockDim.x;
   for (int e = e0 + t; e < e1; e += stride) {
     const int o = a.b.out_orig[e];
     const int pos = a.arc_keep[e0 + o];
@@ -349,11 +351,12 @@ __global__ void __launch_bounds__(128) k_pa_cut(PruneArgs a, PruneArcsArgs p, do
 
 // grid (lattices, tiles): rank of every arc in the sorted order, by original arc index
 __global__ void __launch_bounds__(256) k_pa_rank(PruneArgs a, PruneArcsArgs p) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = p.seg_cnt[l];
   const int e0 = a.b.e_off[l];
   const unsigned int* idx = (p.where[l] ? p.idx_b : p.idx_a) + p.seg_base[l];
-  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < n; q += gridDim.y * blockDim.x) p.rank[e0 + (int)idx[q]] = q;
+  for (int q = lt.tile * blockDim.x + threadIdx.x; q < n; q += lt.tiles * blockDim.x) p.rank[e0 + (int)idx[q]] = q;
 }
 
 // One warp per lattice: fst::Connect over the arcs put back -- accessible from the start
@@ -407,12 +410,13 @@ __global__ void __launch_bounds__(128) k_pa_connect(PruneArgs a, PruneArcsArgs p
 // in the caller's order (k_prune_scan); a state's arcs come out in sorted (cost) order, as AddArc
 // appended them.
 __global__ void __launch_bounds__(256) k_pa_emit(PruneArgs a, PruneArcsArgs p) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const BatchView& b = a.b;
   const int s0 = b.s_off[l], s1 = b.s_off[l + 1];
   const int e0 = b.e_off[l], e1 = b.e_off[l + 1];
   const int64_t out = a.res_off[l];
-  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+  const int t = lt.tile * blockDim.x + threadIdx.x, stride = lt.tiles * blockDim.x;
   for (int e = e0 + t; e < e1; e += stride) {
     const int o = b.out_orig[e];
     if (a.arc_keep[e0 + o] < 0) continue;

@@ -423,6 +423,26 @@ def test_position_cells_equal_generic_pipeline(klu, engine, monkeypatch, shape, 
             assert_rows_match(fa, fb, 1, tol=1e-6, what="cells vs generic, position-post")
 
 
+# ---- segment index by start-frame buckets vs the generic sort-by-key pipeline ------------------
+@pytest.mark.parametrize("shape,n,seed", SHAPES)
+@pytest.mark.parametrize("flags", [dict(), dict(acoustic_scale=0.3, beam=6.0), dict(include_words=[3, 4, 7, 11, 40]),
+                                   dict(exclude_words=[2, 5], graph_scale=0.5, insertion_penalty=0.3)])
+def test_segment_buckets_equal_generic_pipeline(klu, engine, monkeypatch, shape, n, seed, flags):
+    batch = klu.synth_batch(shape, n, seed=seed + 700)
+    # a bucket over the cap (300 parallel arcs out of one state) sends the whole batch down the generic path
+    wide = klu.make_lattice("wide", 3, [(0, 1, 1 + (i % 9), 0.1 * i, 0.05 * (i % 7), 2) for i in range(300)]
+                            + [(1, 2, 4, 0.5, 0.5, 1)], {2: (0.0, 0.0)})
+    for lats in (batch.lattices(), batch.lattices()[:3] + [wide]):
+        monkeypatch.delenv("KLU_GENERIC_SEGMENT", raising=False)
+        engine.load(klu.LatticeBatch.from_lattices(lats))
+        new = engine.segment(**flags)
+        monkeypatch.setenv("KLU_GENERIC_SEGMENT", "1")
+        old = engine.segment(**flags)
+        assert len(new) == len(old) == len(lats)
+        for a, b in zip(new, old):
+            assert a == b  # same keys, same order, bit-identical log-posteriors
+
+
 # ---- lattice-prune-arcs ------------------------------------------------
 @pytest.mark.parametrize("shape,n,seed", SHAPES)
 @pytest.mark.parametrize("flags", [dict(), dict(beam=0.05), dict(beam=0.5), dict(beam=3.0),
