@@ -51,9 +51,19 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
   unsigned int* vout = a.val_b + base;
   for (int i = tid; i < 8 * 256; i += kSortThreads) (&hist[0][0])[i] = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += kSortThreads) {
-    const K k = kin[i] >> a.lo_bit;
-    for (int p = 0; p < npass; ++p) atomicAdd(&hist[p][(unsigned int)(k >> (8 * p)) & 255u], 1u);
+  for (int i0 = 0; i0 < n; i0 += 4 * kSortThreads) {
+    K kk[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {  // four requests in flight per thread
+      const int i = i0 + r * kSortThreads + tid;
+      kk[r] = i < n ? kin[i] : (K)0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (i0 + r * kSortThreads + tid >= n) break;
+      const K k = kk[r] >> a.lo_bit;
+      for (int p = 0; p < npass; ++p) atomicAdd(&hist[p][(unsigned int)(k >> (8 * p)) & 255u], 1u);
+    }
   }
   __syncthreads();
   int executed = 0;
@@ -85,22 +95,34 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
       bin_base[tid] += add;
     }
     __syncthreads();
+    // The loads of a tile are issued together (kSortItems independent requests per thread) and
+    // one tile ahead: the next tile's keys travel while this one is ranked and scattered.
+    K k[kSortItems], kn[kSortItems];
+    unsigned int v[kSortItems], vn[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const int i = (warp * kSortItems + r) * 32 + lane;
+      k[r] = i < n ? kin[i] : (K)0;
+      v[r] = i < n ? vin[i] : 0u;
+    }
     for (int tile = 0; tile < n; tile += kSortTile) {
       for (int i = lane; i < 256; i += 32) warp_cnt[warp][i] = 0;
       __syncwarp();
-      K k[kSortItems];
-      unsigned int v[kSortItems];
       int d[kSortItems];
 #pragma unroll
       for (int r = 0; r < kSortItems; ++r) {
         const int i = tile + (warp * kSortItems + r) * 32 + lane;
         const bool valid = i < n;
-        k[r] = valid ? kin[i] : (K)0;
-        v[r] = valid ? vin[i] : 0u;
         d[r] = valid ? (int)((k[r] >> shift) & 255) : 256 + lane;
         const unsigned int mask = __match_any_sync(0xffffffffu, d[r]);
         if (valid && lane == __ffs(mask) - 1) warp_cnt[warp][d[r]] += __popc(mask);
         __syncwarp();
+      }
+#pragma unroll
+      for (int r = 0; r < kSortItems; ++r) {
+        const int i = tile + kSortTile + (warp * kSortItems + r) * 32 + lane;
+        kn[r] = i < n ? kin[i] : (K)0;
+        vn[r] = i < n ? vin[i] : 0u;
       }
       __syncthreads();
       if (tid < 256) {
@@ -134,6 +156,11 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
         __syncwarp();
       }
       __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kSortItems; ++r) {
+        k[r] = kn[r];
+        v[r] = vn[r];
+      }
     }
     // swap buffers
     K* tk = kin;
