@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
     for (int size = 2; size <= P; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
         for (int t = lane; t < (P >> 1); t += 32) {
-          const int i = ((t / stride) * (stride << 1)) + (t % stride);
+          const int i = (t << 1) - (t & (stride - 1));  // stride is a power of two
           const int p = i + stride;
           const bool up = ((i & size) == 0);
           const unsigned long long x = sk[i], y = sk[p];
