@@ -464,8 +464,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-slices", type=int, default=8, help="slices of the pipelined end-to-end run (1 = off)")
-    ap.add_argument("--e2e-contexts", type=int, default=3, help="contexts (host threads) of the pipelined run")
+    ap.add_argument("--e2e-slices", type=int, default=24, help="slices of the pipelined end-to-end run (1 = off)")
+    ap.add_argument("--e2e-contexts", type=int, default=6, help="contexts (host threads) of the pipelined run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tools", action="store_true", help="skip the per-tool section")
     ap.add_argument("--tools-steps", type=int, default=3)
@@ -650,6 +650,7 @@ def main():
     single_step = reduce_max(sum(e2e_ms) / len(e2e_ms)) if e2e_ms else None
     if packs:  # pack time of a load with nothing else queued on the GPU (the e2e loads)
         pack_total = reduce_max(float(np.mean([p[1] + p[2] for p in packs])))
+        roofline["pipeline_frac_76B_per_arc_incl_pack"] = pipe_bytes / ((ms_per_step + pack_total) * 1e-3) / 1e9 / peak
     pipe_step = None
     if args.e2e_steps > 0 and args.e2e_slices > 1 and args.tool == "frame_post":
         eng.close()  # its device memory goes to the pipeline contexts

@@ -961,7 +961,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
     ss.hi_bit = segment ? kKeyStateBits : 64;  // segment mode: by destination state first ...
     {
       KLU_LAUNCH(c, "k_seg_radix_sort");
-      k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+      seg_sort_launch(ss, L, c->num_sms, c->stream);
     }
     KLU_TRY(check_launch("k_seg_radix_sort(char)"));
     if (segment) {  // ... then, stably, by (parent, label, frame tag)
@@ -981,7 +981,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
       ss.hi_bit = 64;
       {
         KLU_LAUNCH(c, "k_seg_radix_sort");
-        k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+        seg_sort_launch(ss, L, c->num_sms, c->stream);
       }
       KLU_TRY(check_launch("k_seg_radix_sort(char keys)"));
     }
@@ -1090,7 +1090,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   ss.hi_bit = 32;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+    seg_sort_launch(ss, L, c->num_sms, c->stream);
   }
   KLU_TRY(check_launch("k_seg_radix_sort(rows by node)"));
   int64_t max_rows = 0;
@@ -1124,7 +1124,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   ss.hi_bit = 64;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+    seg_sort_launch(ss, L, c->num_sms, c->stream);
   }
   KLU_TRY(check_launch("k_seg_radix_sort(rows by logp)"));
   r.key_a = ss.key_a;

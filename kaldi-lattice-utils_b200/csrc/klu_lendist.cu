@@ -173,7 +173,7 @@ int run_length_dist(klu_ctx* c, const klu_opts* o) {
   ss.hi_bit = 64;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    k_seg_radix_sort<<<L, kSortThreads, 0, c->stream>>>(ss);
+    seg_sort_launch(ss, L, c->num_sms, c->stream);
   }
   KLU_TRY(check_launch("k_seg_radix_sort(length dist)"));
   {

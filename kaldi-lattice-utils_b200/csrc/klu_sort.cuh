@@ -10,10 +10,7 @@
 
 namespace klu {
 
-constexpr int kSortThreads = 512;
 constexpr int kSortItems = 4;
-constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortTile = kSortThreads * kSortItems;
 
 template <typename K>
 struct SegSortArgsT {
@@ -30,8 +27,11 @@ typedef SegSortArgsT<unsigned long long> SegSortArgs;
 typedef SegSortArgsT<unsigned int> SegSortArgs32;  // 32-bit keys: a third less traffic per pass
 
 #ifdef __CUDACC__
-template <typename K>
+// kSortThreads = 512, or 1024 when there are too few segments to fill the SMs with 512-thread CTAs
+template <typename K, int kSortThreads>
 static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSortArgsT<K> a) {
+  constexpr int kSortWarps = kSortThreads / 32;
+  constexpr int kSortTile = kSortThreads * kSortItems;
   __shared__ unsigned int hist[8][256];
   __shared__ unsigned int bin_base[256];
   __shared__ unsigned int warp_cnt[kSortWarps][256];
@@ -174,8 +174,14 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
   }
   if (tid == 0) a.where[seg] = (unsigned char)(executed & 1);
 }
-#define k_seg_radix_sort k_seg_radix_sort_t<unsigned long long>
-#define k_seg_radix_sort32 k_seg_radix_sort_t<unsigned int>
+template <typename K>
+static inline void seg_sort_launch(const SegSortArgsT<K>& a, int nseg, int num_sms, cudaStream_t stream) {
+  if (nseg <= 0) return;
+  if (nseg < num_sms * 3)  // fewer CTAs than the SMs can hold at 512 threads: larger CTAs instead
+    k_seg_radix_sort_t<K, 1024><<<nseg, 1024, 0, stream>>>(a);
+  else
+    k_seg_radix_sort_t<K, 512><<<nseg, 512, 0, stream>>>(a);
+}
 
 // After a sort that looked at the bits >= a.lo_bit only: every run of elements whose keys agree
 // there is put in full-key order by a stable insertion sort, one thread per run (the runs are

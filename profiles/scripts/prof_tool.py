@@ -23,6 +23,16 @@ print("gen %.2fs arcs %d" % (time.time() - t0, batch.num_arcs), flush=True)
 t0 = time.time()
 eng.load(batch)
 print("load %.3fs" % (time.time() - t0), eng.load_times(), flush=True)
+if os.environ.get("PROF_LOAD"):  # per-kernel times of a second (warm) load + the lazily built indexes
+    eng.profile(True)
+    eng.load(batch)
+    bench.run_tool(eng, klu, tool, flags)
+    eng.sync()
+    prof = eng.profile_json()
+    eng.profile(False)
+    print("warm load + first run:", eng.load_times(), flush=True)
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        print("   %-28s %3d launches %10.3f ms" % (k, v["launches"], v["ms"]), flush=True)
 for it in range(2):
     eng.profile(True)
     t0 = time.time()
