@@ -131,6 +131,30 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def numa_bind(local):
+    """Pins this rank (and the pinned buffers it is about to allocate: first touch) to the CPUs of the
+    NUMA node its GPU hangs off, so 8 ranks' uploads do not all cross one socket's memory controller.
+    Best effort (sysfs only); returns what it did for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"node": None, "note": "no NUMA affinity reported for %s" % bdf}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "note": "node has no CPU this process may use"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as ex:  # no sysfs / no torch attribute: leave the affinity alone
+        return {"node": None, "note": "%s: %s" % (type(ex).__name__, ex)}
+
+
 def dist_setup(n):
     """Returns (rank, world, reduce_max, barrier, gather_obj)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -481,6 +505,8 @@ def main():
     rank, world, reduce_max, barrier, gather_obj = dist_setup(args.gpus)
     klu = load_package()
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    all_cpus = os.sched_getaffinity(0)
+    numa = numa_bind(local) if not os.environ.get("KLU_BENCH_NO_NUMA") else {"node": None, "note": "disabled"}
     eng = klu.Engine(local)
     tool = TOOLS[args.tool]
     flags = flags_for(args.tool)
@@ -711,6 +737,7 @@ def main():
                    "pipelined call sequence when `pipeline` is set, else the single call sequence"}
 
     # ---- CPU baseline (rank 0, bounded sample of the same workload) ----
+    os.sched_setaffinity(0, all_cpus)  # the CPU arms get every host thread again
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.tool == "char_position":
         from oracle import ora
@@ -764,7 +791,7 @@ def main():
                          "`value_incl_pack` adds it to every step",
             "strong_scaling": strong,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "tools": tools, "clocks": sampler.summary()}))
+            "tools": tools, "clocks": sampler.summary(), "numa": numa}))
     if eng.h:
         eng.close()
     if world > 1:
