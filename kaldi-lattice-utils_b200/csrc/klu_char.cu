@@ -179,27 +179,26 @@ __device__ __forceinline__ long long cell_of(const CharArgs& a, int l, int s) {
 // A[s][n][g] = log-sum of all paths start -> s whose last arc has group g and which
 // crossed n word-counting group boundaries (fstext/fstext-utils2.h:413-513: a
 // transition into group vg from a different group ug counts when vg is a counting
-// group).  One warp per lattice; a lane owns one (state, n, g) cell of the level.
-__global__ void __launch_bounds__(128) k_char_fwd(CharArgs a) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// group).  One CTA per lattice; a thread owns one (state, n, g) cell of the level.
+__global__ void __launch_bounds__(256) k_char_fwd(CharArgs a) {
+  const int lane = threadIdx.x, nth = blockDim.x;
   const BatchView& b = a.b;
-  if (warp >= b.L) return;
-  const int l = warp;
+  const int l = blockIdx.x;
   const int s0 = b.s_off[l], s1 = b.s_off[l + 1];
   if (s0 == s1) return;
   const int* lv = b.lvl_start + b.lvl_off[l];
   const int nl = b.lvl_off[l + 1] - b.lvl_off[l] - 1;
   const int NG = a.NG;
-  for (int s = lv[0] + lane; s < lv[1]; s += 32) {
+  for (int s = lv[0] + lane; s < lv[1]; s += nth) {
     const long long c0 = cell_of(a, l, s);
     for (int q = 0; q < a.cell_cnt[s]; ++q) a.A[c0 + q] = (s == s0 && q == a.eps) ? 0.0 : neg_inf();
   }
-  __syncwarp();
+  __syncthreads();
   for (int j = 1; j < nl; ++j) {
     const int a0 = lv[j], a1 = lv[j + 1];
     const int q0 = a.cell_loc[a0];
     const int q1 = a1 < s1 ? a.cell_loc[a1] : a.cell_loc[a1 - 1] + a.cell_cnt[a1 - 1];
-    for (int q = q0 + lane; q < q1; q += 32) {
+    for (int q = q0 + lane; q < q1; q += nth) {
       int lo = a0, hi = a1 - 1;  // last state of the level with cell_loc <= q
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(128) k_char_fwd(CharArgs a) {
       }
       a.A[a.cell_base[l] + q] = acc;
     }
-    __syncwarp();
+    __syncthreads();
   }
 }
 
@@ -581,21 +580,43 @@ struct RowArgs {
   int32_t* o_chars;
 };
 
+// (pool slots of one lattice are contiguous per depth, so a warp's rows nearly always belong to one
+// lattice: the lanes are grouped by lattice and one atomic per group is issued)
 __global__ void __launch_bounds__(256) k_char_rowcount(RowArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pool; i += stride) {
-    const int l = a.nd_lat[i];
-    if (l >= 0 && a.nd_total[i] > neg_inf()) atomicAdd(a.row_cnt + l, 1);
+  const int lane = threadIdx.x & 31;
+  const int64_t rounds = (a.pool + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int l = -1;
+    if (i < a.pool) {
+      l = a.nd_lat[i];
+      if (l >= 0 && !(a.nd_total[i] > neg_inf())) l = -1;
+    }
+    const unsigned int grp = __match_any_sync(0xffffffffu, l);
+    if (l >= 0 && lane == __ffs(grp) - 1) atomicAdd(a.row_cnt + l, __popc(grp));
   }
 }
 
 // rows into per-lattice segments (arrival order; the two stable sorts that follow make it deterministic)
 __global__ void __launch_bounds__(256) k_char_rowfill(RowArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pool; i += stride) {
-    const int l = a.nd_lat[i];
-    if (l < 0 || !(a.nd_total[i] > neg_inf())) continue;
-    const int64_t o = a.row_base[l] + atomicAdd(a.cursor + l, 1);
+  const int lane = threadIdx.x & 31;
+  const int64_t rounds = (a.pool + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int l = -1;
+    if (i < a.pool) {
+      l = a.nd_lat[i];
+      if (l >= 0 && !(a.nd_total[i] > neg_inf())) l = -1;
+    }
+    const unsigned int grp = __match_any_sync(0xffffffffu, l);
+    const int leader = __ffs(grp) - 1;
+    int first = 0;
+    if (l >= 0 && lane == leader) first = atomicAdd(a.cursor + l, __popc(grp));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    if (l < 0) continue;
+    const int64_t o = a.row_base[l] + first + __popc(grp & ((1u << lane) - 1u));
     a.key[o] = (unsigned long long)i;  // first sort: node id (creation order = depth, then key order)
     a.val[o] = (unsigned int)i;
   }
@@ -808,7 +829,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   a.exitw = sc[C_EXIT].as<double>();
   {
     KLU_LAUNCH(c, "k_char_fwd");
-    k_char_fwd<<<lat_warps_grid, 128, 0, c->stream>>>(a);
+    k_char_fwd<<<L, 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_char_fwd"));
   {
