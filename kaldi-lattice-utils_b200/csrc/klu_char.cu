@@ -982,7 +982,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
     ss.hi_bit = segment ? kKeyStateBits : 64;  // segment mode: by destination state first ...
     {
       KLU_LAUNCH(c, "k_seg_radix_sort");
-      seg_sort_launch(ss, L, c->num_sms, c->stream);
+      KLU_TRY(seg_sort_launch(c, ss, L, ncand));
     }
     KLU_TRY(check_launch("k_seg_radix_sort(char)"));
     if (segment) {  // ... then, stably, by (parent, label, frame tag)
@@ -1002,7 +1002,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
       ss.hi_bit = 64;
       {
         KLU_LAUNCH(c, "k_seg_radix_sort");
-        seg_sort_launch(ss, L, c->num_sms, c->stream);
+        KLU_TRY(seg_sort_launch(c, ss, L, ncand));
       }
       KLU_TRY(check_launch("k_seg_radix_sort(char keys)"));
     }
@@ -1111,7 +1111,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   ss.hi_bit = 32;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(ss, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, ss, L, nrows));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(rows by node)"));
   int64_t max_rows = 0;
@@ -1145,7 +1145,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   ss.hi_bit = 64;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(ss, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, ss, L, nrows));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(rows by logp)"));
   r.key_a = ss.key_a;

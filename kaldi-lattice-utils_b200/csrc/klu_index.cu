@@ -922,7 +922,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
     s1.hi_bit = key_bits + 1;  // + the drop bit; degenerate digits are skipped per lattice
     {
       KLU_LAUNCH(c, "k_seg_radix_sort");
-      seg_sort_launch(s1, nl, c->num_sms, c->stream);
+      KLU_TRY(seg_sort_launch(c, s1, nl, N));
     }
     KLU_TRY(check_launch("k_seg_radix_sort(keys)"));
 
@@ -1038,7 +1038,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       s2.hi_bit = 32;
       {
         KLU_LAUNCH(c, "k_seg_radix_sort");
-        seg_sort_launch(s2, nl, c->num_sms, c->stream);
+        KLU_TRY(seg_sort_launch(c, s2, nl, N));
       }
       KLU_TRY(check_launch("k_seg_radix_sort(order)"));
       OrderFixArgs f;
@@ -1066,7 +1066,7 @@ int run_index_tool(klu_ctx* c, int tool, const klu_opts* o) {
       s2.hi_bit = 64;
       {
         KLU_LAUNCH(c, "k_seg_radix_sort");
-        seg_sort_launch(s2, nl, c->num_sms, c->stream);
+        KLU_TRY(seg_sort_launch(c, s2, nl, N));
       }
       KLU_TRY(check_launch("k_seg_radix_sort(order)"));
     }

@@ -721,7 +721,7 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
   s1.hi_bit = a.bits_label + 1;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(s1, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, s1, L, c->E));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(words)"));
   {
@@ -900,7 +900,7 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
       s2.hi_bit = 32;
       {
         KLU_LAUNCH(c, "k_seg_radix_sort");
-        seg_sort_launch(s2, nl, c->num_sms, c->stream);
+        KLU_TRY(seg_sort_launch(c, s2, nl, N));
       }
       KLU_TRY(check_launch("k_seg_radix_sort(order)"));
       PosFixArgs f;
@@ -929,7 +929,7 @@ int run_position_tool(klu_ctx* c, int tool, const klu_opts* o) {
       s2.hi_bit = 64;
       {
         KLU_LAUNCH(c, "k_seg_radix_sort");
-        seg_sort_launch(s2, nl, c->num_sms, c->stream);
+        KLU_TRY(seg_sort_launch(c, s2, nl, N));
       }
       KLU_TRY(check_launch("k_seg_radix_sort(order)"));
     }

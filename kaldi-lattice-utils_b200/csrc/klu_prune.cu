@@ -548,7 +548,7 @@ int run_prune_arcs(klu_ctx* c, const klu_opts* o) {
   ss.hi_bit = 64;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(ss, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, ss, L, c->E));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(arc costs)"));
   {

@@ -427,7 +427,7 @@ int ensure_segment_buckets(klu_ctx* c) {
     ss.hi_bit = std::min(32, bits_for(c->max_time));
     {
       KLU_LAUNCH(c, "k_seg_radix_sort");
-      seg_sort_launch(ss, L, c->num_sms, c->stream);
+      KLU_TRY(seg_sort_launch(c, ss, L, c->E));
     }
     KLU_TRY(check_launch("k_seg_radix_sort(start frames)"));
     {
@@ -544,7 +544,7 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
   s2.hi_bit = 32;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(s2, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, s2, L, c->E));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(order)"));
   int64_t max_arcs = 0;
