@@ -889,9 +889,9 @@ int build_frame_groups(klu_ctx* c) {
         st.hi_bit = bits_time;
         {
           KLU_LAUNCH(c, "k_seg_radix_sort");
-          seg_sort_launch(st, L, c->num_sms, c->stream);
+          rc = seg_sort_launch(c, st, L, c->E);
         }
-        rc = check_launch("k_seg_radix_sort(arc start times)");
+        if (!rc) rc = check_launch("k_seg_radix_sort(arc start times)");
       }
       if (!rc) {
         KLU_LAUNCH(c, "k_fg_time_copy");
@@ -919,7 +919,7 @@ int build_frame_groups(klu_ctx* c) {
       ss.lo_bit = 0;
       ss.hi_bit = bits_label + bits_time;
       KLU_LAUNCH(c, "k_seg_radix_sort");
-      seg_sort_launch(ss, L, c->num_sms, c->stream);
+      if ((rc = seg_sort_launch(c, ss, L, N))) break;
     } else {
       SegSortArgs ss;
       ss.seg_base = d_inst_base;
@@ -932,7 +932,7 @@ int build_frame_groups(klu_ctx* c) {
       ss.lo_bit = 0;
       ss.hi_bit = bits_label + bits_time;
       KLU_LAUNCH(c, "k_seg_radix_sort");
-      seg_sort_launch(ss, L, c->num_sms, c->stream);
+      if ((rc = seg_sort_launch(c, ss, L, N))) break;
     }
     if ((rc = check_launch("k_seg_radix_sort(frame groups)"))) break;
     a.res_off = c->d_fr_res_off.as<int64_t>();

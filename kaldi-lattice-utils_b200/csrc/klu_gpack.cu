@@ -717,7 +717,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   ss.hi_bit = 32;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(ss, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, ss, L, (int64_t)S));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(states)"));
   {
@@ -741,7 +741,7 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   ss.seg_cnt = c->d_res[7].as<int32_t>() + L;
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    seg_sort_launch(ss, L, c->num_sms, c->stream);
+    KLU_TRY(seg_sort_launch(c, ss, L, (int64_t)E));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(arcs)"));
   {

@@ -550,7 +550,10 @@ static inline int seg_sort_launch(klu_ctx* c, const SegSortArgsT<K>& a, int nseg
   if (nseg <= 0) return 0;
   static const bool single_only = getenv("KLU_SORT_SINGLE") != nullptr;
   static const bool multi_only = getenv("KLU_SORT_MULTI") != nullptr;  // tests
-  const bool multi = multi_only || (!single_only && nseg < c->num_sms * 8 && total / nseg >= 4 * kMsTile);
+  // few segments of a few tiles at least, or very large ones; thousands of mid-sized segments (the
+  // packer's sorts at 10 k lattices) run faster one CTA each (41 vs 54 ms)
+  const int64_t avg = total / nseg;
+  const bool multi = multi_only || (!single_only && avg >= 2 * kMsTile && (nseg < c->num_sms * 8 || avg >= 64 * kMsTile));
   if (!multi) {
     seg_sort_launch(a, nseg, c->num_sms, c->stream);
     return 0;
