@@ -7,6 +7,7 @@ The oracle runs on all host threads (ctypes releases the GIL); results are compa
 columns (a c2 lattice has ~1.5 M position entries)."""
 import os
 import subprocess
+import sys
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -254,3 +255,19 @@ def test_klu_devices_on_several_gpus(klu, tmp_path, tool, args):
     many = subprocess.run([os.path.join(BIN, tool)] + args + ["ark:" + ark, "ark:-"], capture_output=True, env=envn)
     assert one.returncode == 0 and many.returncode == 0, many.stderr.decode()[-2000:]
     assert len(one.stdout) > 100000 and many.stdout == one.stdout
+
+
+# ---- the multi-CTA sort passes (klu_sort.cuh) on the whole parity suite --------------------------
+def test_parity_suite_with_multi_cta_sorts():
+    """seg_sort_launch picks the multi-CTA passes only for large segments, which the small parity
+    shapes never reach: run the parity tests of every tool that sorts once more with
+    KLU_SORT_MULTI=1 (the switch is read once per process, hence the child process)."""
+    env = dict(os.environ, KLU_SORT_MULTI="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "gpurun_out", "multi_sort_suite.log") if os.path.isdir(os.path.join(root, "gpurun_out"))
+              else os.devnull, "w") as log:
+        rc = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"),
+                             os.path.join(root, "tests", "test_gpu_char.py"), "-m", "gpu", "-x", "-q",
+                             "--timeout", "300", "--timeout-method", "thread", "-p", "no:cacheprovider"],
+                            env=env, cwd=root, stdout=log, stderr=subprocess.STDOUT, timeout=900).returncode
+    assert rc == 0, "parity suite failed with KLU_SORT_MULTI=1 (gpurun_out/multi_sort_suite.log)"
