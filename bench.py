@@ -207,7 +207,8 @@ def fetch_for(eng, klu, tool, out=None):
     """(rows, bytes brought to the host) of the last run."""
     t = TOOLS[tool]
     if t == klu.FRAME_POST:
-        r = eng.fetch_frame_post(out=out)
+        # the rows as the reference's Posterior holds them: per-frame row offsets instead of a frame column
+        r = eng.fetch_frame_post_csr(out=out)
     elif t == klu.SEGMENT:
         r = eng.fetch_segment()
     elif t == klu.POSITION:
@@ -646,16 +647,20 @@ def main():
         buf[:x.size] = x
         return buf[:x.size]
 
-    dur8, d16 = pinned_copy(dur8), pinned_copy(d16)
-    up = dict(state_num_arcs=narcs, dur_u8=dur8, dst_delta_u16=d16)
+    # ... and labels as 16-bit words when the vocabulary allows (klu_lattices.arc_label_u16): 13 bytes per arc
+    lab16 = klu.binding.compact_labels(batch)
+    dur8, d16, lab16 = pinned_copy(dur8), pinned_copy(d16), pinned_copy(lab16)
+    up = dict(state_num_arcs=narcs, dur_u8=dur8, dst_delta_u16=d16, label_u16=lab16)
     h2d = sum(int(x.nbytes) for x in (batch.state_off, batch.arc_off, narcs, d16 if d16 is not None else batch.dst,
-                                      batch.label, dur8 if dur8 is not None else batch.dur,
+                                      lab16 if lab16 is not None else batch.label, dur8 if dur8 is not None else batch.dur,
                                       batch.graph, batch.acoustic, batch.fin_graph, batch.fin_acoustic,
                                       batch.fin_dur))
     d2h = 0
     out = None
     if args.tool == "frame_post":  # results land in pinned host buffers
-        out = (eng.pinned_array(np.int32, entries), eng.pinned_array(np.int32, entries),
+        nf_all = eng.fetch_frame_post_csr()[1].astype(np.int64)  # frames per lattice: sizes the row-offset array
+        slot_off = np.concatenate([[0], np.cumsum(nf_all + 1)])
+        out = (eng.pinned_array(np.int64, int(slot_off[-1])), eng.pinned_array(np.int32, entries),
                eng.pinned_array(np.float32, entries))
     e2e_ms, parts, packs = [], [], []
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
@@ -686,7 +691,8 @@ def main():
         subs = [batch.slice(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
         sub_up = [dict(state_num_arcs=narcs[int(batch.state_off[a]):int(batch.state_off[b])],
                        dur_u8=None if dur8 is None else dur8[int(batch.arc_off[a]):int(batch.arc_off[b])],
-                       dst_delta_u16=None if d16 is None else d16[int(batch.arc_off[a]):int(batch.arc_off[b])])
+                       dst_delta_u16=None if d16 is None else d16[int(batch.arc_off[a]):int(batch.arc_off[b])],
+                       label_u16=None if lab16 is None else lab16[int(batch.arc_off[a]):int(batch.arc_off[b])])
                   for a, b in zip(cuts[:-1], cuts[1:])]
         engines = [klu.Engine(local) for _ in range(min(args.e2e_contexts, nsl))]
         row_off = np.concatenate([[0], np.cumsum([0] * nsl)])  # filled by the first pass
@@ -701,8 +707,9 @@ def main():
                     sub_rows[j] = int(e.offsets()[-1])
                 else:
                     a = int(row_off[j])
-                    o = tuple(x[a:a + sub_rows[j]] for x in out)
-                    e.fetch_frame_post(out=o)
+                    o = (out[0][int(slot_off[cuts[j]]):int(slot_off[cuts[j + 1]])], out[1][a:a + sub_rows[j]],
+                         out[2][a:a + sub_rows[j]])
+                    e.fetch_frame_post_csr(out=o)
 
         pipe_ms = []
         for i in range(args.e2e_steps + 2):

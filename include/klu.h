@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define KLU_VERSION 2
+#define KLU_VERSION 3
 
 typedef struct klu_ctx klu_ctx; /* one per GPU; owns a stream and all device buffers */
 
@@ -88,6 +88,9 @@ typedef struct klu_lattices {
    * per arc together with state_num_arcs. */
   const uint8_t* arc_dur_u8;
   const uint16_t* arc_dst_delta_u16;
+  /* Labels that all fit 16 bits (a vocabulary below 65536 words): replaces arc_label, 15 -> 13
+   * bytes per arc. */
+  const uint16_t* arc_label_u16;
 } klu_lattices;
 
 /* Command-line flags of the tools.  klu_opts_default() fills the
@@ -160,6 +163,12 @@ int klu_fetch_utterance(klu_ctx* ctx, int32_t* word, double* logp);
 /* frame-post: num_frames[num_lattices] (Posterior length incl. empty frames);
  * entries carry their frame index. */
 int klu_fetch_frame_post(klu_ctx* ctx, int32_t* num_frames, int32_t* frame, int32_t* word, float* logp);
+/* The same rows without the per-row frame column (a third of the download): frame_row_off has
+ * num_frames[l] + 1 entries per lattice, lattice after lattice; entry k of lattice l is the first
+ * row of frame k counted from the lattice's first row (klu_result_offsets), the last entry the
+ * lattice's row count -- the shape of the Posterior the reference writes
+ * (latbin/lattice-to-word-frame-post.cc:106-128: one vector of (word, post) pairs per frame). */
+int klu_fetch_frame_post_csr(klu_ctx* ctx, int32_t* num_frames, int64_t* frame_row_off, int32_t* word, float* logp);
 /* position-post: num_positions[num_lattices] (Posterior length = longest label sequence);
  * entries carry their 0-based position index. */
 int klu_fetch_position_post(klu_ctx* ctx, int32_t* num_positions, int32_t* position, int32_t* word, float* logp);

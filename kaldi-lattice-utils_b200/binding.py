@@ -24,7 +24,7 @@ INT_MAX = 2**31 - 1
 # every symbol include/klu.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["klu_last_error", "klu_version", "klu_opts_default", "klu_device_count", "klu_create", "klu_destroy",
            "klu_host_alloc", "klu_host_free", "klu_topsort", "klu_load", "klu_run", "klu_sync", "klu_result_offsets",
-           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_position_post", "klu_fetch_length_dist",
+           "klu_fetch_segment", "klu_fetch_position", "klu_fetch_utterance", "klu_fetch_frame_post", "klu_fetch_frame_post_csr", "klu_fetch_position_post", "klu_fetch_length_dist",
            "klu_fetch_best_path2", "klu_fetch_prune", "klu_result_char_sizes", "klu_fetch_char_position", "klu_fetch_char_segment",
            "klu_fetch_fwd_bwd", "klu_timer_start", "klu_timer_stop", "klu_launch_count", "klu_profile_enable",
            "klu_profile_json", "klu_batch_stats", "klu_flush_l2", "klu_load_times"]
@@ -35,7 +35,7 @@ class KluLattices(C.Structure):
                 ("arc_src", C.c_void_p), ("arc_dst", C.c_void_p), ("arc_label", C.c_void_p), ("arc_dur", C.c_void_p),
                 ("arc_graph", C.c_void_p), ("arc_acoustic", C.c_void_p), ("fin_graph", C.c_void_p),
                 ("fin_acoustic", C.c_void_p), ("fin_dur", C.c_void_p), ("state_num_arcs", C.c_void_p),
-                ("arc_dur_u8", C.c_void_p), ("arc_dst_delta_u16", C.c_void_p)]
+                ("arc_dur_u8", C.c_void_p), ("arc_dst_delta_u16", C.c_void_p), ("arc_label_u16", C.c_void_p)]
 
 
 class KluOpts(C.Structure):
@@ -112,6 +112,12 @@ def compact_arcs(batch):
     return dur8, d16
 
 
+def compact_labels(batch):
+    """klu_lattices.arc_label_u16 of a batch, or None when a label does not fit 16 bits."""
+    lab = batch.label
+    return lab.astype(np.uint16) if lab.size == 0 or (lab.min() >= 0 and lab.max() < 65536) else None
+
+
 def make_opts(acoustic_scale=1.0, graph_scale=1.0, insertion_penalty=0.0, beam=float("inf"), include_words=(),
               exclude_words=(), beam_ratio=0.9, min_beam=1e-3, max_arcs=INT_MAX, max_states=INT_MAX, nbest=100,
               label_group=None, inc_groups=(), del_groups=()):
@@ -160,15 +166,18 @@ class Engine:
         return buf
 
     # -- data -----------------------------------------------------------------
-    def load(self, batch, state_num_arcs=None, dur_u8=None, dst_delta_u16=None):
+    def load(self, batch, state_num_arcs=None, dur_u8=None, dst_delta_u16=None, label_u16=None):
         """state_num_arcs (optional, int32 per state): upload without the per-arc source array;
-        dur_u8 / dst_delta_u16 (optional, see compact_arcs()): the compact forms of arc_dur / arc_dst."""
+        dur_u8 / dst_delta_u16 / label_u16 (optional, see compact_arcs(), compact_labels()): the compact
+        forms of arc_dur / arc_dst / arc_label."""
         kl = KluLattices(len(batch), _p(batch.state_off), _p(batch.arc_off),
                          None if state_num_arcs is not None else _p(batch.src),
                          None if dst_delta_u16 is not None else _p(batch.dst),
-                         _p(batch.label), None if dur_u8 is not None else _p(batch.dur), _p(batch.graph),
+                         None if label_u16 is not None else _p(batch.label),
+                         None if dur_u8 is not None else _p(batch.dur), _p(batch.graph),
                          _p(batch.acoustic), _p(batch.fin_graph),
-                         _p(batch.fin_acoustic), _p(batch.fin_dur), _p(state_num_arcs), _p(dur_u8), _p(dst_delta_u16))
+                         _p(batch.fin_acoustic), _p(batch.fin_dur), _p(state_num_arcs), _p(dur_u8), _p(dst_delta_u16),
+                         _p(label_u16))
         _chk(self.L.klu_load(self.h, C.byref(kl)))
         self.batch = batch
 
@@ -231,6 +240,22 @@ class Engine:
             lp = np.zeros(n, np.float32)
         _chk(self.L.klu_fetch_frame_post(self.h, _p(nf), _p(fr), _p(w), _p(lp)))
         return off, nf, fr, w, lp
+
+    def fetch_frame_post_csr(self, out=None):
+        """Rows without the per-row frame column: (off, num_frames, frame_row_off, word, logp); lattice l's
+        frame_row_off entries start at sum(num_frames[:l] + 1).  out: optional (frame_row_off, word, logp)
+        arrays (e.g. pinned) of sufficient size."""
+        off = self.offsets()
+        n = int(off[-1])
+        nf = np.zeros(len(self.batch), np.int32)
+        _chk(self.L.klu_fetch_frame_post_csr(self.h, _p(nf), None, None, None))  # frame counts only: sizes frame_row_off
+        slots = int(nf.sum(dtype=np.int64)) + len(nf)
+        if out is not None and out[0].size >= slots and out[1].size >= n:
+            fo, w, lp = out[0][:slots], out[1][:n], out[2][:n]
+        else:
+            fo, w, lp = np.zeros(slots, np.int64), np.zeros(n, np.int32), np.zeros(n, np.float32)
+        _chk(self.L.klu_fetch_frame_post_csr(self.h, _p(nf), _p(fo), _p(w), _p(lp)))
+        return off, nf, fo, w, lp
 
     def fetch_position_post(self):
         off = self.offsets()
@@ -309,6 +334,20 @@ class Engine:
             for k, ww, p in zip(fr[a:b].tolist(), w[a:b].tolist(), lp[a:b].tolist()):
                 frames[k].append((ww, p))
             res.append(frames)
+        return res
+
+    def frame_post_csr(self, **o):
+        """frame_post() through klu_fetch_frame_post_csr (no per-row frame column)."""
+        self.run(FRAME_POST, **o)
+        off, nf, fo, w, lp = self.fetch_frame_post_csr()
+        res, slot = [], 0
+        for l, (a, b) in enumerate(zip(off[:-1], off[1:])):
+            T = int(nf[l])
+            fl = fo[slot:slot + T + 1]
+            slot += T + 1
+            assert int(fl[T]) == int(b - a)
+            res.append([list(zip(w[a + int(fl[k]):a + int(fl[k + 1])].tolist(), lp[a + int(fl[k]):a + int(fl[k + 1])].tolist()))
+                        for k in range(T)])
         return res
 
     def position_post(self, **o):

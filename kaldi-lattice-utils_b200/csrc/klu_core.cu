@@ -337,13 +337,17 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
   c->h_frame_res_off.assign(1, 0);
   c->fr_items = 0;
   klu_lattices with_src;
-  std::vector<int32_t> src_tmp, dst_tmp, dur_tmp;
+  std::vector<int32_t> src_tmp, dst_tmp, dur_tmp, label_tmp;
   if (!lats->arc_dst && !lats->arc_dst_delta_u16) {
     set_error("klu_load: arc_dst and arc_dst_delta_u16 are both NULL");
     return 1;
   }
   if (!lats->arc_dur && !lats->arc_dur_u8) {
     set_error("klu_load: arc_dur and arc_dur_u8 are both NULL");
+    return 1;
+  }
+  if (!lats->arc_label && !lats->arc_label_u16) {
+    set_error("klu_load: arc_label and arc_label_u16 are both NULL");
     return 1;
   }
   if (!lats->arc_src) {
@@ -375,7 +379,7 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
       lats = &with_src;
     }
   }
-  if (getenv("KLU_HOST_PACKER") && (!lats->arc_dst || !lats->arc_dur)) {  // the host twin wants 32-bit arrays
+  if (getenv("KLU_HOST_PACKER") && (!lats->arc_dst || !lats->arc_dur || !lats->arc_label)) {  // the host twin wants 32-bit arrays
     const size_t E = (size_t)lats->arc_off[lats->num_lattices];
     if (lats != &with_src) {
       with_src = *lats;
@@ -390,6 +394,11 @@ int klu_load(klu_ctx* c, const klu_lattices* lats) {
       dur_tmp.resize(E);
       for (size_t e = 0; e < E; ++e) dur_tmp[e] = (int32_t)with_src.arc_dur_u8[e];
       with_src.arc_dur = dur_tmp.data();
+    }
+    if (!with_src.arc_label) {
+      label_tmp.resize(E);
+      for (size_t e = 0; e < E; ++e) label_tmp[e] = (int32_t)with_src.arc_label_u16[e];
+      with_src.arc_label = label_tmp.data();
     }
   }
   c->load_upload_ms = c->load_pack_ms = c->lazy_pack_ms = 0.f;

@@ -99,12 +99,14 @@ __global__ void __launch_bounds__(256) k_gp_expand_src(GP a, int32_t* src_out) {
 }
 
 // compact input forms -> the 32-bit arrays the packer works on (klu_lattices.arc_dur_u8 / arc_dst_delta_u16)
-__global__ void __launch_bounds__(256) k_gp_expand_compact(const uint8_t* dur8, const uint16_t* delta16, const int32_t* src,
-                                                           int32_t* dur, int32_t* dst, int64_t E) {
+__global__ void __launch_bounds__(256) k_gp_expand_compact(const uint8_t* dur8, const uint16_t* delta16, const uint16_t* label16,
+                                                           const int32_t* src, int32_t* dur, int32_t* dst, int32_t* label,
+                                                           int64_t E) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     if (dur8) dur[e] = (int32_t)dur8[e];
     if (delta16) dst[e] = src[e] + (int32_t)delta16[e];
+    if (label16) label[e] = (int32_t)label16[e];
   }
 }
 
@@ -478,7 +480,11 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
     KLU_TRY(sc[R_DST].reserve(4 * E1));
     KLU_TRY(upload(c, sc[R_KEYB], in->arc_dst_delta_u16, 2 * (size_t)E));  // expanded on the device below
   }
-  KLU_TRY(upload(c, sc[R_LABEL], in->arc_label, 4 * (size_t)E));
+  if (in->arc_label) KLU_TRY(upload(c, sc[R_LABEL], in->arc_label, 4 * (size_t)E));
+  else {
+    KLU_TRY(sc[R_LABEL].reserve(4 * E1));
+    KLU_TRY(upload(c, sc[R_VALA], in->arc_label_u16, 2 * (size_t)E));
+  }
   if (in->arc_dur) KLU_TRY(upload(c, sc[R_DUR], in->arc_dur, 4 * (size_t)E));
   else {
     KLU_TRY(sc[R_DUR].reserve(4 * E1));
@@ -606,11 +612,12 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
     }
     KLU_TRY(check_launch("k_gp_expand_src"));
   }
-  if (!in->arc_dst || !in->arc_dur) {
+  if (!in->arc_dst || !in->arc_dur || !in->arc_label) {
     KLU_LAUNCH(c, "k_gp_expand_compact");
     k_gp_expand_compact<<<c->num_sms * 8, 256, 0, c->stream>>>(
         in->arc_dur ? nullptr : sc[R_KEYA].as<uint8_t>(), in->arc_dst ? nullptr : sc[R_KEYB].as<uint16_t>(),
-        sc[R_SRC].as<int32_t>(), sc[R_DUR].as<int32_t>(), sc[R_DST].as<int32_t>(), E);
+        in->arc_label ? nullptr : sc[R_VALA].as<uint16_t>(), sc[R_SRC].as<int32_t>(), sc[R_DUR].as<int32_t>(),
+        sc[R_DST].as<int32_t>(), sc[R_LABEL].as<int32_t>(), E);
     KLU_TRY(check_launch("k_gp_expand_compact"));
   }
   {

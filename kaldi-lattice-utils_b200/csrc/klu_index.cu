@@ -1229,6 +1229,40 @@ int klu_fetch_frame_post(klu_ctx* c, int32_t* num_frames, int32_t* frame, int32_
   return 0;
 }
 
+int klu_fetch_frame_post_csr(klu_ctx* c, int32_t* num_frames, int64_t* frame_row_off, int32_t* word, float* logp) {
+  if (c->last_tool != KLU_FRAME_POST) {
+    set_error("klu_fetch_frame_post_csr: last run was not KLU_FRAME_POST");
+    return 1;
+  }
+  KLU_TRY(ensure_offsets(c));
+  const size_t n = (size_t)c->last_entries;
+  const int32_t L = c->L;
+  if (num_frames) memcpy(num_frames, c->h_num_frames.data(), sizeof(int32_t) * L);
+  if (frame_row_off && c->frame_col_static) {
+    // the frame-synchronous path keeps the per-frame row offsets of the batch on the device (klu_frame.cu)
+    KLU_TRY(d2h(c, frame_row_off, c->d_fr_gloc.p, 8 * (size_t)c->h_fr_base[L]));
+  } else if (frame_row_off) {
+    // generic pipeline (KLU_GENERIC_FRAME_POST): count the rows of every frame from its frame column
+    std::vector<int32_t> fr(n);
+    KLU_TRY(d2h(c, fr.data(), c->d_res[0].p, n * 4));
+    KLU_CUDA(cudaStreamSynchronize(c->stream));
+    size_t o = 0;
+    for (int32_t l = 0; l < L; ++l) {
+      const size_t a = (size_t)c->h_res_off[l], e = (size_t)c->h_res_off[l + 1];
+      size_t i = a;
+      for (int32_t k = 0; k < c->h_num_frames[l]; ++k) {
+        frame_row_off[o++] = (int64_t)(i - a);
+        while (i < e && fr[i] == k) ++i;
+      }
+      frame_row_off[o++] = (int64_t)(e - a);
+    }
+  }
+  KLU_TRY(d2h(c, word, c->d_res[1].p, n * 4));
+  KLU_TRY(d2h(c, logp, c->d_res[4].p, n * 4));
+  KLU_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int klu_fetch_length_dist(klu_ctx* c, int32_t* length, float* logp) {
   if (c->last_tool != KLU_LENGTH_DIST) {
     set_error("klu_fetch_length_dist: last run was not KLU_LENGTH_DIST");

@@ -125,10 +125,11 @@ struct Batch {
   // What goes over PCIe: per-state arc counts instead of per-arc sources (the arcs are grouped by
   // source state, as OpenFst stores them), durations as bytes and destinations as 16-bit distances
   // from the source when they all fit (klu_lattices.state_num_arcs / arc_dur_u8 /
-  // arc_dst_delta_u16): 15 instead of 24 bytes per arc.  Built once per batch on the I/O threads.
+  // arc_dst_delta_u16), labels as 16-bit words (arc_label_u16): 13 instead of 24 bytes per arc.
+  // Built once per batch on the I/O threads.
   mutable std::vector<int32_t> num_arcs_;
   mutable std::vector<uint8_t> dur8_;
-  mutable std::vector<uint16_t> delta16_;
+  mutable std::vector<uint16_t> delta16_, label16_;
   klu_lattices View() const {
     klu_lattices v;
     memset(&v, 0, sizeof(v));
@@ -149,20 +150,24 @@ struct Batch {
     num_arcs_.assign(S, 0);
     dur8_.resize(E);
     delta16_.resize(E);
-    std::atomic<int> dur_ok(1), delta_ok(1), grouped(1);
+    label16_.resize(E);
+    std::atomic<int> dur_ok(1), delta_ok(1), grouped(1), label_ok(1);
     ParallelFor(nl, [&](size_t l) {
       const size_t e0 = (size_t)arc_off[l], e1 = (size_t)arc_off[l + 1], s0 = (size_t)state_off[l];
       const int32_t ns = (int32_t)(state_off[l + 1] - state_off[l]);
-      bool d_ok = true, t_ok = true, g_ok = true;
+      bool d_ok = true, t_ok = true, g_ok = true, l_ok = true;
       for (size_t e = e0; e < e1; ++e) {
-        const int32_t u = src[e], dd = dst[e] - u, du = dur[e];
+        const int32_t u = src[e], dd = dst[e] - u, du = dur[e], lb = label[e];
         if (u < 0 || u >= ns || (e > e0 && src[e - 1] > u)) { g_ok = false; break; }
         ++num_arcs_[s0 + (size_t)u];
         if (du < 0 || du > 255) d_ok = false;
         if (dd < 0 || dd > 65535) t_ok = false;
+        if (lb < 0 || lb > 65535) l_ok = false;
         dur8_[e] = (uint8_t)du;
         delta16_[e] = (uint16_t)dd;
+        label16_[e] = (uint16_t)lb;
       }
+      if (!l_ok) label_ok = 0;
       if (!d_ok) dur_ok = 0;
       if (!t_ok) delta_ok = 0;
       if (!g_ok) grouped = 0;
@@ -177,6 +182,10 @@ struct Batch {
       if (delta_ok) {
         v.arc_dst = nullptr;
         v.arc_dst_delta_u16 = delta16_.data();
+      }
+      if (label_ok) {
+        v.arc_label = nullptr;
+        v.arc_label_u16 = label16_.data();
       }
     }
     return v;
@@ -243,8 +252,22 @@ void ComputeBatch(klu_ctx* ctx, const klu_opts* opts, const Batch* b, Results* r
     r->i2.resize(n), r->i3.resize(n), r->d0.resize(n);
     KLU_CHECK(klu_fetch_char_segment(ctx, r->coff.data(), r->chars.data(), r->i2.data(), r->i3.data(), r->d0.data()));
 #elif KLU_TOOL == 3 /* KLU_FRAME_POST */
+    // rows without the per-row frame column (a third of the download); the writer below shares
+    // its loop with the position-post / length-dist tools, which carry one, so it is rebuilt here
     r->i0.resize(L), r->i1.resize(n), r->i2.resize(n), r->f0.resize(n);
-    KLU_CHECK(klu_fetch_frame_post(ctx, r->i0.data(), r->i1.data(), r->i2.data(), r->f0.data()));
+    KLU_CHECK(klu_fetch_frame_post_csr(ctx, r->i0.data(), nullptr, nullptr, nullptr));  // frame counts
+    {
+      std::vector<int64_t> slot((size_t)L + 1, 0);
+      for (int32_t l = 0; l < L; ++l) slot[l + 1] = slot[l] + r->i0[l] + 1;
+      std::vector<int64_t> fo((size_t)slot[L]);
+      KLU_CHECK(klu_fetch_frame_post_csr(ctx, r->i0.data(), fo.data(), r->i2.data(), r->f0.data()));
+      ParallelFor((size_t)L, [&](size_t l) {
+        const int64_t* f = fo.data() + slot[l];
+        const size_t a = (size_t)r->off[l];
+        for (int32_t k = 0; k < r->i0[l]; ++k)
+          for (int64_t i = f[k]; i < f[k + 1]; ++i) r->i1[a + (size_t)i] = k;
+      });
+    }
 #elif KLU_TOOL == 10 /* KLU_LENGTH_DIST */
     // one Posterior frame per lattice (latbin/lattice-to-transcript-length-dist.cc:111)
     r->i0.assign(L, 1), r->i1.assign(n, 0), r->i2.resize(n), r->f0.resize(n);

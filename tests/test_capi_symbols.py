@@ -25,7 +25,7 @@ def test_header_symbols_exported(klu):
 
 def test_version_and_defaults(klu):
     lib = klu.binding.lib()
-    assert lib.klu_version() == 2
+    assert lib.klu_version() == 3
     o = klu.binding.KluOpts()
     lib.klu_opts_default(C.byref(o))
     assert o.acoustic_scale == 1.0 and o.graph_scale == 1.0 and o.insertion_penalty == 0.0

@@ -307,6 +307,42 @@ def test_load_from_compact_arc_arrays(klu, engine, monkeypatch):
         engine.load(batch, dst_delta_u16=bad)
 
 
+def test_load_from_16_bit_labels(klu, engine, monkeypatch):
+    """klu_lattices.arc_label_u16 (13 bytes per arc on the way up with the other compact forms)."""
+    batch = klu.synth_batch("small", 7, seed=33)
+    engine.load(batch)
+    want = dict(seg=engine.segment(acoustic_scale=0.3), pos=engine.position(), fp=engine.frame_post(),
+                utt=engine.utterance(), bp=engine.best_path2())
+    lab16 = klu.binding.compact_labels(batch)
+    dur8, d16 = klu.binding.compact_arcs(batch)
+    assert lab16 is not None
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("KLU_HOST_PACKER", "1")
+        for kw in (dict(label_u16=lab16), dict(label_u16=lab16, dur_u8=dur8, dst_delta_u16=d16,
+                                              state_num_arcs=batch.state_num_arcs())):
+            engine.load(batch, **kw)
+            got = dict(seg=engine.segment(acoustic_scale=0.3), pos=engine.position(), fp=engine.frame_post(),
+                       utt=engine.utterance(), bp=engine.best_path2())
+            assert got == want
+    wide = klu.make_lattice("wide-label", 2, [(0, 1, 70000, 0.5, 0.5, 1)], {1: (0.0, 0.0)})
+    assert klu.binding.compact_labels(klu.LatticeBatch.from_lattices([wide])) is None
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_frame_post_rows_by_frame_offsets(klu, engine, monkeypatch, generic):
+    """klu_fetch_frame_post_csr: the same rows as klu_fetch_frame_post, per-frame offsets instead of a frame
+    column (empty lattices and frames without a word included)."""
+    lats = klu.synth_batch("small", 6, seed=34).lattices() + klu.synth_batch("tiny", 9, seed=35).lattices()
+    lats.insert(2, klu.make_lattice("empty", 0, [], {}))
+    lats.insert(5, klu.make_lattice("eps-only", 3, [(0, 1, 0, 0.5, 0.5, 2), (1, 2, 0, 0.1, 0.2, 1)], {2: (0.0, 0.0)}))
+    if generic:
+        monkeypatch.setenv("KLU_GENERIC_FRAME_POST", "1")
+    engine.load(klu.LatticeBatch.from_lattices(lats))
+    for flags in (dict(), dict(acoustic_scale=0.1)):
+        assert engine.frame_post_csr(**flags) == engine.frame_post(**flags)
+
+
 # ---- device packer vs host packer ----------------------------------------------
 def test_gpu_packer_equals_host_packer(klu, engine, monkeypatch):
     lats = klu.synth_batch("small", 9, seed=2024).lattices()
