@@ -489,8 +489,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-slices", type=int, default=24, help="slices of the pipelined end-to-end run (1 = off)")
-    ap.add_argument("--e2e-contexts", type=int, default=6, help="contexts (host threads) of the pipelined run")
+    ap.add_argument("--e2e-slices", type=int, default=16, help="slices of the pipelined end-to-end run (1 = off)")
+    ap.add_argument("--e2e-contexts", type=int, default=8, help="contexts (host threads) of the pipelined run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tools", action="store_true", help="skip the per-tool section")
     ap.add_argument("--tools-steps", type=int, default=3)
