@@ -140,17 +140,35 @@ __global__ void __launch_bounds__(128) k_gp_levels(GP a, int* counter) {
     __threadfence();
     __syncwarp();
     int times_ok = 1, max_label = 0;
+    // The arcs of a state do not depend on what the walk computes: the first 32 of the NEXT state
+    // (and its arc range) are fetched before the current state's values are waited for, so only
+    // the level / time / band loads stay on the chain of ns dependent steps.
+    int f0 = a.first_arc[s0], f1 = a.first_arc[s0 + 1];
+    int pd = 0, pl = 0, pu = 0;
+    if (f0 + lane < f1) {
+      pd = a.dst[f0 + lane];
+      pl = a.label[f0 + lane];
+      pu = a.dur[f0 + lane];
+    }
     for (int s = 0; s < ns; ++s) {
       const int gs = s0 + s;
+      const int nf0 = f1, nf1 = s + 1 < ns ? a.first_arc[gs + 2] : f1;
+      int nd = 0, nlb = 0, nu = 0;
+      if (nf0 + lane < nf1) {
+        nd = a.dst[nf0 + lane];
+        nlb = a.label[nf0 + lane];
+        nu = a.dur[nf0 + lane];
+      }
       const int lev = ld_cg_i32(a.level + gs), ts = ld_cg_i32(a.time + gs);
       const int lo = ld_cg_i32(a.blo + gs), hi = ld_cg_i32(a.bhi + gs);
-      const int f0 = a.first_arc[gs], f1 = a.first_arc[gs + 1];
       for (int e = f0 + lane; e < f1; e += 32) {
-        const int d = s0 + a.dst[e];
-        const int lab = a.label[e];
+        const bool first = e < f0 + 32;
+        const int d = s0 + (first ? pd : a.dst[e]);
+        const int lab = first ? pl : a.label[e];
+        const int du = first ? pu : a.dur[e];
         atomicMax(a.level + d, lev + 1);
         if (ts >= 0) {
-          const int tv = ts + a.dur[e];
+          const int tv = ts + du;
           const int old = atomicCAS(a.time + d, -1, tv);
           if (old != -1 && old != tv) times_ok = 0;
         }
@@ -163,6 +181,11 @@ __global__ void __launch_bounds__(128) k_gp_levels(GP a, int* counter) {
       }
       __threadfence();
       __syncwarp();
+      f0 = nf0;
+      f1 = nf1;
+      pd = nd;
+      pl = nlb;
+      pu = nu;
     }
     int nl = 0, frames = -1, maxlen = 0, maxtime = 0;
     for (int s = lane; s < ns; s += 32) {
