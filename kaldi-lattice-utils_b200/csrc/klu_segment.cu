@@ -30,9 +30,7 @@ namespace klu {
 namespace {
 
 constexpr int kBucketCap = 512;   // arcs of one lattice starting in one frame
-constexpr int kRankBits = 9;
 constexpr int kBucketWarps = 8;   // per CTA; 16 B of shared memory per warp and bucket slot
-constexpr unsigned long long kNoKey = ~0ULL;
 
 struct SegArgs {
   BatchView b;
@@ -59,6 +57,7 @@ struct SegArgs {
   ulonglong2* rec;       // {key (word, t0, span), bits of the log-posterior}
   int tiles;             // CTAs per lattice
   int cap;               // shared-memory slots per warp: power of two >= the largest bucket
+  int rank_bits;         // log2(cap): low bits of a sort word = the arc's rank in its bucket
   unsigned int* key32;   // order keys (high half of the f64 key); holes = 0xffffffff
   unsigned int* idx;     // lattice-local arena index
   int32_t* rcnt;         // [L] entries
@@ -153,11 +152,15 @@ struct SegRunSum {
 
 // One warp per bucket (the arcs of a lattice that start in one frame).  Grid lattices x tiles, tile fastest:
 // the CTAs running at the same time work on a few lattices, whose alpha / beta / times stay in L2.
+// KT: 32-bit sort words when (word, span, rank) fit (half the shared-memory traffic of the network)
+template <typename KT>
 __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
   extern __shared__ unsigned long long s_dyn[];
+  constexpr KT kNoKey = (KT)~(KT)0;
+  const int kRankBits = a.rank_bits;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long* sk = s_dyn + (size_t)warp * a.cap;
-  double* sv = reinterpret_cast<double*>(s_dyn + (size_t)kBucketWarps * a.cap) + (size_t)warp * a.cap;
+  double* sv = reinterpret_cast<double*>(s_dyn) + (size_t)warp * a.cap;
+  KT* sk = reinterpret_cast<KT*>(s_dyn + (size_t)kBucketWarps * a.cap) + (size_t)warp * a.cap;
   const BatchView& b = a.b;
   const int l = blockIdx.x / a.tiles, tile = blockIdx.x % a.tiles;  // tile fastest: see above
   const int e0 = b.e_off[l];
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
     while (P < n) P <<= 1;
     // ---- keys {(word, span), arc rank in the bucket} and values of the bucket's arcs
     for (int j = lane; j < P; j += 32) {
-      unsigned long long k = kNoKey;
+      KT k = kNoKey;
       double v = neg_inf();
       if (j < n) {
         const int e = e0 + (int)perm[j0 + j];
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
           // fw[s] + arc_lkh + bw[next], kwsbin2/lattice-word-index-segment.cc:160-162
           v = __dadd_rn(__dadd_rn(a.alpha[s], -rec_cost(r, a.cp)), a.beta[r.x]);
           const unsigned long long span = (unsigned long long)(b.time[r.x] - b.time[s]);
-          k = (((((unsigned long long)(unsigned int)r.w) << a.bits_span) | span) << kRankBits) | (unsigned long long)j;
+          k = (KT)((((((unsigned long long)(unsigned int)r.w) << a.bits_span) | span) << kRankBits) | (unsigned long long)j);
         }
       }
       sk[j] = k;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
           const int i = (t << 1) - (t & (stride - 1));  // stride is a power of two
           const int p = i + stride;
           const bool up = ((i & size) == 0);
-          const unsigned long long x = sk[i], y = sk[p];
+          const KT x = sk[i], y = sk[p];
           if ((x > y) == up) {
             sk[i] = y;
             sk[p] = x;
@@ -218,23 +221,23 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
     int carry = 0;
     for (int i0 = 0; i0 < P; i0 += 32) {
       const int i = i0 + lane;
-      const unsigned long long k = sk[i];
+      const KT k = sk[i];
       const bool head = k != kNoKey && (i == 0 || (sk[i - 1] >> kRankBits) != (k >> kRankBits));
       const unsigned int hm = __ballot_sync(0xffffffffu, head);
       if (head) {
         const int rank = carry + __popc(hm & ((1u << lane) - 1u));
-        double sum = sv[(int)(k & (unsigned long long)(kBucketCap - 1))];
+        double sum = sv[(int)(k & (KT)(a.cap - 1))];
         int q = i + 1;
         if (q + 1 < P && (sk[q + 1] >> kRankBits) == (k >> kRankBits)) {  // three or more terms
           SegRunSum rs;
           rs.add(sum);
-          for (; q < P && (sk[q] >> kRankBits) == (k >> kRankBits); ++q) rs.add(sv[(int)(sk[q] & (unsigned long long)(kBucketCap - 1))]);
+          for (; q < P && (sk[q] >> kRankBits) == (k >> kRankBits); ++q) rs.add(sv[(int)(sk[q] & (KT)(a.cap - 1))]);
           sum = rs.value();
         } else {
-          for (; q < P && (sk[q] >> kRankBits) == (k >> kRankBits); ++q) sum = log_add(sum, sv[(int)(sk[q] & (unsigned long long)(kBucketCap - 1))]);
+          for (; q < P && (sk[q] >> kRankBits) == (k >> kRankBits); ++q) sum = log_add(sum, sv[(int)(sk[q] & (KT)(a.cap - 1))]);
         }
         const double logp = sum - total;
-        const unsigned long long ws = k >> kRankBits;  // (word, span)
+        const unsigned long long ws = (unsigned long long)(k >> kRankBits);  // (word, span)
         const unsigned long long word = ws >> a.bits_span, span = ws & ((1ULL << a.bits_span) - 1ULL);
         a.rec[j0 + rank] = make_ulonglong2((((word << a.bits_time) | t0) << a.bits_span) | span,
                                            (unsigned long long)__double_as_longlong(logp));
@@ -463,7 +466,7 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
   for (int32_t l = 0; l < L; ++l)
     if (!c->h_times_ok[l]) return 0;  // the generic path reports the error
   const int bits_label = bits_for(c->max_label), bits_time = bits_for(c->max_time), bits_span = bits_for(c->max_span);
-  if (bits_label + bits_span + kRankBits > 63 || bits_label + bits_time + bits_span > 62) return 0;
+  if (bits_label + bits_span + 9 > 63 || bits_label + bits_time + bits_span > 62) return 0;  // 9 = log2(kBucketCap)
   KLU_TRY(ensure_segment_buckets(c));
   if (c->seg_max_bucket > kBucketCap) return 0;
   const bool use_beam = o->beam != INFINITY;
@@ -516,7 +519,12 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
   a.num_slots = c->seg_slots;
   a.rec = sc[S_REC].as<ulonglong2>();
   a.cap = 32;
-  while (a.cap < c->seg_max_bucket) a.cap <<= 1;
+  a.rank_bits = 5;
+  while (a.cap < c->seg_max_bucket) {
+    a.cap <<= 1;
+    ++a.rank_bits;
+  }
+  const bool narrow = bits_label + bits_span + a.rank_bits <= 31;
   a.key32 = sc[S_K32A].as<unsigned int>();
   a.idx = sc[S_IDXA].as<unsigned int>();
   a.rcnt = sc[S_RCNT].as<int32_t>();
@@ -528,8 +536,15 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
     for (int32_t l = 0; l < L; ++l) max_slots = std::max(max_slots, c->h_maxtime[l] + 2);
     const int btiles = std::max(1, std::min((max_slots + kBucketWarps * 4 - 1) / (kBucketWarps * 4), 64));
     a.tiles = btiles;
-    KLU_CUDA(cudaFuncSetAttribute(k_sg_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, kBucketWarps * kBucketCap * 16));  // per device
-    k_sg_buckets<<<(unsigned int)((int64_t)L * btiles), kBucketWarps * 32, (size_t)kBucketWarps * a.cap * 16, c->stream>>>(a);
+    if (narrow) {
+      KLU_CUDA(cudaFuncSetAttribute(k_sg_buckets<unsigned int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kBucketWarps * kBucketCap * 12));  // per device
+      k_sg_buckets<unsigned int><<<(unsigned int)((int64_t)L * btiles), kBucketWarps * 32, (size_t)kBucketWarps * a.cap * 12, c->stream>>>(a);
+    } else {
+      KLU_CUDA(cudaFuncSetAttribute(k_sg_buckets<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kBucketWarps * kBucketCap * 16));
+      k_sg_buckets<unsigned long long><<<(unsigned int)((int64_t)L * btiles), kBucketWarps * 32, (size_t)kBucketWarps * a.cap * 16, c->stream>>>(a);
+    }
   }
   KLU_TRY(check_launch("k_sg_buckets"));
   SegSortArgs32 s2;
