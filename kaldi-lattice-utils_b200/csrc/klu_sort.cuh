@@ -46,29 +46,48 @@ static __device__ __forceinline__ unsigned int match_digit(int d, bool valid) {
   return m;
 }
 
-// kSortThreads = 512, or 1024 when there are too few segments to fill the SMs with 512-thread CTAs
-template <typename K, int kSortThreads>
+// BITS = digit width (8, 9 or 10): 26-bit (frame, word) keys take three 9-bit passes instead of
+// four 8-bit ones, 10-bit frame numbers one pass instead of two (seg_sort_launch picks the width).
+constexpr int kSortThreads = 512;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+template <int BITS>
+static __device__ __forceinline__ unsigned int match_digit_w(int d, bool valid) {
+  unsigned int m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < BITS; ++b) {
+    const bool bit = (d >> b) & 1;
+    const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
+template <typename K, int BITS>
 static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSortArgsT<K> a) {
-  constexpr int kSortWarps = kSortThreads / 32;
-  constexpr int kSortTile = kSortThreads * kSortItems;
-  __shared__ unsigned int hist[8][256];
-  __shared__ unsigned int bin_base[256];
-  __shared__ unsigned int warp_cnt[kSortWarps][256];
+  constexpr int NB = 1 << BITS;
+  constexpr int PER = NB > kSortThreads ? NB / kSortThreads : 1;  // bins per thread in the bin scan
+  extern __shared__ unsigned int sort_smem[];
+  __shared__ unsigned int wsum[kSortWarps];
   __shared__ int skip_flag;
   const int seg = blockIdx.x;
   const int n = a.seg_cnt[seg];
   const int64_t base = a.seg_base[seg];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int npass = (a.hi_bit - a.lo_bit + 7) / 8;
+  const int npass = (a.hi_bit - a.lo_bit + BITS - 1) / BITS;
   if (n <= 1 || npass <= 0) {
     if (tid == 0) a.where[seg] = 0;
     return;
   }
+  unsigned int* bin_base = sort_smem;                                  // [NB]
+  unsigned int(*warp_cnt)[NB] = reinterpret_cast<unsigned int(*)[NB]>(sort_smem + NB);  // [kSortWarps][NB]
+  unsigned int(*hist)[NB] = reinterpret_cast<unsigned int(*)[NB]>(sort_smem + NB + kSortWarps * NB);  // [npass][NB]
   K* kin = a.key_a + base;
   unsigned int* vin = a.val_a + base;
   K* kout = a.key_b + base;
   unsigned int* vout = a.val_b + base;
-  for (int i = tid; i < 8 * 256; i += kSortThreads) (&hist[0][0])[i] = 0;
+  for (int i = tid; i < npass * NB; i += kSortThreads) (&hist[0][0])[i] = 0;
   __syncthreads();
   for (int i0 = 0; i0 < n; i0 += 4 * kSortThreads) {
     K kk[4];
@@ -81,37 +100,45 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
     for (int r = 0; r < 4; ++r) {
       if (i0 + r * kSortThreads + tid >= n) break;
       const K k = kk[r] >> a.lo_bit;
-      for (int p = 0; p < npass; ++p) atomicAdd(&hist[p][(unsigned int)(k >> (8 * p)) & 255u], 1u);
+      for (int p = 0; p < npass; ++p) atomicAdd(&hist[p][(unsigned int)(k >> (BITS * p)) & (unsigned int)(NB - 1)], 1u);
     }
   }
   __syncthreads();
   int executed = 0;
   for (int p = 0; p < npass; ++p) {
-    const int shift = a.lo_bit + 8 * p;
+    const int shift = a.lo_bit + BITS * p;
     if (tid == 0) skip_flag = 0;
     __syncthreads();
-    if (tid < 256 && hist[p][tid] == (unsigned)n) skip_flag = 1;
+    for (int b = tid; b < NB; b += kSortThreads)
+      if (hist[p][b] == (unsigned)n) skip_flag = 1;
     __syncthreads();
     if (skip_flag) continue;
-    // exclusive scan of hist[p] -> bin_base (first 256 threads = 8 warps)
-    if (tid < 256) {
-      unsigned int v = hist[p][tid];
-      unsigned int x = v;
+    // exclusive scan of hist[p] -> bin_base: thread t owns bins [t * PER, (t + 1) * PER)
+    {
+      unsigned int mine[PER];
+      unsigned int tot = 0;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int b = tid * PER + q;
+        mine[q] = b < NB ? hist[p][b] : 0u;
+        tot += mine[q];
+      }
+      unsigned int x = tot;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
       }
-      warp_cnt[0][tid] = x;  // inclusive within warp (scratch)
-      __syncwarp();
-      bin_base[tid] = x - v;
-    }
-    __syncthreads();
-    if (tid < 256) {
-      unsigned int add = 0;
-      for (int w = 0; w < warp; ++w) add += warp_cnt[0][w * 32 + 31];
-      __syncwarp();
-      bin_base[tid] += add;
+      if (lane == 31) wsum[warp] = x;
+      __syncthreads();
+      unsigned int run = x - tot;
+      for (int w = 0; w < warp; ++w) run += wsum[w];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int b = tid * PER + q;
+        if (b < NB) bin_base[b] = run;
+        run += mine[q];
+      }
     }
     __syncthreads();
     // The loads of a tile are issued together (kSortItems independent requests per thread) and
@@ -125,7 +152,7 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
       v[r] = i < n ? vin[i] : 0u;
     }
     for (int tile = 0; tile < n; tile += kSortTile) {
-      for (int i = lane; i < 256; i += 32) warp_cnt[warp][i] = 0;
+      for (int i = lane; i < NB; i += 32) warp_cnt[warp][i] = 0;
       __syncwarp();
       int d[kSortItems];
       unsigned int mk[kSortItems];
@@ -133,8 +160,8 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
       for (int r = 0; r < kSortItems; ++r) {
         const int i = tile + (warp * kSortItems + r) * 32 + lane;
         const bool valid = i < n;
-        d[r] = valid ? (int)((k[r] >> shift) & 255) : 0;
-        mk[r] = match_digit(d[r], valid);
+        d[r] = valid ? (int)((k[r] >> shift) & (K)(NB - 1)) : 0;
+        mk[r] = match_digit_w<BITS>(d[r], valid);
         if (valid && lane == __ffs(mk[r]) - 1) warp_cnt[warp][d[r]] += __popc(mk[r]);
         __syncwarp();
       }
@@ -145,15 +172,15 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
         vn[r] = i < n ? vin[i] : 0u;
       }
       __syncthreads();
-      if (tid < 256) {
-        unsigned int run = bin_base[tid];
+      for (int b = tid; b < NB; b += kSortThreads) {
+        unsigned int run = bin_base[b];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
-          const unsigned int cnt = warp_cnt[w][tid];
-          warp_cnt[w][tid] = run;
+          const unsigned int cnt = warp_cnt[w][b];
+          warp_cnt[w][b] = run;
           run += cnt;
         }
-        bin_base[tid] = run;
+        bin_base[b] = run;
       }
       __syncthreads();
 #pragma unroll
@@ -194,13 +221,34 @@ static __global__ void __launch_bounds__(kSortThreads) k_seg_radix_sort_t(SegSor
   }
   if (tid == 0) a.where[seg] = (unsigned char)(executed & 1);
 }
+
+// digit width: 8 bits unless 9 or 10 save a pass (keys of at most 30 bits: the wider histograms
+// live in shared memory per pass)
+static inline int seg_sort_digit_bits(int bits) {
+  if (bits <= 0 || bits > 30) return 8;
+  const int np8 = (bits + 7) / 8, np9 = (bits + 8) / 9, np10 = (bits + 9) / 10;
+  if (np9 < np8) return 9;
+  if (np10 < np8) return 10;
+  return 8;
+}
+
+template <typename K, int BITS>
+static inline void seg_sort_launch_w(const SegSortArgsT<K>& a, int nseg, cudaStream_t stream) {
+  const int npass = (a.hi_bit - a.lo_bit + BITS - 1) / BITS;
+  const size_t smem = (size_t)(1 + kSortWarps + std::max(npass, 1)) * (1u << BITS) * 4;
+  cudaFuncSetAttribute(k_seg_radix_sort_t<K, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
+  k_seg_radix_sort_t<K, BITS><<<nseg, kSortThreads, smem, stream>>>(a);
+}
+
 template <typename K>
 static inline void seg_sort_launch(const SegSortArgsT<K>& a, int nseg, int num_sms, cudaStream_t stream) {
+  (void)num_sms;
   if (nseg <= 0) return;
-  if (nseg < num_sms * 3)  // fewer CTAs than the SMs can hold at 512 threads: larger CTAs instead
-    k_seg_radix_sort_t<K, 1024><<<nseg, 1024, 0, stream>>>(a);
-  else
-    k_seg_radix_sort_t<K, 512><<<nseg, 512, 0, stream>>>(a);
+  static const bool narrow_only = getenv("KLU_SORT_8BIT") != nullptr;
+  const int w = narrow_only ? 8 : seg_sort_digit_bits(a.hi_bit - a.lo_bit);
+  if (w == 9) seg_sort_launch_w<K, 9>(a, nseg, stream);
+  else if (w == 10) seg_sort_launch_w<K, 10>(a, nseg, stream);
+  else seg_sort_launch_w<K, 8>(a, nseg, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
