@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(256) k_fg_time_keys(GroupArgs a) {
   const int l = blockIdx.x;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
-    a.key[e] = (unsigned long long)max(a.b.time[a.b.out_src[e]], 0);
+    reinterpret_cast<unsigned int*>(a.key)[e] = (unsigned int)max(a.b.time[a.b.out_src[e]], 0);  // 32-bit keys
     a.val[e] = (unsigned int)(e - e0);
   }
 }
@@ -877,12 +877,12 @@ int build_frame_groups(klu_ctx* c) {
       }
       rc = check_launch("k_fg_time_keys");
       if (!rc) {
-        SegSortArgs st;
+        SegSortArgs32 st;  // frame numbers: one 10-bit pass at T <= 1023
         st.seg_base = seg.as<int64_t>();
         st.seg_cnt = reinterpret_cast<const int32_t*>(seg.as<char>() + 8 * (size_t)(L + 1));
-        st.key_a = a.key_a ? key_a.as<unsigned long long>() : nullptr;
+        st.key_a = key_a.as<unsigned int>();
         st.val_a = val_a.as<unsigned int>();
-        st.key_b = key_b.as<unsigned long long>();
+        st.key_b = key_b.as<unsigned int>();
         st.val_b = val_b.as<unsigned int>();
         st.where = d_where;
         st.lo_bit = 0;

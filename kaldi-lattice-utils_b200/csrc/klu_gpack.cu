@@ -423,22 +423,50 @@ __global__ void __launch_bounds__(256) k_gp_band_counts2(GP a) {
   }
 }
 
-// grid (L, tiles): frame histogram (phase 0) / fill (phase 1) of the frame -> arc CSR
-template <int PHASE>
+// grid (L, tiles): +1 at the first frame of every word arc, -1 at the frame after its last one
+// (two atomics per arc, not one per arc x frame); k_gp_frame_counts turns the differences into the
+// arcs alive in every frame
 __global__ void __launch_bounds__(256) k_gp_frames(GP a) {
   const int l = blockIdx.x;
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
   const int T = a.fr_base[l + 1] - a.fr_base[l] - 1;
   int32_t* cnt = a.fr_cnt + a.fr_base[l];
-  const int64_t* fo = a.fr_off + a.fr_base[l];
   for (int p = e0 + blockIdx.y * blockDim.x + threadIdx.x; p < e1; p += gridDim.y * blockDim.x) {
     const int4 r = a.out_rec[p];
     if (r.w == 0) continue;
     const int fa = max(a.ptime[a.out_src[p]], 0), fb = min(a.ptime[r.x], T);
-    for (int k = fa; k < fb; ++k) {
-      const int pos = atomicAdd(cnt + k, 1);
-      if (PHASE == 1) a.frame_arc[fo[k] + pos] = p;
+    if (fb <= fa) continue;
+    atomicAdd(cnt + fa, 1);
+    atomicAdd(cnt + fb, -1);  // fb <= T: the slot that closes the lattice takes the last ones
+  }
+}
+
+// one CTA per lattice: in-place inclusive scan of the frame slots (T + 1 of them)
+__global__ void __launch_bounds__(256) k_gp_frame_counts(GP a) {
+  __shared__ int warp_sum[8];
+  __shared__ int carry_s;
+  const int l = blockIdx.x;
+  const int n = a.fr_base[l + 1] - a.fr_base[l];
+  int32_t* cnt = a.fr_cnt + a.fr_base[l];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int tile = 0; tile < n; tile += 256) {
+    const int i = tile + tid;
+    int x = i < n ? cnt[i] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    int add = carry_s;
+    for (int w = 0; w < warp; ++w) add += warp_sum[w];
+    if (i < n) cnt[i] = add + x;
+    __syncthreads();
+    if (tid == 255) carry_s = add + x;
+    __syncthreads();
   }
 }
 
@@ -875,9 +903,14 @@ int ensure_frame_index(klu_ctx* c) {
   KLU_TRY(small_h2d(c, a.lat_tot, fa_base.data(), 8 * (size_t)(L + 1)));
   {
     KLU_LAUNCH(c, "k_gp_frames");
-    k_gp_frames<0><<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a);
+    k_gp_frames<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a);
   }
   KLU_TRY(check_launch("k_gp_frames(count)"));
+  {
+    KLU_LAUNCH(c, "k_gp_frame_counts");
+    k_gp_frame_counts<<<L, 256, 0, c->stream>>>(a);
+  }
+  KLU_TRY(check_launch("k_gp_frame_counts"));
   {
     // frame slots of lattice l: fr_base[l] .. fr_base[l+1]-1 (the last one closes the lattice)
     KLU_LAUNCH(c, "k_gp_lat_scan");
