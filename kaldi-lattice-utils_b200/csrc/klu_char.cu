@@ -287,6 +287,7 @@ struct Frontier {
   int32_t *n_node, *n_state, *n_t0;
   double *n_wsum, *n_wmax;
   int32_t* ncnt;            // [L] items of the next depth
+  int32_t *tile_i, *tile_n;  // per tile of 256 sorted candidates: item / node heads (then: heads before it)
   int64_t node_pool_base;   // first pool slot of the depth being created
   int64_t parent_pool_base; // first pool slot of the current depth (parents)
   int depth;
@@ -455,20 +456,26 @@ __global__ void __launch_bounds__(256) k_char_rekey(Frontier f, unsigned long lo
   }
 }
 
-// One CTA per lattice: sorted candidates -> merged items (runs of equal key) and new
-// trie nodes (runs of equal (parent, label)); both keep the candidates' slot range.
+// Sorted candidates -> merged items (runs of equal key) and new trie nodes (runs of equal
+// (parent, label)); both keep the candidates' slot range.  A lattice's candidates (up to millions
+// at the deeper levels) are cut into tiles of 256 handled by many CTAs: COUNT = true leaves the
+// item / node heads of every tile in tile_i / tile_n, k_char_tile_scan turns them into the heads
+// before the tile, COUNT = false writes the items and nodes.
+__device__ __forceinline__ int char_tile_slot(const Frontier& f, int l, int tile) {
+  return (int)(f.cbase[l] >> 8) + l + tile;  // disjoint per lattice: ceil(ccnt / 256) <= slots to the next base
+}
+
+template <bool COUNT>
 __global__ void __launch_bounds__(256) k_char_reduce(CharArgs a, Frontier f) {
   __shared__ int warp_i[8], warp_n[8];
-  __shared__ int carry_i, carry_n;
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = f.ccnt[l];
   const int64_t cb = f.cbase[l];
   const unsigned long long* key = (f.where[l] ? f.key_b : f.key_a) + cb;
   const unsigned int* val = (f.where[l] ? f.val_b : f.val_a) + cb;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_i = carry_n = 0;
-  __syncthreads();
-  for (int tile = 0; tile < n; tile += 256) {
+  for (int tile = lt.tile * 256; tile < n; tile += lt.tiles * 256) {
     const int i = tile + tid;
     unsigned long long k = 0;
     bool ihead = false, nhead = false;
@@ -499,7 +506,21 @@ __global__ void __launch_bounds__(256) k_char_reduce(CharArgs a, Frontier f) {
       warp_n[warp] = xn;
     }
     __syncthreads();
-    int addi = carry_i, addn = carry_n;
+    const int slot_t = char_tile_slot(f, l, tile >> 8);
+    if (COUNT) {
+      if (tid == 0) {
+        int ti = 0, tn = 0;
+        for (int w = 0; w < 8; ++w) {
+          ti += warp_i[w];
+          tn += warp_n[w];
+        }
+        f.tile_i[slot_t] = ti;
+        f.tile_n[slot_t] = tn;
+      }
+      __syncthreads();
+      continue;
+    }
+    int addi = f.tile_i[slot_t], addn = f.tile_n[slot_t];  // heads of this lattice before the tile
     for (int w = 0; w < warp; ++w) {
       addi += warp_i[w];
       addn += warp_n[w];
@@ -545,6 +566,46 @@ __global__ void __launch_bounds__(256) k_char_reduce(CharArgs a, Frontier f) {
           f.nd_len[node] = f.nd_len[parent] + 1;
         }
       }
+    }
+    __syncthreads();  // warp_i / warp_n are rewritten by the next tile
+  }
+}
+
+// one CTA per lattice: exclusive scan of its tiles' head counts; the lattice's item count
+__global__ void __launch_bounds__(256) k_char_tile_scan(Frontier f) {
+  __shared__ int warp_i[8], warp_n[8];
+  __shared__ int carry_i, carry_n;
+  const int l = blockIdx.x;
+  const int nt = (f.ccnt[l] + 255) >> 8;
+  const int s0 = char_tile_slot(f, l, 0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_i = carry_n = 0;
+  __syncthreads();
+  for (int base = 0; base < nt; base += 256) {
+    const int t = base + tid;
+    const int ci = t < nt ? f.tile_i[s0 + t] : 0, cn = t < nt ? f.tile_n[s0 + t] : 0;
+    int xi = ci, xn = cn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int yi = __shfl_up_sync(0xffffffffu, xi, o), yn = __shfl_up_sync(0xffffffffu, xn, o);
+      if (lane >= o) {
+        xi += yi;
+        xn += yn;
+      }
+    }
+    if (lane == 31) {
+      warp_i[warp] = xi;
+      warp_n[warp] = xn;
+    }
+    __syncthreads();
+    int addi = carry_i, addn = carry_n;
+    for (int w = 0; w < warp; ++w) {
+      addi += warp_i[w];
+      addn += warp_n[w];
+    }
+    if (t < nt) {
+      f.tile_i[s0 + t] = addi + xi - ci;
+      f.tile_n[s0 + t] = addn + xn - cn;
     }
     __syncthreads();
     if (tid == 255) {
@@ -850,6 +911,7 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
   DevBuf &nd_parent = buf(), &nd_chr = buf(), &nd_cnt = buf(), &nd_grp = buf(), &nd_lat = buf(), &nd_t0 = buf(),
          &nd_t1 = buf(), &nd_len = buf(), &nd_total = buf(), &nd_best = buf();
   DevBuf &d_ibase = buf(), &d_icnt = buf(), &d_cbase = buf(), &d_ccnt = buf(), &d_ncnt = buf();
+  DevBuf &tile_i = buf(), &tile_n = buf();
   KLU_TRY(d_ibase.reserve(8 * (size_t)(L + 1)));
   KLU_TRY(d_icnt.reserve(4 * (size_t)L));
   KLU_TRY(d_cbase.reserve(8 * (size_t)(L + 1)));
@@ -1018,8 +1080,28 @@ int run_char_index(klu_ctx* c, const klu_opts* o, bool segment) {
     f.n_wmax = n_wmax.as<double>();
     f.ncnt = d_ncnt.as<int32_t>();
     {
-      KLU_LAUNCH(c, "k_char_reduce");
-      k_char_reduce<<<L, 256, 0, c->stream>>>(a, f);
+      int64_t max_c = 0;
+      for (int32_t l = 0; l < L; ++l) max_c = std::max<int64_t>(max_c, h_cnt[l]);
+      const size_t slots = (size_t)(ncand >> 8) + (size_t)L + 2;
+      KLU_TRY(tile_i.reserve(4 * slots));
+      KLU_TRY(tile_n.reserve(4 * slots));
+      f.tile_i = tile_i.as<int32_t>();
+      f.tile_n = tile_n.as<int32_t>();
+      const unsigned rt = (unsigned)std::max<int64_t>(1, std::min<int64_t>((max_c + 255) / 256, 2048));
+      {
+        KLU_LAUNCH(c, "k_char_reduce");
+        k_char_reduce<true><<<dim3(L, rt), 256, 0, c->stream>>>(a, f);
+      }
+      KLU_TRY(check_launch("k_char_reduce(count)"));
+      {
+        KLU_LAUNCH(c, "k_char_tile_scan");
+        k_char_tile_scan<<<L, 256, 0, c->stream>>>(f);
+      }
+      KLU_TRY(check_launch("k_char_tile_scan"));
+      {
+        KLU_LAUNCH(c, "k_char_reduce");
+        k_char_reduce<false><<<dim3(L, rt), 256, 0, c->stream>>>(a, f);
+      }
     }
     KLU_TRY(check_launch("k_char_reduce"));
     // ---- the merged items become the current frontier (they keep the candidates' slot ranges) ----
