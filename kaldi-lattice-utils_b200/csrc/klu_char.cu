@@ -113,9 +113,12 @@ __global__ void __launch_bounds__(256) k_char_scan(SegRange rg, const int32_t* c
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int tile = 0; tile < n; tile += 256) {
-    const int i = tile + tid;
-    const long long c = i < n ? cnt[beg + i] : 0;
+  for (int tile = 0; tile < n; tile += 1024) {  // four consecutive elements per thread
+    const int i0 = tile + tid * 4;
+    int cc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cc[q] = i0 + q < n ? cnt[beg + i0 + q] : 0;
+    const long long c = (long long)cc[0] + cc[1] + cc[2] + cc[3];
     long long x = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -126,7 +129,12 @@ __global__ void __launch_bounds__(256) k_char_scan(SegRange rg, const int32_t* c
     __syncthreads();
     long long add = carry_s;
     for (int w = 0; w < warp; ++w) add += warp_sum[w];
-    if (i < n) out_loc[beg + i] = (int32_t)(add + x - c);
+    long long run = add + x - c;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i0 + q < n) out_loc[beg + i0 + q] = (int32_t)run;
+      run += cc[q];
+    }
     __syncthreads();
     if (tid == 255) carry_s = add + x;
     __syncthreads();
