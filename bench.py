@@ -388,15 +388,15 @@ def bench_tools(klu, local, args, peak):
              ("position@c2", "position", "c2", args.tools_scale * 256, cores),
              ("utterance@c4", "utterance", "c4", args.tools_scale * 32, cores),
              ("prune_dyn_beam->best_path2@c2", "prune_dyn_beam", "c2", args.tools_scale * 1024, 2 * cores),
-             ("char_position@c5", "char_position", "c5", args.tools_scale * 64, 2 * cores)]
+             ("char_position@c5", "char_position", "c5", args.tools_scale * 256, 2 * cores)]
     for name, tool, shape, nlat, ncpu in specs:
         nlat = int(max(1, nlat))
         if tool == "char_position":
             # The character tool runs in a process of its own, up to three times, at the batch size
-            # the drop-in binaries use for it (64 lattices): batches of several hundred c5 lattices,
-            # whose trie frontier passes 3e8 candidates at one depth, have ended in an illegal memory
-            # access (also with round 1's library; DESIGN.md "known issues"), which would take this
-            # process's CUDA context with it.
+            # the drop-in binaries use for it (256 lattices): before the merge kernel and the sorts
+            # were rewritten, batches of 448+ c5 lattices (trie frontier past 3e8 candidates at one
+            # depth) ended in an illegal memory access in 2 runs of 5 (DESIGN.md "known issues"; not
+            # seen since in 14 runs), which would take this process's CUDA context with it.
             out[name] = char_tool_entry(args, shape, nlat, ncpu, cores, local)
             continue
         eng = klu.Engine(local)

@@ -55,8 +55,9 @@ namespace {
 // bounds the per-lattice host metadata of a batch); the library itself has no such limit.
 #if KLU_TOOL == 6 /* KLU_CHAR_POSITION */ || KLU_TOOL == 9 /* KLU_CHAR_SEGMENT */
 // The character tools keep every same-group sub-path of a batch in device memory at once (a trie
-// whose frontier can grow by the branching factor per character): small batches bound that.
-constexpr size_t kMaxBatchLattices = 64;
+// whose frontier can grow by the branching factor per character): small batches bound that
+// (256 c5 lattices: ~1.6e8 candidates at the deepest level, a few GB).
+constexpr size_t kMaxBatchLattices = 256;
 #else
 constexpr size_t kMaxBatchLattices = (size_t)1 << 20;
 #endif
