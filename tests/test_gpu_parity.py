@@ -468,7 +468,11 @@ def test_segment_buckets_equal_generic_pipeline(klu, engine, monkeypatch, shape,
     # a bucket over the cap (300 parallel arcs out of one state) sends the whole batch down the generic path
     wide = klu.make_lattice("wide", 3, [(0, 1, 1 + (i % 9), 0.1 * i, 0.05 * (i % 7), 2) for i in range(300)]
                             + [(1, 2, 4, 0.5, 0.5, 1)], {2: (0.0, 0.0)})
-    for lats in (batch.lattices(), batch.lattices()[:3] + [wide]):
+    # labels near 2^31 with a long arc: 32-bit sort words no longer fit, 64-bit ones do
+    big = klu.make_lattice("big-labels", 4, [(0, 1, 2**31 - 2, 0.5, 0.25, 3), (0, 1, 2**31 - 2, 0.75, 0.5, 3),
+                                             (0, 1, 2**30 + 5, 0.1, 0.2, 3), (1, 2, 7, 0.3, 0.3, 200), (1, 2, 7, 0.2, 0.1, 200),
+                                             (2, 3, 2**31 - 2, 0.0, 0.1, 1)], {3: (0.0, 0.0)})
+    for lats in (batch.lattices(), batch.lattices()[:3] + [wide], batch.lattices()[:2] + [big]):
         monkeypatch.delenv("KLU_GENERIC_SEGMENT", raising=False)
         engine.load(klu.LatticeBatch.from_lattices(lats))
         new = engine.segment(**flags)
