@@ -369,10 +369,11 @@ __global__ void __launch_bounds__(256) k_char_emit0(CharArgs a, Frontier f) {
 // node scores of the current depth: the first item of every node folds the node's
 // items (they are sorted by state) with their exit weights
 __global__ void __launch_bounds__(256) k_char_accum(CharArgs a, Frontier f) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = f.icnt[l];
   const int64_t base = f.ibase[l];
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     const int node = f.it_node[base + i];
     if (i > 0 && f.it_node[base + i - 1] == node) continue;
     const int g = f.nd_grp[node];
@@ -400,11 +401,12 @@ __global__ void __launch_bounds__(256) k_char_accum(CharArgs a, Frontier f) {
 
 // expansion: candidates per item = same-group out arcs of its state
 __global__ void __launch_bounds__(256) k_char_count(CharArgs a, Frontier f) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   const BatchView& b = a.b;
-  const int l = blockIdx.x;
+  const int l = lt.l;
   const int n = f.icnt[l];
   const int64_t base = f.ibase[l];
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     const int x = f.it_state[base + i];
     const int g = f.nd_grp[f.it_node[base + i]];
     int c = 0;
@@ -417,11 +419,12 @@ __global__ void __launch_bounds__(256) k_char_count(CharArgs a, Frontier f) {
 }
 
 __global__ void __launch_bounds__(256) k_char_expand(CharArgs a, Frontier f) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   const BatchView& b = a.b;
-  const int l = blockIdx.x;
+  const int l = lt.l;
   const int n = f.icnt[l];
   const int64_t base = f.ibase[l], cb = f.cbase[l];
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     if (f.cand_cnt[base + i] == 0) continue;
     const int x = f.it_state[base + i];
     const int node = f.it_node[base + i];
@@ -453,11 +456,12 @@ __global__ void __launch_bounds__(256) k_char_expand(CharArgs a, Frontier f) {
 // segment mode, between the two stable sorts: candidates are ordered by destination
 // state; give them their main key (always in buffer A) for the second sort
 __global__ void __launch_bounds__(256) k_char_rekey(Frontier f, unsigned long long* key_a, unsigned int* val_a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = f.ccnt[l];
   const int64_t cb = f.cbase[l];
   const unsigned int* val = (f.where[l] ? f.val_b : f.val_a) + cb;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     const unsigned int j = val[i];
     key_a[cb + i] = f.c_main[cb + j];
     val_a[cb + i] = j;
@@ -693,11 +697,12 @@ __global__ void __launch_bounds__(256) k_char_rowfill(RowArgs a) {
 
 // second sort key: descending log-probability
 __global__ void __launch_bounds__(256) k_char_rowkey(RowArgs a, int L) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = a.row_cnt[l];
   const int64_t base = a.row_base[l];
   const unsigned int* val = (a.where[l] ? a.val_b : a.val_a) + base;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+  for (int i = lt.tile * blockDim.x + threadIdx.x; i < n; i += lt.tiles * blockDim.x) {
     const unsigned int node = val[i];
     const double logp = a.nd_total[node] - a.beta[a.s_off[l]];
     a.key[base + i] = ~ord_f64(logp + 0.0);

@@ -547,9 +547,10 @@ struct GroupArgs {
 
 // grid (L, tiles): sort input for the time order: key = start frame, val = out-order arc (lattice-local)
 __global__ void __launch_bounds__(256) k_fg_time_keys(GroupArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
-  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
+  for (int e = e0 + lt.tile * blockDim.x + threadIdx.x; e < e1; e += lt.tiles * blockDim.x) {
     reinterpret_cast<unsigned int*>(a.key)[e] = (unsigned int)max(a.b.time[a.b.out_src[e]], 0);  // 32-bit keys
     a.val[e] = (unsigned int)(e - e0);
   }
@@ -557,10 +558,11 @@ __global__ void __launch_bounds__(256) k_fg_time_keys(GroupArgs a) {
 
 // grid (L, tiles): the time-ordered arc copy and the inverse permutation
 __global__ void __launch_bounds__(256) k_fg_time_copy(GroupArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const unsigned int* val = (a.where[l] ? a.val_b : a.val_a) + e0;
-  for (int j = e0 + blockIdx.y * blockDim.x + threadIdx.x; j < e1; j += gridDim.y * blockDim.x) {
+  for (int j = e0 + lt.tile * blockDim.x + threadIdx.x; j < e1; j += lt.tiles * blockDim.x) {
     const int e = e0 + (int)val[j - e0];
     const int4 r = a.b.out_rec[e];
     a.tarc[j] = make_int4(a.b.out_src[e], r.x, r.y, r.z);

@@ -61,10 +61,11 @@ __device__ __forceinline__ int ld_cg_i32(const int32_t* p) { return __ldcg(p); }
 
 // grid (L, tiles): first arc of every state + layout validation
 __global__ void __launch_bounds__(256) k_gp_first_arc(GP a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
-  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+  const int t = lt.tile * blockDim.x + threadIdx.x, stride = lt.tiles * blockDim.x;
   for (int s = t; s < ns; s += stride) {
     int lo = e0, hi = e1;  // first arc with src >= s
     while (lo < hi) {
@@ -231,13 +232,14 @@ __global__ void __launch_bounds__(256) k_gp_state_keys(GP a, unsigned long long*
 __global__ void __launch_bounds__(256) k_gp_state_perm(GP a, const unsigned long long* key_a,
                                                         const unsigned long long* key_b, const unsigned int* val_a,
                                                         const unsigned int* val_b, const unsigned char* where) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const unsigned long long* key = (where[l] ? key_b : key_a) + s0;
   const unsigned int* val = (where[l] ? val_b : val_a) + s0;
   int32_t* lv = a.lvl_start + a.lvl_off[l];
   const int nl = a.lvl_off[l + 1] - a.lvl_off[l] - 1;
-  for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < ns; n += gridDim.y * blockDim.x) {
+  for (int n = lt.tile * blockDim.x + threadIdx.x; n < ns; n += lt.tiles * blockDim.x) {
     const int old = (int)val[n];
     const int lev = (int)key[n];
     const int go = s0 + old, gn = s0 + n;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(256) k_gp_state_perm(GP a, const unsigned long
     if (n == 0 || (int)key[n - 1] != lev) lv[lev] = gn;
     if (n == ns - 1) lv[nl] = s0 + ns;
   }
-  if (ns == 0 && blockIdx.y == 0 && threadIdx.x == 0) lv[0] = s0;
+  if (ns == 0 && lt.tile == 0 && threadIdx.x == 0) lv[0] = s0;
 }
 
 // One CTA per lattice: exclusive scan of per-state int32 counts.  MODE 0: out32 =
@@ -332,14 +334,15 @@ __global__ void __launch_bounds__(256) k_gp_add_base(int64_t* off, const int32_t
 
 // grid (L, tiles): arcs to source order + per-lattice capacities of the expansions
 __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* key, unsigned int* val) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   __shared__ long long red[2][8];
-  const int l = blockIdx.x;
+  const int l = lt.l;
   const int s0 = a.s_off[l];
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
   const int T = a.meta[l * M_STRIDE + M_FRAMES];
   long long cf = 0, cp = 0;
   int span = 0;
-  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
+  for (int e = e0 + lt.tile * blockDim.x + threadIdx.x; e < e1; e += lt.tiles * blockDim.x) {
     const int go = s0 + a.src[e], gd = s0 + a.dst[e];
     span = max(span, a.dur[e]);
     const int n = a.old2new[go], d = a.old2new[gd];
@@ -385,12 +388,13 @@ __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* ke
 __global__ void __launch_bounds__(256) k_gp_in_build(GP a, const unsigned long long* key_a,
                                                      const unsigned long long* key_b, const unsigned int* val_a,
                                                      const unsigned int* val_b, const unsigned char* where) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const int e0 = a.e_off[l], na = a.e_off[l + 1] - e0;
   const unsigned long long* key = (where[l] ? key_b : key_a) + e0;
   const unsigned int* val = (where[l] ? val_b : val_a) + e0;
-  const int t = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+  const int t = lt.tile * blockDim.x + threadIdx.x, stride = lt.tiles * blockDim.x;
   for (int q = t; q < na; q += stride) {
     const int p = e0 + (int)val[q];
     const int4 r = a.out_rec[p];
@@ -427,17 +431,31 @@ __global__ void __launch_bounds__(256) k_gp_band_counts2(GP a) {
 // (two atomics per arc, not one per arc x frame); k_gp_frame_counts turns the differences into the
 // arcs alive in every frame
 __global__ void __launch_bounds__(256) k_gp_frames(GP a) {
+  // (lattice-fastest grid on purpose: tile-fastest puts the CTAs in flight on the same few lattices'
+  // frame counters and the atomics collide -- 5.8 vs 10.1 ms)
   const int l = blockIdx.x;
   const int e0 = a.e_off[l], e1 = a.e_off[l + 1];
   const int T = a.fr_base[l + 1] - a.fr_base[l] - 1;
   int32_t* cnt = a.fr_cnt + a.fr_base[l];
-  for (int p = e0 + blockIdx.y * blockDim.x + threadIdx.x; p < e1; p += gridDim.y * blockDim.x) {
-    const int4 r = a.out_rec[p];
-    if (r.w == 0) continue;
-    const int fa = max(a.ptime[a.out_src[p]], 0), fb = min(a.ptime[r.x], T);
-    if (fb <= fa) continue;
-    atomicAdd(cnt + fa, 1);
-    atomicAdd(cnt + fb, -1);  // fb <= T: the slot that closes the lattice takes the last ones
+  // consecutive arcs leave the same state, i.e. start in the same frame (and mostly end in one of a
+  // few): the lanes of a warp are grouped by frame and one atomic per group is issued
+  const int lane = threadIdx.x & 31;
+  for (int p0 = e0 + blockIdx.y * blockDim.x; p0 < e1; p0 += gridDim.y * blockDim.x) {
+    const int p = p0 + threadIdx.x;
+    int fa = -1, fb = -1;
+    if (p < e1) {
+      const int4 r = a.out_rec[p];
+      if (r.w != 0) {
+        const int x = max(a.ptime[a.out_src[p]], 0), y = min(a.ptime[r.x], T);
+        if (y > x) {
+          fa = x;
+          fb = y;  // fb <= T: the slot that closes the lattice takes the last ones
+        }
+      }
+    }
+    const unsigned int ga = __match_any_sync(0xffffffffu, fa), gb = __match_any_sync(0xffffffffu, fb);
+    if (fa >= 0 && lane == __ffs(ga) - 1) atomicAdd(cnt + fa, __popc(ga));
+    if (fb >= 0 && lane == __ffs(gb) - 1) atomicAdd(cnt + fb, -__popc(gb));
   }
 }
 

@@ -122,10 +122,11 @@ __device__ __forceinline__ int64_t tile_slot(const int64_t* base, int l, int l_f
 
 // grid (lattices, tiles): sort key of every out-order arc = its word (or the drop key)
 __global__ void __launch_bounds__(256) k_pos_keys(PosArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
   const bool plain = a.tool != KLU_POSITION;
-  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
+  for (int e = e0 + lt.tile * blockDim.x + threadIdx.x; e < e1; e += lt.tiles * blockDim.x) {
     const int4 r = a.b.out_rec[e];
     const int s = a.b.out_src[e];
     bool valid = plain ? r.w != 0 : pos_label_valid(a, r.w);
@@ -143,10 +144,11 @@ __global__ void __launch_bounds__(256) k_pos_keys(PosArgs a) {
 
 // grid (lattices, tiles): group heads per 256-arc tile of the sorted arcs
 __global__ void __launch_bounds__(256) k_pos_head_count(PosArgs a) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int n = a.seg_cnt[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + a.seg_base[l];
-  for (int tile = blockIdx.y * 256; tile < n; tile += gridDim.y * 256) {
+  for (int tile = lt.tile * 256; tile < n; tile += lt.tiles * 256) {
     const int i = tile + threadIdx.x;
     bool head = false;
     if (i < n) {
@@ -194,14 +196,15 @@ __global__ void __launch_bounds__(256) k_tile_prefix(const int64_t* base, const 
 // grid (lattices, tiles): the head of a group walks its arcs: word, extent in the sorted list,
 // range of positions [plo, phi) its arcs' source bands cover
 __global__ void __launch_bounds__(256) k_pos_groups(PosArgs a) {
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   __shared__ int warp_sum[8];
-  const int l = blockIdx.x;
+  const int l = lt.l;
   const int n = a.seg_cnt[l];
   const int e0 = a.b.e_off[l];
   const unsigned long long* key = (a.where[l] ? a.key_b : a.key_a) + a.seg_base[l];
   const unsigned int* idx = (a.where[l] ? a.idx_b : a.idx_a) + a.seg_base[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int tile = blockIdx.y * 256; tile < n; tile += gridDim.y * 256) {
+  for (int tile = lt.tile * 256; tile < n; tile += lt.tiles * 256) {
     const int i = tile + tid;
     unsigned long long k = a.drop_key;
     bool head = false;

@@ -315,9 +315,10 @@ struct PruneArcsArgs {
 // grid (lattices, tiles): sort key of every arc, laid out in the caller's arc order (the
 // stable sort then breaks ties by that order)
 __global__ void __launch_bounds__(256) k_pa_keys(PruneArgs a, PruneArcsArgs p) {
-  const int l = blockIdx.x;
+  const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
+  const int l = lt.l;
   const int e0 = a.b.e_off[l], e1 = a.b.e_off[l + 1];
-  for (int e = e0 + blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += gridDim.y * blockDim.x) {
+  for (int e = e0 + lt.tile * blockDim.x + threadIdx.x; e < e1; e += lt.tiles * blockDim.x) {
     const int4 r = a.b.out_rec[e];
     const int s = a.b.out_src[e];
     const int o = a.b.out_orig[e];
