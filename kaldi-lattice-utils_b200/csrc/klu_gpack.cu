@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) k_gp_add_base(int64_t* off, const int32_t
 }
 
 // grid (L, tiles): arcs to source order + per-lattice capacities of the expansions
-__global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* key, unsigned int* val) {
+__global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned int* key, unsigned int* val) {
   const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   __shared__ long long red[2][8];
   const int l = lt.l;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* ke
     a.out_rec[p] = make_int4(d, __float_as_int(a.g[e]), __float_as_int(a.a[e]), lab);
     a.out_src[p] = n;
     a.out_orig[p] = e - e0;
-    key[p] = (unsigned long long)(unsigned int)(d - s0);  // sort key of the in-order: local packed dst
+    key[p] = (unsigned int)(d - s0);  // sort key of the in-order: local packed dst (32-bit keys)
     val[p] = (unsigned int)(p - e0);
     if (lab != 0) {
       const int fa = max(a.time[go], 0), fb = min(a.time[gd], T);
@@ -385,14 +385,14 @@ __global__ void __launch_bounds__(256) k_gp_scatter(GP a, unsigned long long* ke
 }
 
 // grid (L, tiles): destination-ordered records from the sorted (dst, out position) pairs
-__global__ void __launch_bounds__(256) k_gp_in_build(GP a, const unsigned long long* key_a,
-                                                     const unsigned long long* key_b, const unsigned int* val_a,
+__global__ void __launch_bounds__(256) k_gp_in_build(GP a, const unsigned int* key_a,
+                                                     const unsigned int* key_b, const unsigned int* val_a,
                                                      const unsigned int* val_b, const unsigned char* where) {
   const LatTile lt = lat_tile();  // CTAs that run together share lattices (L2 locality)
   const int l = lt.l;
   const int s0 = a.s_off[l], ns = a.s_off[l + 1] - s0;
   const int e0 = a.e_off[l], na = a.e_off[l + 1] - e0;
-  const unsigned long long* key = (where[l] ? key_b : key_a) + e0;
+  const unsigned int* key = (where[l] ? key_b : key_a) + e0;
   const unsigned int* val = (where[l] ? val_b : val_a) + e0;
   const int t = lt.tile * blockDim.x + threadIdx.x, stride = lt.tiles * blockDim.x;
   for (int q = t; q < na; q += stride) {
@@ -810,19 +810,32 @@ int pack_and_upload_gpu(klu_ctx* c, const klu_lattices* in) {
   // ---- arcs: source order by block move, destination order by stable sort ----
   {
     KLU_LAUNCH(c, "k_gp_scatter");
-    k_gp_scatter<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, key_a, val_a);
+    k_gp_scatter<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, reinterpret_cast<unsigned int*>(key_a), val_a);
   }
   KLU_TRY(check_launch("k_gp_scatter"));
-  ss.seg_base = seg64 + L + 1;
-  ss.seg_cnt = c->d_res[7].as<int32_t>() + L;
+  SegSortArgs32 sa;  // keys = lattice-local destination states: as many bits as the largest lattice needs
+  sa.seg_base = seg64 + L + 1;
+  sa.seg_cnt = c->d_res[7].as<int32_t>() + L;
+  sa.key_a = reinterpret_cast<unsigned int*>(key_a);
+  sa.key_b = reinterpret_cast<unsigned int*>(key_b);
+  sa.val_a = val_a;
+  sa.val_b = val_b;
+  sa.where = where;
+  sa.lo_bit = 0;
+  {
+    int64_t max_ns = 1;
+    for (int32_t l = 0; l < L; ++l) max_ns = std::max<int64_t>(max_ns, in->state_off[l + 1] - in->state_off[l]);
+    sa.hi_bit = 1;
+    while (sa.hi_bit < 32 && ((int64_t)1 << sa.hi_bit) < max_ns) ++sa.hi_bit;
+  }
   {
     KLU_LAUNCH(c, "k_seg_radix_sort");
-    KLU_TRY(seg_sort_launch(c, ss, L, (int64_t)E));
+    KLU_TRY(seg_sort_launch(c, sa, L, (int64_t)E));
   }
   KLU_TRY(check_launch("k_seg_radix_sort(arcs)"));
   {
     KLU_LAUNCH(c, "k_gp_in_build");
-    k_gp_in_build<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, key_a, key_b, val_a, val_b, where);
+    k_gp_in_build<<<dim3(L, arc_tiles), 256, 0, c->stream>>>(a, sa.key_a, sa.key_b, val_a, val_b, where);
   }
   KLU_TRY(check_launch("k_gp_in_build"));
   // ---- band offsets: per-lattice scan + lattice bases ----
