@@ -807,35 +807,51 @@ __global__ void __launch_bounds__(kBandThreads) k_banded_alpha(SweepArgs a, doub
           const int len = ss_lo[lo] + (int)(cell - ss_cell[lo]);
           LogSumRun acc;
           if (staged) {
-            // Two passes over the state's staged arcs, both free of loop-carried chains longer than
-            // one instruction: the maximum (independent loads), then the exp terms into two
-            // accumulators.  A serial running log-sum-exp here made a level cost its arcs x
-            // (load latency + exp latency) per thread.
+            // ONE pass over the state's staged arcs: the exp terms are taken around alpha[s] of the
+            // plain sweep (run just before), which bounds every term from above -- alpha[s] is the
+            // log-sum over all lengths of what this cell sums for one -- so no maximum has to be
+            // found first; two accumulators, no loop-carried chain longer than one add.  The first
+            // two finite terms are kept for Kaldi's exact LogAdd; a sum that leaves [1e-280, 1e280]
+            // (a cell more than ~645 nats below alpha[s], or inconsistent scores) is redone around
+            // its own maximum.
             const int i0 = ss_arc[lo] - e_base, i1 = ss_arc[lo + 1] - e_base;
-            double m = neg_inf();
+            const double ref = a.alpha[s0 + lo];
+            double sum0 = 0.0, sum1 = 0.0;
             int nterm = 0;
-#pragma unroll 4
-            for (int i = i0; i < i1; ++i) {
-              const int2 rg = sa_range[i];
-              const double x = (len >= rg.x && len < rg.y) ? alpha2[sa_base[i] + len] - sa_cost[i] : neg_inf();
-              nterm += x > neg_inf() ? 1 : 0;
-              m = fmax(m, x);
-            }
-            if (nterm >= 3) {
-              double sum0 = 0.0, sum1 = 0.0;
+            {
               int i = i0;
-              for (; i + 1 < i1; i += 2) {
+              for (; i + 1 < i1; i += 2) {  // branch-free: exp(-inf) = 0 for the arcs that do not reach this length
                 const int2 ra = sa_range[i], rb = sa_range[i + 1];
                 const double xa = (len >= ra.x && len < ra.y) ? alpha2[sa_base[i] + len] - sa_cost[i] : neg_inf();
                 const double xb = (len >= rb.x && len < rb.y) ? alpha2[sa_base[i + 1] + len] - sa_cost[i + 1] : neg_inf();
-                sum0 += fast_exp(xa - m);  // exp(-inf) = 0 for the arcs that do not reach this length
-                sum1 += fast_exp(xb - m);
+                nterm += (xa > neg_inf() ? 1 : 0) + (xb > neg_inf() ? 1 : 0);
+                sum0 += fast_exp(xa - ref);
+                sum1 += fast_exp(xb - ref);
               }
               if (i < i1) {
                 const int2 ra = sa_range[i];
-                if (len >= ra.x && len < ra.y) sum0 += fast_exp(alpha2[sa_base[i] + len] - sa_cost[i] - m);
+                const double xa = (len >= ra.x && len < ra.y) ? alpha2[sa_base[i] + len] - sa_cost[i] : neg_inf();
+                nterm += xa > neg_inf() ? 1 : 0;
+                sum0 += fast_exp(xa - ref);
               }
-              alpha2[cell] = m + fast_log(sum0 + sum1);
+            }
+            if (nterm >= 3) {
+              const double ssum = sum0 + sum1;
+              if (ssum >= 1e-280 && ssum <= 1e280) {
+                alpha2[cell] = ref + fast_log(ssum);
+                continue;
+              }
+              double m = neg_inf();  // rare: around the cell's own maximum
+              for (int i = i0; i < i1; ++i) {
+                const int2 rg = sa_range[i];
+                if (len >= rg.x && len < rg.y) m = fmax(m, alpha2[sa_base[i] + len] - sa_cost[i]);
+              }
+              double sum = 0.0;
+              for (int i = i0; i < i1; ++i) {
+                const int2 rg = sa_range[i];
+                if (len >= rg.x && len < rg.y) sum += fast_exp(alpha2[sa_base[i] + len] - sa_cost[i] - m);
+              }
+              alpha2[cell] = m + fast_log(sum);
               continue;
             }
             if (nterm > 0)  // one or two terms: Kaldi's LogAdd exactly
