@@ -209,8 +209,9 @@ int klu_profile_enable(klu_ctx* ctx, int on);
 int klu_profile_json(klu_ctx* ctx, char* buf, size_t cap);
 /* Device-side cost of the last klu_load, for honest throughput figures: upload_ms = wall
  * clock of the host-to-device copies of the caller's arrays; pack_ms = CUDA-event time of
- * the device packer (levels, CSR, bands); frame_index_ms = CUDA-event time of the frame index
- * that the first KLU_FRAME_POST run on the batch builds (0 until then). */
+ * the device packer (levels, CSR, bands); frame_index_ms = CUDA-event time of the per-batch
+ * indexes built on first use: the frame index of the first KLU_FRAME_POST run on the batch, the
+ * start-frame buckets of the first KLU_SEGMENT run (0 until then). */
 int klu_load_times(klu_ctx* ctx, float* upload_ms, float* pack_ms, float* frame_index_ms);
 /* Totals of the loaded batch: {lattices, states, arcs, levels, entries of last run}. */
 int klu_batch_stats(klu_ctx* ctx, int64_t stats[8]);
