@@ -683,9 +683,16 @@ def main():
         pack_total = reduce_max(float(np.mean([p[1] + p[2] for p in packs])))
         roofline["pipeline_frac_76B_per_arc_incl_pack"] = pipe_bytes / ((ms_per_step + pack_total) * 1e-3) / 1e9 / peak
     pipe_step = None
-    if args.e2e_steps > 0 and args.e2e_slices > 1 and args.tool == "frame_post":
+    # contexts (host threads) per rank: no more than the host's cores divided among the ranks
+    # (8 ranks x 8 spinning threads on a 32-core host get in each other's way); two slices per context
+    n_ctx = args.e2e_contexts
+    n_slices = args.e2e_slices
+    if world > 1:
+        n_ctx = max(3, min(n_ctx, len(all_cpus) // world))
+        n_slices = min(n_slices, 2 * n_ctx) if n_ctx < args.e2e_contexts else n_slices
+    if args.e2e_steps > 0 and n_slices > 1 and args.tool == "frame_post":
         eng.close()  # its device memory goes to the pipeline contexts
-        nsl = min(args.e2e_slices, nlat)
+        nsl = min(n_slices, nlat)
         cuts = np.searchsorted(batch.arc_off, np.linspace(0, batch.arc_off[-1], nsl + 1)[1:-1]).tolist()
         cuts = [0] + [int(x) for x in cuts] + [nlat]
         subs = [batch.slice(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
@@ -694,7 +701,7 @@ def main():
                        dst_delta_u16=None if d16 is None else d16[int(batch.arc_off[a]):int(batch.arc_off[b])],
                        label_u16=None if lab16 is None else lab16[int(batch.arc_off[a]):int(batch.arc_off[b])])
                   for a, b in zip(cuts[:-1], cuts[1:])]
-        engines = [klu.Engine(local) for _ in range(min(args.e2e_contexts, nsl))]
+        engines = [klu.Engine(local) for _ in range(min(n_ctx, nsl))]
         row_off = np.concatenate([[0], np.cumsum([0] * nsl)])  # filled by the first pass
         sub_rows = [0] * nsl
 
@@ -738,7 +745,7 @@ def main():
            if parts else None,
            "single_call_ms_upload_pack_frameindex": [round(float(np.mean([p[k] for p in packs])), 2) for k in range(3)]
            if packs else None,
-           "pipeline": {"slices": args.e2e_slices, "contexts": args.e2e_contexts} if pipe_step else None,
+           "pipeline": {"slices": n_slices, "contexts": n_ctx} if pipe_step else None,
            "note": "klu_load (H2D of the caller's pinned SoA arrays + device packer) + klu_run + klu_fetch "
                    "(D2H of the full index into pinned buffers), wall clock, max over ranks; value = the "
                    "pipelined call sequence when `pipeline` is set, else the single call sequence"}
