@@ -10,8 +10,9 @@
 // other per-batch indexes) and every run sorts each bucket -- the ~80 arcs that start in one
 // frame -- by (word, duration) in shared memory: one warp per bucket, a bitonic network over
 // 64-bit words {key, arc rank}, then the run heads fold their arcs with LogAdd in arc order.
-// The reduced entries land in an arena indexed like the sorted arcs (holes at the end of every
-// bucket, keyed to sort last), so the order sort by log-posterior follows directly.
+// The reduced entries land in an arena indexed like the sorted arcs (a bucket's entries at the
+// start of its arc range), a per-lattice scan of the buckets' entry counts packs their (order key,
+// arena index) pairs back to back, and the order sort by log-posterior runs on those.
 //
 // Buckets larger than kBucketCap arcs (or keys that do not fit) send the whole batch through
 // the generic pipeline instead (run_index_tool) -- e.g. a lattice with hundreds of parallel arcs
@@ -58,9 +59,13 @@ struct SegArgs {
   int tiles;             // CTAs per lattice
   int cap;               // shared-memory slots per warp: power of two >= the largest bucket
   int rank_bits;         // log2(cap): low bits of a sort word = the arc's rank in its bucket
-  unsigned int* key32;   // order keys (high half of the f64 key); holes = 0xffffffff
+  unsigned int* key32;   // order keys (high half of the f64 key), at arena positions
   unsigned int* idx;     // lattice-local arena index
   int32_t* rcnt;         // [L] entries
+  int32_t* slot_cnt;     // per bucket slot: entries (run heads) it produced
+  int32_t* slot_dense;   // per bucket slot: lattice-local first dense position of its entries
+  unsigned int* key32_d;  // dense copies of key32 / idx (what the order sort works on)
+  unsigned int* idx_d;
 };
 
 __device__ __forceinline__ bool seg_label_valid(const SegArgs& a, int label) {
@@ -167,11 +172,13 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
   const int slot0 = a.slot_base[l], nslots = a.slot_base[l + 1] - slot0;
   const unsigned int* perm = (a.where[l] ? a.perm_b : a.perm_a);
   const double total = a.total[l];
-  int heads_here = 0;
   for (int f = tile * kBucketWarps + warp; f < nslots; f += a.tiles * kBucketWarps) {
     const int slot = slot0 + f;
     const int j0 = a.boff[slot], n = a.boff[slot + 1] - j0;
-    if (n <= 0) continue;
+    if (n <= 0) {
+      if (lane == 0) a.slot_cnt[slot] = 0;
+      continue;
+    }
     const unsigned long long t0 = (unsigned long long)f;
     int P = 32;
     while (P < n) P <<= 1;
@@ -246,19 +253,62 @@ __global__ void __launch_bounds__(kBucketWarps * 32) k_sg_buckets(SegArgs a) {
       }
       carry += __popc(hm);
     }
-    for (int r = carry + lane; r < n; r += 32) {  // holes: sort last
-      a.key32[j0 + r] = 0xffffffffu;
-      a.idx[j0 + r] = (unsigned int)(j0 + r - e0);
-    }
-    heads_here += carry;
+    if (lane == 0) a.slot_cnt[slot] = carry;  // the rest of the bucket's arena range stays unused
     __syncwarp();
   }
-  if (lane == 0 && heads_here > 0) atomicAdd(a.rcnt + l, heads_here);
+}
+
+// one CTA per lattice: exclusive scan of its buckets' entry counts -> where each bucket's entries go
+// in the dense order-sort input; the lattice's entry count
+__global__ void __launch_bounds__(256) k_sg_dense_offsets(SegArgs a) {
+  __shared__ int warp_sum[8];
+  __shared__ int carry_s;
+  const int l = blockIdx.x;
+  const int slot0 = a.slot_base[l], nslots = a.slot_base[l + 1] - slot0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nslots; base += 256) {
+    const int i = base + tid;
+    const int c = i < nslots ? a.slot_cnt[slot0 + i] : 0;
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    int add = carry_s;
+    for (int w = 0; w < warp; ++w) add += warp_sum[w];
+    if (i < nslots) a.slot_dense[slot0 + i] = add + x - c;
+    __syncthreads();
+    if (tid == 255) carry_s = add + x;
+    __syncthreads();
+  }
+  if (tid == 0) a.rcnt[l] = carry_s;
+}
+
+// one warp per bucket: its entries' (order key, arena index) pairs to the dense arrays
+template <typename KT>
+__global__ void __launch_bounds__(kBucketWarps * 32) k_sg_densify(SegArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l = blockIdx.x / a.tiles, tile = blockIdx.x % a.tiles;
+  const int e0 = a.b.e_off[l];
+  const int slot0 = a.slot_base[l], nslots = a.slot_base[l + 1] - slot0;
+  for (int f = tile * kBucketWarps + warp; f < nslots; f += a.tiles * kBucketWarps) {
+    const int slot = slot0 + f;
+    const int cnt = a.slot_cnt[slot];
+    const int j0 = a.boff[slot], d0 = e0 + a.slot_dense[slot];
+    for (int r = lane; r < cnt; r += 32) {
+      a.key32_d[d0 + r] = a.key32[j0 + r];
+      a.idx_d[d0 + r] = a.idx[j0 + r];
+    }
+  }
 }
 
 // After the 32-bit order sort: runs of equal high halves are put in the reference's full
-// order -- (logp desc, word, t0, t1) -- by a stable insertion sort, one thread per run; the
-// run of holes at the end of every lattice is left alone.
+// order -- (logp desc, word, t0, t1) -- by a stable insertion sort, one thread per run.
 struct SegFixArgs {
   const int64_t* seg_base;
   const int32_t* seg_cnt;
@@ -479,13 +529,14 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
   KLU_TRY(run_log_sweeps(c, cp, use_beam, o->beam));
   const size_t E1 = (size_t)c->E;
   DevBuf* sc = c->d_scratch;
-  enum { S_REC = 4, S_K32A, S_K32B, S_IDXA, S_IDXB, S_RCNT };
+  enum { S_REC = 4, S_K32A, S_K32B, S_IDXA, S_IDXB, S_RCNT, S_SLOTS };
   KLU_TRY(sc[S_REC].reserve(16 * E1));
   KLU_TRY(sc[S_K32A].reserve(4 * E1));
   KLU_TRY(sc[S_K32B].reserve(4 * E1));
   KLU_TRY(sc[S_IDXA].reserve(4 * E1));
   KLU_TRY(sc[S_IDXB].reserve(4 * E1));
   KLU_TRY(sc[S_RCNT].reserve(4 * (size_t)L + (size_t)L + 64));
+  KLU_TRY(sc[S_SLOTS].reserve(8 * ((size_t)c->seg_slots + 2)));
   KLU_TRY(c->d_res[5].reserve(8 * (size_t)(L + 1)));
   int fmode = 0, fn = 0;
   KLU_TRY(upload_filter(c, o, &fmode, &fn));
@@ -528,8 +579,11 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
   a.key32 = sc[S_K32A].as<unsigned int>();
   a.idx = sc[S_IDXA].as<unsigned int>();
   a.rcnt = sc[S_RCNT].as<int32_t>();
+  a.slot_cnt = sc[S_SLOTS].as<int32_t>();
+  a.slot_dense = a.slot_cnt + c->seg_slots + 1;
+  a.key32_d = sc[S_K32B].as<unsigned int>();
+  a.idx_d = sc[S_IDXB].as<unsigned int>();
   unsigned char* where2 = reinterpret_cast<unsigned char*>(a.rcnt + L);
-  KLU_CUDA(cudaMemsetAsync(a.rcnt, 0, 4 * (size_t)L, c->stream));
   {
     KLU_LAUNCH(c, "k_sg_buckets");
     int max_slots = 1;
@@ -547,13 +601,24 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
     }
   }
   KLU_TRY(check_launch("k_sg_buckets"));
+  // the entries (~0.7 per arc) back to back per lattice: the order sort moves no holes
+  {
+    KLU_LAUNCH(c, "k_sg_dense_offsets");
+    k_sg_dense_offsets<<<L, 256, 0, c->stream>>>(a);
+  }
+  KLU_TRY(check_launch("k_sg_dense_offsets"));
+  {
+    KLU_LAUNCH(c, "k_sg_densify");
+    k_sg_densify<unsigned int><<<(unsigned int)((int64_t)L * a.tiles), kBucketWarps * 32, 0, c->stream>>>(a);
+  }
+  KLU_TRY(check_launch("k_sg_densify"));
   SegSortArgs32 s2;
   s2.seg_base = d_seg_base;
-  s2.seg_cnt = d_seg_cnt;
-  s2.key_a = a.key32;
-  s2.val_a = a.idx;
-  s2.key_b = sc[S_K32B].as<unsigned int>();
-  s2.val_b = sc[S_IDXB].as<unsigned int>();
+  s2.seg_cnt = a.rcnt;
+  s2.key_a = a.key32_d;
+  s2.val_a = a.idx_d;
+  s2.key_b = a.key32;
+  s2.val_b = a.idx;
   s2.where = where2;
   s2.lo_bit = 0;
   s2.hi_bit = 32;
@@ -567,7 +632,7 @@ int run_segment_buckets(klu_ctx* c, const klu_opts* o, bool* done) {
   const int tiles = (int)std::max<int64_t>(1, std::min<int64_t>((max_arcs + 255) / 256, 64));
   SegFixArgs f;
   f.seg_base = d_seg_base;
-  f.seg_cnt = d_seg_cnt;
+  f.seg_cnt = a.rcnt;
   f.where = where2;
   f.key_a = s2.key_a;
   f.key_b = s2.key_b;
